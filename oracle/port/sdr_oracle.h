@@ -1,0 +1,64 @@
+/* ORACLE (test infrastructure; never shipped, never on the product path).
+ *
+ * Plain-C restatement of the reference's baseband-to-channel DSP hot path, written from the closed
+ * forms in SURVEY.md Appendix A.  Each function cites the reference file:line it follows (paths are
+ * relative to /root/reference).  Pinned by tests/ against (a) oracle/_ref/libsdrref.so, the unmodified
+ * reference compiled in place, and (b) the golden vectors in tests/golden/ that were generated from it.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load this library.
+ */
+#ifndef SDR_ORACLE_H
+#define SDR_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { ORC_MODE_INF = 0, ORC_MODE_SUP = 1, ORC_MODE_CEN = 2 };
+enum { ORC_FMT_I16 = 0, ORC_FMT_F32 = 1 };
+
+/* sdrbench input generators: sdrbench/mainbench.cpp:30-31,76-79 (mt19937 default seed, 2N-1 draws, last = 0) */
+void orc_sdrbench_gen_s16(int16_t* buf, int n_scalars);
+void orc_sdrbench_gen_f32(float* buf, int n_scalars);
+
+/* Decimators<qint32,qint16,16,InputBits>: sdrbase/dsp/decimators.h:279-341 and the entry points below it */
+void* orc_decim_ii_create(int input_bits);
+void  orc_decim_ii_destroy(void* h);
+int   orc_decim_ii_run(void* h, int log2, int mode, const int16_t* buf, int len, int16_t* out);
+
+/* DecimatorsFI / DecimatorsFF / DecimatorsIF: sdrbase/dsp/decimatorsfi.cpp, decimatorsff.cpp, decimatorsif.h */
+void* orc_decim_f_create(int in_fmt, int out_fmt, int input_bits);
+void  orc_decim_f_destroy(void* h);
+int   orc_decim_f_run(void* h, int log2, int mode, const void* buf, int len, void* out);
+
+/* DownChannelizer: sdrbase/dsp/downchannelizer.cpp:50-91,165-189,250-287 */
+void* orc_chan_create(void);
+void  orc_chan_destroy(void* h);
+int   orc_chan_configure(void* h, int input_rate, int requested_rate, int center_offset,
+                         int* out_rate, int* residual_offset, int* modes, int modes_cap);
+int   orc_chan_feed(void* h, const int16_t* iq, int n, int16_t* out, int cap);
+
+/* NCO + Interpolator as wired by a channel plugin: nco.cpp:30-64, interpolator.cpp:21-129, interpolator.h:23-36,
+ * plugins/channelrx/demodnfm/nfmdemod.cpp:152-155,315,462-470 */
+void  orc_nco_table(float* table4096);
+int   orc_nco_increment(float freq, float rate);
+int   orc_interp_ntaps(int phase_steps, double taps_per_phase);
+void  orc_interp_taps(int phase_steps, double rate, double cutoff, double taps_per_phase, float* taps);
+void* orc_frontend_create(float nco_freq, float nco_rate, int phase_steps, double interp_rate, double cutoff,
+                          double taps_per_phase, float distance);
+void  orc_frontend_destroy(void* h);
+int   orc_frontend_feed(void* h, const int16_t* iq, int n, float* out, int cap, int32_t* idx, int32_t* phase);
+
+/* FFTWindow / KissFFT / SpectrumVis: fftwindow.cpp:20-73, kissfft.h:44-80,127-238, sdrgui/dsp/spectrumvis.cpp:77-327 */
+void  orc_fft_window(int function, int n, float* w);
+void  orc_kissfft_forward(int n, const float* in, float* out);
+void* orc_spectrum_create(float scalef);
+void  orc_spectrum_destroy(void* h);
+void  orc_spectrum_configure(void* h, int fft_size, int overlap_pct, unsigned avg_nb, int avg_mode, int window, int linear);
+int   orc_spectrum_feed(void* h, const int16_t* iq, int n, int positive_only, float* frames, int cap_frames);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
