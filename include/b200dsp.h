@@ -1,0 +1,89 @@
+/* b200dsp.h — C ABI of the B200-native SDRangel baseband-to-channel DSP hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, opaque handles, no C++/torch/Qt types.
+ * The reference has no C plugin ABI (its plugins instantiate the DSP classes by value), so every
+ * entry point below names the reference class/method it replaces (paths relative to the reference
+ * tree); include/sdrangel_b200/dsp/ holds header-only C++ wrappers with the reference's class names and
+ * method signatures that forward here.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative B200DSP_E* code on failure; b200dsp_last_error()
+ *     returns a thread-local message for the last failure on the calling thread.
+ *   - one handle == one reference object; a handle is single-writer (like the reference objects) and
+ *     owns a CUDA stream; different handles may be driven from different host threads concurrently.
+ *   - host-pointer calls return when the outputs are host-visible; `_dev` calls take device pointers
+ *     (16-byte aligned) and are asynchronous on the given stream (NULL = the handle's stream).
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with B200DSP_ENODEV.
+ */
+#ifndef B200DSP_H
+#define B200DSP_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200DSP_OK        0
+#define B200DSP_EINVAL   -1   /* bad argument */
+#define B200DSP_ENODEV   -2   /* no CUDA device / driver */
+#define B200DSP_ECUDA    -3   /* CUDA runtime error (message in last_error) */
+#define B200DSP_ENOMEM   -4
+#define B200DSP_ESTATE   -5   /* call not valid in this state (e.g. not configured) */
+
+/* sample formats */
+#define B200DSP_FMT_I16   0   /* int16 interleaved I,Q  (reference: qint16 buffers / Sample, dsptypes.h:44-65) */
+#define B200DSP_FMT_F32   1   /* float interleaved I,Q  (reference: FSample, dsptypes.h:67-93) */
+/* fc position, same meaning as the reference's m_fcPos switch (plugins/samplesource/airspy/airspythread.cpp:118-202) */
+#define B200DSP_MODE_INF  0
+#define B200DSP_MODE_SUP  1
+#define B200DSP_MODE_CEN  2
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+int         b200dsp_init(int device_ordinal);      /* selects the device for handles created afterwards */
+int         b200dsp_device_count(void);            /* 0 when no usable CUDA device */
+const char* b200dsp_last_error(void);
+const char* b200dsp_version(void);
+int         b200dsp_sm_count(void);
+
+/* ---- K1/K2: half-band decimation cascades ---------------------------------------------------------------
+ * One handle == one reference decimator object with its six half-band stages of state:
+ *   in I16, out I16 : Decimators<qint32,qint16,16,input_bits>   sdrbase/dsp/decimators.h:277-341
+ *   in F32, out I16 : DecimatorsFI                               sdrbase/dsp/decimatorsfi.h:26-55
+ *   in F32, out F32 : DecimatorsFF                               sdrbase/dsp/decimatorsff.h
+ *   in I16, out F32 : DecimatorsIF<qint16,input_bits>            sdrbase/dsp/decimatorsif.h:53-83
+ * input_bits in {8,12,16} selects decimation_shifts<16,input_bits> (decimators.h:79-167) / the IF scale.
+ */
+typedef struct b200dsp_decim b200dsp_decim_t;
+
+int b200dsp_decim_create(b200dsp_decim_t** h, int in_fmt, int out_fmt, int input_bits);
+int b200dsp_decim_destroy(b200dsp_decim_t* h);
+
+/* float arithmetic flavour: 0 (default) = fused multiply-add accumulation (within 1e-5 rel. RMS of the
+ * reference), 1 = separately rounded add/mul/add in the reference's order (bit-identical to the reference
+ * compiled without -ffast-math).  No effect on the integer cascade, which is always bit-exact. */
+int b200dsp_decim_set_exact_float(b200dsp_decim_t* h, int exact);
+
+/* == decimate{1,2,4,...,64}_{inf,sup,cen}(SampleVector::iterator* it, const T* buf, qint32 len)
+ *    (decimators.h:344-3886, decimatorsfi.cpp:19-1172): `len` counts scalars (2 per IQ sample); the trailing
+ *    partial block is dropped exactly as the reference's loops do; filter state carries to the next call.
+ *    out receives *n_out IQ samples (2 scalars each).  log2_decim 0..6. */
+int b200dsp_decim_run(b200dsp_decim_t* h, int log2_decim, int mode,
+                      const void* in, int32_t len_scalars, void* out, int32_t* n_out);
+int b200dsp_decim_run_dev(b200dsp_decim_t* h, int log2_decim, int mode,
+                          const void* d_in, int64_t len_scalars, void* d_out, int64_t* n_out, void* cuda_stream);
+/* number of output IQ samples decimate*_ would write for `len_scalars` (pure host arithmetic, no device) */
+int64_t b200dsp_decim_out_count(int in_fmt, int out_fmt, int log2_decim, int mode, int64_t len_scalars);
+
+/* Filter state = for each of the six stages the last 64 stage inputs (I then Q, oldest first), as the
+ * reference keeps them in IntHalfbandFilterEO::m_even/m_odd (inthalfbandfiltereo.h:743-749).
+ * 6*2*64 elements of int32 (integer cascade) or float (float cascades). */
+#define B200DSP_DECIM_STATE_ELEMS (6 * 2 * 64)
+int b200dsp_decim_get_state(b200dsp_decim_t* h, void* state_host);
+int b200dsp_decim_set_state(b200dsp_decim_t* h, const void* state_host);
+int b200dsp_decim_reset(b200dsp_decim_t* h);
+int b200dsp_decim_sync(b200dsp_decim_t* h);        /* wait for the handle's stream */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DSP_H */

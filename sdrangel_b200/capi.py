@@ -1,0 +1,72 @@
+"""ctypes binding of libb200dsp.so (include/b200dsp.h).  Fails loudly when the library is not built."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200dsp.so")
+
+FMT_I16, FMT_F32 = 0, 1
+MODE_INF, MODE_SUP, MODE_CEN = 0, 1, 2
+DECIM_STATE_ELEMS = 6 * 2 * 64
+ENODEV = -2
+
+
+class B200DspError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("b200dsp error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+_vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+_pvp, _pi32, _pi64 = C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+
+# name -> (restype, argtypes); every symbol include/b200dsp.h declares
+SIGNATURES = {
+    "b200dsp_init": (_i32, [_i32]),
+    "b200dsp_device_count": (_i32, []),
+    "b200dsp_last_error": (C.c_char_p, []),
+    "b200dsp_version": (C.c_char_p, []),
+    "b200dsp_sm_count": (_i32, []),
+    "b200dsp_decim_create": (_i32, [_pvp, _i32, _i32, _i32]),
+    "b200dsp_decim_destroy": (_i32, [_vp]),
+    "b200dsp_decim_set_exact_float": (_i32, [_vp, _i32]),
+    "b200dsp_decim_run": (_i32, [_vp, _i32, _i32, _vp, _i32, _vp, _pi32]),
+    "b200dsp_decim_run_dev": (_i32, [_vp, _i32, _i32, _vp, _i64, _vp, _pi64, _vp]),
+    "b200dsp_decim_out_count": (_i64, [_i32, _i32, _i32, _i32, _i64]),
+    "b200dsp_decim_get_state": (_i32, [_vp, _vp]),
+    "b200dsp_decim_set_state": (_i32, [_vp, _vp]),
+    "b200dsp_decim_reset": (_i32, [_vp]),
+    "b200dsp_decim_sync": (_i32, [_vp]),
+}
+
+
+def lib():
+    """The loaded library.  Raises ImportError (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libb200dsp.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "or `make -C sdrangel_b200/csrc`. There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise B200DspError(rc, lib().b200dsp_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+def device_count():
+    return lib().b200dsp_device_count()
+
+
+def init(device=0):
+    check(lib().b200dsp_init(device))

@@ -1,0 +1,121 @@
+"""Host-side mirrors of the reference's decimator classes over the C ABI.
+
+Names and call semantics follow the reference (sdrbase/dsp/decimators.h:277-341, decimatorsfi.h:26-55,
+decimatorsff.h, decimatorsif.h:53-83): one object holds six half-band stages of state; `decimateN_{inf,sup,cen}`
+take an interleaved I/Q buffer, drop the trailing partial block, carry filter state to the next call and return
+the produced samples (the C++ wrappers in include/sdrangel_b200/dsp/ write through `SampleVector::iterator*`
+exactly like the reference; in Python the samples are returned as an (n, 2) array).
+"""
+import ctypes as C
+import numpy as np
+from . import capi
+
+MODE_INF, MODE_SUP, MODE_CEN = capi.MODE_INF, capi.MODE_SUP, capi.MODE_CEN
+_MODES = {"inf": MODE_INF, "sup": MODE_SUP, "cen": MODE_CEN}
+
+
+class _DecimatorsBase:
+    IN_FMT = capi.FMT_I16
+    OUT_FMT = capi.FMT_I16
+
+    def __init__(self, input_bits=12, device=None):
+        L = capi.lib()
+        if device is not None:
+            capi.init(device)
+        h = C.c_void_p()
+        capi.check(L.b200dsp_decim_create(C.byref(h), self.IN_FMT, self.OUT_FMT, input_bits))
+        self._h = h
+        self.input_bits = input_bits
+        self.in_dtype = np.int16 if self.IN_FMT == capi.FMT_I16 else np.float32
+        self.out_dtype = np.int16 if self.OUT_FMT == capi.FMT_I16 else np.float32
+        self.state_dtype = np.int32 if (self.IN_FMT, self.OUT_FMT) == (capi.FMT_I16, capi.FMT_I16) else np.float32
+
+    def close(self):
+        if getattr(self, "_h", None):
+            capi.lib().b200dsp_decim_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- generic entry points -------------------------------------------------------------------------
+    def out_count(self, log2, mode, len_scalars):
+        return int(capi.lib().b200dsp_decim_out_count(self.IN_FMT, self.OUT_FMT, log2, mode, len_scalars))
+
+    def run(self, log2, mode, buf):
+        """Host-buffer call == decimate<2^log2>_<mode>(&it, buf, len): returns the (n_out, 2) samples written."""
+        buf = np.ascontiguousarray(buf, dtype=self.in_dtype).reshape(-1)
+        n = self.out_count(log2, mode, buf.size)
+        if n < 0:
+            raise ValueError("bad log2/mode")
+        out = np.empty((max(n, 1), 2), dtype=self.out_dtype)
+        n_out = C.c_int32(0)
+        capi.check(capi.lib().b200dsp_decim_run(self._h, log2, mode, buf.ctypes.data, buf.size, out.ctypes.data, C.byref(n_out)))
+        assert n_out.value == n
+        return out[:n]
+
+    def run_dev(self, log2, mode, d_in, len_scalars, d_out, stream=None):
+        """Device-resident call (metric path): d_in / d_out are device pointers (ints); asynchronous."""
+        n_out = C.c_int64(0)
+        capi.check(capi.lib().b200dsp_decim_run_dev(self._h, log2, mode, C.c_void_p(d_in), len_scalars, C.c_void_p(d_out),
+                                                    C.byref(n_out), C.c_void_p(stream or 0)))
+        return n_out.value
+
+    def set_exact_float(self, exact=True):
+        capi.check(capi.lib().b200dsp_decim_set_exact_float(self._h, int(bool(exact))))
+
+    def get_state(self):
+        st = np.empty((6, 2, 64), dtype=self.state_dtype)
+        capi.check(capi.lib().b200dsp_decim_get_state(self._h, st.ctypes.data))
+        return st
+
+    def set_state(self, st):
+        st = np.ascontiguousarray(st, dtype=self.state_dtype).reshape(6, 2, 64)
+        capi.check(capi.lib().b200dsp_decim_set_state(self._h, st.ctypes.data))
+
+    def reset(self):
+        capi.check(capi.lib().b200dsp_decim_reset(self._h))
+
+    def sync(self):
+        capi.check(capi.lib().b200dsp_decim_sync(self._h))
+
+    def decimate1(self, buf):
+        return self.run(0, MODE_CEN, buf)
+
+
+def _add_entry_points(cls):
+    for log2 in range(1, 7):
+        for name, mode in _MODES.items():
+            def f(self, buf, _l=log2, _m=mode):
+                return self.run(_l, _m, buf)
+            f.__name__ = "decimate%d_%s" % (1 << log2, name)
+            f.__doc__ = "== %s::decimate%d_%s(it, buf, len)" % (cls.__name__, 1 << log2, name)
+            setattr(cls, f.__name__, f)
+    return cls
+
+
+@_add_entry_points
+class Decimators(_DecimatorsBase):
+    """Decimators<qint32, qint16, 16, input_bits> (sdrbase/dsp/decimators.h:277-341)."""
+    IN_FMT, OUT_FMT = capi.FMT_I16, capi.FMT_I16
+
+
+@_add_entry_points
+class DecimatorsFI(_DecimatorsBase):
+    """DecimatorsFI (sdrbase/dsp/decimatorsfi.h:26-55): float in, int16 out."""
+    IN_FMT, OUT_FMT = capi.FMT_F32, capi.FMT_I16
+
+
+@_add_entry_points
+class DecimatorsFF(_DecimatorsBase):
+    """DecimatorsFF (sdrbase/dsp/decimatorsff.h): float in, float out."""
+    IN_FMT, OUT_FMT = capi.FMT_F32, capi.FMT_F32
+
+
+@_add_entry_points
+class DecimatorsIF(_DecimatorsBase):
+    """DecimatorsIF<qint16, input_bits> (sdrbase/dsp/decimatorsif.h:53-83): int16 in, float out."""
+    IN_FMT, OUT_FMT = capi.FMT_I16, capi.FMT_F32

@@ -1,0 +1,153 @@
+"""GPU parity tests of K1/K2 (hb64 cascade) through the C ABI: against the golden vectors generated from the
+reference, against the oracle port on larger seeded inputs, and through size-independent properties at
+BASELINE sizes.  Integer path: bit-exact.  Float path: exact mode bit-exact vs the strict reference build,
+default (fma) mode within 1e-5 relative RMS (north_star tolerance) and <= 1 LSB on int16 outputs."""
+import numpy as np
+import pytest
+
+from conftest import MODES, fnv1a64_u16, rel_rms, stream_input
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("bits", [8, 12, 16])
+def test_decimators_stream_golden_bit_exact(gpu_lib, golden, golden_meta, bits):
+    from sdrangel_b200 import Decimators
+    x = stream_input()
+    cuts = golden_meta["decim_ii_stream"]["cuts"]
+    for log2 in range(7):
+        for mname, mode in MODES.items():
+            d = Decimators(bits)
+            outs = [d.run(log2, mode, x[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+            assert [o.shape[0] for o in outs] == golden[f"decim_ii_stream_counts/{bits}/{log2}/{mname}"].tolist()
+            got = np.concatenate(outs)
+            want = golden[f"decim_ii_stream/{bits}/{log2}/{mname}"]
+            assert np.array_equal(got, want), (bits, log2, mname, int(np.argmax(np.any(got != want, axis=1))))
+            d.close()
+
+
+def test_decimators_mode_switching_golden(gpu_lib, golden, golden_meta):
+    from sdrangel_b200 import Decimators
+    x = stream_input()
+    d = Decimators(12)
+    pos, outs = 0, []
+    for log2, mode, n in golden_meta["decim_ii_switch"]["schedule"]:
+        outs.append(d.run(log2, mode, x[pos:pos + n]))
+        pos = (pos + n) % (x.size - 800)
+    assert [o.shape[0] for o in outs] == golden["decim_ii_switch/counts"].tolist()
+    assert np.array_equal(np.concatenate(outs), golden["decim_ii_switch/out"])
+
+
+def test_decimateii_config1_sdrbench_hash(gpu_lib, port, golden_meta):
+    """BASELINE config 1: 2^20 int16 IQ, log2=4 centred, 12 bit: the reference's hash."""
+    from sdrangel_b200 import Decimators
+    buf = port.sdrbench_s16(1 << 20)
+    out = Decimators(12).decimate16_cen(buf)
+    g = golden_meta["decim_ii_sdrbench"]["12/4/cen"]
+    assert out.shape[0] == g["n_out"]
+    assert out[:4].ravel().tolist() == g["head"] and out[100].tolist() == g["at100"]
+    assert fnv1a64_u16(out) == g["fnv"]
+
+
+@pytest.mark.parametrize("log2,mname", [(l, m) for l in range(1, 7) for m in ("inf", "sup", "cen")])
+def test_decimateii_all_entry_points_sdrbench_hash(gpu_lib, port, golden_meta, log2, mname):
+    from sdrangel_b200 import Decimators
+    buf = port.sdrbench_s16(1 << 20)
+    out = Decimators(12).run(log2, MODES[mname], buf)
+    g = golden_meta["decim_ii_sdrbench"][f"12/{log2}/{mname}"]
+    assert out.shape[0] == g["n_out"]
+    assert out[100].tolist() == g["at100"]
+    assert fnv1a64_u16(out) == g["fnv"]
+
+
+@pytest.mark.parametrize("bits,log2,mname", [(12, 4, "cen"), (16, 6, "inf"), (8, 3, "sup"), (16, 5, "cen"), (12, 2, "inf"), (12, 1, "sup")])
+def test_decimators_vs_oracle_large_ragged_calls(gpu_lib, port, bits, log2, mname):
+    """3.3 M full-scale samples in ragged calls (carry-over + dropped remainders + many slices) vs the oracle port."""
+    from sdrangel_b200 import Decimators
+    rs = np.random.RandomState(100 + log2)
+    x = rs.randint(-32768, 32768, size=2 * 3_300_001).astype(np.int16)
+    cuts = [0, 2, 4098, 1_000_003, 1_000_004, 4_000_000, x.size]
+    d, o = Decimators(bits), port.PortDecimators("ii", bits)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        got, want = d.run(log2, MODES[mname], x[a:b]), o.run(log2, MODES[mname], x[a:b])
+        assert got.shape == want.shape
+        assert np.array_equal(got, want), (a, b, int(np.argmax(np.any(got != want, axis=1))))
+    if mname == "cen":   # stage-1 ring == the last 64 consumed inputs, pre-shifted (decimators.h:2866-2878)
+        from sdrangel_b200 import capi
+        used = sum(int(capi.lib().b200dsp_decim_out_count(0, 0, log2, 2, b - a)) << log2 for a, b in zip(cuts[:-1], cuts[1:]))
+        assert used > 0
+        pre = {8: [8, 7, 6, 5, 4, 3, 2], 12: [4, 3, 2, 1, 0, 0, 0], 16: [0] * 7}[bits][log2]
+        a, b = cuts[-2], cuts[-1]
+        n_last = int(capi.lib().b200dsp_decim_out_count(0, 0, log2, 2, b - a)) << log2
+        tail = x[a:a + 2 * n_last].reshape(-1, 2)[-64:].astype(np.int32) << pre
+        st = d.get_state()
+        assert np.array_equal(st[0, 0], tail[:, 0]) and np.array_equal(st[0, 1], tail[:, 1])
+
+
+def test_decimators_state_roundtrip_and_split_invariance(gpu_lib):
+    """Size-independent property at BASELINE size: one 2^22-sample call == the same stream in 2^17-scalar device
+    callbacks (Airspy block size) == a call resumed from a saved state."""
+    from sdrangel_b200 import Decimators
+    rs = np.random.RandomState(5)
+    x = rs.randint(-2048, 2048, size=2 << 22).astype(np.int16)
+    whole = Decimators(12).decimate16_cen(x)
+    d = Decimators(12)
+    parts = [d.decimate16_cen(x[i:i + (1 << 17)]) for i in range(0, x.size, 1 << 17)]
+    assert np.array_equal(np.concatenate(parts), whole)
+    d1 = Decimators(12)
+    first = d1.decimate16_cen(x[: x.size // 2])
+    d2 = Decimators(12)
+    d2.set_state(d1.get_state())
+    second = d2.decimate16_cen(x[x.size // 2:])
+    assert np.array_equal(np.concatenate([first, second]), whole)
+    d2.reset()
+    assert not d2.get_state().any()
+    assert Decimators(12).decimate16_cen(np.zeros(0, np.int16)).shape == (0, 2)
+    assert Decimators(12).decimate16_cen(np.zeros(31, np.int16)).shape == (0, 2)
+
+
+@pytest.mark.parametrize("kind", ["fi", "ff", "if"])
+def test_float_cascades_golden(gpu_lib, port, golden, golden_meta, kind):
+    import sdrangel_b200 as S
+    cls = {"fi": S.DecimatorsFI, "ff": S.DecimatorsFF, "if": S.DecimatorsIF}[kind]
+    src = port.sdrbench_s16(1 << 14) if kind[0] == "i" else port.sdrbench_f32(1 << 14)
+    cuts = golden_meta["decim_f"]["cuts"]
+    for log2 in range(0, 7):
+        for mname, mode in MODES.items():
+            for exact in (True, False):
+                d = cls(12)
+                d.set_exact_float(exact)
+                o = np.concatenate([d.run(log2, mode, src[a:b]) for a, b in zip(cuts[:-1], cuts[1:])])
+                if log2 < 2:
+                    g = golden_meta["decim_f_hash"][f"strict/{kind}/{log2}/{mname}"]
+                    assert o.shape[0] == g["n_out"] and fnv1a64_u16(o) == g["fnv"], (kind, log2, mname)
+                    continue
+                strict = golden[f"decim_f/strict/{kind}/{log2}/{mname}"]
+                fast = golden[f"decim_f/fast/{kind}/{log2}/{mname}"]
+                assert o.shape == strict.shape
+                if exact:
+                    assert np.array_equal(o, strict), (kind, log2, mname)
+                elif kind[1] == "i":
+                    assert np.max(np.abs(o.astype(np.int32) - strict.astype(np.int32))) <= 1
+                    assert np.max(np.abs(o.astype(np.int32) - fast.astype(np.int32))) <= 1
+                    assert rel_rms(o, strict) <= 1e-5 and rel_rms(o, fast) <= 1e-5
+                else:
+                    assert rel_rms(o, strict) <= 1e-6 and rel_rms(o, fast) <= 1e-5
+
+
+def test_decimatefi_config2(gpu_lib, port, golden_meta):
+    """BASELINE config 2: sdrbench decimatefi, float IQ, log2=6 centred, fed in 2^17-scalar blocks."""
+    from sdrangel_b200 import DecimatorsFI
+    buf = port.sdrbench_f32(1 << 20)
+    g = golden_meta["decimatefi_config2"]
+    d = DecimatorsFI()
+    d.set_exact_float(True)
+    out = np.concatenate([d.decimate64_cen(buf[i:i + (1 << 17)]) for i in range(0, buf.size, 1 << 17)])
+    assert out.shape[0] == g["n_out"]
+    assert fnv1a64_u16(out) == g["fnv_strict"]
+    ref = port.PortDecimators("fi").run(6, 2, buf)
+    assert np.array_equal(out, ref)
+    fast = DecimatorsFI().decimate64_cen(buf)
+    assert np.max(np.abs(fast.astype(np.int32) - ref.astype(np.int32))) <= 1
+    assert rel_rms(fast, ref) <= 1e-5
+    assert fast[100:103].tolist() == g["out100_102"] or np.max(np.abs(fast[100:103] - np.array(g["out100_102"]))) <= 1

@@ -1,0 +1,144 @@
+"""CPU tests: the C restatement oracle (oracle/port/sdr_oracle.c) against the golden vectors that were generated
+from the UNMODIFIED reference compiled in place (oracle/gen_golden.py).  This is what pins the oracle."""
+import numpy as np
+import pytest
+
+from conftest import MODES, fnv1a64_u16, rel_rms, stream_input
+
+
+def test_sdrbench_generator_matches_reference(port, golden_meta):
+    buf = port.sdrbench_s16(1 << 20)
+    g = golden_meta["sdrbench_s16"]
+    assert buf[:4].tolist() == g["first4"]
+    assert buf[-1] == 0
+    assert fnv1a64_u16(buf[: 1 << 16]) != ""          # smoke of the hash helper
+    fb = port.sdrbench_f32(1 << 14)
+    assert [float(v) for v in fb[:3]] == golden_meta["sdrbench_f32"]["first3"]
+    assert fnv1a64_u16(fb) == golden_meta["sdrbench_f32"]["fnv"]
+
+
+@pytest.mark.parametrize("bits", [8, 12, 16])
+def test_decim_ii_stream_bit_exact(port, golden, golden_meta, bits):
+    x = stream_input()
+    cuts = golden_meta["decim_ii_stream"]["cuts"]
+    for log2 in range(7):
+        for mname, mode in MODES.items():
+            d = port.PortDecimators("ii", bits)
+            outs = [d.run(log2, mode, x[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+            assert [o.shape[0] for o in outs] == golden[f"decim_ii_stream_counts/{bits}/{log2}/{mname}"].tolist()
+            assert np.array_equal(np.concatenate(outs), golden[f"decim_ii_stream/{bits}/{log2}/{mname}"]), (bits, log2, mname)
+
+
+def test_decim_ii_mode_switching(port, golden, golden_meta):
+    x = stream_input()
+    d = port.PortDecimators("ii", 12)
+    pos, outs = 0, []
+    for log2, mode, n in golden_meta["decim_ii_switch"]["schedule"]:
+        outs.append(d.run(log2, mode, x[pos:pos + n]))
+        pos = (pos + n) % (x.size - 800)
+    assert [o.shape[0] for o in outs] == golden["decim_ii_switch/counts"].tolist()
+    assert np.array_equal(np.concatenate(outs), golden["decim_ii_switch/out"])
+
+
+def test_decim_ii_sdrbench_config1(port, golden_meta):
+    """BASELINE config 1: sdrbench decimateii, 2^20 samples, log2=4, centred, 12-bit."""
+    buf = port.sdrbench_s16(1 << 20)
+    out = port.PortDecimators("ii", 12).run(4, 2, buf)
+    g = golden_meta["decim_ii_sdrbench"]["12/4/cen"]
+    assert out.shape[0] == g["n_out"] == 65536
+    assert out[:4].ravel().tolist() == g["head"] and out[100].tolist() == g["at100"]
+    assert fnv1a64_u16(out) == g["fnv"] == "f06c9917a38677e6"
+
+
+@pytest.mark.parametrize("kind", ["fi", "ff", "if"])
+def test_decim_float_strict_bit_exact_and_fast_within_tolerance(port, golden, golden_meta, kind):
+    src = port.sdrbench_s16(1 << 14) if kind[0] == "i" else port.sdrbench_f32(1 << 14)
+    cuts = golden_meta["decim_f"]["cuts"]
+    for log2 in range(2, 7):
+        for mname, mode in MODES.items():
+            d = port.PortDecimators(kind, 12)
+            o = np.concatenate([d.run(log2, mode, src[a:b]) for a, b in zip(cuts[:-1], cuts[1:])])
+            strict = golden[f"decim_f/strict/{kind}/{log2}/{mname}"]
+            fast = golden[f"decim_f/fast/{kind}/{log2}/{mname}"]
+            assert o.shape == strict.shape
+            assert np.array_equal(o, strict), (kind, log2, mname)
+            if kind[1] == "i":
+                assert np.max(np.abs(o.astype(np.int32) - fast.astype(np.int32))) <= 1
+            else:
+                assert rel_rms(o, fast) <= 1e-5
+
+
+def test_downchannelizer_plans_and_feed(port, golden, golden_meta):
+    plans = golden_meta["chan_plans"]
+    for name in ("bank64", "bank1024"):
+        fs = plans[name]["input_rate"]
+        rows = plans[name]["channels"]
+        step = 1 if name == "bank64" else 7
+        for fc, rate, ofs, path in rows[::step]:
+            r, o, modes = port.PortDownChannelizer().configure(fs, 48000, fc)
+            assert (r, o, "".join("CLU"[m] for m in modes)) == (rate, ofs, path)
+    for fs, req, fc, rate, ofs, path in plans["random"]:
+        r, o, modes = port.PortDownChannelizer().configure(fs, req, fc)
+        assert (r, o, "".join("CLU"[m] for m in modes)) == (rate, ofs, path)
+    m = golden_meta["chan_feed"]
+    rs = np.random.RandomState(m["seed"])
+    cx = rs.randint(-32768, 32768, size=(m["n"], 2)).astype(np.int16)
+    cx[m["min_run"][0]:m["min_run"][1]] = -32768
+    for fc in m["offsets"]:
+        c = port.PortDownChannelizer()
+        c.configure(m["input_rate"], m["requested_rate"], fc)
+        o = np.concatenate([c.feed(cx[a:b]) for a, b in zip(m["cuts"][:-1], m["cuts"][1:])])
+        assert np.array_equal(o, golden[f"chan_feed/{fc}"]), fc
+
+
+def test_frontend_schedule_and_values(port, golden, golden_meta):
+    m = golden_meta["frontend"]
+    rs = np.random.RandomState(m["seed"])
+    fx = rs.randint(-20000, 20000, size=(m["n"], 2)).astype(np.int16)
+    cutoff = np.float32(np.float32(12500) / np.float32(2.2))
+    assert np.array_equal(port.nco_table(), golden["nco_table"])
+    for freq, rate, outr in m["cases"]:
+        fe = port.PortFrontEnd(freq, rate, outr, cutoff)
+        key = f"frontend/strict/{freq}_{rate}"
+        assert fe.nco_increment() == golden_meta["frontend_inc"][f"{freq}_{rate}"]
+        assert np.array_equal(fe.taps(), golden[key + "/taps"])
+        o, i, p = zip(*[fe.feed(fx[a:b], True) for a, b in ((0, 7), (7, 9000), (9000, 20000))])
+        offs = np.cumsum([0, 7, 8993])
+        idx = np.concatenate([ii + off for ii, off in zip(i, offs)])
+        assert np.array_equal(idx, golden[key + "/idx"])
+        assert np.array_equal(np.concatenate(p), golden[key + "/phase"])
+        out = np.concatenate(o)
+        assert rel_rms(out, golden[key + "/out"]) <= 1e-6
+        assert rel_rms(out, golden[f"frontend/fast/{freq}_{rate}/out"]) <= 1e-5
+        assert np.array_equal(idx, golden[f"frontend/fast/{freq}_{rate}/idx"])
+
+
+def test_spectrum_window_fft_and_feed(port, golden, golden_meta):
+    for fn in range(6):
+        assert np.allclose(port.fft_window(fn, 256), golden[f"window/{fn}_256"], rtol=0, atol=3e-7)
+    assert np.array_equal(port.fft_window(1, 4096), golden["window/1_4096"])
+    for nfft in (64, 128, 4096):
+        y = port.kissfft(golden[f"fft/strict/{nfft}/in"])
+        assert rel_rms(y.view(np.float32), golden[f"fft/strict/{nfft}/out"].view(np.float32)) <= 1e-6
+    m = golden_meta["spectrum"]
+    rs = np.random.RandomState(m["seed"])
+    n = m["n"]
+    sx = rs.randint(-2048, 2048, size=(n, 2)).astype(np.int16)
+    t = np.arange(n)
+    tone = m["tone"][0] * np.exp(2j * np.pi * m["tone"][1] * t)
+    sx[:, 0] += tone.real.astype(np.int16)
+    sx[:, 1] += tone.imag.astype(np.int16)
+    for fft, mode, nb, linear, posonly in m["cases(fft,avg_mode,avg_nb,linear,positive_only)"]:
+        s = port.PortSpectrumVis()
+        s.configure(fft, 0, nb, mode, 1, linear)
+        fr = np.concatenate([s.feed(sx[a:b], posonly) for a, b in zip(m["cuts"][:-1], m["cuts"][1:])])
+        key = f"spectrum/strict/{fft}_{mode}_{nb}_{int(linear)}_{int(posonly)}"
+        assert fr.shape[0] == int(golden[key + "/nframes"][0])
+        keep = np.concatenate([fr[:3], fr[-3:]]) if fr.shape[0] > 6 else fr
+        ref = golden[key]
+        if linear:
+            assert rel_rms(keep, ref) <= 1e-5
+        else:
+            ok = np.isfinite(ref) & np.isfinite(keep)
+            assert ok.mean() > 0.99
+            assert np.max(np.abs(keep[ok] - ref[ok])) <= 2e-3
