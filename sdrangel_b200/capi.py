@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200dsp.so")
+LIB_PATH = os.environ.get("B200DSP_LIB") or os.path.join(_HERE, "lib", "libb200dsp.so")   # env override: kernel tuning experiments only
 
 FMT_I16, FMT_F32 = 0, 1
 MODE_INF, MODE_SUP, MODE_CEN = 0, 1, 2

@@ -259,6 +259,7 @@ int launch_plan(b200dsp_decim* h, const Plan& pl, const void* d_in, void* d_out,
     p.n0 = pl.n0; p.n_out = pl.n_out; p.L = pl.L;
     p.pre = pl.pre; p.post = pl.post; p.out_scale = pl.out_scale; p.div4 = pl.div4_kind;
     memcpy(p.rot, pl.rot, sizeof(p.rot));
+    p.opq_zero = 0; p.opq_one = 1; p.opq_mone = -1;
     const long long U = (long long) HB_IN << (pl.L - 1);
     const long long sp_total = (pl.n0 + U - 1) / U;
     const long long max_warps = (long long) h->sm_count * g.warps_per_sm;

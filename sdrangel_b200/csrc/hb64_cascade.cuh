@@ -62,6 +62,7 @@ struct CascadeParams {
     int         pre, post;   // integer pre/post shifts (decimation_shifts<>)
     float       out_scale;   // float output scale (IF: 1/2^(bits-1))
     int         div4;        // DIV4_* flavour for the /4 front-end loaders
+    int         opq_zero, opq_one, opq_mone;   // 0, 1, -1 passed as data so ptxas keeps the 3-input / multiply forms
     signed char rot[8];      // rot[s], s = 1..L : 0 centred, +1 Inf/LowerHalf (+j), -1 Sup/UpperHalf (-j)
 };
 
@@ -114,25 +115,63 @@ __device__ __forceinline__ void rot_jq(T& re, T& im, int q)
 //   csgn: +1/-1 runtime sign of the centre term for rotated stages (depends on component and sigma)
 // Output r (k = 12j + r):  XO[k-i] = w[32+r-i],  XO[k-31+i] = w[1+r+i],  XE[k-15] = c[1+r]
 // ---------------------------------------------------------------------------------------------------------
+// Pipe placement (B200, measured: profiles/r01_microbench2_pipes.txt): IMAD issues on the FMA-heavy pipe and IADD3 on the
+// ALU pipe, each 64 lanes/clk/SM; ptxas by itself turns most 2-input adds into IMAD.IADD and overloads the heavy pipe
+// (ncu r01 v1: fmaheavy 74 % busy, alu 37 %).  The pre-adds are therefore written as explicit 3-input adds with an
+// opaque zero (=> IADD3, ALU pipe) except the first HB_XH taps per output, which use an opaque-one multiply-add
+// (=> IMAD, heavy pipe), so both pipes carry the same load.
+struct IntOpaque { int zero, one, mone; };
+#ifndef HB_XH
+#define HB_XH 2
+#endif
+__device__ __forceinline__ uint32_t add_alu(uint32_t a, uint32_t b, int z)
+{
+    uint32_t r;
+    asm("{.reg .u32 t; add.u32 t, %1, %2; add.u32 %0, t, %3;}" : "=r"(r) : "r"(a), "r"(b), "r"(z));
+    return r;
+}
+__device__ __forceinline__ uint32_t sub_alu(uint32_t a, uint32_t b, int z)
+{
+    uint32_t r;
+    asm("{.reg .u32 t; sub.u32 t, %1, %2; add.u32 %0, t, %3;}" : "=r"(r) : "r"(a), "r"(b), "r"(z));
+    return r;
+}
+__device__ __forceinline__ uint32_t mad_fma(uint32_t a, int m, uint32_t b)     // a*m + b with a register multiplier
+{
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(m), "r"(b));
+    return r;
+}
+
 template<bool ROT, bool EXACT>
-__device__ __forceinline__ void hb64_item(const int32_t (&w)[44], const int32_t (&c)[16], int csgn, int32_t (&y)[HB_R])
+__device__ __forceinline__ void hb64_item(const int32_t (&w)[44], const int32_t (&c)[16], int csgn, const IntOpaque& q, int32_t (&y)[HB_R])
 {
 #pragma unroll
     for (int r = 0; r < HB_R; ++r) {
         uint32_t acc;
         if (!ROT) {
             acc = (uint32_t) c[1 + r] << 11;
+            // tap 0: h = -1  =>  acc - a - b in one 3-input add
+            asm("{.reg .u32 t; sub.u32 t, %0, %1; sub.u32 %0, t, %2;}" : "+r"(acc) : "r"(w[32 + r]), "r"(w[1 + r]));
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-                acc += (uint32_t) hb64_h(i) * ((uint32_t) w[32 + r - i] + (uint32_t) w[1 + r + i]);
+            for (int i = 1; i < 16; ++i) {
+                const uint32_t a = (uint32_t) w[32 + r - i], b = (uint32_t) w[1 + r + i];
+                const uint32_t s = (i <= HB_XH) ? mad_fma(a, q.one, b) : add_alu(a, b, q.zero);
+                acc += (uint32_t) hb64_h(i) * s;
+            }
         } else {
             // y = s_k * [ sum (-1)^i h_i (XO[k-i] - XO[k-31+i]) + csgn * 2048 * XEother[k-15] ],  s_k = (-1)^(k+1)
             const int sk = (r & 1) ? 1 : -1;
             acc = (uint32_t) c[1 + r] * (uint32_t) (csgn * sk * 2048);
+            // tap 0: coefficient -s_k  =>  acc -/+ a +/- b in one 3-input add
+            if (sk > 0) asm("{.reg .u32 t; sub.u32 t, %0, %1; add.u32 %0, t, %2;}" : "+r"(acc) : "r"(w[32 + r]), "r"(w[1 + r]));
+            else        asm("{.reg .u32 t; add.u32 t, %0, %1; sub.u32 %0, t, %2;}" : "+r"(acc) : "r"(w[32 + r]), "r"(w[1 + r]));
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
+            for (int i = 1; i < 16; ++i) {
                 const int g = ((i & 1) ? -sk : sk) * hb64_h(i);
-                acc += (uint32_t) g * ((uint32_t) w[32 + r - i] - (uint32_t) w[1 + r + i]);
+                const uint32_t a = (uint32_t) w[32 + r - i], b = (uint32_t) w[1 + r + i];
+                const uint32_t d = (i <= HB_XH) ? mad_fma(b, q.mone, a) : sub_alu(a, b, q.zero);
+                acc += (uint32_t) g * d;
             }
         }
         y[r] = (int32_t) acc >> 11;
@@ -140,7 +179,7 @@ __device__ __forceinline__ void hb64_item(const int32_t (&w)[44], const int32_t 
 }
 
 template<bool ROT, bool EXACT>
-__device__ __forceinline__ void hb64_item(const float (&w)[44], const float (&c)[16], int csgn, float (&y)[HB_R])
+__device__ __forceinline__ void hb64_item(const float (&w)[44], const float (&c)[16], int csgn, const IntOpaque&, float (&y)[HB_R])
 {
 #pragma unroll
     for (int r = 0; r < HB_R; ++r) {
@@ -489,6 +528,7 @@ __global__ void hb64_cascade_kernel(const CascadeParams p)
     const int L = p.L;
     T* X = reinterpret_cast<T*>(hb64_smem) + (size_t) wib * L * HB_STAGE_WORDS;
     const int comp = lane >> 4, j = lane & 15;
+    const IntOpaque opq = { p.opq_zero, p.opq_one, p.opq_mone };
 
     const long long U = (long long) HB_IN << (L - 1);           // stage-0 samples per superphase
     const long long sp_total = (p.n0 + U - 1) / U;
@@ -516,8 +556,8 @@ __global__ void hb64_cascade_kernel(const CascadeParams p)
             const int sigma = HASROT ? (int) p.rot[s] : 0;
             T wv[44], cv[16], y[HB_R];
             hb64_load_windows<T>(Xin, comp, j, sigma != 0, wv, cv);
-            if (HASROT && sigma != 0) hb64_item<true, EXACT>(wv, cv, comp ? sigma : -sigma, y);
-            else                      hb64_item<false, EXACT>(wv, cv, 0, y);
+            if (HASROT && sigma != 0) hb64_item<true, EXACT>(wv, cv, comp ? sigma : -sigma, opq, y);
+            else                      hb64_item<false, EXACT>(wv, cv, 0, opq, y);
             const long long done = (pos + HB_IN) >> (s - 1);    // stage-(s-1) samples consumed so far (call-absolute)
             if (last) {
                 const long long n_s = p.n0 >> (s - 1);
