@@ -90,10 +90,12 @@ typedef void (*cascade_fn)(const CascadeParams);
 template<typename T, int IN, int OUT, bool HASROT, bool EXACT>
 cascade_fn kfn() { return hb64_cascade_kernel<T, IN, OUT, HASROT, EXACT>; }
 
-cascade_fn pick_kernel(int in_fmt, int out_fmt, bool div4, bool hasrot, bool exact)
+cascade_fn pick_kernel(int in_fmt, int out_fmt, bool div4, bool hasrot, bool exact, bool pre)
 {
-    if (in_fmt == B200DSP_FMT_I16 && out_fmt == B200DSP_FMT_I16)
+    if (in_fmt == B200DSP_FMT_I16 && out_fmt == B200DSP_FMT_I16) {
+        if (pre) return hasrot ? kfn<int32_t, IN_I16_PRE, OUT_I16_SHIFT, true, false>() : kfn<int32_t, IN_I16_PRE, OUT_I16_SHIFT, false, false>();
         return hasrot ? kfn<int32_t, IN_I16, OUT_I16_SHIFT, true, false>() : kfn<int32_t, IN_I16, OUT_I16_SHIFT, false, false>();
+    }
     if (in_fmt == B200DSP_FMT_F32 && out_fmt == B200DSP_FMT_I16) {
         if (div4) return exact ? kfn<float, IN_F32_DIV4, OUT_I16_SCALE, false, true>() : kfn<float, IN_F32_DIV4, OUT_I16_SCALE, false, false>();
         return exact ? kfn<float, IN_F32, OUT_I16_SCALE, false, true>() : kfn<float, IN_F32, OUT_I16_SCALE, false, false>();
@@ -250,7 +252,7 @@ int launch_plan(b200dsp_decim* h, const Plan& pl, const void* d_in, void* d_out,
         else ew_float_kernel<int16_t, OUT_F32><<<(unsigned) blocks, threads, 0, st>>>(ep);
         return B200_CUDA_CHECK(cudaGetLastError());
     }
-    cascade_fn fn = pick_kernel(h->in_fmt, h->out_fmt, pl.div4, pl.hasrot, h->exact != 0);
+    cascade_fn fn = pick_kernel(h->in_fmt, h->out_fmt, pl.div4, pl.hasrot, h->exact != 0, pl.pre != 0);
     const LaunchGeom g = pick_geom(fn, pl.L);
     CascadeParams p;
     memset(&p, 0, sizeof(p));

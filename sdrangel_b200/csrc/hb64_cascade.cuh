@@ -45,7 +45,7 @@ constexpr int HB_STAGE_BYTES = HB_STAGE_WORDS * 4;
 constexpr int HB_MAX_STAGES  = 6;
 constexpr int HB_STATE_ELEMS = 64;            // per stage, per component (canonical carried state)
 
-enum : int { IN_I16 = 0, IN_F32 = 1, IN_I16F = 2, IN_F32_DIV4 = 3, IN_I16F_DIV4 = 4 };
+enum : int { IN_I16 = 0, IN_F32 = 1, IN_I16F = 2, IN_F32_DIV4 = 3, IN_I16F_DIV4 = 4, IN_I16_PRE = 5 };
 enum : int { DIV4_INF = 0, DIV4_SUP = 1, DIV4_SUP16 = 2 };   // /4 front-end flavours (decimatorsfi.cpp:95-367)
 enum : int { OUT_I16_SHIFT = 0, OUT_I16_SCALE = 1, OUT_F32 = 2 };
 
@@ -122,7 +122,7 @@ __device__ __forceinline__ void rot_jq(T& re, T& im, int q)
 // (=> IMAD, heavy pipe), so both pipes carry the same load.
 struct IntOpaque { int zero, one, mone; };
 #ifndef HB_XH
-#define HB_XH 2
+#define HB_XH 1
 #endif
 __device__ __forceinline__ uint32_t add_alu(uint32_t a, uint32_t b, int z)
 {
@@ -224,13 +224,14 @@ __device__ __forceinline__ void hb64_load_windows(const T* __restrict__ Xin, int
 
 // keep the last 64 samples of a consumed batch as the next batch's history: positions [192,224) -> [0,32) of 4 arrays
 template<typename T>
-__device__ __forceinline__ void hb64_tail_copy(T* Xin, int lane)
+__device__ __forceinline__ typename vec4<T>::type hb64_tail_load(const T* Xin, int lane)
 {
-    using V4 = typename vec4<T>::type;
-    T* a = Xin + (lane >> 3) * HB_ARR + 4 * (lane & 7);
-    V4 v = *reinterpret_cast<const V4*>(a + HB_BATCH);
-    __syncwarp();
-    *reinterpret_cast<V4*>(a) = v;
+    return *reinterpret_cast<const typename vec4<T>::type*>(Xin + (lane >> 3) * HB_ARR + 4 * (lane & 7) + HB_BATCH);
+}
+template<typename T>
+__device__ __forceinline__ void hb64_tail_store(T* Xin, int lane, const typename vec4<T>::type& v)
+{
+    *reinterpret_cast<typename vec4<T>::type*>(Xin + (lane >> 3) * HB_ARR + 4 * (lane & 7)) = v;
 }
 
 // store 12 outputs of lane (comp, j) as the next stage's input: even k -> even array, odd k -> odd array
@@ -251,7 +252,8 @@ __device__ __forceinline__ void hb64_store_next(T* Xout, int comp, int j, int fi
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Loaders: fill X0 positions [32, 224) of the 4 arrays with 384 stage-0 samples starting at sample index pos.
+// Loaders: a phase's 384 stage-0 samples go global -> registers (fetch, issued one phase AHEAD so the HBM latency
+// hides behind the previous phase's arithmetic) -> X0 positions [32, 224) of the 4 arrays (store).
 // Samples at or beyond n0 read as zero.  (pos, n0 are multiples of 4 for int16 input, of 2 for float input.)
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int4 ldg_nc_v4(const void* p)
@@ -261,93 +263,108 @@ __device__ __forceinline__ int4 ldg_nc_v4(const void* p)
     return r;
 }
 
-__device__ __forceinline__ int32_t sext_lo16(int32_t v) { return (int32_t) (short) (v & 0xffff); }
+// sign-extend the low / high half of a packed int16 pair: one PRMT each (byte selector 8|n replicates byte n's sign)
+__device__ __forceinline__ int32_t sext_lo16(int32_t v)
+{
+    int32_t r;
+    asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ int32_t sext_hi16(int32_t v)
+{
+    int32_t r;
+    asm("prmt.b32 %0, %1, 0, 0xbb32;" : "=r"(r) : "r"(v));
+    return r;
+}
 
 template<int IN, typename T> struct Loader;
 
-// int16 IQ -> int32 (Decimators<>: value << pre, decimators.h:2866-2878)
-template<> struct Loader<IN_I16, int32_t> {
-    static constexpr int IN_PER_S0 = 1;      // input samples per stage-0 sample
-    __device__ static __forceinline__ void load(const CascadeParams& p, int32_t* X0, long long pos, int lane)
+// int16 IQ -> int32 (Decimators<>: value << pre, decimators.h:2866-2878).  PRE = whether a pre-shift is applied.
+template<bool PRE> struct LoaderI16 {
+    static constexpr int NV = 3;                // int4 registers per lane per phase
+    __device__ static __forceinline__ void fetch(const CascadeParams& p, long long pos, int lane, int4 (&v)[NV])
     {
-        const int32_t* in = reinterpret_cast<const int32_t*>(p.in);
-        int4 v[3];
+        const int32_t* in = reinterpret_cast<const int32_t*>(p.in) + pos + 4 * lane;
+        if (pos + HB_IN <= p.n0) {              // warp-uniform fast path: whole batch in range
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            const long long s = pos + 4 * (lane + 32 * q);
-            v[q] = (s < p.n0) ? ldg_nc_v4(in + s) : make_int4(0, 0, 0, 0);
+            for (int q = 0; q < NV; ++q) v[q] = ldg_nc_v4(in + 128 * q);
+        } else {
+#pragma unroll
+            for (int q = 0; q < NV; ++q)
+                v[q] = (pos + 4 * (lane + 32 * q) < p.n0) ? ldg_nc_v4(in + 128 * q) : make_int4(0, 0, 0, 0);
         }
-        const int pre = p.pre;
+    }
+    __device__ static __forceinline__ void store(const CascadeParams& p, int32_t* X0, int lane, const int4 (&v)[NV])
+    {
+        const int pre = PRE ? p.pre : 0;
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
+        for (int q = 0; q < NV; ++q) {
             int32_t* a = X0 + HB_HIST + 2 * (lane + 32 * q);
-            int2 re_e = make_int2(sext_lo16(v[q].x) << pre, sext_lo16(v[q].z) << pre);
-            int2 re_o = make_int2(sext_lo16(v[q].y) << pre, sext_lo16(v[q].w) << pre);
-            int2 im_e = make_int2((v[q].x >> 16) << pre, (v[q].z >> 16) << pre);
-            int2 im_o = make_int2((v[q].y >> 16) << pre, (v[q].w >> 16) << pre);
-            *reinterpret_cast<int2*>(a) = re_e;
-            *reinterpret_cast<int2*>(a + HB_ARR) = re_o;
-            *reinterpret_cast<int2*>(a + 2 * HB_ARR) = im_e;
-            *reinterpret_cast<int2*>(a + 3 * HB_ARR) = im_o;
+            *reinterpret_cast<int2*>(a)              = make_int2(sext_lo16(v[q].x) << pre, sext_lo16(v[q].z) << pre);
+            *reinterpret_cast<int2*>(a + HB_ARR)     = make_int2(sext_lo16(v[q].y) << pre, sext_lo16(v[q].w) << pre);
+            *reinterpret_cast<int2*>(a + 2 * HB_ARR) = make_int2(sext_hi16(v[q].x) << pre, sext_hi16(v[q].z) << pre);
+            *reinterpret_cast<int2*>(a + 3 * HB_ARR) = make_int2(sext_hi16(v[q].y) << pre, sext_hi16(v[q].w) << pre);
         }
     }
 };
+template<> struct Loader<IN_I16, int32_t>     : LoaderI16<false> {};
+template<> struct Loader<IN_I16_PRE, int32_t> : LoaderI16<true> {};
 
 // float IQ -> float (DecimatorsFI/FF *_cen, decimatorsfi.cpp:33-53,369-1172)
 template<> struct Loader<IN_F32, float> {
-    static constexpr int IN_PER_S0 = 1;
-    __device__ static __forceinline__ void load(const CascadeParams& p, float* X0, long long pos, int lane)
+    static constexpr int NV = 6;
+    __device__ static __forceinline__ void fetch(const CascadeParams& p, long long pos, int lane, int4 (&v)[NV])
     {
-        const float2* in = reinterpret_cast<const float2*>(p.in);
+        const float2* in = reinterpret_cast<const float2*>(p.in) + pos + 2 * lane;
+        if (pos + HB_IN <= p.n0) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            int4 v[3];
+            for (int q = 0; q < NV; ++q) v[q] = ldg_nc_v4(in + 64 * q);
+        } else {
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                const long long s = pos + 2 * (lane + 32 * (q + 3 * h));
-                v[q] = (s < p.n0) ? ldg_nc_v4(in + s) : make_int4(0, 0, 0, 0);
-            }
+            for (int q = 0; q < NV; ++q)
+                v[q] = (pos + 2 * (lane + 32 * q) < p.n0) ? ldg_nc_v4(in + 64 * q) : make_int4(0, 0, 0, 0);
+        }
+    }
+    __device__ static __forceinline__ void store(const CascadeParams&, float* X0, int lane, const int4 (&v)[NV])
+    {
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                float* a = X0 + HB_HIST + (lane + 32 * (q + 3 * h));
-                a[0] = __int_as_float(v[q].x);
-                a[2 * HB_ARR] = __int_as_float(v[q].y);
-                a[HB_ARR] = __int_as_float(v[q].z);
-                a[3 * HB_ARR] = __int_as_float(v[q].w);
-            }
+        for (int q = 0; q < NV; ++q) {
+            float* a = X0 + HB_HIST + (lane + 32 * q);
+            a[0]          = __int_as_float(v[q].x);
+            a[2 * HB_ARR] = __int_as_float(v[q].y);
+            a[HB_ARR]     = __int_as_float(v[q].z);
+            a[3 * HB_ARR] = __int_as_float(v[q].w);
         }
     }
 };
 
-// int16 IQ -> float (DecimatorsIF *_cen: raw integer values enter the cascade, scale applied at the output,
-// decimatorsif.h / decimatorsif.cpp)
+// int16 IQ -> float (DecimatorsIF *_cen: raw integer values enter the cascade, the 2^-k scale is applied at the
+// output, which is exact; decimatorsif.h:142-163)
 template<> struct Loader<IN_I16F, float> {
-    static constexpr int IN_PER_S0 = 1;
-    __device__ static __forceinline__ void load(const CascadeParams& p, float* X0, long long pos, int lane)
+    static constexpr int NV = 3;
+    __device__ static __forceinline__ void fetch(const CascadeParams& p, long long pos, int lane, int4 (&v)[NV])
     {
-        const int32_t* in = reinterpret_cast<const int32_t*>(p.in);
-        int4 v[3];
+        LoaderI16<false>::fetch(p, pos, lane, v);
+    }
+    __device__ static __forceinline__ void store(const CascadeParams&, float* X0, int lane, const int4 (&v)[NV])
+    {
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            const long long s = pos + 4 * (lane + 32 * q);
-            v[q] = (s < p.n0) ? ldg_nc_v4(in + s) : make_int4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
+        for (int q = 0; q < NV; ++q) {
             float* a = X0 + HB_HIST + 2 * (lane + 32 * q);
-            *reinterpret_cast<float2*>(a) = make_float2((float) sext_lo16(v[q].x), (float) sext_lo16(v[q].z));
-            *reinterpret_cast<float2*>(a + HB_ARR) = make_float2((float) sext_lo16(v[q].y), (float) sext_lo16(v[q].w));
-            *reinterpret_cast<float2*>(a + 2 * HB_ARR) = make_float2((float) (v[q].x >> 16), (float) (v[q].z >> 16));
-            *reinterpret_cast<float2*>(a + 3 * HB_ARR) = make_float2((float) (v[q].y >> 16), (float) (v[q].w >> 16));
+            *reinterpret_cast<float2*>(a)              = make_float2((float) sext_lo16(v[q].x), (float) sext_lo16(v[q].z));
+            *reinterpret_cast<float2*>(a + HB_ARR)     = make_float2((float) sext_lo16(v[q].y), (float) sext_lo16(v[q].w));
+            *reinterpret_cast<float2*>(a + 2 * HB_ARR) = make_float2((float) sext_hi16(v[q].x), (float) sext_hi16(v[q].z));
+            *reinterpret_cast<float2*>(a + 3 * HB_ARR) = make_float2((float) sext_hi16(v[q].y), (float) sext_hi16(v[q].w));
         }
     }
 };
 
 // FI/FF/IF inf/sup: unfiltered /4 rotate-and-add of 4 input samples per stage-0 sample
-// (decimatorsfi.cpp:95-367; association as written there: N=4,8 vs N>=16 differ for sup's imaginary part)
+// (decimatorsfi.cpp:95-367; association as written there: N=4,8 vs N>=16 differ for sup's imaginary part).
+// 4x the input bytes per stage-0 sample: fetched and combined in `store` (no register prefetch, NV = 0).
 template<bool FROM_I16>
 struct LoaderDiv4 {
-    static constexpr int IN_PER_S0 = 4;
+    static constexpr int NV = 1;
     __device__ static __forceinline__ void combine(int VARIANT, const float (&B)[8], float& xr, float& yi)
     {
         if (VARIANT == DIV4_INF) {
@@ -359,8 +376,14 @@ struct LoaderDiv4 {
             else              yi = __fadd_rn(__fadd_rn(__fsub_rn(-B[0], B[3]), B[4]), B[7]);
         }
     }
-    __device__ static __forceinline__ void load(const CascadeParams& p, float* X0, long long pos, int lane)
+    // the position travels in the register slot; the data is read in store()
+    __device__ static __forceinline__ void fetch(const CascadeParams&, long long pos, int, int4 (&v)[NV])
     {
+        v[0].x = (int) (pos & 0xffffffffll); v[0].y = (int) (pos >> 32);
+    }
+    __device__ static __forceinline__ void store(const CascadeParams& p, float* X0, int lane, const int4 (&v)[NV])
+    {
+        const long long pos = ((long long) v[0].y << 32) | (unsigned int) v[0].x;
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
             float B[3][8];
@@ -369,11 +392,11 @@ struct LoaderDiv4 {
                 const int i = lane + 32 * (q + 3 * h);       // stage-0 sample within the batch
                 const long long s = pos + i;
                 if (FROM_I16) {
-                    int4 v = (s < p.n0) ? ldg_nc_v4(reinterpret_cast<const int4*>(p.in) + s) : make_int4(0, 0, 0, 0);
-                    B[q][0] = (float) sext_lo16(v.x); B[q][1] = (float) (v.x >> 16);
-                    B[q][2] = (float) sext_lo16(v.y); B[q][3] = (float) (v.y >> 16);
-                    B[q][4] = (float) sext_lo16(v.z); B[q][5] = (float) (v.z >> 16);
-                    B[q][6] = (float) sext_lo16(v.w); B[q][7] = (float) (v.w >> 16);
+                    int4 w = (s < p.n0) ? ldg_nc_v4(reinterpret_cast<const int4*>(p.in) + s) : make_int4(0, 0, 0, 0);
+                    B[q][0] = (float) sext_lo16(w.x); B[q][1] = (float) sext_hi16(w.x);
+                    B[q][2] = (float) sext_lo16(w.y); B[q][3] = (float) sext_hi16(w.y);
+                    B[q][4] = (float) sext_lo16(w.z); B[q][5] = (float) sext_hi16(w.z);
+                    B[q][6] = (float) sext_lo16(w.w); B[q][7] = (float) sext_hi16(w.w);
                 } else {
                     int4 v0 = make_int4(0, 0, 0, 0), v1 = v0;
                     if (s < p.n0) {
@@ -427,9 +450,10 @@ template<> struct Epilogue<OUT_F32, float> {                // DecimatorsFF (sca
 
 // lane (comp 0, j) holds re of outputs 12j..12j+11, lane (comp 1, j) holds im.  After one shuffle each lane owns
 // 6 complete IQ samples: comp 0 -> outputs 12j..12j+5, comp 1 -> outputs 12j+6..12j+11.
+// `out` points at the warp's first (warm-up) output; krel/lo/hi are relative to it.
 template<int OUT, typename T>
-__device__ __forceinline__ void hb64_epilogue(const CascadeParams& p, const T (&y)[HB_R], int comp, int j,
-                                              long long k_base, long long out_lo, long long out_hi)
+__device__ __forceinline__ void hb64_epilogue(const CascadeParams& p, void* out, const T (&y)[HB_R], int comp, int j,
+                                              int krel, int lo, int hi)
 {
     using E = Epilogue<OUT, T>;
     int32_t mine[6], other[6];
@@ -440,9 +464,9 @@ __device__ __forceinline__ void hb64_epilogue(const CascadeParams& p, const T (&
         mine[t] = comp ? b : a;
         other[t] = __shfl_xor_sync(0xffffffffu, send, 16);
     }
-    const long long k0 = k_base + HB_R * j + 6 * comp;      // first of this lane's 6 output samples
-    if (k0 >= out_hi || k0 + 6 <= out_lo) return;
-    const bool full = (k0 >= out_lo) && (k0 + 6 <= out_hi);
+    const int k0 = krel + HB_R * j + 6 * comp;      // first of this lane's 6 output samples
+    if (k0 >= hi || k0 + 6 <= lo) return;
+    const bool full = (k0 >= lo) && (k0 + 6 <= hi);
     if (E::WORDS == 1) {
         uint32_t wds[6];
 #pragma unroll
@@ -450,20 +474,20 @@ __device__ __forceinline__ void hb64_epilogue(const CascadeParams& p, const T (&
             const int32_t re = comp ? other[t] : mine[t], im = comp ? mine[t] : other[t];
             wds[t] = ((uint32_t) re & 0xffffu) | ((uint32_t) im << 16);
         }
-        uint32_t* o = reinterpret_cast<uint32_t*>(p.out) + k0;
+        uint32_t* o = reinterpret_cast<uint32_t*>(out) + k0;
         if (full) {
 #pragma unroll
             for (int t = 0; t < 3; ++t) *reinterpret_cast<uint2*>(o + 2 * t) = make_uint2(wds[2 * t], wds[2 * t + 1]);
         } else {
 #pragma unroll
-            for (int t = 0; t < 6; ++t) if (k0 + t >= out_lo && k0 + t < out_hi) o[t] = wds[t];
+            for (int t = 0; t < 6; ++t) if (k0 + t >= lo && k0 + t < hi) o[t] = wds[t];
         }
     } else {
-        int2* o = reinterpret_cast<int2*>(p.out) + k0;
+        int2* o = reinterpret_cast<int2*>(out) + k0;
 #pragma unroll
         for (int t = 0; t < 6; ++t) {
             const int32_t re = comp ? other[t] : mine[t], im = comp ? mine[t] : other[t];
-            if (full || (k0 + t >= out_lo && k0 + t < out_hi)) o[t] = make_int2(re, im);
+            if (full || (k0 + t >= lo && k0 + t < hi)) o[t] = make_int2(re, im);
         }
     }
 }
@@ -516,10 +540,20 @@ __device__ __noinline__ void hb64_state_save(const CascadeParams& p, const T* Xs
 // ---------------------------------------------------------------------------------------------------------
 // The kernel.  blockDim.x = 32 * warps; dynamic shared memory = warps * L * HB_STAGE_BYTES.
 // ---------------------------------------------------------------------------------------------------------
+// last slice only: when the batch of buffer b consumed at this point holds the stream's final stage-b sample, save state
+template<typename T>
+__device__ __noinline__ void hb64_state_check(const CascadeParams& p, const T* Xin, int b, long long pos_after, int lane)
+{
+    const long long done = pos_after >> b;                 // stage-b samples consumed so far (call-absolute)
+    const long long n_b = p.n0 >> b;
+    if (n_b > done - HB_IN && n_b <= done) hb64_state_save<T>(p, Xin, b, done - HB_IN, n_b, lane);
+}
+
 template<typename T, int IN, int OUT, bool HASROT, bool EXACT>
-__global__ void hb64_cascade_kernel(const CascadeParams p)
+__global__ void __launch_bounds__(256, 2) hb64_cascade_kernel(const CascadeParams p)
 {
     extern __shared__ __align__(16) unsigned char hb64_smem[];
+    using LD = Loader<IN, T>;
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int w = blockIdx.x * (blockDim.x >> 5) + wib;
@@ -540,15 +574,22 @@ __global__ void hb64_cascade_kernel(const CascadeParams p)
 
     if (first) hb64_state_load<T>(p, X, lane);
     else       hb64_state_zero<T>(p, X, lane);
-    __syncwarp();
 
-    const long long out_lo = a0 * HB_BATCH;
-    const long long out_hi = (a1 * HB_BATCH < p.n_out) ? a1 * HB_BATCH : p.n_out;
+    // outputs relative to the first one this warp produces (warm-up included): 32-bit bookkeeping in the loop
+    const long long k_first = sp_begin * HB_BATCH;
+    const int lo = (int) (a0 * HB_BATCH - k_first);
+    const long long hi_abs = (a1 * HB_BATCH < p.n_out) ? a1 * HB_BATCH : p.n_out;
+    const int hi = (int) (hi_abs - k_first);
+    void* out = reinterpret_cast<char*>(p.out) + k_first * (Epilogue<OUT, T>::WORDS * 4);
     const int nph = (int) ((a1 - sp_begin) << (L - 1));
     long long pos = sp_begin * U;
 
-    for (int ph = 0; ph < nph; ++ph, pos += HB_IN) {
-        Loader<IN, T>::load(p, X, pos, lane);
+    int4 pre[LD::NV];
+    LD::fetch(p, pos, lane, pre);
+    for (int ph = 0; ph < nph; ++ph) {
+        LD::store(p, X, lane, pre);
+        pos += HB_IN;
+        if (ph + 1 < nph) LD::fetch(p, pos, lane, pre);         // next phase's input: in flight during this phase's math
         __syncwarp();
         for (int s = 1; s <= L; ++s) {
             if (((ph + 1) & ((1 << (s - 1)) - 1)) != 0) break;
@@ -556,20 +597,17 @@ __global__ void hb64_cascade_kernel(const CascadeParams p)
             const int sigma = HASROT ? (int) p.rot[s] : 0;
             T wv[44], cv[16], y[HB_R];
             hb64_load_windows<T>(Xin, comp, j, sigma != 0, wv, cv);
+            const typename vec4<T>::type tail = hb64_tail_load<T>(Xin, lane);
+            if (last) hb64_state_check<T>(p, Xin, s - 1, pos, lane);
             if (HASROT && sigma != 0) hb64_item<true, EXACT>(wv, cv, comp ? sigma : -sigma, opq, y);
             else                      hb64_item<false, EXACT>(wv, cv, 0, opq, y);
-            const long long done = (pos + HB_IN) >> (s - 1);    // stage-(s-1) samples consumed so far (call-absolute)
-            if (last) {
-                const long long n_s = p.n0 >> (s - 1);
-                if (n_s > done - HB_IN && n_s <= done) hb64_state_save<T>(p, Xin, s - 1, done - HB_IN, n_s, lane);
-            }
-            __syncwarp();
-            hb64_tail_copy<T>(Xin, lane);
+            __syncwarp();                                       // every lane has read its windows of Xin
+            hb64_tail_store<T>(Xin, lane, tail);
             if (s < L) {
                 const int fill = ((((ph + 1) >> (s - 1)) - 1) & 1) * (HB_BATCH / 2);
                 hb64_store_next<T>(X + s * HB_STAGE_WORDS, comp, j, fill, y);
             } else {
-                hb64_epilogue<OUT, T>(p, y, comp, j, (done >> 1) - HB_BATCH, out_lo, out_hi);
+                hb64_epilogue<OUT, T>(p, out, y, comp, j, (((ph + 1) >> (L - 1)) - 1) * HB_BATCH, lo, hi);
             }
             __syncwarp();
         }
