@@ -83,6 +83,45 @@ int b200dsp_decim_set_state(b200dsp_decim_t* h, const void* state_host);
 int b200dsp_decim_reset(b200dsp_decim_t* h);
 int b200dsp_decim_sync(b200dsp_decim_t* h);        /* wait for the handle's stream */
 
+/* ---- K3/K4: DownChannelizer bank + channel plugin front-end -----------------------------------------------
+ * A bank == many reference (DownChannelizer, NCO, Interpolator) triples fed from ONE baseband stream:
+ *   DownChannelizer::feed / applyConfiguration / createFilterChain   sdrbase/dsp/downchannelizer.cpp:50-91,165-189,250-287
+ *   the channel plugin front-end  c *= nco.nextIQ(); interpolator.decimate(...)
+ *                                                                     plugins/channelrx/demodnfm/nfmdemod.cpp:150-155,315,453-476
+ * Channels are added first (each add runs the reference's filter-chain selection and reports what
+ * MsgChannelizerNotification would: output rate and residual offset), then samples are fed.  Adding a channel or a
+ * front-end after feeding restarts all filter state (the plan is rebuilt).
+ * The outputs of a feed stay valid until the next feed, like DownChannelizer's m_sampleBuffer (downchannelizer.cpp:86-89).
+ */
+typedef struct b200dsp_bank b200dsp_bank_t;
+
+#define B200DSP_STAGE_CHANNELIZER 0   /* int16 IQ at input_rate / 2^S   (what DownChannelizer hands to its sink) */
+#define B200DSP_STAGE_FRONTEND    1   /* float IQ after NCO mix + Interpolator::decimate (complex64) */
+
+int b200dsp_bank_create(b200dsp_bank_t** b, int input_rate_hz);
+int b200dsp_bank_destroy(b200dsp_bank_t* b);
+/* internal time-chunk (input samples per pass over the tree); default 786432, rounded to a multiple of 768 */
+int b200dsp_bank_set_chunk(b200dsp_bank_t* b, int64_t samples);
+/* == DSPConfigureChannelizer(requested_rate, center_offset) -> MsgChannelizerNotification(out_rate, residual_offset) */
+int b200dsp_bank_add_channel(b200dsp_bank_t* b, int requested_rate_hz, int center_offset_hz,
+                             int* chan_id, int* out_rate_hz, int* residual_offset_hz);
+/* filter stages chosen for the channel: 0 centre, 1 lower half, 2 upper half (downchannelizer.h:72-76); returns S */
+int b200dsp_bank_channel_path(b200dsp_bank_t* b, int chan_id, int* modes, int cap);
+/* number of distinct half-band stages (tree nodes) the bank evaluates for all its channels */
+int b200dsp_bank_node_count(b200dsp_bank_t* b);
+/* == m_nco.setFreq(nco_freq, rate); m_interpolator.create(phase_steps, rate, cutoff, taps_per_phase);
+ *    m_interpolatorDistance = rate / out_rate  with rate = the channel's channelizer output rate (nfmdemod.cpp:462-470) */
+int b200dsp_bank_set_frontend(b200dsp_bank_t* b, int chan_id, float nco_freq_hz, int phase_steps, double cutoff_hz,
+                              double taps_per_phase, int out_rate_hz);
+int b200dsp_bank_frontend_info(b200dsp_bank_t* b, int chan_id, int* nco_increment, int* taps_per_phase, float* taps, int taps_cap);
+/* == DownChannelizer::feed(begin, end, positiveOnly) for every channel of the bank (+ the front-ends) */
+int b200dsp_bank_feed(b200dsp_bank_t* b, const int16_t* iq, int64_t n_samples);
+int b200dsp_bank_feed_dev(b200dsp_bank_t* b, const void* d_iq, int64_t n_samples, void* cuda_stream);
+/* outputs produced by the last feed for one channel; stage selects int16 IQ (4 bytes/sample) or complex64 (8 bytes) */
+int b200dsp_bank_fetch(b200dsp_bank_t* b, int chan_id, int stage, void* out, int64_t cap_samples, int64_t* n_samples);
+int b200dsp_bank_fetch_dev(b200dsp_bank_t* b, int chan_id, int stage, const void** d_ptr, int64_t* n_samples);
+int b200dsp_bank_sync(b200dsp_bank_t* b);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,7 +39,21 @@ SIGNATURES = {
     "b200dsp_decim_set_state": (_i32, [_vp, _vp]),
     "b200dsp_decim_reset": (_i32, [_vp]),
     "b200dsp_decim_sync": (_i32, [_vp]),
+    "b200dsp_bank_create": (_i32, [_pvp, _i32]),
+    "b200dsp_bank_destroy": (_i32, [_vp]),
+    "b200dsp_bank_set_chunk": (_i32, [_vp, _i64]),
+    "b200dsp_bank_add_channel": (_i32, [_vp, _i32, _i32, _pi32, _pi32, _pi32]),
+    "b200dsp_bank_channel_path": (_i32, [_vp, _i32, _pi32, _i32]),
+    "b200dsp_bank_node_count": (_i32, [_vp]),
+    "b200dsp_bank_set_frontend": (_i32, [_vp, _i32, _f32, _i32, C.c_double, C.c_double, _i32]),
+    "b200dsp_bank_frontend_info": (_i32, [_vp, _i32, _pi32, _pi32, _vp, _i32]),
+    "b200dsp_bank_feed": (_i32, [_vp, _vp, _i64]),
+    "b200dsp_bank_feed_dev": (_i32, [_vp, _vp, _i64, _vp]),
+    "b200dsp_bank_fetch": (_i32, [_vp, _i32, _i32, _vp, _i64, _pi64]),
+    "b200dsp_bank_fetch_dev": (_i32, [_vp, _i32, _i32, _pvp, _pi64]),
+    "b200dsp_bank_sync": (_i32, [_vp]),
 }
+STAGE_CHANNELIZER, STAGE_FRONTEND = 0, 1
 
 
 def lib():

@@ -1,0 +1,603 @@
+// bank_api.cu — C ABI of the DownChannelizer bank (K3) and the per-channel plugin front-end (K4): b200dsp_bank_*
+//
+// Host-side mirror of (paths relative to the reference tree):
+//   DownChannelizer::applyConfiguration / createFilterChain   sdrbase/dsp/downchannelizer.cpp:165-189,250-287
+//   DownChannelizer::feed (output count / phase carry)        sdrbase/dsp/downchannelizer.cpp:50-91
+//   NCO::setFreq                                              sdrbase/dsp/nco.cpp:48-52
+//   Interpolator::create / createPolyphaseLowPass             sdrbase/dsp/interpolator.cpp:21-129
+//   the NFM plugin's front-end wiring                         plugins/channelrx/demodnfm/nfmdemod.cpp:453-476
+#include "common.cuh"
+#include "hb48_tree.cuh"
+#include "frontend.cuh"
+#include <math.h>
+#include <string>
+#include <vector>
+
+using namespace b200dsp;
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------
+// small kernels around the level kernel
+// ---------------------------------------------------------------------------------------------------------
+// new_tail[t] = parent sample (C_after - 64 + t), t = 0..64   (64 history + the possibly pending sample)
+__global__ void hb48_tail_kernel(const uint32_t* in_base, long long in_stride, const uint32_t* tail_in, uint32_t* tail_out,
+                                 const int* fam, int n_in, int pend, int in_limit)
+{
+    const int parent = fam[4 * blockIdx.x];
+    const int t = threadIdx.x;
+    if (t > 64) return;
+    const int i = n_in - 64 + t;
+    uint32_t v;
+    if (i < pend) v = tail_in[(long long) parent * TAIL_WORDS + i + 64];
+    else          v = (i < in_limit) ? in_base[(long long) parent * in_stride + i] : 0u;
+    tail_out[(long long) parent * TAIL_WORDS + t] = v;
+}
+
+struct LeafChan { const uint32_t* src; uint32_t* dst; int shift; };
+
+// channel output = trunc_toward_zero(y / 2^S) per component (downchannelizer.cpp:78-83)
+__global__ void hb48_finalize_kernel(const LeafChan* chans, int n_new_max, const int* n_new_per_chan)
+{
+    const LeafChan c = chans[blockIdx.y];
+    const int n = n_new_per_chan[blockIdx.y];
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t w = c.src[k];
+        int re = (int) (short) (w & 0xffffu), im = (int) w >> 16;
+        const int bias = (1 << c.shift) - 1;
+        re = (re + ((re >> 31) & bias)) >> c.shift;
+        im = (im + ((im >> 31) & bias)) >> c.shift;
+        c.dst[k] = ((uint32_t) re & 0xffffu) | ((uint32_t) im << 16);
+    }
+}
+
+__global__ void copy_words_kernel(const uint32_t* src, uint32_t* dst, long long n)
+{
+    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// createFilterChain in the reference's float32/double mix (downchannelizer.cpp:250-287)
+// ---------------------------------------------------------------------------------------------------------
+bool band_contains(float ss, float se, float cs, float ce)
+{
+    if (se <= ss || ce <= cs) return false;
+    return ss <= cs && se >= ce;
+}
+
+float filter_chain(float ss, float se, float cs, float ce, std::vector<int>& modes)
+{
+    while (modes.size() < 30) {
+        const float bw = se - ss;
+        const float quarter = bw / 4;
+        const float low_end = (float) ((double) ss + (double) bw / 2.0);
+        const float up_start = se - bw / 2.0f;
+        if (band_contains(ss, low_end, cs, ce)) { modes.push_back(1); se = low_end; continue; }
+        if (band_contains(up_start, se, cs, ce)) { modes.push_back(2); ss = up_start; continue; }
+        const float cs2 = ss + quarter, ce2 = se - quarter;
+        if (band_contains(cs2, ce2, cs, ce)) { modes.push_back(0); ss = cs2; se = ce2; continue; }
+        break;
+    }
+    return (float) (((double) (float) (ce - cs) / 2.0 + (double) cs) - ((double) (float) (se - ss) / 2.0 + (double) ss));
+}
+
+struct Node { int depth, mode, parent, child[3], index; };      // index = position within its level
+
+struct Channel {
+    int requested_rate, center_offset;
+    std::vector<int> modes;
+    int node, S, out_rate, residual;
+    // front-end
+    bool fe;
+    float nco_freq; int phase_steps; double cutoff, taps_per_phase; int fe_out_rate;
+    int inc, ntaps; float ratio;
+    std::vector<float> taps;
+    // device
+    uint32_t* d_out; long long out_cap; long long out_count;       // channelizer outputs since the last feed start
+    float2* d_z; float* d_taps; float2* d_fe_out; int* d_sched; int* d_state; long long fe_cap; long long fe_count;
+};
+
+const double PI_D = 3.14159265358979323846;
+
+// Interpolator::create(phaseSteps, sampleRate, cutoff, nbTapsPerPhase): interpolator.cpp:21-56,74-110
+void interp_taps(int phase_steps, double rate, double cutoff, double taps_per_phase, std::vector<float>& out, int* per_phase)
+{
+    int ntaps = (int) (taps_per_phase * phase_steps);
+    if (ntaps % 2) ntaps++;
+    const int np = ntaps;
+    ntaps *= phase_steps;
+    std::vector<float> taps(ntaps, 0.0f), window(ntaps);
+    for (int n = 0; n < ntaps; n++) window[n] = (float) (0.54 - 0.46 * cos((2 * PI_D * n) / (ntaps - 1)));
+    const int M = (ntaps - 1) / 2;
+    const double fwT0 = 2 * PI_D * cutoff / (phase_steps * rate);
+    for (int n = -M; n <= M; n++)
+        taps[n + M] = (n == 0) ? (float) (fwT0 / PI_D * window[n + M]) : (float) (sin(n * fwT0) / (n * PI_D) * window[n + M]);
+    double mx = taps[M];
+    for (int n = 1; n <= M; n++) mx += 2.0 * taps[n + M];
+    const double gain = 1.0 / mx;
+    for (int i = 0; i < ntaps; i++) taps[i] = (float) (taps[i] * gain);
+    out.assign(ntaps, 0.0f);
+    for (int p = 0; p < phase_steps; p++) {
+        float sum = 0;
+        for (int i = 0; i < np; i++) { out[p * np + i] = taps[i * phase_steps + p]; sum += out[p * np + i]; }
+        for (int i = 0; i < np; i++) out[p * np + i] /= sum;
+    }
+    *per_phase = np;
+}
+
+} // namespace
+
+struct b200dsp_bank {
+    int device, sm_count;
+    int input_rate;
+    cudaStream_t stream;
+    std::vector<Channel> chans;
+    bool built;
+    // tree
+    std::vector<Node> nodes;
+    std::vector<std::vector<int>> levels;        // node ids per depth (levels[0] = {root})
+    std::vector<std::vector<int>> fams;          // per depth d>=1: flat [parent index, child C, child L, child U] of families producing depth d
+    int depth;
+    // device
+    long long chunk;                             // max input samples per internal pass
+    std::vector<uint32_t*> d_level;  std::vector<long long> stride;   // per depth >= 1
+    std::vector<uint32_t*> d_tail[2];            // per depth (parents), ping-pong
+    std::vector<int*> d_fam;
+    uint32_t* d_root; long long root_cap;        // staging for host feeds / odd-pending device feeds
+    std::vector<long long> produced;             // P[d]
+    int tcur;
+    LeafChan* d_leaf; int* d_nnew; FrontendChan* d_fe; float* d_nco;
+    std::vector<LeafChan> h_leaf; std::vector<int> h_nnew; std::vector<FrontendChan> h_fe;
+    std::vector<int> fe_index;                   // channel ids with a front-end
+};
+
+namespace {
+
+void free_device(b200dsp_bank* b)
+{
+    for (auto p : b->d_level) if (p) cudaFree(p);
+    for (int k = 0; k < 2; ++k) { for (auto p : b->d_tail[k]) if (p) cudaFree(p); b->d_tail[k].clear(); }
+    for (auto p : b->d_fam) if (p) cudaFree(p);
+    b->d_level.clear(); b->d_fam.clear(); b->stride.clear();
+    if (b->d_leaf) cudaFree(b->d_leaf);
+    if (b->d_nnew) cudaFree(b->d_nnew);
+    if (b->d_fe) cudaFree(b->d_fe);
+    b->d_leaf = nullptr; b->d_nnew = nullptr; b->d_fe = nullptr;
+    for (auto& c : b->chans) {
+        if (c.d_out) cudaFree(c.d_out);
+        if (c.d_z) cudaFree(c.d_z);
+        if (c.d_taps) cudaFree(c.d_taps);
+        if (c.d_fe_out) cudaFree(c.d_fe_out);
+        if (c.d_sched) cudaFree(c.d_sched);
+        if (c.d_state) cudaFree(c.d_state);
+        c.d_out = nullptr; c.d_z = nullptr; c.d_taps = nullptr; c.d_fe_out = nullptr; c.d_sched = nullptr; c.d_state = nullptr;
+        c.out_cap = c.fe_cap = 0;
+    }
+    b->built = false;
+}
+
+// Build the shared-prefix tree and all device state (filter histories zero, like freshly constructed reference objects).
+int build(b200dsp_bank* b)
+{
+    free_device(b);
+    b->nodes.clear(); b->levels.clear(); b->fams.clear();
+    Node root = { 0, 0, -1, { -1, -1, -1 }, 0 };
+    b->nodes.push_back(root);
+    b->depth = 0;
+    for (auto& c : b->chans) {
+        int cur = 0;
+        for (size_t s = 0; s < c.modes.size(); ++s) {
+            const int m = c.modes[s];
+            if (b->nodes[cur].child[m] < 0) {
+                Node n = { (int) s + 1, m, cur, { -1, -1, -1 }, 0 };
+                b->nodes[cur].child[m] = (int) b->nodes.size();
+                b->nodes.push_back(n);
+            }
+            cur = b->nodes[cur].child[m];
+        }
+        c.node = cur;
+        if ((int) c.modes.size() > b->depth) b->depth = (int) c.modes.size();
+    }
+    b->levels.assign(b->depth + 1, std::vector<int>());
+    for (size_t i = 0; i < b->nodes.size(); ++i) {
+        Node& n = b->nodes[i];
+        n.index = (int) b->levels[n.depth].size();
+        b->levels[n.depth].push_back((int) i);
+    }
+    b->fams.assign(b->depth + 1, std::vector<int>());
+    for (int d = 1; d <= b->depth; ++d)
+        for (int id : b->levels[d - 1]) {
+            const Node& n = b->nodes[id];
+            if (n.child[0] < 0 && n.child[1] < 0 && n.child[2] < 0) continue;
+            b->fams[d].push_back(n.index);
+            for (int m = 0; m < 3; ++m) b->fams[d].push_back(n.child[m] >= 0 ? b->nodes[n.child[m]].index : -1);
+        }
+    int rc;
+    b->d_level.assign(b->depth + 1, nullptr); b->stride.assign(b->depth + 1, 0);
+    b->d_tail[0].assign(b->depth + 1, nullptr); b->d_tail[1].assign(b->depth + 1, nullptr);
+    b->d_fam.assign(b->depth + 1, nullptr);
+    for (int d = 1; d <= b->depth; ++d) {
+        b->stride[d] = (((b->chunk >> d) + 16) + 3) & ~3ll;
+        const size_t bytes = (size_t) b->levels[d].size() * b->stride[d] * 4;
+        if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_level[d], bytes))) || (rc = B200_CUDA_CHECK(cudaMemset(b->d_level[d], 0, bytes)))) return rc;
+        const size_t fb = b->fams[d].size() * sizeof(int);
+        if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_fam[d], fb))) ||
+            (rc = B200_CUDA_CHECK(cudaMemcpy(b->d_fam[d], b->fams[d].data(), fb, cudaMemcpyHostToDevice)))) return rc;
+    }
+    for (int d = 0; d < b->depth; ++d)
+        for (int k = 0; k < 2; ++k) {
+            const size_t bytes = (size_t) b->levels[d].size() * TAIL_WORDS * 4;
+            if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_tail[k][d], bytes))) || (rc = B200_CUDA_CHECK(cudaMemset(b->d_tail[k][d], 0, bytes)))) return rc;
+        }
+    b->produced.assign(b->depth + 1, 0);
+    b->tcur = 0;
+    const size_t nc = b->chans.size();
+    if (nc) {
+        if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_leaf, nc * sizeof(LeafChan)))) || (rc = B200_CUDA_CHECK(cudaMalloc(&b->d_nnew, nc * sizeof(int)))) ||
+            (rc = B200_CUDA_CHECK(cudaMalloc(&b->d_fe, nc * sizeof(FrontendChan))))) return rc;
+    }
+    b->h_leaf.resize(nc); b->h_nnew.resize(nc);
+    b->fe_index.clear();
+    for (size_t i = 0; i < nc; ++i) {
+        Channel& c = b->chans[i];
+        c.out_count = 0;
+        if (!c.fe) continue;
+        b->fe_index.push_back((int) i);
+        const size_t tb = c.taps.size() * sizeof(float);
+        if ((rc = B200_CUDA_CHECK(cudaMalloc(&c.d_taps, tb))) || (rc = B200_CUDA_CHECK(cudaMemcpy(c.d_taps, c.taps.data(), tb, cudaMemcpyHostToDevice))) ||
+            (rc = B200_CUDA_CHECK(cudaMalloc(&c.d_state, 4 * sizeof(int)))) || (rc = B200_CUDA_CHECK(cudaMemset(c.d_state, 0, 4 * sizeof(int))))) return rc;
+    }
+    b->h_fe.resize(b->fe_index.size());
+    if (!b->d_nco) {
+        std::vector<float> t(4096);
+        for (int i = 0; i < 4096; i++) t[i] = (float) cos((2.0 * PI_D * i) / 4096);       // NCO::initTable, nco.cpp:30-39
+        if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_nco, 4096 * sizeof(float)))) ||
+            (rc = B200_CUDA_CHECK(cudaMemcpy(b->d_nco, t.data(), 4096 * sizeof(float), cudaMemcpyHostToDevice)))) return rc;
+    }
+    b->built = true;
+    return 0;
+}
+
+// make sure per-channel output buffers can take the outputs of a feed of n input samples
+int reserve_outputs(b200dsp_bank* b, long long n)
+{
+    int rc;
+    for (auto& c : b->chans) {
+        const long long need = (n >> c.S) + 2;
+        if (c.out_cap < need) {
+            if (c.d_out) cudaFree(c.d_out);
+            c.d_out = nullptr; c.out_cap = 0;
+            if ((rc = B200_CUDA_CHECK(cudaMalloc(&c.d_out, (size_t) need * 4)))) return rc;
+            c.out_cap = need;
+        }
+        if (c.fe && c.fe_cap < need) {
+            if (c.d_fe_out) cudaFree(c.d_fe_out);
+            if (c.d_sched) cudaFree(c.d_sched);
+            float2* oldz = c.d_z;
+            c.d_fe_out = nullptr; c.d_sched = nullptr; c.d_z = nullptr; c.fe_cap = 0;
+            float2* newz = nullptr;
+            if ((rc = B200_CUDA_CHECK(cudaMalloc(&c.d_fe_out, (size_t) need * sizeof(float2)))) ||
+                (rc = B200_CUDA_CHECK(cudaMalloc(&c.d_sched, (size_t) need * sizeof(int)))) ||
+                (rc = B200_CUDA_CHECK(cudaMalloc(&newz, (size_t) (need + FE_MAX_TAPS) * sizeof(float2)))) ||
+                (rc = B200_CUDA_CHECK(cudaMemset(newz, 0, (size_t) (need + FE_MAX_TAPS) * sizeof(float2))))) return rc;
+            if (oldz) {      // growing the buffer keeps the interpolator history
+                if ((rc = B200_CUDA_CHECK(cudaMemcpy(newz, oldz, FE_MAX_TAPS * sizeof(float2), cudaMemcpyDeviceToDevice)))) return rc;
+                cudaFree(oldz);
+            }
+            c.d_z = newz;
+            c.fe_cap = need;
+        }
+    }
+    return 0;
+}
+
+// one internal pass over n <= chunk input samples available at device pointer d_in (16-byte aligned)
+int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t st, bool first_pass)
+{
+    int rc;
+    const int D = b->depth;
+    std::vector<long long> Pb = b->produced, Pa(D + 1);
+    Pa[0] = Pb[0] + n;
+    for (int d = 1; d <= D; ++d) Pa[d] = Pa[d - 1] / 2;
+    // root buffer: B[i] = root sample (C_before + i); with one pending sample the new data has to sit at B[1]
+    const uint32_t* rootB = d_in;
+    const int root_pend = (D >= 1) ? (int) (Pb[0] - 2 * Pb[1]) : 0;
+    if (root_pend || ((uintptr_t) d_in & 15)) {
+        const long long need = n + 8;
+        if (b->root_cap < need) {
+            if (b->d_root) cudaFree(b->d_root);
+            b->d_root = nullptr; b->root_cap = 0;
+            if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_root, (size_t) need * 4)))) return rc;
+            b->root_cap = need;
+        }
+        if (d_in != b->d_root + root_pend) {
+            copy_words_kernel<<<(unsigned) ((n + 1023) / 1024 < 2048 ? (n + 1023) / 1024 : 2048), 256, 0, st>>>(d_in, b->d_root + root_pend, n);
+            if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
+        }
+        rootB = b->d_root;
+    }
+    const int tc = b->tcur, tn = tc ^ 1;
+    for (int d = 1; d <= D; ++d) {
+        const int n_fam = (int) (b->fams[d].size() / 4);
+        if (n_fam == 0) continue;
+        LevelParams p;
+        memset(&p, 0, sizeof(p));
+        p.in_base = (d == 1) ? rootB : b->d_level[d - 1];
+        p.in_stride = (d == 1) ? 0 : b->stride[d - 1];
+        p.out_base = b->d_level[d]; p.out_stride = b->stride[d];
+        p.tail_in = b->d_tail[tc][d - 1];
+        p.fam = b->d_fam[d]; p.n_fam = n_fam;
+        const long long Cb = 2 * Pb[d], Ca = 2 * Pa[d];
+        p.n_in = (int) (Ca - Cb);
+        p.pend = (int) (Pb[d - 1] - Cb);
+        p.in_limit = p.pend + (int) (Pa[d - 1] - Pb[d - 1]);
+        p.wo = (int) (Pb[d] & 1);
+        p.flip = (int) (Pb[d] & 1);
+        p.opq_zero = 0; p.opq_one = 1; p.opq_mone = -1;
+        if (p.n_in > 0) {
+            const int nb = (p.n_in + HB_IN - 1) / HB_IN;
+            long long target = (long long) b->sm_count * 16;
+            long long slices = (target + n_fam - 1) / n_fam;
+            if (slices > nb) slices = nb;
+            if (slices < 1) slices = 1;
+            const int bps = (int) ((nb + slices - 1) / slices);
+            slices = (nb + bps - 1) / bps;
+            p.slices = (int) slices; p.bps = bps;
+            const long long warps = (long long) n_fam * slices;
+            const int wpb = 4;
+            hb48_level_kernel<<<(unsigned) ((warps + wpb - 1) / wpb), wpb * 32, wpb * HB_STAGE_BYTES, st>>>(p);
+            if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
+        }
+        hb48_tail_kernel<<<n_fam, 96, 0, st>>>(p.in_base, p.in_stride, p.tail_in, b->d_tail[tn][d - 1], b->d_fam[d], p.n_in, p.pend, p.in_limit);
+        if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
+    }
+    // channel outputs of this pass
+    const size_t nc = b->chans.size();
+    int max_new = 0;
+    for (size_t i = 0; i < nc; ++i) {
+        Channel& c = b->chans[i];
+        const int n_new = (int) (Pa[c.S] - Pb[c.S]);
+        b->h_nnew[i] = n_new;
+        if (n_new > max_new) max_new = n_new;
+        const uint32_t* src = (c.S == 0) ? d_in : b->d_level[c.S] + (long long) b->nodes[c.node].index * b->stride[c.S] + (Pb[c.S] & 1);
+        b->h_leaf[i].src = src; b->h_leaf[i].dst = c.d_out + c.out_count; b->h_leaf[i].shift = c.S;
+    }
+    if (nc && max_new > 0) {
+        if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(b->d_leaf, b->h_leaf.data(), nc * sizeof(LeafChan), cudaMemcpyHostToDevice, st))) ||
+            (rc = B200_CUDA_CHECK(cudaMemcpyAsync(b->d_nnew, b->h_nnew.data(), nc * sizeof(int), cudaMemcpyHostToDevice, st)))) return rc;
+        int gx = (max_new + 255) / 256;
+        if (gx > 64) gx = 64;
+        hb48_finalize_kernel<<<dim3(gx, (unsigned) nc), 256, 0, st>>>(b->d_leaf, max_new, b->d_nnew);
+        if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
+    }
+    // K4 front-ends
+    if (!b->fe_index.empty() && max_new > 0) {
+        size_t smem = 0;
+        for (size_t k = 0; k < b->fe_index.size(); ++k) {
+            Channel& c = b->chans[b->fe_index[k]];
+            FrontendChan& f = b->h_fe[k];
+            f.in = c.d_out + c.out_count; f.z = c.d_z; f.taps = c.d_taps; f.out = c.d_fe_out; f.sched = c.d_sched; f.state = c.d_state;
+            f.m = b->h_nnew[b->fe_index[k]]; f.first_pass = first_pass ? 1 : 0; f.inc = c.inc; f.ntaps = c.ntaps; f.phase_steps = c.phase_steps; f.ratio = c.ratio;
+            const size_t s = c.taps.size() * sizeof(float);
+            if (s > smem) smem = s;
+        }
+        if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(b->d_fe, b->h_fe.data(), b->h_fe.size() * sizeof(FrontendChan), cudaMemcpyHostToDevice, st)))) return rc;
+        frontend_kernel<<<(unsigned) b->h_fe.size(), 256, smem, st>>>(b->d_fe, b->d_nco);
+        if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
+    }
+    // The descriptor arrays are reused by the next pass: they live in pageable host vectors, so cudaMemcpyAsync has
+    // already staged them when it returns.
+    for (size_t i = 0; i < nc; ++i) b->chans[i].out_count += b->h_nnew[i];
+    b->produced = Pa;
+    b->tcur = tn;
+    return 0;
+}
+
+int feed_common(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t st)
+{
+    int rc;
+    if (!b->built && (rc = build(b))) return rc;
+    if ((rc = reserve_outputs(b, n))) return rc;
+    for (auto& c : b->chans) c.out_count = 0;
+    long long done = 0;
+    while (done < n) {
+        const long long m = (n - done) < b->chunk ? (n - done) : b->chunk;
+        if ((rc = feed_chunk(b, d_in + done, m, st, done == 0))) return rc;
+        done += m;
+    }
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int b200dsp_bank_create(b200dsp_bank_t** out, int input_rate_hz)
+{
+    if (!out) return b200_fail(B200DSP_EINVAL, "bank_create: null handle pointer");
+    *out = nullptr;
+    if (input_rate_hz <= 0) return b200_fail(B200DSP_EINVAL, "bank_create: input rate must be positive");
+    int rc = b200_require_device();
+    if (rc) return rc;
+    b200dsp_bank* b = new (std::nothrow) b200dsp_bank();
+    if (!b) return b200_fail(B200DSP_ENOMEM, "bank_create: out of host memory");
+    b->device = b200_current_device();
+    b->sm_count = b200_sm_count_of(b->device);
+    b->input_rate = input_rate_hz;
+    b->built = false; b->depth = 0; b->chunk = 3ll << 18; b->d_root = nullptr; b->root_cap = 0;
+    b->d_leaf = nullptr; b->d_nnew = nullptr; b->d_fe = nullptr; b->d_nco = nullptr; b->tcur = 0;
+    if ((rc = B200_CUDA_CHECK(cudaSetDevice(b->device))) || (rc = B200_CUDA_CHECK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)))) { delete b; return rc; }
+    *out = b;
+    return 0;
+}
+
+int b200dsp_bank_destroy(b200dsp_bank_t* b)
+{
+    if (!b) return 0;
+    cudaSetDevice(b->device);
+    cudaStreamSynchronize(b->stream);
+    free_device(b);
+    if (b->d_root) cudaFree(b->d_root);
+    if (b->d_nco) cudaFree(b->d_nco);
+    cudaStreamDestroy(b->stream);
+    delete b;
+    return 0;
+}
+
+int b200dsp_bank_set_chunk(b200dsp_bank_t* b, int64_t samples)
+{
+    if (!b || samples < 768) return b200_fail(B200DSP_EINVAL, "bank_set_chunk: bad argument");
+    cudaSetDevice(b->device);
+    cudaStreamSynchronize(b->stream);
+    b->chunk = (samples + 767) / 768 * 768;
+    free_device(b);
+    return 0;
+}
+
+int b200dsp_bank_add_channel(b200dsp_bank_t* b, int requested_rate_hz, int center_offset_hz, int* chan_id, int* out_rate_hz, int* residual_offset_hz)
+{
+    if (!b) return b200_fail(B200DSP_EINVAL, "null handle");
+    if (requested_rate_hz <= 0) return b200_fail(B200DSP_EINVAL, "bank_add_channel: requested rate must be positive");
+    Channel c{};
+    c.requested_rate = requested_rate_hz; c.center_offset = center_offset_hz;
+    c.fe = false; c.d_out = nullptr; c.out_cap = 0; c.out_count = 0;
+    c.d_z = nullptr; c.d_taps = nullptr; c.d_fe_out = nullptr; c.d_sched = nullptr; c.d_state = nullptr; c.fe_cap = 0;
+    // downchannelizer.cpp:169-171: integer divides first, then int -> Real
+    const float ofs = filter_chain((float) (b->input_rate / -2), (float) (b->input_rate / 2),
+                                   (float) (center_offset_hz - requested_rate_hz / 2), (float) (center_offset_hz + requested_rate_hz / 2), c.modes);
+    c.S = (int) c.modes.size();
+    c.out_rate = b->input_rate / (1 << c.S);
+    c.residual = (int) ofs;
+    if (b->built) { cudaSetDevice(b->device); cudaStreamSynchronize(b->stream); free_device(b); }   // plan changes: state restarts
+    b->chans.push_back(c);
+    if (chan_id) *chan_id = (int) b->chans.size() - 1;
+    if (out_rate_hz) *out_rate_hz = c.out_rate;
+    if (residual_offset_hz) *residual_offset_hz = c.residual;
+    return 0;
+}
+
+int b200dsp_bank_channel_path(b200dsp_bank_t* b, int chan_id, int* modes, int cap)
+{
+    if (!b || chan_id < 0 || chan_id >= (int) b->chans.size()) return b200_fail(B200DSP_EINVAL, "bank_channel_path: bad channel");
+    const Channel& c = b->chans[chan_id];
+    for (int i = 0; i < c.S && i < cap; ++i) if (modes) modes[i] = c.modes[i];
+    return c.S;
+}
+
+int b200dsp_bank_node_count(b200dsp_bank_t* b)
+{
+    if (!b) return b200_fail(B200DSP_EINVAL, "null handle");
+    if (!b->built) { int rc = B200_CUDA_CHECK(cudaSetDevice(b->device)); if (rc) return rc; if ((rc = build(b))) return rc; }
+    return (int) b->nodes.size() - 1;
+}
+
+int b200dsp_bank_set_frontend(b200dsp_bank_t* b, int chan_id, float nco_freq_hz, int phase_steps, double cutoff_hz, double taps_per_phase, int out_rate_hz)
+{
+    if (!b || chan_id < 0 || chan_id >= (int) b->chans.size()) return b200_fail(B200DSP_EINVAL, "bank_set_frontend: bad channel");
+    if (phase_steps < 1 || phase_steps > 255 || out_rate_hz <= 0 || taps_per_phase <= 0) return b200_fail(B200DSP_EINVAL, "bank_set_frontend: bad parameters");
+    Channel& c = b->chans[chan_id];
+    int np = 0;
+    interp_taps(phase_steps, (double) c.out_rate, cutoff_hz, taps_per_phase, c.taps, &np);
+    if (np > FE_MAX_TAPS) return b200_fail(B200DSP_EINVAL, "bank_set_frontend: %d taps per phase exceed the supported %d", np, FE_MAX_TAPS);
+    c.fe = true; c.nco_freq = nco_freq_hz; c.phase_steps = phase_steps; c.cutoff = cutoff_hz; c.taps_per_phase = taps_per_phase; c.fe_out_rate = out_rate_hz;
+    c.ntaps = np;
+    c.inc = (int) ((nco_freq_hz * 4096) / (float) c.out_rate);                 // NCO::setFreq: float arithmetic, truncation (nco.cpp:50)
+    c.ratio = (float) c.out_rate / (float) out_rate_hz;                        // nfmdemod.cpp:469-470
+    if (b->built) { cudaSetDevice(b->device); cudaStreamSynchronize(b->stream); free_device(b); }
+    return 0;
+}
+
+int b200dsp_bank_frontend_info(b200dsp_bank_t* b, int chan_id, int* nco_increment, int* taps_per_phase, float* taps, int taps_cap)
+{
+    if (!b || chan_id < 0 || chan_id >= (int) b->chans.size() || !b->chans[chan_id].fe) return b200_fail(B200DSP_EINVAL, "bank_frontend_info: no front-end on this channel");
+    const Channel& c = b->chans[chan_id];
+    if (nco_increment) *nco_increment = c.inc;
+    if (taps_per_phase) *taps_per_phase = c.ntaps;
+    if (taps) for (int i = 0; i < (int) c.taps.size() && i < taps_cap; ++i) taps[i] = c.taps[i];
+    return 0;
+}
+
+int b200dsp_bank_feed_dev(b200dsp_bank_t* b, const void* d_iq, int64_t n_samples, void* cuda_stream)
+{
+    if (!b) return b200_fail(B200DSP_EINVAL, "null handle");
+    if (n_samples < 0 || (n_samples > 0 && !d_iq)) return b200_fail(B200DSP_EINVAL, "bank_feed: bad buffer");
+    int rc = B200_CUDA_CHECK(cudaSetDevice(b->device));
+    if (rc) return rc;
+    return feed_common(b, (const uint32_t*) d_iq, n_samples, cuda_stream ? (cudaStream_t) cuda_stream : b->stream);
+}
+
+int b200dsp_bank_feed(b200dsp_bank_t* b, const int16_t* iq, int64_t n_samples)
+{
+    if (!b) return b200_fail(B200DSP_EINVAL, "null handle");
+    if (n_samples < 0 || (n_samples > 0 && !iq)) return b200_fail(B200DSP_EINVAL, "bank_feed: bad buffer");
+    int rc = B200_CUDA_CHECK(cudaSetDevice(b->device));
+    if (rc) return rc;
+    if (!b->built && (rc = build(b))) return rc;
+    if ((rc = reserve_outputs(b, n_samples))) return rc;
+    for (auto& c : b->chans) c.out_count = 0;
+    long long done = 0;
+    while (done < n_samples) {
+        const long long m = (n_samples - done) < b->chunk ? (n_samples - done) : b->chunk;
+        const int pend = (b->depth >= 1) ? (int) (b->produced[0] - 2 * b->produced[1]) : 0;
+        if (b->root_cap < m + 8) {
+            if ((rc = B200_CUDA_CHECK(cudaStreamSynchronize(b->stream)))) return rc;
+            if (b->d_root) cudaFree(b->d_root);
+            b->d_root = nullptr; b->root_cap = 0;
+            const long long cap = (b->chunk > m ? b->chunk : m) + 8;
+            if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_root, (size_t) cap * 4)))) return rc;
+            b->root_cap = cap;
+        }
+        // the previous pass may still be reading d_root
+        if ((rc = B200_CUDA_CHECK(cudaStreamSynchronize(b->stream)))) return rc;
+        if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(b->d_root + pend, iq + 2 * done, (size_t) m * 4, cudaMemcpyHostToDevice, b->stream)))) return rc;
+        if ((rc = feed_chunk(b, b->d_root + pend, m, b->stream, done == 0))) return rc;
+        done += m;
+    }
+    return B200_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+}
+
+int b200dsp_bank_fetch(b200dsp_bank_t* b, int chan_id, int stage, void* out, int64_t cap, int64_t* n)
+{
+    if (!b || chan_id < 0 || chan_id >= (int) b->chans.size()) return b200_fail(B200DSP_EINVAL, "bank_fetch: bad channel");
+    int rc = B200_CUDA_CHECK(cudaSetDevice(b->device));
+    if (rc) return rc;
+    if ((rc = B200_CUDA_CHECK(cudaStreamSynchronize(b->stream)))) return rc;
+    Channel& c = b->chans[chan_id];
+    if (stage == B200DSP_STAGE_CHANNELIZER) {
+        if (n) *n = c.out_count;
+        if (c.out_count > cap) return b200_fail(B200DSP_EINVAL, "bank_fetch: buffer too small (%lld needed)", c.out_count);
+        if (c.out_count && out) return B200_CUDA_CHECK(cudaMemcpy(out, c.d_out, (size_t) c.out_count * 4, cudaMemcpyDeviceToHost));
+        return 0;
+    }
+    if (stage == B200DSP_STAGE_FRONTEND) {
+        if (!c.fe) return b200_fail(B200DSP_ESTATE, "bank_fetch: channel has no front-end");
+        long long total = 0;
+        if (c.d_state && b->built && c.d_fe_out) {
+            int s[4];
+            if ((rc = B200_CUDA_CHECK(cudaMemcpy(s, c.d_state, sizeof(s), cudaMemcpyDeviceToHost)))) return rc;
+            total = s[3];
+        }
+        if (n) *n = total;
+        if (total > cap) return b200_fail(B200DSP_EINVAL, "bank_fetch: buffer too small (%lld needed)", total);
+        if (total && out) return B200_CUDA_CHECK(cudaMemcpy(out, c.d_fe_out, (size_t) total * sizeof(float2), cudaMemcpyDeviceToHost));
+        return 0;
+    }
+    return b200_fail(B200DSP_EINVAL, "bank_fetch: bad stage");
+}
+
+int b200dsp_bank_fetch_dev(b200dsp_bank_t* b, int chan_id, int stage, const void** d_ptr, int64_t* n)
+{
+    if (!b || chan_id < 0 || chan_id >= (int) b->chans.size() || !d_ptr) return b200_fail(B200DSP_EINVAL, "bank_fetch_dev: bad argument");
+    Channel& c = b->chans[chan_id];
+    if (stage == B200DSP_STAGE_CHANNELIZER) { *d_ptr = c.d_out; if (n) *n = c.out_count; return 0; }
+    if (stage == B200DSP_STAGE_FRONTEND && c.fe) { *d_ptr = c.d_fe_out; if (n) *n = -1; return 0; }
+    return b200_fail(B200DSP_EINVAL, "bank_fetch_dev: bad stage");
+}
+
+int b200dsp_bank_sync(b200dsp_bank_t* b)
+{
+    if (!b) return b200_fail(B200DSP_EINVAL, "null handle");
+    return B200_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+}
+
+} // extern "C"

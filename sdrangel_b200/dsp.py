@@ -119,3 +119,79 @@ class DecimatorsFF(_DecimatorsBase):
 class DecimatorsIF(_DecimatorsBase):
     """DecimatorsIF<qint16, input_bits> (sdrbase/dsp/decimatorsif.h:53-83): int16 in, float out."""
     IN_FMT, OUT_FMT = capi.FMT_I16, capi.FMT_F32
+
+
+class DownChannelizerBank:
+    """A bank of reference (DownChannelizer [+ NCO + Interpolator]) channels fed from one baseband stream.
+
+    Mirrors, per channel: DSPConfigureChannelizer -> MsgChannelizerNotification (add_channel), the NFM plugin's
+    applyChannelSettings front-end wiring (set_frontend) and DownChannelizer::feed (feed); sdrbase/dsp/downchannelizer.cpp,
+    plugins/channelrx/demodnfm/nfmdemod.cpp:150-155,453-476."""
+
+    def __init__(self, input_rate, device=None):
+        L = capi.lib()
+        if device is not None:
+            capi.init(device)
+        h = C.c_void_p()
+        capi.check(L.b200dsp_bank_create(C.byref(h), int(input_rate)))
+        self._h = h
+        self.input_rate = int(input_rate)
+        self.channels = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            capi.lib().b200dsp_bank_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_chunk(self, samples):
+        capi.check(capi.lib().b200dsp_bank_set_chunk(self._h, int(samples)))
+
+    def add_channel(self, requested_rate, center_offset):
+        """Returns (chan_id, out_rate, residual_offset, path) with path a string over 'C','L','U'."""
+        cid, rate, ofs = C.c_int32(), C.c_int32(), C.c_int32()
+        capi.check(capi.lib().b200dsp_bank_add_channel(self._h, int(requested_rate), int(center_offset), C.byref(cid), C.byref(rate), C.byref(ofs)))
+        modes = (C.c_int32 * 32)()
+        n = capi.lib().b200dsp_bank_channel_path(self._h, cid.value, modes, 32)
+        path = "".join("CLU"[modes[i]] for i in range(n))
+        self.channels.append((cid.value, rate.value, ofs.value, path))
+        return cid.value, rate.value, ofs.value, path
+
+    def node_count(self):
+        n = capi.lib().b200dsp_bank_node_count(self._h)
+        if n < 0:
+            capi.check(n)
+        return n
+
+    def set_frontend(self, chan_id, nco_freq, cutoff, out_rate, phase_steps=16, taps_per_phase=4.5):
+        capi.check(capi.lib().b200dsp_bank_set_frontend(self._h, chan_id, float(nco_freq), phase_steps, float(cutoff), float(taps_per_phase), int(out_rate)))
+
+    def frontend_info(self, chan_id):
+        inc, nt = C.c_int32(), C.c_int32()
+        capi.check(capi.lib().b200dsp_bank_frontend_info(self._h, chan_id, C.byref(inc), C.byref(nt), None, 0))
+        taps = np.empty(nt.value * 256, dtype=np.float32)
+        capi.check(capi.lib().b200dsp_bank_frontend_info(self._h, chan_id, C.byref(inc), C.byref(nt), taps.ctypes.data, taps.size))
+        return inc.value, nt.value, taps
+
+    def feed(self, iq):
+        iq = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1)
+        capi.check(capi.lib().b200dsp_bank_feed(self._h, iq.ctypes.data, iq.size // 2))
+
+    def feed_dev(self, d_iq, n_samples, stream=None):
+        capi.check(capi.lib().b200dsp_bank_feed_dev(self._h, C.c_void_p(d_iq), int(n_samples), C.c_void_p(stream or 0)))
+
+    def sync(self):
+        capi.check(capi.lib().b200dsp_bank_sync(self._h))
+
+    def fetch(self, chan_id, stage=capi.STAGE_CHANNELIZER):
+        n = C.c_int64(0)
+        capi.check(capi.lib().b200dsp_bank_fetch(self._h, chan_id, stage, None, 1 << 62, C.byref(n)))
+        dt = np.int16 if stage == capi.STAGE_CHANNELIZER else np.float32
+        out = np.empty((max(n.value, 1), 2), dtype=dt)
+        capi.check(capi.lib().b200dsp_bank_fetch(self._h, chan_id, stage, out.ctypes.data, out.shape[0], C.byref(n)))
+        return out[:n.value]

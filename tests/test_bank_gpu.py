@@ -1,0 +1,149 @@
+"""GPU parity tests of K3 (shared-prefix HB48 tree) and K4 (NCO + polyphase Interpolator front-end) through the
+C ABI.  Channelizer outputs: bit-exact (int16).  Front-end: identical output count/schedule, values within
+1e-5 relative RMS (north_star tolerance)."""
+import numpy as np
+import pytest
+
+from conftest import rel_rms
+
+pytestmark = pytest.mark.gpu
+
+
+def chan_input(meta):
+    m = meta["chan_feed"]
+    rs = np.random.RandomState(m["seed"])
+    cx = rs.randint(-32768, 32768, size=(m["n"], 2)).astype(np.int16)
+    cx[m["min_run"][0]:m["min_run"][1]] = -32768
+    return m, cx
+
+
+def test_filter_chain_plans_match_reference(gpu_lib, golden_meta):
+    from sdrangel_b200 import DownChannelizerBank
+    plans = golden_meta["chan_plans"]
+    for name in ("bank64", "bank1024"):
+        b = DownChannelizerBank(plans[name]["input_rate"])
+        for fc, rate, ofs, path in plans[name]["channels"]:
+            cid, r, o, p = b.add_channel(48000, fc)
+            assert (r, o, p) == (rate, ofs, path), (name, fc)
+        b.close()
+    for fs, req, fc, rate, ofs, path in plans["random"]:
+        b = DownChannelizerBank(fs)
+        assert b.add_channel(req, fc)[1:] == (rate, ofs, path)
+        b.close()
+
+
+def test_bank_feed_golden_bit_exact(gpu_lib, golden, golden_meta):
+    """6 channels sharing one tree, awkward feed splits (odd lengths), a run of -32768 (int16 negation wrap)."""
+    from sdrangel_b200 import DownChannelizerBank
+    m, cx = chan_input(golden_meta)
+    b = DownChannelizerBank(m["input_rate"])
+    ids = [b.add_channel(m["requested_rate"], fc)[0] for fc in m["offsets"]]
+    outs = {c: [] for c in ids}
+    for a, e in zip(m["cuts"][:-1], m["cuts"][1:]):
+        b.feed(cx[a:e])
+        for c in ids:
+            outs[c].append(b.fetch(c).copy())
+    for c, fc in zip(ids, m["offsets"]):
+        got, want = np.concatenate(outs[c]), golden[f"chan_feed/{fc}"]
+        assert got.shape == want.shape, (fc, got.shape, want.shape)
+        assert np.array_equal(got, want), (fc, int(np.argmax(np.any(got != want, axis=1))))
+
+
+@pytest.mark.parametrize("chunk", [768, 3 << 18])
+def test_bank64_vs_oracle_per_call_counts(gpu_lib, port, golden_meta, chunk):
+    """BASELINE config 3 plan (64 NFM channels @ 10 MS/s): every channel, every call, vs one oracle chain per channel."""
+    from sdrangel_b200 import DownChannelizerBank
+    plan = golden_meta["chan_plans"]["bank64"]
+    rs = np.random.RandomState(33)
+    n = 300_000
+    x = rs.randint(-32768, 32768, size=(n, 2)).astype(np.int16)
+    b = DownChannelizerBank(plan["input_rate"])
+    b.set_chunk(chunk)
+    chans = plan["channels"][::5] + plan["channels"][-1:]
+    ids = [b.add_channel(48000, fc)[0] for fc, _, _, _ in chans]
+    assert b.node_count() > 0
+    oracles = []
+    for fc, _, _, _ in chans:
+        o = port.PortDownChannelizer()
+        o.configure(plan["input_rate"], 48000, fc)
+        oracles.append(o)
+    cuts = [0, 1, 4, 1001, 65536 + 1001, 65536 + 1002, 200_001, n]
+    for a, e in zip(cuts[:-1], cuts[1:]):
+        b.feed(x[a:e])
+        for cid, o in zip(ids, oracles):
+            got, want = b.fetch(cid), o.feed(x[a:e])
+            assert got.shape == want.shape, (a, e, cid, got.shape, want.shape)
+            assert np.array_equal(got, want), (a, e, cid)
+
+
+def test_bank_shared_tree_is_smaller_than_independent_chains(gpu_lib, golden_meta):
+    from sdrangel_b200 import DownChannelizerBank
+    plan = golden_meta["chan_plans"]["bank64"]
+    b = DownChannelizerBank(plan["input_rate"])
+    total = 0
+    for fc, _, _, path in plan["channels"]:
+        b.add_channel(48000, fc)
+        total += len(path)
+    assert b.node_count() < total
+    assert b.node_count() == len({p[:k] for _, _, _, p in plan["channels"] for k in range(1, len(p) + 1)})
+
+
+def test_frontend_schedule_and_values_golden(gpu_lib, golden, golden_meta):
+    """NCO + Interpolator::decimate on a stage-less channel (requested rate = input rate => DownChannelizer forwards
+    samples unchanged), same inputs/cuts as the golden fixtures."""
+    from sdrangel_b200 import DownChannelizerBank, capi
+    m = golden_meta["frontend"]
+    rs = np.random.RandomState(m["seed"])
+    fx = rs.randint(-20000, 20000, size=(m["n"], 2)).astype(np.int16)
+    cutoff = np.float32(np.float32(12500) / np.float32(2.2))
+    for freq, rate, outr in m["cases"]:
+        b = DownChannelizerBank(rate)
+        cid, r, ofs, path = b.add_channel(rate, 0)
+        assert path == "" and r == rate
+        b.set_frontend(cid, freq, float(cutoff), outr)
+        inc, nt, taps = b.frontend_info(cid)
+        key = f"frontend/strict/{freq}_{rate}"
+        assert inc == golden_meta["frontend_inc"][f"{freq}_{rate}"]
+        assert nt == 72 and np.array_equal(taps[: 16 * 72].reshape(16, 72), golden[key + "/taps"])
+        outs = []
+        for a, e in ((0, 7), (7, 9000), (9000, 20000)):
+            b.feed(fx[a:e])
+            assert np.array_equal(b.fetch(cid), fx[a:e])
+            outs.append(b.fetch(cid, capi.STAGE_FRONTEND).copy())
+        out = np.concatenate(outs)
+        want = golden[key + "/out"]
+        assert out.shape == want.shape          # same schedule length: the float32 distance recurrence is replayed exactly
+        assert rel_rms(out, want) <= 1e-5
+        assert rel_rms(out, golden[f"frontend/fast/{freq}_{rate}/out"]) <= 1e-5
+        b.close()
+
+
+def test_bank_with_frontends_vs_oracle(gpu_lib, port, golden_meta):
+    """Config-3 style channels end to end: HB48 tree -> NCO(-residual) -> Interpolator to 48 kS/s, vs oracle chains."""
+    from sdrangel_b200 import DownChannelizerBank, capi
+    plan = golden_meta["chan_plans"]["bank64"]
+    rs = np.random.RandomState(44)
+    n = 2_000_000
+    x = (rs.randint(-6000, 6000, size=(n, 2))).astype(np.int16)
+    b = DownChannelizerBank(plan["input_rate"])
+    chans = plan["channels"][3::16]
+    cutoff = np.float32(np.float32(12500) / np.float32(2.2))
+    ids = []
+    for fc, rate, ofs, path in chans:
+        cid = b.add_channel(48000, fc)[0]
+        b.set_frontend(cid, -ofs, float(cutoff), 48000)
+        ids.append(cid)
+    refs = []
+    for fc, rate, ofs, path in chans:
+        o = port.PortDownChannelizer()
+        o.configure(plan["input_rate"], 48000, fc)
+        refs.append((o, port.PortFrontEnd(-ofs, rate, 48000, cutoff)))
+    for a, e in ((0, 1_000_001), (1_000_001, n)):
+        b.feed(x[a:e])
+        for cid, (o, fe) in zip(ids, refs):
+            ch = o.feed(x[a:e])
+            assert np.array_equal(b.fetch(cid), ch)
+            want = fe.feed(ch)
+            got = b.fetch(cid, capi.STAGE_FRONTEND)
+            assert got.shape == want.shape
+            assert rel_rms(got, want) <= 1e-5
