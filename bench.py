@@ -4,15 +4,18 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
 
 Workloads (BASELINE.json configs):
-  decimateii   sdrbench decimateii: int16 IQ, log2 decimation 4, centred, 12 bit  (config 1; N=1 default)
-  decimatefi   sdrbench decimatefi: float IQ, log2 decimation 6, centred          (config 2)
-A "step" is one decimate call over one batch of synthetic IQ that is larger than L2 (so every step streams from HBM).
-`value` is device-resident throughput (inputs already in HBM), `e2e` goes through the host-pointer C-ABI call
-(b200dsp_decim_run == Decimators::decimate16_cen on a host buffer) with H2D/D2H inside the timed region.
-N > 1: the single-stream decimators do not shard ("replicas only"): every rank runs an independent
-replica on its own GPU (weak scaling), timed as max over ranks.
---impl reference times the reference's own CPU code (oracle/_ref, compiled from the reference sources) on the host
-cores, on the same metric.
+  decimateii   sdrbench decimateii: int16 IQ, log2 decimation 4, centred, 12 bit          (config 1; default at N=1)
+  decimatefi   sdrbench decimatefi: float IQ, log2 decimation 6, centred                  (config 2)
+  bank64       64 NFM channels off a 10 MS/s baseband: HB48 tree + NCO + Interpolator     (config 3)
+  bank1024     1024 channels over a 122.88 MS/s stream, channels sharded over the ranks,
+               baseband NCCL-broadcast from rank 0 every step                             (config 5; default at N>1)
+A "step" is one pass of the hot path over one batch of synthetic IQ that is larger than L2 (every step streams from
+HBM).  `value` is device-resident throughput (inputs already in HBM), `e2e` goes through the host-pointer C-ABI call
+with H2D/D2H inside the timed region.  The single-stream decimators do not shard ("replicas only"): with
+N > 1 every rank runs an independent replica (weak scaling); the bank shards by channel (strong scaling: the same
+stream, 1024/N channels per GPU).  --impl reference times the reference's own CPU code (oracle/_ref, compiled from
+the reference sources) on the host cores, on the same metric.  At N=1 the default line also carries the other
+workloads' numbers under "also".
 """
 import argparse
 import ctypes as C
@@ -29,12 +32,24 @@ sys.path.insert(0, ROOT)
 
 METRIC = "input MS/s: sdrbench decimators + N-channel DownChannelizer bank, 1/2/4/8 GPU"
 
+
+def plan64():
+    return 10_000_000, [((c - 32) * 150000 + 6250) for c in range(64)]
+
+
+def plan1024():
+    return 122_880_000, [((c - 512) * 120000 + 60000 + 1250 * ((c % 9) - 4)) for c in range(1024)]
+
+
 WORKLOADS = {
-    # name: (kind, log2, mode, bytes per input sample in, bytes out per input sample, default samples per step)
-    "decimateii": dict(kind="ii", log2=4, mode=2, in_dtype="int16", in_bytes=4, out_bytes=4 / 16, n=1 << 28,
+    "decimateii": dict(type="decim", kind="ii", log2=4, mode=2, in_dtype="int16", in_bytes=4, out_bytes=4 / 16, n=1 << 28,
                        desc="sdrbench decimateii: Decimators<qint32,qint16,16,12>::decimate16_cen, synthetic int16 IQ"),
-    "decimatefi": dict(kind="fi", log2=6, mode=2, in_dtype="float32", in_bytes=8, out_bytes=4 / 64, n=1 << 27,
+    "decimatefi": dict(type="decim", kind="fi", log2=6, mode=2, in_dtype="float32", in_bytes=8, out_bytes=4 / 64, n=1 << 27,
                        desc="sdrbench decimatefi: DecimatorsFI::decimate64_cen, synthetic float IQ"),
+    "bank64": dict(type="bank", plan=plan64, n=3 << 22,
+                   desc="64 NFM 12.5 kHz channels off a synthetic 10 MS/s int16 baseband: DownChannelizer tree + NCO + Interpolator to 48 kS/s"),
+    "bank1024": dict(type="bank", plan=plan1024, n=3 << 22,
+                     desc="1024 channels over a synthetic 122.88 MS/s int16 stream: DownChannelizer tree + NCO + Interpolator to 48 kS/s, channels sharded"),
 }
 
 
@@ -70,7 +85,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.005)
 
     def start(self):
         if self.nv:
@@ -87,64 +102,105 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference
-def cpu_reference_throughput(wl, seconds=12.0, threads=None):
-    """Times the reference's own C++ (oracle/_ref/libsdrref.so) if present, else the oracle port, the way sdrbench
-    does (mainbench.cpp:83-104): a 2^20-sample buffer fed repeatedly with the filter state carried; one
-    independent decimator object per host thread."""
+def _oracle_mod():
     from oracle import refbind, portbind
-    kind = "reference" if refbind.available() else "port"
-    n = 1 << 20
-    if kind == "reference":
-        buf = refbind.sdrbench_s16(n) if wl["kind"][0] == "i" else refbind.sdrbench_f32(n)
-        mk = lambda: refbind.RefDecimators(wl["kind"], 12)
-    else:
-        import subprocess
-        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"])
-        buf = portbind.sdrbench_s16(n) if wl["kind"][0] == "i" else portbind.sdrbench_f32(n)
-        mk = lambda: portbind.PortDecimators(wl["kind"], 12)
-    threads = threads or (os.cpu_count() or 1)
-    objs = [mk() for _ in range(threads)]
-    objs[0].run(wl["log2"], wl["mode"], buf)            # warm
-    counts = [0] * threads
-    t_end = time.perf_counter() + seconds
-    per_thread_time = [0.0] * threads
+    if refbind.available():
+        return "reference", refbind
+    import subprocess
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"])
+    return "port", portbind
 
-    def work(i):
-        t0 = time.perf_counter()
-        while time.perf_counter() < t_end:
-            objs[i].run(wl["log2"], wl["mode"], buf)
-            counts[i] += 1
-        per_thread_time[i] = time.perf_counter() - t0
 
+def _run_threads(work, threads):
     ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
     t0 = time.perf_counter()
     for t in ts:
         t.start()
     for t in ts:
         t.join()
-    wall = time.perf_counter() - t0
+    return time.perf_counter() - t0
+
+
+def cpu_reference_decim(wl, seconds, threads=None):
+    """The reference's own C++ (oracle/_ref) timed the way sdrbench does (mainbench.cpp:83-104): a 2^20-sample buffer
+    fed repeatedly with the filter state carried; one independent decimator object per host thread."""
+    kind, mod = _oracle_mod()
+    n = 1 << 20
+    buf = mod.sdrbench_s16(n) if wl["kind"][0] == "i" else mod.sdrbench_f32(n)
+    mk = (lambda: mod.RefDecimators(wl["kind"], 12)) if kind == "reference" else (lambda: mod.PortDecimators(wl["kind"], 12))
+    threads = threads or (os.cpu_count() or 1)
+    objs = [mk() for _ in range(threads)]
+    objs[0].run(wl["log2"], wl["mode"], buf)
+    counts = [0] * threads
+    t_end = time.perf_counter() + seconds
+
+    def work(i):
+        while time.perf_counter() < t_end:
+            objs[i].run(wl["log2"], wl["mode"], buf)
+            counts[i] += 1
+
+    wall = _run_threads(work, threads)
     total = sum(counts) * n
     return {"value": total / wall / 1e6, "unit": "input MS/s", "cores": threads, "kind": kind,
-            "sample": "%d x 2^20-sample sdrbench buffer per thread, state carried (sdrbench -r), %.1f s wall" % (max(counts), wall),
-            "per_core": total / wall / 1e6 / threads}
+            "sample": "%d x 2^20-sample sdrbench buffer per thread, state carried (sdrbench -r), %.1f s wall" % (max(counts), wall)}
+
+
+def cpu_reference_bank(wl, seconds, threads=None):
+    """One reference (DownChannelizer + NCO + Interpolator) chain per channel, channels spread over the host threads
+    (the reference's thread-per-channel model, threadedbasebandsamplesink.cpp:74-78), on a subset of the plan's
+    channels; the bank figure is the subset's rate scaled by subset/plan channel count (stated in `sample`)."""
+    kind, mod = _oracle_mod()
+    fs, fcs = wl["plan"]()
+    threads = threads or (os.cpu_count() or 1)
+    per_thread = 2
+    sub = fcs[:: max(1, len(fcs) // (threads * per_thread))][: threads * per_thread]
+    rs = np.random.RandomState(1)
+    n = 1 << 18
+    x = rs.randint(-2048, 2048, size=(n, 2)).astype(np.int16)
+    cutoff = float(np.float32(np.float32(12500) / np.float32(2.2)))
+    Chan = mod.RefDownChannelizer if kind == "reference" else mod.PortDownChannelizer
+    FE = mod.RefFrontEnd if kind == "reference" else mod.PortFrontEnd
+    chains = []
+    for fc in sub:
+        c = Chan()
+        rate, ofs, _ = c.configure(fs, 48000, fc)
+        chains.append((c, FE(-ofs, rate, 48000, cutoff)))
+    counts = [0] * threads
+    t_end = time.perf_counter() + seconds
+
+    def work(i):
+        mine = chains[i::threads]
+        while time.perf_counter() < t_end:
+            for c, fe in mine:
+                fe.feed(c.feed(x))
+            counts[i] += len(mine)
+
+    wall = _run_threads(work, threads)
+    chan_samples = sum(counts) * n                       # (channel, input sample) pairs processed
+    return {"value": chan_samples / len(fcs) / wall / 1e6, "unit": "input MS/s", "cores": threads, "kind": kind,
+            "sample": "%d-channel subset of the %d-channel plan, 2^18-sample feeds for %.1f s; bank rate = subset channel-samples/s / %d channels"
+                      % (len(sub), len(fcs), wall, len(fcs))}
+
+
+def cpu_reference(wl, seconds):
+    return cpu_reference_decim(wl, seconds) if wl["type"] == "decim" else cpu_reference_bank(wl, seconds)
 
 
 def run_reference(args, wl_name, wl):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     t0 = time.perf_counter()
-    vals = []
     per = max(2.0, min(10.0, 60.0 / max(1, args.steps + args.warmup)))
+    vals = []
     for i in range(args.warmup + args.steps):
-        r = cpu_reference_throughput(wl, seconds=per)
+        r = cpu_reference(wl, per)
         if i >= args.warmup:
             vals.append(r)
     v = float(np.mean([r["value"] for r in vals]))
     line = {"metric": METRIC, "value": v, "unit": "input MS/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "s32" if wl["kind"] == "ii" else "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": wl_name, "desc": wl["desc"], "log2_decim": wl["log2"], "fc_pos": "cen"},
+            "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong" if wl["type"] == "bank" else "weak", "vs_baseline": None,
+            "dtype": "f32" if wl.get("kind") in ("fi", "ff", "if") else "s32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": wl_name, "desc": wl["desc"]},
             "cpu_baseline": {"value": v, "unit": "input MS/s", "cores": vals[-1]["cores"], "kind": vals[-1]["kind"], "sample": vals[-1]["sample"]},
             "e2e": {"value": v, "unit": "input MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
@@ -152,48 +208,96 @@ def run_reference(args, wl_name, wl):
 
 
 # ------------------------------------------------------------------------------------------------ ours
-def run_ours(args, wl_name, wl):
+class Ctx:
+    pass
+
+
+def setup():
     import torch
     import torch.distributed as dist
-    import sdrangel_b200 as S
     from sdrangel_b200 import capi
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    c = Ctx()
+    c.torch, c.dist, c.capi = torch, dist, capi
+    c.world = int(os.environ.get("WORLD_SIZE", "1"))
+    c.rank = int(os.environ.get("RANK", "0"))
+    c.local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    capi.init(local)
+    torch.cuda.set_device(c.local)
+    c.dev = torch.device("cuda", c.local)
+    if c.world > 1:
+        dist.init_process_group("nccl", device_id=c.dev)
+    capi.init(c.local)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    c.hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    c.peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    c.sm_count = capi.lib().b200dsp_sm_count()
+    return c
 
+
+def barrier(c):
+    if c.world > 1:
+        c.dist.barrier()
+    c.torch.cuda.synchronize()
+
+
+def max_over_ranks(c, v):
+    if c.world > 1:
+        t = c.torch.tensor([v], device=c.dev, dtype=c.torch.float64)
+        c.dist.all_reduce(t, op=c.dist.ReduceOp.MAX)
+        return float(t.item())
+    return v
+
+
+def timed_steps(c, stream, step, steps, warmup):
+    """W warm-up steps, then K steps timed with CUDA events on the launching stream, barrier + synchronize on both
+    sides, max over ranks.  Returns (total_ms, per-step kernel ms list, clocks)."""
+    torch = c.torch
+    with torch.cuda.stream(stream):
+        for _ in range(max(warmup, 3)):
+            step()
+        barrier(c)
+        sampler = ClockSampler(c.local)
+        sampler.start()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for a, b in evs:
+            a.record(stream)
+            step()
+            b.record(stream)
+        e1.record(stream)
+        barrier(c)
+        clocks = sampler.stop()
+    total_ms = max_over_ranks(c, e0.elapsed_time(e1))
+    return total_ms, [a.elapsed_time(b) for a, b in evs], clocks
+
+
+def bench_decim(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=True):
+    import sdrangel_b200 as S
+    torch, capi = c.torch, c.capi
     n = args.samples or wl["n"]
     cls = {"ii": S.Decimators, "fi": S.DecimatorsFI, "ff": S.DecimatorsFF, "if": S.DecimatorsIF}[wl["kind"]]
     dec = cls(12)
-    g = torch.Generator(device=dev)
-    g.manual_seed(5489 + rank)
+    g = torch.Generator(device=c.dev)
+    g.manual_seed(5489 + c.rank)
     if wl["in_dtype"] == "int16":
-        x = torch.randint(-2048, 2048, (2 * n,), dtype=torch.int16, device=dev, generator=g)
+        x = torch.randint(-2048, 2048, (2 * n,), dtype=torch.int16, device=c.dev, generator=g)
     else:
-        x = torch.rand((2 * n,), dtype=torch.float32, device=dev, generator=g) * 2 - 1
+        x = torch.rand((2 * n,), dtype=torch.float32, device=c.dev, generator=g) * 2 - 1
     n_out = dec.out_count(wl["log2"], wl["mode"], 2 * n)
     out_dt = torch.int16 if wl["kind"][1] == "i" else torch.float32
-    y = torch.empty((n_out, 2), dtype=out_dt, device=dev)
-    stream = torch.cuda.Stream(device=dev)
+    y = torch.empty((n_out, 2), dtype=out_dt, device=c.dev)
+    stream = torch.cuda.Stream(device=c.dev)
     sptr = stream.cuda_stream
 
-    # parity spot check against the oracle on the first 2^20 samples (oracle = checker only)
     parity = None
-    if rank == 0:
+    if c.rank == 0 and want_parity:       # oracle = checker only: first 2^20 samples, exact arithmetic flavour
+        _, mod = _oracle_mod()
         from oracle import portbind
         import subprocess
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"])
@@ -201,7 +305,7 @@ def run_ours(args, wl_name, wl):
         chk = cls(12)
         if wl["kind"] != "ii":
             chk.set_exact_float(True)
-        yy = torch.empty((chk.out_count(wl["log2"], wl["mode"], 2 * m), 2), dtype=out_dt, device=dev)
+        yy = torch.empty((chk.out_count(wl["log2"], wl["mode"], 2 * m), 2), dtype=out_dt, device=c.dev)
         chk.run_dev(wl["log2"], wl["mode"], x.data_ptr(), 2 * m, yy.data_ptr(), sptr)
         stream.synchronize()
         want = portbind.PortDecimators(wl["kind"], 12).run(wl["log2"], wl["mode"], x[: 2 * m].cpu().numpy())
@@ -211,48 +315,28 @@ def run_ours(args, wl_name, wl):
     def step():
         dec.run_dev(wl["log2"], wl["mode"], x.data_ptr(), 2 * n, y.data_ptr(), sptr)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    with torch.cuda.stream(stream):
-        for _ in range(max(args.warmup, 3)):
-            step()
-        barrier()
-        sampler = ClockSampler(local)
-        sampler.start()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for a, b in evs:
-            a.record(stream)
-            step()
-            b.record(stream)
-        e1.record(stream)
-        barrier()
-        clocks = sampler.stop()
-    total_ms = e0.elapsed_time(e1)
-    kern_ms = [a.elapsed_time(b) for a, b in evs]
-    if world > 1:
-        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    value = world * n * args.steps / (total_ms * 1e-3) / 1e6
+    total_ms, kern_ms, clocks = timed_steps(c, stream, step, steps, warmup)
+    value = c.world * n * steps / (total_ms * 1e-3) / 1e6
     kern_avg_ms = float(np.mean(kern_ms))
     alg_bytes = n * (wl["in_bytes"] + wl["out_bytes"])
     achieved = alg_bytes / (kern_avg_ms * 1e-3) / 1e9
-
-    # issue-rate view of the same kernel: 2 comps * 34 instr per stage output, sum over stages
     L = wl["log2"]
-    instr_per_sample = 2 * 34 * (1 - 2.0 ** -L)
-    sm_count = capi.lib().b200dsp_sm_count()
+    instr_per_sample = 2 * 33 * (1 - 2.0 ** -L)
     f_clk = (clocks.get("sm_mhz") or 1965) * 1e6
-    issue_roof = sm_count * 128 * f_clk / instr_per_sample / 1e6
-
-    # end-to-end through the host-pointer C-ABI call (pinned host buffers, H2D + D2H inside the timed region)
-    e2e = None
-    if not args.no_e2e:
+    issue_roof = c.sm_count * 128 * f_clk / instr_per_sample / 1e6
+    res = {"value": value, "ms_per_step": total_ms / steps, "clocks": clocks, "parity": parity, "launches": steps,
+           "config": {"workload": wl_name, "desc": wl["desc"], "samples_per_step": n, "log2_decim": L, "fc_pos": "cen", "input_bits": 12,
+                      "l2": "input %.0f MiB per step > 126 MB L2, streamed from HBM every step" % (n * wl["in_bytes"] / 2 ** 20),
+                      "parallelism": "replicas x%d (single-stream decimator does not shard)" % c.world},
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": c.hbm_peak, "unit": "GB/s", "frac": achieved / c.hbm_peak,
+                        "traffic": None, "peak_source": c.peak_src, "kernel": "hb64_cascade_kernel", "kernel_ms": kern_avg_ms,
+                        "algorithmic_bytes_per_sample": wl["in_bytes"] + wl["out_bytes"],
+                        "issue": {"instr_per_sample": instr_per_sample, "roof_MSps_at_sampled_clk": issue_roof,
+                                  "frac": (n / (kern_avg_ms * 1e-3) / 1e6) / issue_roof,
+                                  "note": "binding roof (DESIGN.md): 33 instructions per real stage output, 15-16 IMAD on the FMA-heavy pipe "
+                                          "(64 lanes/clk/SM) + 16-17 IADD3/shift on the ALU pipe (64 lanes/clk/SM)"}},
+           "dtype": "s32" if wl["kind"] == "ii" else "f32", "scaling": "weak"}
+    if want_e2e:
         n_e = min(n, args.e2e_samples)
         hx = torch.empty((2 * n_e,), dtype=x.dtype, pin_memory=True)
         hx.copy_(x[: 2 * n_e])
@@ -267,44 +351,159 @@ def run_ours(args, wl_name, wl):
 
         for _ in range(2):
             e2e_step()
-        barrier()
+        barrier(c)
         t0 = time.perf_counter()
-        ksteps = max(3, min(args.steps, 10))
+        ksteps = max(3, min(steps, 10))
         for _ in range(ksteps):
             e2e_step()
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": world * n_e * ksteps / dt / 1e6, "unit": "input MS/s", "h2d_bytes_per_step": int(n_e * wl["in_bytes"]),
-               "d2h_bytes_per_step": int(n_out_e * (4 if out_dt == torch.int16 else 8)), "steps": ksteps,
-               "api": "b200dsp_decim_run (host pointers, pinned; chunked H2D/compute overlap)", "samples_per_step": n_e}
-        launches_e2e = ksteps * ((2 * n_e + (8 << 20) - 1) // (8 << 20))
+        dt = max_over_ranks(c, time.perf_counter() - t0)
+        res["e2e"] = {"value": c.world * n_e * ksteps / dt / 1e6, "unit": "input MS/s", "h2d_bytes_per_step": int(n_e * wl["in_bytes"]),
+                      "d2h_bytes_per_step": int(n_out_e * (4 if out_dt == torch.int16 else 8)), "steps": ksteps,
+                      "api": "b200dsp_decim_run (host pointers, pinned; chunked H2D/compute overlap)", "samples_per_step": n_e}
         d2.close()
+    dec.close()
+    return res
 
-    if rank == 0:
-        cpu = None
-        if not args.no_cpu:
-            cpu = cpu_reference_throughput(wl, seconds=args.cpu_seconds)
-        line = {"metric": METRIC, "value": value, "unit": "input MS/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "s32" if wl["kind"] == "ii" else "f32", "data": "synthetic",
-                "config": {"workload": wl_name, "desc": wl["desc"], "samples_per_step": n, "log2_decim": wl["log2"], "fc_pos": "cen",
-                           "input_bits": 12, "l2": "input %.0f MiB per step > 126 MB L2, streamed from HBM every step" % (n * wl["in_bytes"] / 2 ** 20),
-                           "parallelism": "replicas x%d (single-stream decimator does not shard)" % world},
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                             "traffic": None, "peak_source": peak_src, "kernel": "hb64_cascade_kernel", "kernel_ms": kern_avg_ms,
-                             "algorithmic_bytes_per_sample": wl["in_bytes"] + wl["out_bytes"],
-                             "issue": {"instr_per_sample": instr_per_sample, "roof_MSps_at_sampled_clk": issue_roof,
-                                       "frac": (n / (kern_avg_ms * 1e-3) / 1e6) / issue_roof,
-                                       "note": "binding roof: 16 IMAD (FMA-heavy pipe) + 16 IADD (ALU pipe) per real output"}},
-                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks, "parity_checked_vs_oracle": parity,
-                "sm_count": sm_count}
+
+def bench_bank(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=True):
+    import sdrangel_b200 as S
+    torch, capi, dist = c.torch, c.capi, c.dist
+    fs, fcs = wl["plan"]()
+    n = args.samples or wl["n"]
+    # shard: contiguous-in-frequency blocks of channels per rank
+    per = (len(fcs) + c.world - 1) // c.world
+    mine = fcs[c.rank * per: (c.rank + 1) * per]
+    cutoff = float(np.float32(np.float32(12500) / np.float32(2.2)))
+    bank = S.DownChannelizerBank(fs)
+    info = []
+    for fc in mine:
+        cid, rate, ofs, path = bank.add_channel(48000, fc)
+        bank.set_frontend(cid, -ofs, cutoff, 48000)
+        info.append((cid, rate, ofs, path))
+    nodes = bank.node_count()
+    stage_inputs = sum(2.0 ** -(k - 1) for k in _node_depths([p for _, _, _, p in info]))
+    g = torch.Generator(device=c.dev)
+    g.manual_seed(1)
+    x = torch.randint(-2048, 2048, (2 * n,), dtype=torch.int16, device=c.dev, generator=g) if c.rank == 0 else \
+        torch.empty((2 * n,), dtype=torch.int16, device=c.dev)
+    stream = torch.cuda.Stream(device=c.dev)
+    sptr = stream.cuda_stream
+
+    parity = None
+    if c.rank == 0 and want_parity:       # oracle = checker only: 3 channels, first 2^19 samples
+        _, _ = _oracle_mod()
+        from oracle import portbind
+        m = 1 << 19
+        bank.feed_dev(x.data_ptr(), m, sptr)
+        stream.synchronize()
+        xs = x[: 2 * m].cpu().numpy().reshape(-1, 2)
+        ok = True
+        for k in (0, len(info) // 2, len(info) - 1):
+            cid, rate, ofs, path = info[k]
+            o = portbind.PortDownChannelizer()
+            o.configure(fs, 48000, mine[k])
+            ch = o.feed(xs)
+            ok = ok and np.array_equal(bank.fetch(cid), ch)
+            fe = portbind.PortFrontEnd(-ofs, rate, 48000, cutoff).feed(ch)
+            got = bank.fetch(cid, capi.STAGE_FRONTEND)
+            ok = ok and got.shape == fe.shape and float(np.sqrt(np.mean((got - fe) ** 2)) / np.sqrt(np.mean(fe ** 2))) <= 1e-5
+        parity = bool(ok)
+    barrier(c)
+
+    def step():
+        if c.world > 1:
+            dist.broadcast(x, src=0)               # NCCL broadcast of the wideband baseband over NVLink, every step
+        bank.feed_dev(x.data_ptr(), n, sptr)
+
+    total_ms, kern_ms, clocks = timed_steps(c, stream, step, steps, warmup)
+    value = n * steps / (total_ms * 1e-3) / 1e6
+    step_ms = float(np.mean(kern_ms))
+    out_bytes = sum(48000.0 / fs * 8 for _ in mine)
+    alg_bytes = n * (4 + out_bytes)
+    achieved = alg_bytes / (step_ms * 1e-3) / 1e9
+    instr_per_sample = stage_inputs * 27 + len(mine) * 48000.0 / fs * 160
+    f_clk = (clocks.get("sm_mhz") or 1965) * 1e6
+    issue_roof = c.sm_count * 128 * f_clk / instr_per_sample / 1e6
+    passes = (n + (3 << 18) - 1) // (3 << 18)
+    depth = max(len(p) for _, _, _, p in info)
+    res = {"value": value, "ms_per_step": total_ms / steps, "clocks": clocks, "parity": parity,
+           "launches": steps * passes * (2 * depth + 2),
+           "config": {"workload": wl_name, "desc": wl["desc"], "samples_per_step": n, "input_rate": fs, "channels": len(fcs),
+                      "channels_this_rank": len(mine), "tree_nodes_this_rank": nodes, "stage_inputs_per_sample_this_rank": stage_inputs,
+                      "l2": "input %.0f MiB per step, streamed from HBM; tree levels evaluated on 3 MiB-sample chunks that stay L2-resident" % (n * 4 / 2 ** 20),
+                      "parallelism": "channels sharded x%d (contiguous frequency blocks), baseband %s" % (c.world, "NCCL broadcast per step" if c.world > 1 else "local")},
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": c.hbm_peak, "unit": "GB/s", "frac": achieved / c.hbm_peak,
+                        "traffic": None, "peak_source": c.peak_src, "kernel": "hb48_level_kernel (one launch per tree level per chunk)",
+                        "kernel_ms": step_ms, "algorithmic_bytes_per_sample": 4 + out_bytes,
+                        "issue": {"instr_per_sample": instr_per_sample, "roof_MSps_at_sampled_clk": issue_roof,
+                                  "frac": (n / (step_ms * 1e-3) / 1e6) / issue_roof,
+                                  "note": "binding roof: 27 instructions per stage-input sample over the shared-prefix tree + ~160 per front-end output"}},
+           "dtype": "s32", "scaling": "strong"}
+    if want_e2e:
+        n_e = min(n, 3 << 20)
+        hx = torch.empty((2 * n_e,), dtype=torch.int16, pin_memory=True)
+        if c.rank == 0:
+            hx.copy_(x[: 2 * n_e])
+        L_ = capi.lib()
+        outs = [torch.empty((int(n_e * 48000 / rate * (rate / fs)) + 64, 2), dtype=torch.float32, pin_memory=True) for _, rate, _, _ in info]
+        nn = C.c_int64(0)
+
+        def e2e_step():
+            capi.check(L_.b200dsp_bank_feed(bank._h, hx.data_ptr(), n_e))
+            for (cid, _, _, _), o in zip(info, outs):
+                capi.check(L_.b200dsp_bank_fetch(bank._h, cid, capi.STAGE_FRONTEND, o.data_ptr(), o.shape[0], C.byref(nn)))
+
+        e2e_step()
+        barrier(c)
+        t0 = time.perf_counter()
+        ksteps = 3
+        for _ in range(ksteps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = max_over_ranks(c, time.perf_counter() - t0)
+        res["e2e"] = {"value": n_e * ksteps / dt / 1e6, "unit": "input MS/s", "h2d_bytes_per_step": int(n_e * 4),
+                      "d2h_bytes_per_step": int(len(mine) * nn.value * 8), "steps": ksteps,
+                      "api": "b200dsp_bank_feed (host pointer, pinned) + b200dsp_bank_fetch of every channel's front-end output", "samples_per_step": n_e}
+    bank.close()
+    return res
+
+
+def _node_depths(paths):
+    seen = set()
+    for p in paths:
+        for k in range(1, len(p) + 1):
+            seen.add(p[:k])
+    return [len(s) for s in seen]
+
+
+def run_ours(args, wl_name, wl):
+    c = setup()
+    fn = bench_decim if wl["type"] == "decim" else bench_bank
+    res = fn(c, args, wl_name, wl, args.steps, args.warmup, want_e2e=not args.no_e2e)
+    also = {}
+    if c.world == 1 and not args.no_also and not args.samples:
+        for other in WORKLOADS:
+            if other == wl_name:
+                continue
+            try:
+                o = WORKLOADS[other]
+                r = (bench_decim if o["type"] == "decim" else bench_bank)(c, args, other, o, 5, 3, want_e2e=False)
+                also[other] = {"value": r["value"], "unit": "input MS/s", "ms_per_step": r["ms_per_step"], "hbm_frac": r["roofline"]["frac"],
+                               "issue_frac": r["roofline"]["issue"]["frac"], "parity_checked_vs_oracle": r["parity"],
+                               "samples_per_step": r["config"]["samples_per_step"]}
+            except Exception as e:      # an auxiliary measurement must not take the headline down
+                also[other] = {"error": repr(e)}
+    if c.rank == 0:
+        cpu = None if args.no_cpu else cpu_reference(wl, args.cpu_seconds)
+        line = {"metric": METRIC, "value": res["value"], "unit": "input MS/s", "n_gpus": c.world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": res["scaling"], "vs_baseline": None,
+                "dtype": res["dtype"], "data": "synthetic", "config": res["config"], "roofline": res["roofline"], "cpu_baseline": cpu,
+                "e2e": res.get("e2e"), "gpu_launches": res["launches"], "clocks": res["clocks"], "parity_checked_vs_oracle": res["parity"],
+                "sm_count": c.sm_count, "also": also}
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if c.world > 1:
+        c.dist.destroy_process_group()
 
 
 def main():
@@ -319,8 +518,10 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-also", action="store_true")
     args = ap.parse_args()
-    wl_name = args.workload or "decimateii"
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    wl_name = args.workload or ("decimateii" if max(world, args.gpus) == 1 else "bank1024")
     wl = WORKLOADS[wl_name]
     if args.impl == "reference":
         run_reference(args, wl_name, wl)

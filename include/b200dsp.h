@@ -100,7 +100,7 @@ typedef struct b200dsp_bank b200dsp_bank_t;
 
 int b200dsp_bank_create(b200dsp_bank_t** b, int input_rate_hz);
 int b200dsp_bank_destroy(b200dsp_bank_t* b);
-/* internal time-chunk (input samples per pass over the tree); default 786432, rounded to a multiple of 768 */
+/* internal time-chunk (input samples per pass over the tree); default 12582912, rounded to a multiple of 768 */
 int b200dsp_bank_set_chunk(b200dsp_bank_t* b, int64_t samples);
 /* == DSPConfigureChannelizer(requested_rate, center_offset) -> MsgChannelizerNotification(out_rate, residual_offset) */
 int b200dsp_bank_add_channel(b200dsp_bank_t* b, int requested_rate_hz, int center_offset_hz,

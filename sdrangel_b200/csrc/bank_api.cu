@@ -20,34 +20,23 @@ namespace {
 // ---------------------------------------------------------------------------------------------------------
 // small kernels around the level kernel
 // ---------------------------------------------------------------------------------------------------------
-// new_tail[t] = parent sample (C_after - 64 + t), t = 0..64   (64 history + the possibly pending sample)
-__global__ void hb48_tail_kernel(const uint32_t* in_base, long long in_stride, const uint32_t* tail_in, uint32_t* tail_out,
-                                 const int* fam, int n_in, int pend, int in_limit)
-{
-    const int parent = fam[4 * blockIdx.x];
-    const int t = threadIdx.x;
-    if (t > 64) return;
-    const int i = n_in - 64 + t;
-    uint32_t v;
-    if (i < pend) v = tail_in[(long long) parent * TAIL_WORDS + i + 64];
-    else          v = (i < in_limit) ? in_base[(long long) parent * in_stride + i] : 0u;
-    tail_out[(long long) parent * TAIL_WORDS + t] = v;
-}
-
-struct LeafChan { const uint32_t* src; uint32_t* dst; int shift; };
+struct LeafChan { const uint32_t* src; uint32_t* dst; int depth; };     // static per channel (until a reallocation)
 
 // channel output = trunc_toward_zero(y / 2^S) per component (downchannelizer.cpp:78-83)
-__global__ void hb48_finalize_kernel(const LeafChan* chans, int n_new_max, const int* n_new_per_chan)
+__global__ void hb48_finalize_kernel(const LeafChan* chans, const PassInfo pi)
 {
     const LeafChan c = chans[blockIdx.y];
-    const int n = n_new_per_chan[blockIdx.y];
+    if (c.depth == 0) return;                  // stage-less channel: forwarded by a plain copy
+    const int n = pi.n_new[c.depth];
+    const uint32_t* src = c.src + pi.wo[c.depth];
+    uint32_t* dst = c.dst + pi.out_count[c.depth];
+    const int bias = (1 << c.depth) - 1;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const uint32_t w = c.src[k];
+        const uint32_t w = src[k];
         int re = (int) (short) (w & 0xffffu), im = (int) w >> 16;
-        const int bias = (1 << c.shift) - 1;
-        re = (re + ((re >> 31) & bias)) >> c.shift;
-        im = (im + ((im >> 31) & bias)) >> c.shift;
-        c.dst[k] = ((uint32_t) re & 0xffffu) | ((uint32_t) im << 16);
+        re = (re + ((re >> 31) & bias)) >> c.depth;
+        im = (im + ((im >> 31) & bias)) >> c.depth;
+        dst[k] = ((uint32_t) re & 0xffffu) | ((uint32_t) im << 16);
     }
 }
 
@@ -94,7 +83,7 @@ struct Channel {
     std::vector<float> taps;
     // device
     uint32_t* d_out; long long out_cap; long long out_count;       // channelizer outputs since the last feed start
-    float2* d_z; float* d_taps; float2* d_fe_out; int* d_sched; int* d_state; long long fe_cap; long long fe_count;
+    uint32_t* d_hist; float* d_taps; float2* d_fe_out; int* d_sched; int* d_tile; int* d_state; long long fe_cap;
 };
 
 const double PI_D = 3.14159265358979323846;
@@ -130,7 +119,8 @@ void interp_taps(int phase_steps, double rate, double cutoff, double taps_per_ph
 struct b200dsp_bank {
     int device, sm_count;
     int input_rate;
-    cudaStream_t stream;
+    cudaStream_t stream, side;
+    cudaEvent_t ev_begin, ev_sched;
     std::vector<Channel> chans;
     bool built;
     // tree
@@ -146,8 +136,11 @@ struct b200dsp_bank {
     uint32_t* d_root; long long root_cap;        // staging for host feeds / odd-pending device feeds
     std::vector<long long> produced;             // P[d]
     int tcur;
-    LeafChan* d_leaf; int* d_nnew; FrontendChan* d_fe; float* d_nco;
-    std::vector<LeafChan> h_leaf; std::vector<int> h_nnew; std::vector<FrontendChan> h_fe;
+    LeafChan* d_leaf; FrontendChan* d_fe; float* d_nco;
+    std::vector<LeafChan> h_leaf; std::vector<FrontendChan> h_fe;
+    int fe_parity;                               // current half of the front-ends' ping-pong carried state
+    bool tables_dirty;                           // channel pointer tables must be re-uploaded (after a (re)allocation)
+    std::vector<long long> out_count_depth;      // channel outputs per depth produced in the current feed
     std::vector<int> fe_index;                   // channel ids with a front-end
 };
 
@@ -160,17 +153,17 @@ void free_device(b200dsp_bank* b)
     for (auto p : b->d_fam) if (p) cudaFree(p);
     b->d_level.clear(); b->d_fam.clear(); b->stride.clear();
     if (b->d_leaf) cudaFree(b->d_leaf);
-    if (b->d_nnew) cudaFree(b->d_nnew);
     if (b->d_fe) cudaFree(b->d_fe);
-    b->d_leaf = nullptr; b->d_nnew = nullptr; b->d_fe = nullptr;
+    b->d_leaf = nullptr; b->d_fe = nullptr;
     for (auto& c : b->chans) {
         if (c.d_out) cudaFree(c.d_out);
-        if (c.d_z) cudaFree(c.d_z);
+        if (c.d_hist) cudaFree(c.d_hist);
         if (c.d_taps) cudaFree(c.d_taps);
         if (c.d_fe_out) cudaFree(c.d_fe_out);
         if (c.d_sched) cudaFree(c.d_sched);
+        if (c.d_tile) cudaFree(c.d_tile);
         if (c.d_state) cudaFree(c.d_state);
-        c.d_out = nullptr; c.d_z = nullptr; c.d_taps = nullptr; c.d_fe_out = nullptr; c.d_sched = nullptr; c.d_state = nullptr;
+        c.d_out = nullptr; c.d_hist = nullptr; c.d_taps = nullptr; c.d_fe_out = nullptr; c.d_sched = nullptr; c.d_tile = nullptr; c.d_state = nullptr;
         c.out_cap = c.fe_cap = 0;
     }
     b->built = false;
@@ -231,12 +224,15 @@ int build(b200dsp_bank* b)
         }
     b->produced.assign(b->depth + 1, 0);
     b->tcur = 0;
+    b->fe_parity = 0;
     const size_t nc = b->chans.size();
     if (nc) {
-        if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_leaf, nc * sizeof(LeafChan)))) || (rc = B200_CUDA_CHECK(cudaMalloc(&b->d_nnew, nc * sizeof(int)))) ||
+        if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_leaf, nc * sizeof(LeafChan)))) ||
             (rc = B200_CUDA_CHECK(cudaMalloc(&b->d_fe, nc * sizeof(FrontendChan))))) return rc;
     }
-    b->h_leaf.resize(nc); b->h_nnew.resize(nc);
+    b->h_leaf.resize(nc);
+    b->tables_dirty = true;
+    b->out_count_depth.assign(32, 0);
     b->fe_index.clear();
     for (size_t i = 0; i < nc; ++i) {
         Channel& c = b->chans[i];
@@ -245,7 +241,8 @@ int build(b200dsp_bank* b)
         b->fe_index.push_back((int) i);
         const size_t tb = c.taps.size() * sizeof(float);
         if ((rc = B200_CUDA_CHECK(cudaMalloc(&c.d_taps, tb))) || (rc = B200_CUDA_CHECK(cudaMemcpy(c.d_taps, c.taps.data(), tb, cudaMemcpyHostToDevice))) ||
-            (rc = B200_CUDA_CHECK(cudaMalloc(&c.d_state, 4 * sizeof(int)))) || (rc = B200_CUDA_CHECK(cudaMemset(c.d_state, 0, 4 * sizeof(int))))) return rc;
+            (rc = B200_CUDA_CHECK(cudaMalloc(&c.d_state, 4 * sizeof(int)))) || (rc = B200_CUDA_CHECK(cudaMemset(c.d_state, 0, 4 * sizeof(int)))) ||
+            (rc = B200_CUDA_CHECK(cudaMalloc(&c.d_hist, 2 * FE_HIST_WORDS * 4))) || (rc = B200_CUDA_CHECK(cudaMemset(c.d_hist, 0, 2 * FE_HIST_WORDS * 4)))) return rc;
     }
     b->h_fe.resize(b->fe_index.size());
     if (!b->d_nco) {
@@ -269,23 +266,18 @@ int reserve_outputs(b200dsp_bank* b, long long n)
             c.d_out = nullptr; c.out_cap = 0;
             if ((rc = B200_CUDA_CHECK(cudaMalloc(&c.d_out, (size_t) need * 4)))) return rc;
             c.out_cap = need;
+            b->tables_dirty = true;
         }
         if (c.fe && c.fe_cap < need) {
             if (c.d_fe_out) cudaFree(c.d_fe_out);
             if (c.d_sched) cudaFree(c.d_sched);
-            float2* oldz = c.d_z;
-            c.d_fe_out = nullptr; c.d_sched = nullptr; c.d_z = nullptr; c.fe_cap = 0;
-            float2* newz = nullptr;
+            if (c.d_tile) cudaFree(c.d_tile);
+            c.d_fe_out = nullptr; c.d_sched = nullptr; c.d_tile = nullptr; c.fe_cap = 0;
             if ((rc = B200_CUDA_CHECK(cudaMalloc(&c.d_fe_out, (size_t) need * sizeof(float2)))) ||
                 (rc = B200_CUDA_CHECK(cudaMalloc(&c.d_sched, (size_t) need * sizeof(int)))) ||
-                (rc = B200_CUDA_CHECK(cudaMalloc(&newz, (size_t) (need + FE_MAX_TAPS) * sizeof(float2)))) ||
-                (rc = B200_CUDA_CHECK(cudaMemset(newz, 0, (size_t) (need + FE_MAX_TAPS) * sizeof(float2))))) return rc;
-            if (oldz) {      // growing the buffer keeps the interpolator history
-                if ((rc = B200_CUDA_CHECK(cudaMemcpy(newz, oldz, FE_MAX_TAPS * sizeof(float2), cudaMemcpyDeviceToDevice)))) return rc;
-                cudaFree(oldz);
-            }
-            c.d_z = newz;
+                (rc = B200_CUDA_CHECK(cudaMalloc(&c.d_tile, (size_t) (need / FE_TILE + 4) * sizeof(int))))) return rc;
             c.fe_cap = need;
+            b->tables_dirty = true;
         }
     }
     return 0;
@@ -316,6 +308,42 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
         }
         rootB = b->d_root;
     }
+    // channel outputs of this pass: static pointer tables (re-uploaded only after a reallocation) + per-depth scalars
+    const size_t nc = b->chans.size();
+    PassInfo pi;
+    memset(&pi, 0, sizeof(pi));
+    pi.first_pass = first_pass ? 1 : 0;
+    pi.parity = b->fe_parity;
+    int max_new = 0;
+    for (int d = 0; d <= D && d < 32; ++d) {
+        pi.n_new[d] = (int) (Pa[d] - Pb[d]);
+        pi.wo[d] = (d == 0) ? 0 : (int) (Pb[d] & 1);
+        pi.out_count[d] = b->out_count_depth[d];
+    }
+    for (size_t i = 0; i < nc; ++i) if (pi.n_new[b->chans[i].S] > max_new) max_new = pi.n_new[b->chans[i].S];
+    if (b->tables_dirty && nc) {
+        for (size_t i = 0; i < nc; ++i) {
+            Channel& c = b->chans[i];
+            b->h_leaf[i].src = (c.S == 0) ? nullptr : b->d_level[c.S] + (long long) b->nodes[c.node].index * b->stride[c.S];
+            b->h_leaf[i].dst = c.d_out; b->h_leaf[i].depth = c.S;
+        }
+        for (size_t k = 0; k < b->fe_index.size(); ++k) {
+            Channel& c = b->chans[b->fe_index[k]];
+            FrontendChan& f = b->h_fe[k];
+            f.in = c.d_out; f.hist = c.d_hist; f.taps = c.d_taps; f.out = c.d_fe_out; f.sched = c.d_sched; f.tile_start = c.d_tile; f.state = c.d_state;
+            f.depth = c.S; f.inc = c.inc; f.ntaps = c.ntaps; f.phase_steps = c.phase_steps; f.ratio = c.ratio;
+        }
+        if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(b->d_leaf, b->h_leaf.data(), nc * sizeof(LeafChan), cudaMemcpyHostToDevice, st)))) return rc;
+        if (!b->h_fe.empty() && (rc = B200_CUDA_CHECK(cudaMemcpyAsync(b->d_fe, b->h_fe.data(), b->h_fe.size() * sizeof(FrontendChan), cudaMemcpyHostToDevice, st)))) return rc;
+        b->tables_dirty = false;
+    }
+    // front-end schedules depend only on counts: replay them on the side stream while the tree runs
+    if (!b->fe_index.empty() && max_new > 0) {
+        if ((rc = B200_CUDA_CHECK(cudaEventRecord(b->ev_begin, st))) || (rc = B200_CUDA_CHECK(cudaStreamWaitEvent(b->side, b->ev_begin, 0)))) return rc;
+        const int nfe = (int) b->h_fe.size();
+        frontend_schedule_kernel<<<(nfe + 31) / 32, 32, 0, b->side>>>(b->d_fe, nfe, pi);
+        if ((rc = B200_CUDA_CHECK(cudaGetLastError())) || (rc = B200_CUDA_CHECK(cudaEventRecord(b->ev_sched, b->side)))) return rc;
+    }
     const int tc = b->tcur, tn = tc ^ 1;
     for (int d = 1; d <= D; ++d) {
         const int n_fam = (int) (b->fams[d].size() / 4);
@@ -325,7 +353,7 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
         p.in_base = (d == 1) ? rootB : b->d_level[d - 1];
         p.in_stride = (d == 1) ? 0 : b->stride[d - 1];
         p.out_base = b->d_level[d]; p.out_stride = b->stride[d];
-        p.tail_in = b->d_tail[tc][d - 1];
+        p.tail_in = b->d_tail[tc][d - 1]; p.tail_out = b->d_tail[tn][d - 1];
         p.fam = b->d_fam[d]; p.n_fam = n_fam;
         const long long Cb = 2 * Pb[d], Ca = 2 * Pa[d];
         p.n_in = (int) (Ca - Cb);
@@ -334,60 +362,45 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
         p.wo = (int) (Pb[d] & 1);
         p.flip = (int) (Pb[d] & 1);
         p.opq_zero = 0; p.opq_one = 1; p.opq_mone = -1;
-        if (p.n_in > 0) {
+        {
             const int nb = (p.n_in + HB_IN - 1) / HB_IN;
             long long target = (long long) b->sm_count * 16;
             long long slices = (target + n_fam - 1) / n_fam;
             if (slices > nb) slices = nb;
             if (slices < 1) slices = 1;
             const int bps = (int) ((nb + slices - 1) / slices);
-            slices = (nb + bps - 1) / bps;
+            if (bps > 0) slices = (nb + bps - 1) / bps;
             p.slices = (int) slices; p.bps = bps;
             const long long warps = (long long) n_fam * slices;
             const int wpb = 4;
             hb48_level_kernel<<<(unsigned) ((warps + wpb - 1) / wpb), wpb * 32, wpb * HB_STAGE_BYTES, st>>>(p);
             if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
         }
-        hb48_tail_kernel<<<n_fam, 96, 0, st>>>(p.in_base, p.in_stride, p.tail_in, b->d_tail[tn][d - 1], b->d_fam[d], p.n_in, p.pend, p.in_limit);
-        if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
     }
-    // channel outputs of this pass
-    const size_t nc = b->chans.size();
-    int max_new = 0;
+    // stage-less channels (S == 0) are forwarded unchanged (downchannelizer.cpp:57-60): plain copy of the input
     for (size_t i = 0; i < nc; ++i) {
         Channel& c = b->chans[i];
-        const int n_new = (int) (Pa[c.S] - Pb[c.S]);
-        b->h_nnew[i] = n_new;
-        if (n_new > max_new) max_new = n_new;
-        const uint32_t* src = (c.S == 0) ? d_in : b->d_level[c.S] + (long long) b->nodes[c.node].index * b->stride[c.S] + (Pb[c.S] & 1);
-        b->h_leaf[i].src = src; b->h_leaf[i].dst = c.d_out + c.out_count; b->h_leaf[i].shift = c.S;
+        if (c.S == 0 && n > 0) {
+            if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(c.d_out + b->out_count_depth[0], d_in, (size_t) n * 4, cudaMemcpyDeviceToDevice, st)))) return rc;
+        }
     }
-    if (nc && max_new > 0) {
-        if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(b->d_leaf, b->h_leaf.data(), nc * sizeof(LeafChan), cudaMemcpyHostToDevice, st))) ||
-            (rc = B200_CUDA_CHECK(cudaMemcpyAsync(b->d_nnew, b->h_nnew.data(), nc * sizeof(int), cudaMemcpyHostToDevice, st)))) return rc;
+    if (nc && max_new > 0 && D >= 1) {
         int gx = (max_new + 255) / 256;
         if (gx > 64) gx = 64;
-        hb48_finalize_kernel<<<dim3(gx, (unsigned) nc), 256, 0, st>>>(b->d_leaf, max_new, b->d_nnew);
+        hb48_finalize_kernel<<<dim3(gx, (unsigned) nc), 256, 0, st>>>(b->d_leaf, pi);
         if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
     }
-    // K4 front-ends
     if (!b->fe_index.empty() && max_new > 0) {
         size_t smem = 0;
-        for (size_t k = 0; k < b->fe_index.size(); ++k) {
-            Channel& c = b->chans[b->fe_index[k]];
-            FrontendChan& f = b->h_fe[k];
-            f.in = c.d_out + c.out_count; f.z = c.d_z; f.taps = c.d_taps; f.out = c.d_fe_out; f.sched = c.d_sched; f.state = c.d_state;
-            f.m = b->h_nnew[b->fe_index[k]]; f.first_pass = first_pass ? 1 : 0; f.inc = c.inc; f.ntaps = c.ntaps; f.phase_steps = c.phase_steps; f.ratio = c.ratio;
-            const size_t s = c.taps.size() * sizeof(float);
-            if (s > smem) smem = s;
-        }
-        if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(b->d_fe, b->h_fe.data(), b->h_fe.size() * sizeof(FrontendChan), cudaMemcpyHostToDevice, st)))) return rc;
-        frontend_kernel<<<(unsigned) b->h_fe.size(), 256, smem, st>>>(b->d_fe, b->d_nco);
+        for (int ci : b->fe_index) { const Channel& cc = b->chans[ci]; const size_t s2 = (((size_t) (cc.ntaps | 1) * cc.phase_steps + 3) & ~(size_t) 3) * sizeof(float); if (s2 > smem) smem = s2; }
+        smem += (size_t) (FE_MAX_TAPS + FE_TILE) * sizeof(float2);
+        if ((rc = B200_CUDA_CHECK(cudaStreamWaitEvent(st, b->ev_sched, 0)))) return rc;
+        frontend_kernel<<<dim3((unsigned) ((max_new + FE_TILE - 1) / FE_TILE), (unsigned) b->h_fe.size()), FE_THREADS, smem, st>>>(b->d_fe, b->d_nco, pi);
         if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
+        b->fe_parity ^= 1;
     }
-    // The descriptor arrays are reused by the next pass: they live in pageable host vectors, so cudaMemcpyAsync has
-    // already staged them when it returns.
-    for (size_t i = 0; i < nc; ++i) b->chans[i].out_count += b->h_nnew[i];
+    for (int d = 0; d <= D && d < 32; ++d) b->out_count_depth[d] += pi.n_new[d];
+    for (size_t i = 0; i < nc; ++i) b->chans[i].out_count = b->out_count_depth[b->chans[i].S];
     b->produced = Pa;
     b->tcur = tn;
     return 0;
@@ -399,6 +412,7 @@ int feed_common(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t
     if (!b->built && (rc = build(b))) return rc;
     if ((rc = reserve_outputs(b, n))) return rc;
     for (auto& c : b->chans) c.out_count = 0;
+    b->out_count_depth.assign(32, 0);
     long long done = 0;
     while (done < n) {
         const long long m = (n - done) < b->chunk ? (n - done) : b->chunk;
@@ -424,9 +438,12 @@ int b200dsp_bank_create(b200dsp_bank_t** out, int input_rate_hz)
     b->device = b200_current_device();
     b->sm_count = b200_sm_count_of(b->device);
     b->input_rate = input_rate_hz;
-    b->built = false; b->depth = 0; b->chunk = 3ll << 18; b->d_root = nullptr; b->root_cap = 0;
-    b->d_leaf = nullptr; b->d_nnew = nullptr; b->d_fe = nullptr; b->d_nco = nullptr; b->tcur = 0;
-    if ((rc = B200_CUDA_CHECK(cudaSetDevice(b->device))) || (rc = B200_CUDA_CHECK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)))) { delete b; return rc; }
+    b->built = false; b->depth = 0; b->chunk = 3ll << 22; b->tables_dirty = true; b->d_root = nullptr; b->root_cap = 0;
+    b->d_leaf = nullptr; b->d_fe = nullptr; b->d_nco = nullptr; b->tcur = 0;
+    if ((rc = B200_CUDA_CHECK(cudaSetDevice(b->device))) || (rc = B200_CUDA_CHECK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking))) ||
+        (rc = B200_CUDA_CHECK(cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking))) ||
+        (rc = B200_CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_begin, cudaEventDisableTiming))) ||
+        (rc = B200_CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_sched, cudaEventDisableTiming)))) { delete b; return rc; }
     *out = b;
     return 0;
 }
@@ -436,10 +453,14 @@ int b200dsp_bank_destroy(b200dsp_bank_t* b)
     if (!b) return 0;
     cudaSetDevice(b->device);
     cudaStreamSynchronize(b->stream);
+    cudaStreamSynchronize(b->side);
     free_device(b);
     if (b->d_root) cudaFree(b->d_root);
     if (b->d_nco) cudaFree(b->d_nco);
     cudaStreamDestroy(b->stream);
+    cudaStreamDestroy(b->side);
+    cudaEventDestroy(b->ev_begin);
+    cudaEventDestroy(b->ev_sched);
     delete b;
     return 0;
 }
@@ -461,7 +482,7 @@ int b200dsp_bank_add_channel(b200dsp_bank_t* b, int requested_rate_hz, int cente
     Channel c{};
     c.requested_rate = requested_rate_hz; c.center_offset = center_offset_hz;
     c.fe = false; c.d_out = nullptr; c.out_cap = 0; c.out_count = 0;
-    c.d_z = nullptr; c.d_taps = nullptr; c.d_fe_out = nullptr; c.d_sched = nullptr; c.d_state = nullptr; c.fe_cap = 0;
+    c.d_hist = nullptr; c.d_taps = nullptr; c.d_fe_out = nullptr; c.d_sched = nullptr; c.d_state = nullptr; c.fe_cap = 0;
     // downchannelizer.cpp:169-171: integer divides first, then int -> Real
     const float ofs = filter_chain((float) (b->input_rate / -2), (float) (b->input_rate / 2),
                                    (float) (center_offset_hz - requested_rate_hz / 2), (float) (center_offset_hz + requested_rate_hz / 2), c.modes);
@@ -535,6 +556,7 @@ int b200dsp_bank_feed(b200dsp_bank_t* b, const int16_t* iq, int64_t n_samples)
     if (!b->built && (rc = build(b))) return rc;
     if ((rc = reserve_outputs(b, n_samples))) return rc;
     for (auto& c : b->chans) c.out_count = 0;
+    b->out_count_depth.assign(32, 0);
     long long done = 0;
     while (done < n_samples) {
         const long long m = (n_samples - done) < b->chunk ? (n_samples - done) : b->chunk;

@@ -6,11 +6,11 @@
 //   m_interpolatorDistanceRemain += m_interpolatorDistance           plugins/channelrx/demodnfm/nfmdemod.cpp:315
 //   NCO::nextPhase/nextIQ (phase advanced BEFORE the lookup)         sdrbase/dsp/nco.h:43-50, nco.cpp:60-64
 //
-// B200 design: one CTA per channel per feed.  The reference's float32 "distance" recurrence decides which inputs emit
-// an output and at which of the 16 phases; it depends only on the ratio, not on the data, so lane 0 of warp 0 replays it
-// exactly (same float operations) while the other warps mix the channel's new samples with the table NCO (the phase of
-// sample i is phase0 + (i+1)*inc, so the mix is data-parallel).  After a block barrier every thread computes outputs
-// as 72-tap dot products  y = sum_k taps[phase][k] * z[idx-k]  with the taps in shared memory.
+// B200 design: the reference's float32 "distance" recurrence decides which inputs emit an output and at which of the 16
+// phases; it depends only on the ratio, not on the data, so a schedule kernel replays it exactly (one thread per channel,
+// one iteration per OUTPUT) on a side stream while the tree kernels run.  Then one CTA per channel mixes the channel's new
+// samples with the table NCO (the phase of sample i is phase0 + (i+1)*inc, so the mix is data-parallel) and every thread
+// computes outputs as 72-tap dot products  y = sum_k taps[phase][k] * z[idx-k]  with the taps in shared memory.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -18,71 +18,114 @@
 namespace b200dsp {
 
 constexpr int FE_MAX_TAPS = 128;          // taps per phase supported by the kernel's history area (reference default: 72)
+constexpr int FE_TILE = 1024;             // channel samples per CTA tile
+constexpr int FE_THREADS = 128;
+constexpr int FE_HIST_WORDS = FE_MAX_TAPS + 4;   // per ping-pong half: FE_MAX_TAPS samples + the NCO phase
 
-struct FrontendChan {            // one per channel with a front-end, device array
-    const uint32_t* in;          // channel samples of this feed (packed int16 IQ), m of them
-    float2*         z;           // [FE_MAX_TAPS + cap] mixed samples; z[0..FE_MAX_TAPS) = history (newest at FE_MAX_TAPS-1)
+struct FrontendChan {            // one per channel with a front-end, device array (static between reallocations)
+    const uint32_t* in;          // the channel's channelizer output buffer of this feed (packed int16 IQ)
+    uint32_t*       hist;        // [2][FE_HIST_WORDS] carried state (ping-pong): newest channel samples (packed int16 IQ), NCO phase
     const float*    taps;        // [phase_steps][ntaps]
-    float2*         out;         // outputs of this feed are written from out[out_base]
-    int*            sched;       // [cap] packed (idx << 8 | phase) of this feed's outputs
-    int*            state;       // [4]: nco phase, float distance remain (bits), outputs of the last pass, outputs of this feed
-    int             m;           // new samples
-    int             first_pass;  // 1: first pass of a feed (the feed's output count restarts at 0)
+    float2*         out;         // outputs of this feed
+    int*            sched;       // [cap] packed (idx << 8 | phase) of this pass's outputs
+    int*            tile_start;  // [cap / FE_TILE + 2] first output of each input tile (written by the schedule kernel)
+    int*            state;       // [4]: unused, float distance remain (bits), outputs of the last pass, outputs of this feed
+    int             depth;       // S: selects the per-depth pass counts
     int             inc;         // NCO phase increment
     int             ntaps, phase_steps;
     float           ratio;       // m_interpolatorDistance
 };
 
-__global__ void frontend_kernel(const FrontendChan* __restrict__ chans, const float* __restrict__ nco_table)
-{
-    extern __shared__ float fe_taps[];
-    __shared__ int s_nout, s_base;
-    const FrontendChan c = chans[blockIdx.x];
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const int m = c.m;
-    for (int i = tid; i < c.ntaps * c.phase_steps; i += nthr) fe_taps[i] = c.taps[i];
+// per-pass scalars, identical for all nodes/channels of one depth (every stream of a depth has the same length)
+struct PassInfo {
+    int       n_new[32];         // samples produced at depth d in this pass
+    int       wo[32];            // offset of the first new sample in the depth-d node buffers (0/1)
+    long long out_count[32];     // channel outputs of depth-d channels already produced in this feed
+    int       first_pass;
+    int       parity;            // which half of the ping-pong history is current
+};
 
-    const int phase0 = c.state[0];
-    if (tid == 0) {
-        // exact replay of Interpolator::decimate's schedule (interpolator.h:23-36) and the caller's += (nfmdemod.cpp:315)
-        float d = __int_as_float(c.state[1]);
-        int n = 0;
-        const float steps = (float) c.phase_steps;
-        for (int i = 0; i < m; ++i) {
-            d = __fadd_rn(d, -1.0f);
-            if (d >= 1.0f) continue;
-            int ph = (int) floorf(__fmul_rn(d, steps));
-            if (ph < 0) ph = 0;
-            c.sched[n++] = (i << 8) | ph;
-            d = __fadd_rn(d, c.ratio);
-        }
-        const int base = c.first_pass ? 0 : c.state[3];
-        c.state[1] = __float_as_int(d);
-        c.state[2] = n;
-        c.state[3] = base + n;
-        s_base = base;
-        int p = (int) (((long long) phase0 + (long long) m * c.inc) % 4096);
-        if (p < 0) p += 4096;
-        c.state[0] = p;
-        s_nout = n;
+// Schedule: one thread per channel replays the reference's float32 distance recurrence, one iteration per OUTPUT:
+// after an emission d = fl(r + ratio); every further input subtracts 1.0f, which is exact in float32, until d < 1, so the
+// next emission comes j = max(1, floor(d)) inputs later with r = d - j (exact) and phase = max(0, floor(r * steps)).
+// Bit-identical to the per-input loop of Interpolator::decimate (interpolator.h:23-36) + nfmdemod.cpp:315.
+// Depends only on counts, not on samples: runs on a side stream concurrently with the tree kernels.
+// The loop-carried chain is floor -> max -> sub -> add (the integer conversions are off the chain).
+__global__ void frontend_schedule_kernel(const FrontendChan* __restrict__ chans, int n_chans, const PassInfo pi)
+{
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= n_chans) return;
+    const FrontendChan c = chans[ch];
+    const int m = pi.n_new[c.depth];
+    float d = __int_as_float(c.state[1]);      // distance remain before the next input
+    const float steps = (float) c.phase_steps, ratio = c.ratio;
+    int i = -1, n = 0, tile = 0;               // i = index of the last consumed input
+    int* __restrict__ sched = c.sched;
+    int* __restrict__ tstart = c.tile_start;   // tstart[t] = first output whose input index is >= t * FE_TILE
+    // one emission: consumes j = max(1, floor(d)) inputs
+#define FE_EMIT()                                                                              \
+    {                                                                                          \
+        const float fj = fmaxf(floorf(d), 1.0f);                                               \
+        i += (int) fj;                                                                         \
+        const float r = __fsub_rn(d, fj);                                                      \
+        int ph = (int) floorf(__fmul_rn(r, steps));                                            \
+        if (ph < 0) ph = 0;                                                                    \
+        while (tile * FE_TILE <= i) tstart[tile++] = n;                                        \
+        sched[n++] = (int) (((unsigned) i << 8) | (unsigned) ph);   /* i < 2^24, ph < 256 */   \
+        d = __fadd_rn(r, ratio);                                                               \
     }
-    // NCO mix of the new samples: phase_i = phase0 + (i+1)*inc  (mod 4096)
-    for (int i = tid; i < m; i += nthr) {
-        const uint32_t w = c.in[i];
+    for (;;) {
+        const int j = (int) fmaxf(floorf(d), 1.0f);
+        if (i + j >= m) break;
+        FE_EMIT();
+    }
+#undef FE_EMIT
+    const int ntiles = (m + FE_TILE - 1) / FE_TILE;
+    while (tile <= ntiles) tstart[tile++] = n;
+    d = __fadd_rn(d, -(float) (m - 1 - i));    // the remaining inputs of this pass each subtract 1.0f (exact)
+    const int base = pi.first_pass ? 0 : c.state[3];
+    c.state[1] = __float_as_int(d);
+    c.state[2] = n;
+    c.state[3] = base + n;
+}
+
+// grid = (tiles, channels).  A CTA mixes FE_TILE (+ ntaps-1 halo) channel samples with the table NCO into shared memory
+// and computes every output whose newest input lies in the tile.
+__global__ void __launch_bounds__(FE_THREADS) frontend_kernel(const FrontendChan* __restrict__ chans, const float* __restrict__ nco_table, const PassInfo pi)
+{
+    extern __shared__ float fe_smem[];                     // taps [phase_steps*ntaps] then z [FE_MAX_TAPS + FE_TILE] float2
+    FrontendChan c = chans[blockIdx.y];
+    const int tid = threadIdx.x;
+    const int m = pi.n_new[c.depth];
+    const int t0 = blockIdx.x * FE_TILE;
+    if (t0 >= m && !(blockIdx.x == 0)) return;
+    c.in += pi.out_count[c.depth];
+    const uint32_t* hin = c.hist + pi.parity * FE_HIST_WORDS;
+    const int nt = c.ntaps, nts = c.ntaps | 1;            // odd row stride: the 16 phases start in distinct banks
+    const int ntp = nts * c.phase_steps;
+    float* taps = fe_smem;
+    float2* z = reinterpret_cast<float2*>(fe_smem + ((ntp + 3) & ~3));
+    for (int i = tid; i < nt * c.phase_steps; i += FE_THREADS) taps[(i / nt) * nts + (i % nt)] = c.taps[i];
+    const unsigned phase0 = hin[FE_MAX_TAPS];
+    const int t1 = (t0 + FE_TILE < m) ? t0 + FE_TILE : m;
+    // z[k] holds mixed sample (t0 - FE_MAX_TAPS + k), k in [0, FE_MAX_TAPS + t1 - t0)
+    for (int k = tid; k < FE_MAX_TAPS + (t1 - t0); k += FE_THREADS) {
+        const int i = t0 - FE_MAX_TAPS + k;
+        const uint32_t w = (i >= 0) ? c.in[i] : hin[FE_MAX_TAPS + i];
         const float x = (float) (short) (w & 0xffffu), y = (float) ((int) w >> 16);
-        int p = (int) (((long long) phase0 + (long long) (i + 1) * c.inc) % 4096);
-        if (p < 0) p += 4096;
+        const int p = (int) ((phase0 + (unsigned) (i + 1) * (unsigned) c.inc) & 4095u);   // phase advanced before the lookup; wrap == mod 4096
         const float u = nco_table[p], v = -nco_table[(p + 1024) & 4095];
-        c.z[FE_MAX_TAPS + i] = make_float2(x * u - y * v, x * v + y * u);
+        z[k] = make_float2(x * u - y * v, x * v + y * u);
     }
     __syncthreads();
-    const int n = s_nout, out_base = s_base;
-    const int nt = c.ntaps;
-    for (int o = tid; o < n; o += nthr) {
-        const int s = c.sched[o];
-        const int idx = s >> 8, ph = s & 0xff;
-        const float* t = fe_taps + ph * nt;
-        const float2* zz = c.z + FE_MAX_TAPS + idx;
+    // outputs of this pass whose input index falls in [t0, t1)
+    const int out_base = c.state[3] - c.state[2];
+    const int o0 = c.tile_start[blockIdx.x], o1 = c.tile_start[blockIdx.x + 1];
+    for (int o = o0 + tid; o < o1; o += FE_THREADS) {
+        const unsigned s = (unsigned) c.sched[o];
+        const int idx = (int) (s >> 8), ph = (int) (s & 0xffu);
+        const float* t = taps + ph * nts;
+        const float2* zz = z + (idx - t0 + FE_MAX_TAPS);
         float ra = 0.0f, ia = 0.0f;
 #pragma unroll 8
         for (int k = 0; k < nt; ++k) {
@@ -92,14 +135,15 @@ __global__ void frontend_kernel(const FrontendChan* __restrict__ chans, const fl
         }
         c.out[out_base + o] = make_float2(ra, ia);
     }
-    __syncthreads();
-    // carry the last FE_MAX_TAPS mixed samples as the next feed's history
-    float2 keep[(FE_MAX_TAPS + 127) / 128];
-    int cnt = 0;
-    for (int i = tid; i < FE_MAX_TAPS; i += nthr) keep[cnt++] = c.z[m + i];
-    __syncthreads();
-    cnt = 0;
-    for (int i = tid; i < FE_MAX_TAPS; i += nthr) c.z[i] = keep[cnt++];
+    // the CTA of the last tile carries the newest FE_MAX_TAPS channel samples and the NCO phase to the next pass
+    if (t1 == m && (t0 < m || blockIdx.x == 0)) {
+        uint32_t* hout = c.hist + (pi.parity ^ 1) * FE_HIST_WORDS;
+        for (int k = tid; k < FE_MAX_TAPS; k += FE_THREADS) {
+            const int i = m - FE_MAX_TAPS + k;
+            hout[k] = (i >= 0) ? c.in[i] : hin[FE_MAX_TAPS + i];
+        }
+        if (tid == 0) hout[FE_MAX_TAPS] = (phase0 + (unsigned) m * (unsigned) c.inc) & 4095u;
+    }
 }
 
 } // namespace b200dsp

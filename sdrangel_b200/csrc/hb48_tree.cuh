@@ -29,6 +29,7 @@ struct LevelParams {
     const uint32_t* in_base;  long long in_stride;    // parent-level buffers (packed int16 IQ), B[i] = parent sample C_before + i
     uint32_t*       out_base; long long out_stride;   // child-level buffers
     const uint32_t* tail_in;                          // [parents][TAIL_WORDS]
+    uint32_t*       tail_out;                         // next call's tails (ping-pong): written by each family's last slice
     const int*      fam;                              // [n_fam][4]: parent index, child index for mode 0 (C), 1 (L), 2 (U); -1 = absent
     int n_fam;
     int n_in;          // samples consumed per parent this call (even), B[0 .. n_in)
@@ -176,6 +177,17 @@ __global__ void __launch_bounds__(256, 2) hb48_level_kernel(const LevelParams p)
     const int q0 = slice * p.bps;
     int q1 = q0 + p.bps;
     if (q1 > nb) q1 = nb;
+    if (slice == p.slices - 1) {
+        // carry: new_tail[t] = parent sample (C_after - 64 + t), t = 0..64 (64 history + the possibly pending sample)
+        uint32_t* tout = p.tail_out + (long long) fam.x * TAIL_WORDS;
+        for (int t = lane; t <= 64; t += 32) {
+            const int i = p.n_in - 64 + t;
+            uint32_t v;
+            if (i < p.pend) v = tail[i + 64];
+            else            v = (i < p.in_limit) ? B[i] : 0u;
+            tout[t] = v;
+        }
+    }
     if (q0 >= q1) return;
     const int n_out = p.n_in >> 1;
     const bool rotated = (fam.z >= 0) || (fam.w >= 0);
