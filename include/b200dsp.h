@@ -122,6 +122,33 @@ int b200dsp_bank_fetch(b200dsp_bank_t* b, int chan_id, int stage, void* out, int
 int b200dsp_bank_fetch_dev(b200dsp_bank_t* b, int chan_id, int stage, const void** d_ptr, int64_t* n_samples);
 int b200dsp_bank_sync(b200dsp_bank_t* b);
 
+/* ---- K5: SpectrumVis -------------------------------------------------------------------------------------
+ * One handle == one reference SpectrumVis sink (sdrgui/dsp/spectrumvis.cpp:77-254,283-327) with its FFTWindow
+ * (sdrbase/dsp/fftwindow.cpp:20-73), FFT engine (sdrbase/dsp/kissengine.cpp, kissfft.h) and per-bin averagers
+ * (sdrbase/util/movingaverage2d.h, fixedaverage2d.h).  Every frame the reference would hand to
+ * GLSpectrum::newSpectrum(m_powerSpectrum, fftSize) (spectrumvis.cpp:147,182,231) is returned as one row of fft_size floats.
+ */
+typedef struct b200dsp_spectrum b200dsp_spectrum_t;
+
+#define B200DSP_AVG_NONE    0   /* SpectrumVis::AvgModeNone   */
+#define B200DSP_AVG_MOVING  1   /* SpectrumVis::AvgModeMoving */
+#define B200DSP_AVG_FIXED   2   /* SpectrumVis::AvgModeFixed  */
+/* window: FFTWindow::Function 0 Bartlett, 1 BlackmanHarris, 2 Flattop, 3 Hamming, 4 Hanning, 5 Rectangle (fftwindow.h:30-37) */
+
+int b200dsp_spectrum_create(b200dsp_spectrum_t** s, float scalef);            /* scalef: SpectrumVis(Real scalef), 32768 for 16-bit Rx */
+int b200dsp_spectrum_destroy(b200dsp_spectrum_t* s);
+/* == SpectrumVis::handleConfigure(fftSize, overlapPercent, averageNb, averagingMode, window, linear); restarts the frame
+ *    buffer and the averagers like the reference.  Only overlap 0 is supported. */
+int b200dsp_spectrum_configure(b200dsp_spectrum_t* s, int fft_size, int overlap_percent, unsigned int average_nb,
+                               int averaging_mode, int window, int linear);
+/* frames the next feed of n_samples would emit (pure host arithmetic) */
+int64_t b200dsp_spectrum_frames_for(b200dsp_spectrum_t* s, int64_t n_samples);
+/* == SpectrumVis::feed(begin, end, positiveOnly); out_frames receives *n_frames rows of fft_size floats */
+int b200dsp_spectrum_feed(b200dsp_spectrum_t* s, const int16_t* iq, int64_t n_samples, int positive_only,
+                          float* out_frames, int64_t cap_frames, int64_t* n_frames);
+int b200dsp_spectrum_feed_dev(b200dsp_spectrum_t* s, const void* d_iq, int64_t n_samples, int positive_only,
+                              float* d_out_frames, int64_t cap_frames, int64_t* n_frames, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

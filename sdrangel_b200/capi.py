@@ -52,6 +52,12 @@ SIGNATURES = {
     "b200dsp_bank_fetch": (_i32, [_vp, _i32, _i32, _vp, _i64, _pi64]),
     "b200dsp_bank_fetch_dev": (_i32, [_vp, _i32, _i32, _pvp, _pi64]),
     "b200dsp_bank_sync": (_i32, [_vp]),
+    "b200dsp_spectrum_create": (_i32, [_pvp, _f32]),
+    "b200dsp_spectrum_destroy": (_i32, [_vp]),
+    "b200dsp_spectrum_configure": (_i32, [_vp, _i32, _i32, C.c_uint, _i32, _i32, _i32]),
+    "b200dsp_spectrum_frames_for": (_i64, [_vp, _i64]),
+    "b200dsp_spectrum_feed": (_i32, [_vp, _vp, _i64, _i32, _vp, _i64, _pi64]),
+    "b200dsp_spectrum_feed_dev": (_i32, [_vp, _vp, _i64, _i32, _vp, _i64, _pi64, _vp]),
 }
 STAGE_CHANNELIZER, STAGE_FRONTEND = 0, 1
 

@@ -195,3 +195,51 @@ class DownChannelizerBank:
         out = np.empty((max(n.value, 1), 2), dtype=dt)
         capi.check(capi.lib().b200dsp_bank_fetch(self._h, chan_id, stage, out.ctypes.data, out.shape[0], C.byref(n)))
         return out[:n.value]
+
+
+class SpectrumVis:
+    """SpectrumVis (sdrgui/dsp/spectrumvis.cpp): feed() returns the frames the reference would pass to
+    GLSpectrum::newSpectrum, as an (n_frames, fft_size) float32 array."""
+    AvgModeNone, AvgModeMoving, AvgModeFixed = 0, 1, 2
+
+    def __init__(self, scalef=32768.0, device=None):
+        L = capi.lib()
+        if device is not None:
+            capi.init(device)
+        h = C.c_void_p()
+        capi.check(L.b200dsp_spectrum_create(C.byref(h), float(scalef)))
+        self._h = h
+        self.fft_size = 1024
+
+    def close(self):
+        if getattr(self, "_h", None):
+            capi.lib().b200dsp_spectrum_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def configure(self, fft_size, overlap_pct=0, avg_nb=0, avg_mode=0, window=1, linear=False):
+        capi.check(capi.lib().b200dsp_spectrum_configure(self._h, fft_size, overlap_pct, avg_nb, avg_mode, window, int(linear)))
+        self.fft_size = min(max(fft_size, 64), 4096)
+
+    def frames_for(self, n_samples):
+        return int(capi.lib().b200dsp_spectrum_frames_for(self._h, int(n_samples)))
+
+    def feed(self, iq, positive_only=False):
+        iq = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1)
+        n = iq.size // 2
+        nf = self.frames_for(n)
+        out = np.empty((max(nf, 1), self.fft_size), dtype=np.float32)
+        got = C.c_int64(0)
+        capi.check(capi.lib().b200dsp_spectrum_feed(self._h, iq.ctypes.data, n, int(positive_only), out.ctypes.data, out.shape[0], C.byref(got)))
+        return out[:got.value]
+
+    def feed_dev(self, d_iq, n_samples, d_out, cap_frames, positive_only=False, stream=None):
+        got = C.c_int64(0)
+        capi.check(capi.lib().b200dsp_spectrum_feed_dev(self._h, C.c_void_p(d_iq), int(n_samples), int(positive_only), C.c_void_p(d_out),
+                                                        int(cap_frames), C.byref(got), C.c_void_p(stream or 0)))
+        return got.value
