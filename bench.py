@@ -7,6 +7,7 @@ Workloads (BASELINE.json configs):
   decimateii   sdrbench decimateii: int16 IQ, log2 decimation 4, centred, 12 bit          (config 1; default at N=1)
   decimatefi   sdrbench decimatefi: float IQ, log2 decimation 6, centred                  (config 2)
   bank64       64 NFM channels off a 10 MS/s baseband: HB48 tree + NCO + Interpolator     (config 3)
+  spectrum     SpectrumVis 4096-pt Blackman-Harris FFT, log power, fixed average of 10 frames (config 4)
   bank1024     1024 channels over a 122.88 MS/s stream, channels sharded over the ranks,
                baseband NCCL-broadcast from rank 0 every step                             (config 5; default at N>1)
 A "step" is one pass of the hot path over one batch of synthetic IQ that is larger than L2 (every step streams from
@@ -48,6 +49,8 @@ WORKLOADS = {
                        desc="sdrbench decimatefi: DecimatorsFI::decimate64_cen, synthetic float IQ"),
     "bank64": dict(type="bank", plan=plan64, n=3 << 22,
                    desc="64 NFM 12.5 kHz channels off a synthetic 10 MS/s int16 baseband: DownChannelizer tree + NCO + Interpolator to 48 kS/s"),
+    "spectrum": dict(type="spectrum", n=1 << 26, fft=4096, avg_nb=10, avg_mode=2,
+                     desc="SpectrumVis: 4096-pt Blackman-Harris windowed FFT, log power, fixed averaging over 10 frames, synthetic int16 IQ (61.44 MS/s LimeSDR-rate stream)"),
     "bank1024": dict(type="bank", plan=plan1024, n=3 << 22,
                      desc="1024 channels over a synthetic 122.88 MS/s int16 stream: DownChannelizer tree + NCO + Interpolator to 48 kS/s, channels sharded"),
 }
@@ -182,8 +185,38 @@ def cpu_reference_bank(wl, seconds, threads=None):
                       % (len(sub), len(fcs), wall, len(fcs))}
 
 
+def cpu_reference_spectrum(wl, seconds, threads=None):
+    """The reference's FFTWindow + KissFFT + averaging glue (oracle/_ref), one independent SpectrumVis per host thread."""
+    kind, mod = _oracle_mod()
+    threads = threads or (os.cpu_count() or 1)
+    rs = np.random.RandomState(2)
+    n = wl["fft"] * 64
+    x = rs.randint(-2048, 2048, size=(n, 2)).astype(np.int16)
+    Spec = mod.RefSpectrumVis if kind == "reference" else mod.PortSpectrumVis
+    objs = []
+    for _ in range(threads):
+        s = Spec()
+        s.configure(wl["fft"], 0, wl["avg_nb"], wl["avg_mode"], 1, False)
+        objs.append(s)
+    counts = [0] * threads
+    t_end = time.perf_counter() + seconds
+
+    def work(i):
+        while time.perf_counter() < t_end:
+            objs[i].feed(x)
+            counts[i] += 1
+
+    wall = _run_threads(work, threads)
+    return {"value": sum(counts) * n / wall / 1e6, "unit": "input MS/s", "cores": threads, "kind": kind,
+            "sample": "%d x 64-frame feeds per thread, one stream per thread, %.1f s wall" % (max(counts), wall)}
+
+
 def cpu_reference(wl, seconds):
-    return cpu_reference_decim(wl, seconds) if wl["type"] == "decim" else cpu_reference_bank(wl, seconds)
+    if wl["type"] == "decim":
+        return cpu_reference_decim(wl, seconds)
+    if wl["type"] == "spectrum":
+        return cpu_reference_spectrum(wl, seconds)
+    return cpu_reference_bank(wl, seconds)
 
 
 def run_reference(args, wl_name, wl):
@@ -199,7 +232,7 @@ def run_reference(args, wl_name, wl):
     v = float(np.mean([r["value"] for r in vals]))
     line = {"metric": METRIC, "value": v, "unit": "input MS/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong" if wl["type"] == "bank" else "weak", "vs_baseline": None,
-            "dtype": "f32" if wl.get("kind") in ("fi", "ff", "if") else "s32", "data": "synthetic", "impl": "reference",
+            "dtype": "f32" if (wl.get("kind") in ("fi", "ff", "if") or wl["type"] == "spectrum") else "s32", "data": "synthetic", "impl": "reference",
             "config": {"workload": wl_name, "desc": wl["desc"]},
             "cpu_baseline": {"value": v, "unit": "input MS/s", "cores": vals[-1]["cores"], "kind": vals[-1]["kind"], "sample": vals[-1]["sample"]},
             "e2e": {"value": v, "unit": "input MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -469,6 +502,89 @@ def bench_bank(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=T
     return res
 
 
+def bench_spectrum(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=True):
+    import sdrangel_b200 as S
+    torch, capi = c.torch, c.capi
+    n = args.samples or wl["n"]
+    fft = wl["fft"]
+    sp = S.SpectrumVis()
+    sp.configure(fft, 0, wl["avg_nb"], wl["avg_mode"], 1, False)
+    g = torch.Generator(device=c.dev)
+    g.manual_seed(2 + c.rank)
+    x = torch.randint(-2048, 2048, (2 * n,), dtype=torch.int16, device=c.dev, generator=g)
+    cap = n // fft // max(1, wl["avg_nb"]) + 2
+    y = torch.empty((cap, fft), dtype=torch.float32, device=c.dev)
+    stream = torch.cuda.Stream(device=c.dev)
+    sptr = stream.cuda_stream
+    parity = None
+    if c.rank == 0 and want_parity:       # oracle = checker only: first 40 frames
+        _oracle_mod()
+        from oracle import portbind
+        m = fft * 40
+        chk = S.SpectrumVis()
+        chk.configure(fft, 0, wl["avg_nb"], wl["avg_mode"], 1, False)
+        nf = chk.feed_dev(x.data_ptr(), m, y.data_ptr(), cap, False, sptr)
+        stream.synchronize()
+        o = portbind.PortSpectrumVis()
+        o.configure(fft, 0, wl["avg_nb"], wl["avg_mode"], 1, False)
+        want = o.feed(x[: 2 * m].cpu().numpy().reshape(-1, 2))
+        got = y[:nf].cpu().numpy()
+        ok = np.isfinite(want)
+        parity = bool(got.shape == want.shape and np.max(np.abs(got[ok] - want[ok])) <= 1e-3)
+        chk.close()
+
+    def step():
+        sp.feed_dev(x.data_ptr(), n, y.data_ptr(), cap, False, sptr)
+
+    total_ms, kern_ms, clocks = timed_steps(c, stream, step, steps, warmup)
+    value = c.world * n * steps / (total_ms * 1e-3) / 1e6
+    step_ms = float(np.mean(kern_ms))
+    bps = 4 + 4.0 / max(1, wl["avg_nb"])
+    achieved = n * bps / (step_ms * 1e-3) / 1e9
+    instr_per_sample = 68.0
+    f_clk = (clocks.get("sm_mhz") or 1965) * 1e6
+    issue_roof = c.sm_count * 128 * f_clk / instr_per_sample / 1e6
+    res = {"value": value, "ms_per_step": total_ms / steps, "clocks": clocks, "parity": parity, "launches": steps,
+           "config": {"workload": wl_name, "desc": wl["desc"], "samples_per_step": n, "fft_size": fft, "frames_per_step": n // fft,
+                      "average_nb": wl["avg_nb"], "averaging": "fixed", "window": "BlackmanHarris",
+                      "l2": "input %.0f MiB per step > 126 MB L2, streamed from HBM every step" % (n * 4 / 2 ** 20),
+                      "parallelism": "replicas x%d (one stream per GPU)" % c.world},
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": c.hbm_peak, "unit": "GB/s", "frac": achieved / c.hbm_peak,
+                        "traffic": None, "peak_source": c.peak_src, "kernel": "spectrum_kernel", "kernel_ms": step_ms,
+                        "algorithmic_bytes_per_sample": bps,
+                        "issue": {"instr_per_sample": instr_per_sample, "roof_MSps_at_sampled_clk": issue_roof,
+                                  "frac": (n / (step_ms * 1e-3) / 1e6) / issue_roof,
+                                  "note": "5 N log2 N flops per frame = 60 flop/sample + window/scale/power/log ~ 8 (SURVEY.md 8d)"}},
+           "dtype": "f32", "scaling": "weak"}
+    if want_e2e:
+        n_e = min(n, 1 << 24)
+        hx = torch.empty((2 * n_e,), dtype=torch.int16, pin_memory=True)
+        hx.copy_(x[: 2 * n_e])
+        hy = torch.empty((n_e // fft // max(1, wl["avg_nb"]) + 2, fft), dtype=torch.float32, pin_memory=True)
+        L_ = capi.lib()
+        s2 = S.SpectrumVis()
+        s2.configure(fft, 0, wl["avg_nb"], wl["avg_mode"], 1, False)
+        nn = C.c_int64(0)
+
+        def e2e_step():
+            capi.check(L_.b200dsp_spectrum_feed(s2._h, hx.data_ptr(), n_e, 0, hy.data_ptr(), hy.shape[0], C.byref(nn)))
+
+        e2e_step()
+        barrier(c)
+        t0 = time.perf_counter()
+        ksteps = 5
+        for _ in range(ksteps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = max_over_ranks(c, time.perf_counter() - t0)
+        res["e2e"] = {"value": c.world * n_e * ksteps / dt / 1e6, "unit": "input MS/s", "h2d_bytes_per_step": int(n_e * 4),
+                      "d2h_bytes_per_step": int(nn.value * fft * 4), "steps": ksteps,
+                      "api": "b200dsp_spectrum_feed (host pointers, pinned)", "samples_per_step": n_e}
+        s2.close()
+    sp.close()
+    return res
+
+
 def _node_depths(paths):
     seen = set()
     for p in paths:
@@ -479,8 +595,8 @@ def _node_depths(paths):
 
 def run_ours(args, wl_name, wl):
     c = setup()
-    fn = bench_decim if wl["type"] == "decim" else bench_bank
-    res = fn(c, args, wl_name, wl, args.steps, args.warmup, want_e2e=not args.no_e2e)
+    fns = {"decim": bench_decim, "bank": bench_bank, "spectrum": bench_spectrum}
+    res = fns[wl["type"]](c, args, wl_name, wl, args.steps, args.warmup, want_e2e=not args.no_e2e)
     also = {}
     if c.world == 1 and not args.no_also and not args.samples:
         for other in WORKLOADS:
@@ -488,7 +604,7 @@ def run_ours(args, wl_name, wl):
                 continue
             try:
                 o = WORKLOADS[other]
-                r = (bench_decim if o["type"] == "decim" else bench_bank)(c, args, other, o, 5, 3, want_e2e=False)
+                r = fns[o["type"]](c, args, other, o, 5, 3, want_e2e=False)
                 also[other] = {"value": r["value"], "unit": "input MS/s", "ms_per_step": r["ms_per_step"], "hbm_frac": r["roofline"]["frac"],
                                "issue_frac": r["roofline"]["issue"]["frac"], "parity_checked_vs_oracle": r["parity"],
                                "samples_per_step": r["config"]["samples_per_step"]}
