@@ -420,6 +420,7 @@ def bench_bank(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=T
     g.manual_seed(1)
     x = torch.randint(-2048, 2048, (2 * n,), dtype=torch.int16, device=c.dev, generator=g) if c.rank == 0 else \
         torch.empty((2 * n,), dtype=torch.int16, device=c.dev)
+    xb = x.view(torch.int32)              # NCCL has no int16 type: the broadcast moves raw bytes (one IQ sample per int32)
     stream = torch.cuda.Stream(device=c.dev)
     sptr = stream.cuda_stream
 
@@ -446,7 +447,7 @@ def bench_bank(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=T
 
     def step():
         if c.world > 1:
-            dist.broadcast(x, src=0)               # NCCL broadcast of the wideband baseband over NVLink, every step
+            dist.broadcast(xb, src=0)              # NCCL broadcast of the wideband baseband over NVLink, every step
         bank.feed_dev(x.data_ptr(), n, sptr)
 
     total_ms, kern_ms, clocks = timed_steps(c, stream, step, steps, warmup)
