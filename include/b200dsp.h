@@ -98,6 +98,10 @@ typedef struct b200dsp_bank b200dsp_bank_t;
 #define B200DSP_STAGE_CHANNELIZER 0   /* int16 IQ at input_rate / 2^S   (what DownChannelizer hands to its sink) */
 #define B200DSP_STAGE_FRONTEND    1   /* float IQ after NCO mix + Interpolator::decimate (complex64) */
 
+/* == DownChannelizer::applyConfiguration's filter-chain selection (downchannelizer.cpp:165-177,250-287) as pure host
+ *    arithmetic (no device needed): returns the number of stages S, writes out rate, residual offset and the modes */
+int b200dsp_filter_chain(int input_rate_hz, int requested_rate_hz, int center_offset_hz,
+                         int* out_rate_hz, int* residual_offset_hz, int* modes, int cap);
 int b200dsp_bank_create(b200dsp_bank_t** b, int input_rate_hz);
 int b200dsp_bank_destroy(b200dsp_bank_t* b);
 /* internal time-chunk (input samples per pass over the tree); default 12582912, rounded to a multiple of 768 */

@@ -39,6 +39,7 @@ SIGNATURES = {
     "b200dsp_decim_set_state": (_i32, [_vp, _vp]),
     "b200dsp_decim_reset": (_i32, [_vp]),
     "b200dsp_decim_sync": (_i32, [_vp]),
+    "b200dsp_filter_chain": (_i32, [_i32, _i32, _i32, _pi32, _pi32, _pi32, _i32]),
     "b200dsp_bank_create": (_i32, [_pvp, _i32]),
     "b200dsp_bank_destroy": (_i32, [_vp]),
     "b200dsp_bank_set_chunk": (_i32, [_vp, _i64]),

@@ -426,6 +426,18 @@ int feed_common(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t
 
 extern "C" {
 
+int b200dsp_filter_chain(int input_rate_hz, int requested_rate_hz, int center_offset_hz, int* out_rate_hz, int* residual_offset_hz, int* modes, int cap)
+{
+    if (input_rate_hz <= 0 || requested_rate_hz <= 0) return b200_fail(B200DSP_EINVAL, "filter_chain: rates must be positive");
+    std::vector<int> m;
+    const float ofs = filter_chain((float) (input_rate_hz / -2), (float) (input_rate_hz / 2),
+                                   (float) (center_offset_hz - requested_rate_hz / 2), (float) (center_offset_hz + requested_rate_hz / 2), m);
+    if (out_rate_hz) *out_rate_hz = input_rate_hz / (1 << m.size());
+    if (residual_offset_hz) *residual_offset_hz = (int) ofs;
+    for (int i = 0; i < (int) m.size() && i < cap; ++i) if (modes) modes[i] = m[i];
+    return (int) m.size();
+}
+
 int b200dsp_bank_create(b200dsp_bank_t** out, int input_rate_hz)
 {
     if (!out) return b200_fail(B200DSP_EINVAL, "bank_create: null handle pointer");
