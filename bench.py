@@ -531,7 +531,8 @@ def bench_spectrum(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_pari
         want = o.feed(x[: 2 * m].cpu().numpy().reshape(-1, 2))
         got = y[:nf].cpu().numpy()
         ok = np.isfinite(want)
-        parity = bool(got.shape == want.shape and np.max(np.abs(got[ok] - want[ok])) <= 1e-3)
+        parity = bool(got.shape == want.shape and np.max(np.abs(got[ok] - want[ok])) <= 1e-2 and
+                      float(np.sqrt(np.mean((10 ** (got[ok] / 10) - 10 ** (want[ok] / 10)) ** 2)) / np.sqrt(np.mean((10 ** (want[ok] / 10)) ** 2))) <= 1e-5)
         chk.close()
 
     def step():

@@ -126,6 +126,169 @@ __device__ void load_frame(float2* X, const SpecParams& p, long long f)
     __syncthreads();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// N = 4096 fast path (the SpectrumVis default maximum and BASELINE config 4): 256 threads x 16 points, three register-blocked
+// radix-16 passes (4096 = 16*16*16) with two shared-memory exchanges; thread t ends up owning bins t + 256*j.
+//   n = 256 n1 + n2, k = k1 + 16 k2:  X[k1 + 16 k2] = sum_{n2} W_4096^{n2 k1} ( sum_{n1} x[256 n1 + n2] W_16^{n1 k1} ) W_256^{n2 k2}
+// and the 256-point transforms over n2 = 16 m1 + m2 split the same way (k2 = j1 + 16 j2).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmulc(float2 a, float wr, float wi) { return make_float2(a.x * wr - a.y * wi, a.x * wi + a.y * wr); }
+
+// forward radix-4 butterfly on (a0,a1,a2,a3): y_q = sum_p a_p (-j)^{pq}
+__device__ __forceinline__ void bfly4(float2& a0, float2& a1, float2& a2, float2& a3)
+{
+    const float2 s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = csub(a1, a3);
+    a0 = cadd(s02, s13);
+    a2 = csub(s02, s13);
+    a1 = make_float2(d02.x + d13.y, d02.y - d13.x);
+    a3 = make_float2(d02.x - d13.y, d02.y + d13.x);
+}
+
+// 16-point forward DFT in registers, natural order in and out (radix-4 DIF: n = a + 4p, k = q + 4r)
+__device__ __forceinline__ void fft16(float2 (&v)[16])
+{
+    constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, R2 = 0.70710678118654752f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) bfly4(v[a], v[a + 4], v[a + 8], v[a + 12]);       // v[a + 4q] = y_q of column a
+    // twiddles W_16^{a q}
+    v[1 + 4]  = cmulc(v[1 + 4],  C1, -S1);        // a=1 q=1 : W^1
+    v[1 + 8]  = cmulc(v[1 + 8],  R2, -R2);        // a=1 q=2 : W^2
+    v[1 + 12] = cmulc(v[1 + 12], S1, -C1);        // a=1 q=3 : W^3
+    v[2 + 4]  = cmulc(v[2 + 4],  R2, -R2);        // a=2 q=1 : W^2
+    v[2 + 8]  = make_float2(v[2 + 8].y, -v[2 + 8].x);          // a=2 q=2 : W^4 = -j
+    v[2 + 12] = cmulc(v[2 + 12], -R2, -R2);       // a=2 q=3 : W^6
+    v[3 + 4]  = cmulc(v[3 + 4],  S1, -C1);        // a=3 q=1 : W^3
+    v[3 + 8]  = cmulc(v[3 + 8],  -R2, -R2);       // a=3 q=2 : W^6
+    v[3 + 12] = cmulc(v[3 + 12], -C1, S1);        // a=3 q=3 : W^9
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bfly4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);   // v[4q + r] = X[q + 4r]
+    // reorder to natural order: X[q + 4r] sits in v[4q + r]  -> transpose the 4x4 index
+    float2 t;
+#define SPEC_SWAP(i, j) t = v[i]; v[i] = v[j]; v[j] = t;
+    SPEC_SWAP(1, 4) SPEC_SWAP(2, 8) SPEC_SWAP(3, 12) SPEC_SWAP(6, 9) SPEC_SWAP(7, 13) SPEC_SWAP(11, 14)
+#undef SPEC_SWAP
+}
+
+// MODE: AVG_* ; LINEAR: linear output ; RCP: scalef is a power of two, so x / scalef == x * (1 / scalef) exactly
+template<int MODE, bool LINEAR, bool RCP>
+__global__ void __launch_bounds__(SPEC_THREADS, 2) spectrum_kernel_4096(const SpecParams p)
+{
+    constexpr int K1S = 16 * 17 + 1;                  // k1 stride of the pass-2 output: odd multiple => pass-3 loads hit distinct banks
+    extern __shared__ float2 sm[];                    // [16 * K1S] pass-1 output [k1][n2] (4096) aliased with pass-2 output [k1][m2][17]
+    float* swin = reinterpret_cast<float*>(sm + 16 * K1S);      // [4096] window
+    constexpr int n = 4096, half = 2048;
+    const int tid = threadIdx.x;
+    const int g = blockIdx.x;
+    constexpr bool fixed = (MODE == AVG_FIXED), moving = (MODE == AVG_MOVING);
+    double acc[fixed ? 16 : 1];
+    long long f0, f1;
+    bool emit = true;
+    if (fixed) {
+        f0 = (long long) g * p.avg_nb - p.fix_idx;
+        f1 = f0 + p.avg_nb;
+        if (f0 < 0) f0 = 0;
+        if (f1 > p.frames) { f1 = p.frames; emit = false; }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc[fixed ? k : 0] = (g == 0 && p.fix_idx > 0) ? p.fix_sum[tid + 256 * k] : 0.0;
+    } else { f0 = g; f1 = g + 1; }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) swin[tid + 256 * k] = p.window[tid + 256 * k];
+    const float rs = 1.0f / p.scalef;
+    uint32_t raw[16];
+    auto fetch = [&](long long f) {
+        const long long base = f * n - p.fill + tid;
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) {
+            const long long s = base + 256 * n1;
+            raw[n1] = (s < 0) ? p.partial[(int) (s + p.fill)] : p.in[s];
+        }
+    };
+    fetch(f0);
+    float2 v[16];
+    for (long long f = f0; f < f1; ++f) {
+        __syncthreads();                              // swin ready (first frame) / previous frame's pass-3 reads are done
+        // pass 1: n2 = tid, transform over n1; Complex(re / m_scalef, im / m_scalef) * window (spectrumvis.cpp:98-106)
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) {
+            const float win = swin[256 * n1 + tid];
+            const float xr = (float) (short) (raw[n1] & 0xffffu), xi = (float) ((int) raw[n1] >> 16);
+            v[n1] = RCP ? make_float2(__fmul_rn(__fmul_rn(xr, rs), win), __fmul_rn(__fmul_rn(xi, rs), win))
+                        : make_float2(__fmul_rn(__fdiv_rn(xr, p.scalef), win), __fmul_rn(__fdiv_rn(xi, p.scalef), win));
+        }
+        if (f + 1 < f1) fetch(f + 1);                 // next frame's samples: in flight during the three passes
+        fft16(v);
+#pragma unroll
+        for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], __ldg(&p.tw[tid * k1]));       // W_4096^{n2 k1}
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) sm[k1 * 256 + tid] = v[k1];
+        __syncthreads();
+        // pass 2: k1 = tid >> 4, m2 = tid & 15, transform over m1 (n2 = 16 m1 + m2)
+        {
+            const int k1 = tid >> 4, m2 = tid & 15;
+#pragma unroll
+            for (int m1 = 0; m1 < 16; ++m1) v[m1] = sm[k1 * 256 + 16 * m1 + m2];
+            fft16(v);
+#pragma unroll
+            for (int j1 = 1; j1 < 16; ++j1) v[j1] = cmul(v[j1], __ldg(&p.tw[16 * m2 * j1]));   // W_256^{m2 j1}
+            __syncthreads();                                                       // every thread has read its pass-1 values
+#pragma unroll
+            for (int j1 = 0; j1 < 16; ++j1) sm[k1 * K1S + m2 * 17 + j1] = v[j1];
+        }
+        __syncthreads();
+        // pass 3: k1 = tid & 15, j1 = tid >> 4, transform over m2 -> bins tid + 256 j2
+        {
+            const int k1 = tid & 15, j1 = tid >> 4;
+#pragma unroll
+            for (int m2 = 0; m2 < 16; ++m2) v[m2] = sm[k1 * K1S + m2 * 17 + j1];
+            fft16(v);
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float pw = v[k].x * v[k].x + v[k].y * v[k].y;
+            v[k].x = pw;                               // |X|^2 of the last frame stays in v[k].x
+            if (fixed) acc[fixed ? k : 0] += (double) pw;
+            if (moving) p.power[((long long) (p.avg_nb - 1) + f) * n + tid + 256 * k] = pw;
+        }
+    }
+    if (fixed && !emit) {
+        if (g == p.save_sums) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) p.fix_sum[tid + 256 * k] = acc[fixed ? k : 0];
+        }
+        return;
+    }
+    if (moving) return;
+    float* out = p.out + (long long) g * n;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int b = tid + 256 * k;
+        float res;
+        if (fixed) {
+            const double avg = acc[fixed ? k : 0] / (double) p.avg_nb;
+            res = LINEAR ? v[k].x / p.div : p.mult * log2f((float) avg) + p.ofs;     // spectrumvis.cpp:198,213,222
+        } else {
+            res = LINEAR ? v[k].x / p.div : p.mult * log2f(v[k].x) + p.ofs;
+        }
+        if (p.positive_only) { if (b < half) { out[2 * b] = res; out[2 * b + 1] = res; } }
+        else out[b < half ? b + half : b - half] = res;
+    }
+}
+
+typedef void (*spec4096_fn)(const SpecParams);
+template<int MODE> spec4096_fn pick4096_m(bool linear, bool rcp)
+{
+    if (linear) return rcp ? spectrum_kernel_4096<MODE, true, true> : spectrum_kernel_4096<MODE, true, false>;
+    return rcp ? spectrum_kernel_4096<MODE, false, true> : spectrum_kernel_4096<MODE, false, false>;
+}
+spec4096_fn pick4096(int mode, bool linear, bool rcp)
+{
+    if (mode == AVG_FIXED) return pick4096_m<AVG_FIXED>(linear, rcp);
+    if (mode == AVG_MOVING) return pick4096_m<AVG_MOVING>(linear, rcp);
+    return pick4096_m<AVG_NONE>(linear, rcp);
+}
+
 __global__ void __launch_bounds__(SPEC_THREADS) spectrum_kernel(const SpecParams p)
 {
     extern __shared__ float2 spec_X[];
@@ -293,7 +456,16 @@ int spectrum_feed_impl(b200dsp_spectrum* s, const uint32_t* d_in, long long n_sa
             p.power = s->d_power;
         }
         const int threads = SPEC_THREADS;
-        spectrum_kernel<<<(unsigned) ctas, threads, (size_t) n * sizeof(float2), st>>>(p);
+        int ex = 0;
+        const bool rcp = (frexpf(s->scalef, &ex) == 0.5f);                     // power of two: the reciprocal multiply is exact
+        const int eff_mode = fixed ? AVG_FIXED : (moving ? AVG_MOVING : AVG_NONE);
+        if (n == 4096) {
+            const size_t smem4096 = (size_t) 16 * (16 * 17 + 1) * sizeof(float2) + 4096 * sizeof(float);
+            spec4096_fn fn = pick4096(eff_mode, s->linear != 0, rcp);
+            if ((rc = B200_CUDA_CHECK(cudaFuncSetAttribute((const void*) fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem4096)))) return rc;
+            fn<<<(unsigned) ctas, threads, smem4096, st>>>(p);
+        }
+        else           spectrum_kernel<<<(unsigned) ctas, threads, (size_t) n * sizeof(float2), st>>>(p);
         if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
         if (moving) {
             spectrum_moving_kernel<<<dim3((n + 255) / 256, (unsigned) frames), 256, 0, st>>>(p);
