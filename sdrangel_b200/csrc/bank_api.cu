@@ -83,7 +83,8 @@ struct Channel {
     std::vector<float> taps;
     // device
     uint32_t* d_out; long long out_cap; long long out_count;       // channelizer outputs since the last feed start
-    uint32_t* d_hist; float* d_taps; float2* d_fe_out; int* d_sched; int* d_tile; int* d_state; long long fe_cap;
+    uint32_t* d_hist; float* d_taps; float2* d_fe_out; int* d_sched; int* d_tile; int* d_state; long long* d_plan; long long fe_cap;
+    long long A; int lattice, phshift;
 };
 
 const double PI_D = 3.14159265358979323846;
@@ -163,7 +164,8 @@ void free_device(b200dsp_bank* b)
         if (c.d_sched) cudaFree(c.d_sched);
         if (c.d_tile) cudaFree(c.d_tile);
         if (c.d_state) cudaFree(c.d_state);
-        c.d_out = nullptr; c.d_hist = nullptr; c.d_taps = nullptr; c.d_fe_out = nullptr; c.d_sched = nullptr; c.d_tile = nullptr; c.d_state = nullptr;
+        if (c.d_plan) cudaFree(c.d_plan);
+        c.d_out = nullptr; c.d_hist = nullptr; c.d_taps = nullptr; c.d_fe_out = nullptr; c.d_sched = nullptr; c.d_tile = nullptr; c.d_state = nullptr; c.d_plan = nullptr;
         c.out_cap = c.fe_cap = 0;
     }
     b->built = false;
@@ -242,6 +244,7 @@ int build(b200dsp_bank* b)
         const size_t tb = c.taps.size() * sizeof(float);
         if ((rc = B200_CUDA_CHECK(cudaMalloc(&c.d_taps, tb))) || (rc = B200_CUDA_CHECK(cudaMemcpy(c.d_taps, c.taps.data(), tb, cudaMemcpyHostToDevice))) ||
             (rc = B200_CUDA_CHECK(cudaMalloc(&c.d_state, 4 * sizeof(int)))) || (rc = B200_CUDA_CHECK(cudaMemset(c.d_state, 0, 4 * sizeof(int)))) ||
+            (rc = B200_CUDA_CHECK(cudaMalloc(&c.d_plan, 4 * sizeof(long long)))) || (rc = B200_CUDA_CHECK(cudaMemset(c.d_plan, 0, 4 * sizeof(long long)))) ||
             (rc = B200_CUDA_CHECK(cudaMalloc(&c.d_hist, 2 * FE_HIST_WORDS * 4))) || (rc = B200_CUDA_CHECK(cudaMemset(c.d_hist, 0, 2 * FE_HIST_WORDS * 4)))) return rc;
     }
     b->h_fe.resize(b->fe_index.size());
@@ -330,7 +333,7 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
         for (size_t k = 0; k < b->fe_index.size(); ++k) {
             Channel& c = b->chans[b->fe_index[k]];
             FrontendChan& f = b->h_fe[k];
-            f.in = c.d_out; f.hist = c.d_hist; f.taps = c.d_taps; f.out = c.d_fe_out; f.sched = c.d_sched; f.tile_start = c.d_tile; f.state = c.d_state;
+            f.in = c.d_out; f.hist = c.d_hist; f.taps = c.d_taps; f.out = c.d_fe_out; f.sched = c.d_sched; f.tile_start = c.d_tile; f.state = c.d_state; f.plan = c.d_plan; f.A = c.A; f.lattice = c.lattice; f.phshift = c.phshift;
             f.depth = c.S; f.inc = c.inc; f.ntaps = c.ntaps; f.phase_steps = c.phase_steps; f.ratio = c.ratio;
         }
         if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(b->d_leaf, b->h_leaf.data(), nc * sizeof(LeafChan), cudaMemcpyHostToDevice, st)))) return rc;
@@ -341,7 +344,7 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
     if (!b->fe_index.empty() && max_new > 0) {
         if ((rc = B200_CUDA_CHECK(cudaEventRecord(b->ev_begin, st))) || (rc = B200_CUDA_CHECK(cudaStreamWaitEvent(b->side, b->ev_begin, 0)))) return rc;
         const int nfe = (int) b->h_fe.size();
-        frontend_schedule_kernel<<<(nfe + 31) / 32, 32, 0, b->side>>>(b->d_fe, nfe, pi);
+        frontend_schedule_kernel<<<(nfe + 3) / 4, 128, 0, b->side>>>(b->d_fe, nfe, pi);      // one warp per channel
         if ((rc = B200_CUDA_CHECK(cudaGetLastError())) || (rc = B200_CUDA_CHECK(cudaEventRecord(b->ev_sched, b->side)))) return rc;
     }
     const int tc = b->tcur, tn = tc ^ 1;
@@ -453,7 +456,7 @@ int b200dsp_bank_create(b200dsp_bank_t** out, int input_rate_hz)
     b->built = false; b->depth = 0; b->chunk = 3ll << 22; b->tables_dirty = true; b->d_root = nullptr; b->root_cap = 0;
     b->d_leaf = nullptr; b->d_fe = nullptr; b->d_nco = nullptr; b->tcur = 0;
     if ((rc = B200_CUDA_CHECK(cudaSetDevice(b->device))) || (rc = B200_CUDA_CHECK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking))) ||
-        (rc = B200_CUDA_CHECK(cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking))) ||
+        (rc = B200_CUDA_CHECK(cudaStreamCreateWithPriority(&b->side, cudaStreamNonBlocking, -5))) ||
         (rc = B200_CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_begin, cudaEventDisableTiming))) ||
         (rc = B200_CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_sched, cudaEventDisableTiming)))) { delete b; return rc; }
     *out = b;
@@ -494,7 +497,7 @@ int b200dsp_bank_add_channel(b200dsp_bank_t* b, int requested_rate_hz, int cente
     Channel c{};
     c.requested_rate = requested_rate_hz; c.center_offset = center_offset_hz;
     c.fe = false; c.d_out = nullptr; c.out_cap = 0; c.out_count = 0;
-    c.d_hist = nullptr; c.d_taps = nullptr; c.d_fe_out = nullptr; c.d_sched = nullptr; c.d_state = nullptr; c.fe_cap = 0;
+    c.d_hist = nullptr; c.d_taps = nullptr; c.d_fe_out = nullptr; c.d_sched = nullptr; c.d_state = nullptr; c.d_plan = nullptr; c.fe_cap = 0;
     // downchannelizer.cpp:169-171: integer divides first, then int -> Real
     const float ofs = filter_chain((float) (b->input_rate / -2), (float) (b->input_rate / 2),
                                    (float) (center_offset_hz - requested_rate_hz / 2), (float) (center_offset_hz + requested_rate_hz / 2), c.modes);
@@ -536,6 +539,18 @@ int b200dsp_bank_set_frontend(b200dsp_bank_t* b, int chan_id, float nco_freq_hz,
     c.ntaps = np;
     c.inc = (int) ((nco_freq_hz * 4096) / (float) c.out_rate);                 // NCO::setFreq: float arithmetic, truncation (nco.cpp:50)
     c.ratio = (float) c.out_rate / (float) out_rate_hz;                        // nfmdemod.cpp:469-470
+    // closed-form schedule when no sum r + ratio (< ratio + 1) can ever be rounded: ratio * 2^23 on the coarsest ulp lattice
+    c.lattice = 0; c.A = 0; c.phshift = 0;
+    if (c.ratio >= 1.0f && c.ratio < 64.0f && (phase_steps & (phase_steps - 1)) == 0) {
+        const long long A = (long long) ((double) c.ratio * 8388608.0);
+        long long smax = (long long) (((double) c.ratio + 1.0) * 8388608.0);
+        int bl = 0;
+        while (smax) { ++bl; smax >>= 1; }
+        const long long g = 1ll << (bl > 24 ? bl - 24 : 0);
+        int l2 = 0;
+        while ((1 << l2) < phase_steps) ++l2;
+        if ((double) A == (double) c.ratio * 8388608.0 && A % g == 0) { c.lattice = 1; c.A = A; c.phshift = 23 - l2; }
+    }
     if (b->built) { cudaSetDevice(b->device); cudaStreamSynchronize(b->stream); free_device(b); }
     return 0;
 }

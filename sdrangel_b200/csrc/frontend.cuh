@@ -30,6 +30,10 @@ struct FrontendChan {            // one per channel with a front-end, device arr
     int*            sched;       // [cap] packed (idx << 8 | phase) of this pass's outputs
     int*            tile_start;  // [cap / FE_TILE + 2] first output of each input tile (written by the schedule kernel)
     int*            state;       // [4]: unused, float distance remain (bits), outputs of the last pass, outputs of this feed
+    long long*      plan;        // [4] written by the schedule kernel: k0 (outputs listed in sched), i0, D, closed-form output count
+    long long       A;           // ratio * 2^23 (exact integer)
+    int             lattice;     // 1: every sum of the distance recurrence is exactly representable => closed-form schedule
+    int             phshift;     // 23 - log2(phase_steps)
     int             depth;       // S: selects the per-depth pass counts
     int             inc;         // NCO phase increment
     int             ntaps, phase_steps;
@@ -45,48 +49,103 @@ struct PassInfo {
     int       parity;            // which half of the ping-pong history is current
 };
 
-// Schedule: one thread per channel replays the reference's float32 distance recurrence, one iteration per OUTPUT:
-// after an emission d = fl(r + ratio); every further input subtracts 1.0f, which is exact in float32, until d < 1, so the
-// next emission comes j = max(1, floor(d)) inputs later with r = d - j (exact) and phase = max(0, floor(r * steps)).
-// Bit-identical to the per-input loop of Interpolator::decimate (interpolator.h:23-36) + nfmdemod.cpp:315.
-// Depends only on counts, not on samples: runs on a side stream concurrently with the tree kernels.
-// The loop-carried chain is floor -> max -> sub -> add (the integer conversions are off the chain).
+// Schedule.  The reference's float32 recurrence (interpolator.h:23-36 + nfmdemod.cpp:315): per input d -= 1; if d < 1 emit
+// at phase max(0, floor(d * steps)) and d += ratio.  The -1 steps are exact in float32, so one iteration per OUTPUT is
+// bit-identical: j = max(1, floor d) inputs later, r = d - j, then d = fl(r + ratio).
+//   * General ratios: one thread per channel replays that loop sequentially (exact, but a serial chain per channel).
+//   * "Lattice" ratios: when ratio * 2^23 is a multiple of the coarsest ulp any sum r + ratio can have, every sum is exactly
+//     representable, fl() never rounds, and the recurrence has the closed form  E_k = D + k*A  (units of 2^-23):
+//     output k sits at input i0 + (E_k >> 23) - 1 with r = E_k & (2^23-1).  The thread then only runs the loop while d < 1
+//     (stream start) and leaves the rest to frontend_kernel, which evaluates E_k per output: no serial chain at all
+//     (1.25 = 60 kS/s -> 48 kS/s, the 1024-channel plan, is such a ratio).
+// Depends only on counts, not on samples: runs on a high-priority side stream concurrently with the tree kernels.
+// One WARP per channel: lane 0 runs the serial recurrence (the other lanes idle), then all lanes fill the tile table.
 __global__ void frontend_schedule_kernel(const FrontendChan* __restrict__ chans, int n_chans, const PassInfo pi)
 {
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (ch >= n_chans) return;
     const FrontendChan c = chans[ch];
     const int m = pi.n_new[c.depth];
-    float d = __int_as_float(c.state[1]);      // distance remain before the next input
-    const float steps = (float) c.phase_steps, ratio = c.ratio;
-    int i = -1, n = 0, tile = 0;               // i = index of the last consumed input
     int* __restrict__ sched = c.sched;
     int* __restrict__ tstart = c.tile_start;   // tstart[t] = first output whose input index is >= t * FE_TILE
-    // one emission: consumes j = max(1, floor(d)) inputs
-#define FE_EMIT()                                                                              \
-    {                                                                                          \
-        const float fj = fmaxf(floorf(d), 1.0f);                                               \
-        i += (int) fj;                                                                         \
-        const float r = __fsub_rn(d, fj);                                                      \
-        int ph = (int) floorf(__fmul_rn(r, steps));                                            \
-        if (ph < 0) ph = 0;                                                                    \
-        while (tile * FE_TILE <= i) tstart[tile++] = n;                                        \
-        sched[n++] = (int) (((unsigned) i << 8) | (unsigned) ph);   /* i < 2^24, ph < 256 */   \
-        d = __fadd_rn(r, ratio);                                                               \
-    }
-    for (;;) {
-        const int j = (int) fmaxf(floorf(d), 1.0f);
-        if (i + j >= m) break;
-        FE_EMIT();
-    }
-#undef FE_EMIT
     const int ntiles = (m + FE_TILE - 1) / FE_TILE;
-    while (tile <= ntiles) tstart[tile++] = n;
-    d = __fadd_rn(d, -(float) (m - 1 - i));    // the remaining inputs of this pass each subtract 1.0f (exact)
-    const int base = pi.first_pass ? 0 : c.state[3];
-    c.state[1] = __float_as_int(d);
-    c.state[2] = n;
-    c.state[3] = base + n;
+    int n = 0;
+    long long ncf = 0, i0 = 0, D = 0;
+    if (lane == 0) {
+        float d = __int_as_float(c.state[1]);      // distance remain before the next input
+        const float steps = (float) c.phase_steps, ratio = c.ratio;
+        int i = -1;                                // index of the last consumed input
+        // one emission: consumes j = max(1, floor(d)) inputs.  The loop-carried chain is floor -> max -> sub -> add.
+#define FE_EMIT()                                                                              \
+        {                                                                                      \
+            const float fj = fmaxf(floorf(d), 1.0f);                                           \
+            i += (int) fj;                                                                     \
+            const float r = __fsub_rn(d, fj);                                                  \
+            int ph = (int) floorf(__fmul_rn(r, steps));                                        \
+            ph = ph < 0 ? 0 : ph;                                                              \
+            sched[n++] = (int) (((unsigned) i << 8) | (unsigned) ph);   /* i < 2^24, ph < 256 */ \
+            d = __fadd_rn(r, ratio);                                                           \
+        }
+        if (!c.lattice) {
+            // an emission consumes at most max(1, floor(d)) <= max(d0, ratio + 1) inputs: 8 at a time while that is safe
+            const int per8 = 8 * ((int) fmaxf(ratio + 1.0f, d) + 1);
+            while (m - 1 - i > per8 && d < ratio + 1.0f) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) FE_EMIT();
+            }
+        }
+        for (;;) {
+            if (c.lattice && d >= 1.0f) break;     // the closed form takes over
+            const int j = (int) fmaxf(floorf(d), 1.0f);
+            if (i + j >= m) break;
+            FE_EMIT();
+        }
+#undef FE_EMIT
+        if (c.lattice && d >= 1.0f) {
+            // closed form from here: i0 = inputs consumed so far, D = d in units of 2^-23 (exact: d is on the lattice)
+            const long long A = c.A;
+            i0 = i + 1; D = (long long) (d * 8388608.0f);
+            const long long lim = ((long long) (m - i0) + 1) << 23;            // E_k < lim  <=>  input index < m
+            ncf = (lim - 1 - D >= 0) ? (lim - 1 - D) / A + 1 : 0;
+            long long Dend;
+            if (ncf > 0) {
+                const long long El = D + (ncf - 1) * A;
+                const long long idx_last = i0 + (El >> 23) - 1;
+                Dend = (El & 0x7fffffll) + A - (((long long) m - 1 - idx_last) << 23);
+            } else {
+                Dend = D - (((long long) m - i0) << 23);
+            }
+            d = (float) Dend * (1.0f / 8388608.0f);                            // exact: a value the float recurrence would hold
+        } else {
+            d = __fadd_rn(d, -(float) (m - 1 - i));    // the remaining inputs of this pass each subtract 1.0f (exact)
+        }
+        c.plan[0] = n; c.plan[1] = i0; c.plan[2] = D; c.plan[3] = ncf;
+        const int total = n + (int) ncf;
+        const int base = pi.first_pass ? 0 : c.state[3];
+        c.state[1] = __float_as_int(d);
+        c.state[2] = total;
+        c.state[3] = base + total;
+    }
+    __syncwarp();
+    n = __shfl_sync(0xffffffffu, n, 0);
+    ncf = __shfl_sync(0xffffffffu, ncf, 0);
+    i0 = __shfl_sync(0xffffffffu, i0, 0);
+    D = __shfl_sync(0xffffffffu, D, 0);
+    // tile table, one tile per lane at a time: listed outputs by binary search, closed-form outputs by division
+    for (int t = lane; t <= ntiles; t += 32) {
+        const int T = t * FE_TILE;
+        int lo = 0, hi = n;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int) ((unsigned) sched[mid] >> 8) < T) lo = mid + 1; else hi = mid; }
+        int o = lo;
+        if (lo == n && ncf > 0) {
+            const long long need = (((long long) T - i0 + 1) << 23) - D;
+            long long k = need <= 0 ? 0 : (need + c.A - 1) / c.A;
+            if (k > ncf) k = ncf;
+            o = n + (int) k;
+        }
+        tstart[t] = o;
+    }
 }
 
 // grid = (tiles, channels).  A CTA mixes FE_TILE (+ ntaps-1 halo) channel samples with the table NCO into shared memory
@@ -121,9 +180,18 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(const FrontendChan
     // outputs of this pass whose input index falls in [t0, t1)
     const int out_base = c.state[3] - c.state[2];
     const int o0 = c.tile_start[blockIdx.x], o1 = c.tile_start[blockIdx.x + 1];
+    const int k0 = (int) c.plan[0];
+    const long long pi0 = c.plan[1], D0 = c.plan[2];
     for (int o = o0 + tid; o < o1; o += FE_THREADS) {
-        const unsigned s = (unsigned) c.sched[o];
-        const int idx = (int) (s >> 8), ph = (int) (s & 0xffu);
+        int idx, ph;
+        if (o >= k0) {                                 // closed-form region (lattice ratios)
+            const long long E = D0 + (long long) (o - k0) * c.A;
+            idx = (int) (pi0 + (E >> 23) - 1);
+            ph = (int) ((E & 0x7fffffll) >> c.phshift);
+        } else {
+            const unsigned s = (unsigned) c.sched[o];
+            idx = (int) (s >> 8); ph = (int) (s & 0xffu);
+        }
         const float* t = taps + ph * nts;
         const float2* zz = z + (idx - t0 + FE_MAX_TAPS);
         float ra = 0.0f, ia = 0.0f;

@@ -125,32 +125,25 @@ __device__ __forceinline__ void hb48_load_windows(const int32_t* __restrict__ X,
     }
 }
 
-// pack (re, im) of this lane's outputs with the partner lane and store 6 IQ words at out[k0 ...]
+// Lane (comp 0, j) holds re of outputs 12j..12j+11, lane (comp 1, j) holds im.  One shuffle per output hands the im values
+// to the comp-0 lanes, which pack (PRMT) and store all 12 IQ words (3 x 128-bit, 768 contiguous bytes per warp).
 __device__ __forceinline__ void hb48_store_child(uint32_t* out, const int32_t (&y)[HB_R], int comp, int j, int kbase, int wo, int n_out)
 {
-    int32_t mine[6], other[6];
+    uint32_t wds[HB_R];
 #pragma unroll
-    for (int t = 0; t < 6; ++t) {
-        const int32_t a = y[t], b = y[6 + t];
-        const int32_t send = comp ? a : b;
-        mine[t] = comp ? b : a;
-        other[t] = __shfl_xor_sync(0xffffffffu, send, 16);
+    for (int t = 0; t < HB_R; ++t) {
+        const int32_t im = __shfl_down_sync(0xffffffffu, y[t], 16);
+        asm("prmt.b32 %0, %1, %2, 0x5410;" : "=r"(wds[t]) : "r"(y[t]), "r"(im));      // (re & 0xffff) | (im << 16): int16 wrap = the packing
     }
-    const int k0 = kbase + HB_R * j + 6 * comp;
-    if (k0 >= n_out) return;
-    uint32_t wds[6];
-#pragma unroll
-    for (int t = 0; t < 6; ++t) {
-        const int32_t re = comp ? other[t] : mine[t], im = comp ? mine[t] : other[t];
-        wds[t] = ((uint32_t) re & 0xffffu) | ((uint32_t) im << 16);
-    }
+    const int k0 = kbase + HB_R * j;
+    if (comp != 0 || k0 >= n_out) return;
     uint32_t* o = out + wo + k0;
-    if (k0 + 6 <= n_out && wo == 0) {
+    if (k0 + HB_R <= n_out && wo == 0) {
 #pragma unroll
-        for (int t = 0; t < 3; ++t) *reinterpret_cast<uint2*>(o + 2 * t) = make_uint2(wds[2 * t], wds[2 * t + 1]);
+        for (int t = 0; t < 3; ++t) *reinterpret_cast<uint4*>(o + 4 * t) = make_uint4(wds[4 * t], wds[4 * t + 1], wds[4 * t + 2], wds[4 * t + 3]);
     } else {
 #pragma unroll
-        for (int t = 0; t < 6; ++t) if (k0 + t < n_out) o[t] = wds[t];
+        for (int t = 0; t < HB_R; ++t) if (k0 + t < n_out) o[t] = wds[t];
     }
 }
 
@@ -158,6 +151,16 @@ __device__ __forceinline__ uint32_t has_m32768(uint32_t v)
 {
     const uint32_t t = v ^ 0x80008000u;
     return (t - 0x00010001u) & ~t & 0x80008000u;
+}
+
+// rare path (a -32768 in the batch): explicit rotation with int16 wrap, then the unrotated item.  Not inlined so that its
+// 52 extra live registers do not inflate the common path.
+__device__ __noinline__ void hb48_slow_child(const int32_t* X, int comp, int j, int sigma, int flip, const IntOpaque& opq, int32_t (&y)[HB_R])
+{
+    int32_t wv[36], cv[16], co[16], wr[36], cr[16];
+    hb48_load_windows(X, comp, j, true, wv, cv, co);
+    hb48_rotate_exact(wv, co, comp, sigma, flip, wr, cr);
+    hb48_item<false, false>(wr, cr, 0, opq, y);
 }
 
 __global__ void __launch_bounds__(256, 2) hb48_level_kernel(const LevelParams p)
@@ -248,7 +251,7 @@ __global__ void __launch_bounds__(256, 2) hb48_level_kernel(const LevelParams p)
             hb48_store_child(p.out_base + (long long) fam.y * p.out_stride, y, comp, j, kbase, p.wo, n_out);
         }
 #pragma unroll
-        for (int m = 1; m <= 2; ++m) {
+        for (int m = 1; m <= 2; ++m) {          // lower-half (+j) and upper-half (-j) children
             const int child = (m == 1) ? fam.z : fam.w;
             if (child < 0) continue;
             const int sigma = (m == 1) ? 1 : -1;
@@ -256,9 +259,7 @@ __global__ void __launch_bounds__(256, 2) hb48_level_kernel(const LevelParams p)
                 if (p.flip) hb48_item<true, true>(wv, co, comp ? sigma : -sigma, opq, y);
                 else        hb48_item<true, false>(wv, co, comp ? sigma : -sigma, opq, y);
             } else {
-                int32_t wr[36], cr[16];
-                hb48_rotate_exact(wv, co, comp, sigma, p.flip, wr, cr);
-                hb48_item<false, false>(wr, cr, 0, opq, y);
+                hb48_slow_child(X, comp, j, sigma, p.flip, opq, y);
             }
             hb48_store_child(p.out_base + (long long) child * p.out_stride, y, comp, j, kbase, p.wo, n_out);
         }
