@@ -456,7 +456,7 @@ def bench_bank(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=T
     def step():
         i = state["i"]
         cur = i % len(bufs)
-        if c.world > 1:
+        if c.world > 1 and not os.environ.get("B200_BENCH_NO_BCAST"):      # (developer switch: isolate the compute time)
             if i == 0 or cur not in pending:
                 pending[cur] = dist.broadcast(bviews[cur], src=0, async_op=True)
             pending.pop(cur).wait()                # stream-level wait: the compute stream waits for this step's baseband

@@ -367,8 +367,13 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
         p.opq_zero = 0; p.opq_one = 1; p.opq_mone = -1;
         {
             const int nb = (p.n_in + HB_IN - 1) / HB_IN;
+            // Many short slices (8 batches = 3072 samples each, 64 samples of history re-read per slice): the grid is several
+            // waves deep, so losing SMs to a concurrent kernel (the NCCL broadcast of the next step) costs a few percent, not
+            // a whole extra wave.  Small levels still get at least one slice per resident warp slot.
             long long target = (long long) b->sm_count * 16;
             long long slices = (target + n_fam - 1) / n_fam;
+            const long long by8 = (nb + 7) / 8;
+            if (slices < by8) slices = by8;
             if (slices > nb) slices = nb;
             if (slices < 1) slices = 1;
             const int bps = (int) ((nb + slices - 1) / slices);
@@ -395,7 +400,7 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
     }
     if (!b->fe_index.empty() && max_new > 0) {
         size_t smem = 0;
-        for (int ci : b->fe_index) { const Channel& cc = b->chans[ci]; const size_t s2 = (((size_t) (cc.ntaps | 1) * cc.phase_steps + 3) & ~(size_t) 3) * sizeof(float); if (s2 > smem) smem = s2; }
+        for (int ci : b->fe_index) { const Channel& cc = b->chans[ci]; const size_t s2 = (((size_t) ((cc.ntaps + 2 * FE_PAD) | 1) * cc.phase_steps + 3) & ~(size_t) 3) * sizeof(float); if (s2 > smem) smem = s2; }
         smem += (size_t) (FE_MAX_TAPS + FE_TILE) * sizeof(float2);
         if ((rc = B200_CUDA_CHECK(cudaStreamWaitEvent(st, b->ev_sched, 0)))) return rc;
         frontend_kernel<<<dim3((unsigned) ((max_new + FE_TILE - 1) / FE_TILE), (unsigned) b->h_fe.size()), FE_THREADS, smem, st>>>(b->d_fe, b->d_nco, pi);

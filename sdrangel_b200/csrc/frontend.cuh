@@ -20,6 +20,8 @@ namespace b200dsp {
 constexpr int FE_MAX_TAPS = 128;          // taps per phase supported by the kernel's history area (reference default: 72)
 constexpr int FE_TILE = 1024;             // channel samples per CTA tile
 constexpr int FE_THREADS = 128;
+constexpr int FE_NOUT = 4;                // consecutive outputs per thread (they share the shared-memory reads of z)
+constexpr int FE_PAD = 16;                // zero taps on both sides of every phase row: out-of-range tap indices contribute 0
 constexpr int FE_HIST_WORDS = FE_MAX_TAPS + 4;   // per ping-pong half: FE_MAX_TAPS samples + the NCO phase
 
 struct FrontendChan {            // one per channel with a front-end, device array (static between reallocations)
@@ -160,11 +162,14 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(const FrontendChan
     if (t0 >= m && !(blockIdx.x == 0)) return;
     c.in += pi.out_count[c.depth];
     const uint32_t* hin = c.hist + pi.parity * FE_HIST_WORDS;
-    const int nt = c.ntaps, nts = c.ntaps | 1;            // odd row stride: the 16 phases start in distinct banks
+    const int nt = c.ntaps, nts = (c.ntaps + 2 * FE_PAD) | 1;   // zero-padded rows, odd stride: the phases start in distinct banks
     const int ntp = nts * c.phase_steps;
     float* taps = fe_smem;
     float2* z = reinterpret_cast<float2*>(fe_smem + ((ntp + 3) & ~3));
-    for (int i = tid; i < nt * c.phase_steps; i += FE_THREADS) taps[(i / nt) * nts + (i % nt)] = c.taps[i];
+    for (int i = tid; i < ntp; i += FE_THREADS) {
+        const int ph = i / nts, k = i - ph * nts - FE_PAD;
+        taps[i] = (k >= 0 && k < nt) ? c.taps[ph * nt + k] : 0.0f;
+    }
     const unsigned phase0 = hin[FE_MAX_TAPS];
     const int t1 = (t0 + FE_TILE < m) ? t0 + FE_TILE : m;
     // z[k] holds mixed sample (t0 - FE_MAX_TAPS + k), k in [0, FE_MAX_TAPS + t1 - t0)
@@ -182,26 +187,59 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(const FrontendChan
     const int o0 = c.tile_start[blockIdx.x], o1 = c.tile_start[blockIdx.x + 1];
     const int k0 = (int) c.plan[0];
     const long long pi0 = c.plan[1], D0 = c.plan[2];
-    for (int o = o0 + tid; o < o1; o += FE_THREADS) {
-        int idx, ph;
-        if (o >= k0) {                                 // closed-form region (lattice ratios)
-            const long long E = D0 + (long long) (o - k0) * c.A;
-            idx = (int) (pi0 + (E >> 23) - 1);
-            ph = (int) ((E & 0x7fffffll) >> c.phshift);
+    // FE_NOUT consecutive outputs per thread: one pass over the z samples they share, newest first
+    for (int ob = o0 + FE_NOUT * tid; ob < o1; ob += FE_NOUT * FE_THREADS) {
+        int idx[FE_NOUT];
+        const float* trow[FE_NOUT];
+#pragma unroll
+        for (int q = 0; q < FE_NOUT; ++q) {
+            const int o = (ob + q < o1) ? ob + q : o1 - 1;        // clamp: duplicates are computed but not stored
+            int ph;
+            if (o >= k0) {                                 // closed-form region (lattice ratios)
+                const long long E = D0 + (long long) (o - k0) * c.A;
+                idx[q] = (int) (pi0 + (E >> 23) - 1);
+                ph = (int) ((E & 0x7fffffll) >> c.phshift);
+            } else {
+                const unsigned s = (unsigned) c.sched[o];
+                idx[q] = (int) (s >> 8); ph = (int) (s & 0xffu);
+            }
+            trow[q] = taps + ph * nts + FE_PAD;
+        }
+        float ra[FE_NOUT], ia[FE_NOUT];
+#pragma unroll
+        for (int q = 0; q < FE_NOUT; ++q) { ra[q] = 0.0f; ia[q] = 0.0f; }
+        const int e_hi = idx[FE_NOUT - 1], e_lo = idx[0] - (nt - 1);
+        if (e_hi - idx[0] <= FE_PAD) {
+            // tap index of output q at z sample e is idx[q] - e; outside [0, nt) it lands in the zero padding
+            const float* tq[FE_NOUT];
+#pragma unroll
+            for (int q = 0; q < FE_NOUT; ++q) tq[q] = trow[q] + (idx[q] - e_hi);
+            const float2* zz = z + (e_hi - t0 + FE_MAX_TAPS);
+            const int cnt = e_hi - e_lo + 1;
+#pragma unroll 4
+            for (int k = 0; k < cnt; ++k) {
+                const float2 v = zz[-k];
+#pragma unroll
+                for (int q = 0; q < FE_NOUT; ++q) {
+                    const float t = tq[q][k];
+                    ra[q] = fmaf(t, v.x, ra[q]);
+                    ia[q] = fmaf(t, v.y, ia[q]);
+                }
+            }
         } else {
-            const unsigned s = (unsigned) c.sched[o];
-            idx = (int) (s >> 8); ph = (int) (s & 0xffu);
+            // widely spaced outputs (large decimation ratio): independent dot products
+#pragma unroll
+            for (int q = 0; q < FE_NOUT; ++q) {
+                const float2* zz = z + (idx[q] - t0 + FE_MAX_TAPS);
+                for (int k = 0; k < nt; ++k) {
+                    const float2 v = zz[-k];
+                    ra[q] = fmaf(trow[q][k], v.x, ra[q]);
+                    ia[q] = fmaf(trow[q][k], v.y, ia[q]);
+                }
+            }
         }
-        const float* t = taps + ph * nts;
-        const float2* zz = z + (idx - t0 + FE_MAX_TAPS);
-        float ra = 0.0f, ia = 0.0f;
-#pragma unroll 8
-        for (int k = 0; k < nt; ++k) {
-            const float2 v = zz[-k];
-            ra = fmaf(t[k], v.x, ra);
-            ia = fmaf(t[k], v.y, ia);
-        }
-        c.out[out_base + o] = make_float2(ra, ia);
+#pragma unroll
+        for (int q = 0; q < FE_NOUT; ++q) if (ob + q < o1) c.out[out_base + ob + q] = make_float2(ra[q], ia[q]);
     }
     // the CTA of the last tile carries the newest FE_MAX_TAPS channel samples and the NCO phase to the next pass
     if (t1 == m && (t0 < m || blockIdx.x == 0)) {
