@@ -108,6 +108,24 @@ cascade_fn pick_kernel(int in_fmt, int out_fmt, bool div4, bool hasrot, bool exa
     return exact ? kfn<float, IN_I16F, OUT_F32, false, true>() : kfn<float, IN_I16F, OUT_F32, false, false>();
 }
 
+// kernels of a split cascade (stages [0,3) then [3,L)): the hand-off is raw T pairs in an HBM scratch buffer
+cascade_fn pick_split_a(int in_fmt, int out_fmt, bool hasrot, bool exact, bool pre)
+{
+    if (in_fmt == B200DSP_FMT_I16 && out_fmt == B200DSP_FMT_I16) {
+        if (pre) return hasrot ? kfn<int32_t, IN_I16_PRE, OUT_I32, true, false>() : kfn<int32_t, IN_I16_PRE, OUT_I32, false, false>();
+        return hasrot ? kfn<int32_t, IN_I16, OUT_I32, true, false>() : kfn<int32_t, IN_I16, OUT_I32, false, false>();
+    }
+    if (in_fmt == B200DSP_FMT_F32) return exact ? kfn<float, IN_F32, OUT_F32, false, true>() : kfn<float, IN_F32, OUT_F32, false, false>();
+    return exact ? kfn<float, IN_I16F, OUT_F32, false, true>() : kfn<float, IN_I16F, OUT_F32, false, false>();
+}
+cascade_fn pick_split_b(int in_fmt, int out_fmt, bool hasrot, bool exact)
+{
+    if (in_fmt == B200DSP_FMT_I16 && out_fmt == B200DSP_FMT_I16)
+        return hasrot ? kfn<int32_t, IN_I32, OUT_I16_SHIFT, true, false>() : kfn<int32_t, IN_I32, OUT_I16_SHIFT, false, false>();
+    if (out_fmt == B200DSP_FMT_I16) return exact ? kfn<float, IN_F32, OUT_I16_SCALE, false, true>() : kfn<float, IN_F32, OUT_I16_SCALE, false, false>();
+    return exact ? kfn<float, IN_F32, OUT_F32, false, true>() : kfn<float, IN_F32, OUT_F32, false, false>();
+}
+
 struct LaunchGeom { int wpb; int warps_per_sm; };
 
 } // namespace
@@ -122,6 +140,7 @@ struct b200dsp_decim {
     // device staging for the host-pointer path (double-buffered input)
     void* d_in[2]; size_t d_in_cap;
     void* d_out;   size_t d_out_cap;
+    void* d_mid;   size_t d_mid_cap;      // hand-off buffer of split cascades (log2 >= 5): stage-3 outputs
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -234,6 +253,41 @@ LaunchGeom pick_geom(cascade_fn fn, int L)
     return best;
 }
 
+// one kernel over stages [base, base + L) of the plan; `first`/`final` = this segment reads the call's input / writes its output
+int launch_segment(b200dsp_decim* h, cascade_fn fn, const Plan& pl, int base, int L, const void* d_in, void* d_out, long long n0,
+                   bool first, bool final, cudaStream_t st)
+{
+    const LaunchGeom g = pick_geom(fn, L);
+    CascadeParams p;
+    memset(&p, 0, sizeof(p));
+    p.in = d_in; p.out = d_out;
+    const size_t esz = 4;
+    p.state_in = (const char*) h->d_state[h->cur] + (size_t) base * 128 * esz;
+    p.state_out = (char*) h->d_state[h->cur ^ 1] + (size_t) base * 128 * esz;
+    p.n0 = n0; p.n_out = n0 >> L; p.L = L;
+    p.pre = first ? pl.pre : 0; p.post = final ? pl.post : 0;
+    p.out_scale = final ? pl.out_scale : 1.0f; p.div4 = pl.div4_kind;
+    for (int s = 1; s <= L && s + base < 8; ++s) p.rot[s] = pl.rot[s + base];
+    p.opq_zero = 0; p.opq_one = 1; p.opq_mone = -1;
+    p.copy_end = final ? (HB_MAX_STAGES - base) * 128 : L * 128;
+    const long long U = (long long) HB_IN << (L - 1);
+    const long long sp_total = (n0 + U - 1) / U;
+    const long long max_warps = (long long) h->sm_count * g.warps_per_sm;
+    long long slice_sp = (sp_total + max_warps - 1) / max_warps;
+    if (slice_sp < 1) slice_sp = 1;
+    const long long n_slices = (sp_total + slice_sp - 1) / slice_sp;
+    p.slice_sp = (int) slice_sp; p.n_slices = (int) n_slices;
+    int wpb = g.wpb;
+    if (n_slices < (long long) h->sm_count * wpb) {       // few slices: spread them over the SMs
+        wpb = (int) ((n_slices + h->sm_count - 1) / h->sm_count);
+        if (wpb < 1) wpb = 1;
+    }
+    const unsigned grid = (unsigned) ((n_slices + wpb - 1) / wpb);
+    const size_t smem = (size_t) wpb * L * HB_STAGE_BYTES;
+    fn<<<grid, wpb * 32, smem, st>>>(p);
+    return B200_CUDA_CHECK(cudaGetLastError());
+}
+
 int launch_plan(b200dsp_decim* h, const Plan& pl, const void* d_in, void* d_out, cudaStream_t st)
 {
     if (pl.n_out <= 0) return 0;
@@ -252,32 +306,27 @@ int launch_plan(b200dsp_decim* h, const Plan& pl, const void* d_in, void* d_out,
         else ew_float_kernel<int16_t, OUT_F32><<<(unsigned) blocks, threads, 0, st>>>(ep);
         return B200_CUDA_CHECK(cudaGetLastError());
     }
-    cascade_fn fn = pick_kernel(h->in_fmt, h->out_fmt, pl.div4, pl.hasrot, h->exact != 0, pl.pre != 0);
-    const LaunchGeom g = pick_geom(fn, pl.L);
-    CascadeParams p;
-    memset(&p, 0, sizeof(p));
-    p.in = d_in; p.out = d_out;
-    p.state_in = h->d_state[h->cur]; p.state_out = h->d_state[h->cur ^ 1];
-    p.n0 = pl.n0; p.n_out = pl.n_out; p.L = pl.L;
-    p.pre = pl.pre; p.post = pl.post; p.out_scale = pl.out_scale; p.div4 = pl.div4_kind;
-    memcpy(p.rot, pl.rot, sizeof(p.rot));
-    p.opq_zero = 0; p.opq_one = 1; p.opq_mone = -1;
-    const long long U = (long long) HB_IN << (pl.L - 1);
-    const long long sp_total = (pl.n0 + U - 1) / U;
-    const long long max_warps = (long long) h->sm_count * g.warps_per_sm;
-    long long slice_sp = (sp_total + max_warps - 1) / max_warps;
-    if (slice_sp < 1) slice_sp = 1;
-    const long long n_slices = (sp_total + slice_sp - 1) / slice_sp;
-    p.slice_sp = (int) slice_sp; p.n_slices = (int) n_slices;
-    int wpb = g.wpb;
-    if (n_slices < (long long) h->sm_count * wpb) {       // few slices: spread them over the SMs
-        wpb = (int) ((n_slices + h->sm_count - 1) / h->sm_count);
-        if (wpb < 1) wpb = 1;
+    // Cascades of 5 or 6 stages are run as stages [0,3) + [3,L): per-warp shared memory drops from L*3.5 KB to <= 10.5 KB, so
+    // 16+ warps stay resident per SM instead of 10-12; the hand-off costs 2 x 8 B per 8 input samples of HBM traffic.
+    const bool split = (pl.L >= 5) && !pl.div4;
+    int rc;
+    if (!split) {
+        rc = launch_segment(h, pick_kernel(h->in_fmt, h->out_fmt, pl.div4, pl.hasrot, h->exact != 0, pl.pre != 0), pl, 0, pl.L, d_in, d_out,
+                            pl.n0, true, true, st);
+    } else {
+        const long long n_mid = pl.n0 >> 3;
+        const size_t need = (size_t) n_mid * 8;
+        if (h->d_mid_cap < need) {
+            if ((rc = B200_CUDA_CHECK(cudaStreamSynchronize(st)))) return rc;
+            if (h->d_mid) cudaFree(h->d_mid);
+            h->d_mid = nullptr; h->d_mid_cap = 0;
+            if ((rc = B200_CUDA_CHECK(cudaMalloc(&h->d_mid, need)))) return rc;
+            h->d_mid_cap = need;
+        }
+        rc = launch_segment(h, pick_split_a(h->in_fmt, h->out_fmt, pl.hasrot, h->exact != 0, pl.pre != 0), pl, 0, 3, d_in, h->d_mid, pl.n0, true, false, st);
+        if (rc == 0)
+            rc = launch_segment(h, pick_split_b(h->in_fmt, h->out_fmt, pl.hasrot, h->exact != 0), pl, 3, pl.L - 3, h->d_mid, d_out, n_mid, false, true, st);
     }
-    const unsigned grid = (unsigned) ((n_slices + wpb - 1) / wpb);
-    const size_t smem = (size_t) wpb * pl.L * HB_STAGE_BYTES;
-    fn<<<grid, wpb * 32, smem, st>>>(p);
-    int rc = B200_CUDA_CHECK(cudaGetLastError());
     if (rc == 0) h->cur ^= 1;
     return rc;
 }
@@ -341,6 +390,7 @@ int b200dsp_decim_destroy(b200dsp_decim_t* h)
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
     }
     if (h->d_out) cudaFree(h->d_out);
+    if (h->d_mid) cudaFree(h->d_mid);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     delete h;

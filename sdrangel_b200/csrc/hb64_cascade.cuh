@@ -45,9 +45,9 @@ constexpr int HB_STAGE_BYTES = HB_STAGE_WORDS * 4;
 constexpr int HB_MAX_STAGES  = 6;
 constexpr int HB_STATE_ELEMS = 64;            // per stage, per component (canonical carried state)
 
-enum : int { IN_I16 = 0, IN_F32 = 1, IN_I16F = 2, IN_F32_DIV4 = 3, IN_I16F_DIV4 = 4, IN_I16_PRE = 5 };
+enum : int { IN_I16 = 0, IN_F32 = 1, IN_I16F = 2, IN_F32_DIV4 = 3, IN_I16F_DIV4 = 4, IN_I16_PRE = 5, IN_I32 = 6 };
 enum : int { DIV4_INF = 0, DIV4_SUP = 1, DIV4_SUP16 = 2 };   // /4 front-end flavours (decimatorsfi.cpp:95-367)
-enum : int { OUT_I16_SHIFT = 0, OUT_I16_SCALE = 1, OUT_F32 = 2 };
+enum : int { OUT_I16_SHIFT = 0, OUT_I16_SCALE = 1, OUT_F32 = 2, OUT_I32 = 3 };
 
 struct CascadeParams {
     const void* in;          // interleaved IQ, int16 or float
@@ -63,6 +63,7 @@ struct CascadeParams {
     float       out_scale;   // float output scale (IF: 1/2^(bits-1))
     int         div4;        // DIV4_* flavour for the /4 front-end loaders
     int         opq_zero, opq_one, opq_mone;   // 0, 1, -1 passed as data so ptxas keeps the 3-input / multiply forms
+    int         copy_end;    // state elements [L*128, copy_end) are carried over unchanged by the last slice (stages this call does not use)
     signed char rot[8];      // rot[s], s = 1..L : 0 centred, +1 Inf/LowerHalf (+j), -1 Sup/UpperHalf (-j)
 };
 
@@ -338,6 +339,23 @@ template<> struct Loader<IN_F32, float> {
     }
 };
 
+// int32 IQ pairs -> int32: second half of a split integer cascade (the first half's raw stage outputs)
+template<> struct Loader<IN_I32, int32_t> {
+    static constexpr int NV = 6;
+    __device__ static __forceinline__ void fetch(const CascadeParams& p, long long pos, int lane, int4 (&v)[NV])
+    {
+        Loader<IN_F32, float>::fetch(p, pos, lane, v);
+    }
+    __device__ static __forceinline__ void store(const CascadeParams&, int32_t* X0, int lane, const int4 (&v)[NV])
+    {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            int32_t* a = X0 + HB_HIST + (lane + 32 * q);
+            a[0] = v[q].x; a[2 * HB_ARR] = v[q].y; a[HB_ARR] = v[q].z; a[3 * HB_ARR] = v[q].w;
+        }
+    }
+};
+
 // int16 IQ -> float (DecimatorsIF *_cen: raw integer values enter the cascade, the 2^-k scale is applied at the
 // output, which is exact; decimatorsif.h:142-163)
 template<> struct Loader<IN_I16F, float> {
@@ -442,6 +460,10 @@ template<> struct Epilogue<OUT_I16_SHIFT, int32_t> {        // Decimators<>: (qi
 template<> struct Epilogue<OUT_I16_SCALE, float> {          // DecimatorsFI: (FixReal)(v * 32768), decimatorsfi.cpp:1168-1169
     static constexpr int WORDS = 1;
     __device__ static __forceinline__ int32_t conv(const CascadeParams&, float v) { return cvt_trunc_x86(v * 32768.0f); }
+};
+template<> struct Epilogue<OUT_I32, int32_t> {              // first half of a split integer cascade: raw stage outputs
+    static constexpr int WORDS = 2;
+    __device__ static __forceinline__ int32_t conv(const CascadeParams&, int32_t v) { return v; }
 };
 template<> struct Epilogue<OUT_F32, float> {                // DecimatorsFF (scale 1) / DecimatorsIF (scale 1/2^(bits-1))
     static constexpr int WORDS = 2;
@@ -615,7 +637,7 @@ __global__ void __launch_bounds__(256, 2) hb64_cascade_kernel(const CascadeParam
     if (last) {     // stages not used by this call keep their state
         const T* si = reinterpret_cast<const T*>(p.state_in);
         T* so = reinterpret_cast<T*>(p.state_out);
-        for (int e = L * 128 + lane; e < HB_MAX_STAGES * 128; e += 32) so[e] = si[e];
+        for (int e = L * 128 + lane; e < p.copy_end; e += 32) so[e] = si[e];
     }
 }
 
