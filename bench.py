@@ -272,6 +272,16 @@ def setup():
     return c
 
 
+def measured_traffic(name, samples_per_step, per_launch_scale=1.0):
+    """roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture
+    (profiles/r01_traffic.json), scaled from the captured launch's sample count to this run's."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[name]
+        return (t["dram_read"] + t["dram_write"]) * (samples_per_step / t["samples"]) * per_launch_scale
+    except Exception:
+        return None
+
+
 def barrier(c):
     if c.world > 1:
         c.dist.barrier()
@@ -362,7 +372,7 @@ def bench_decim(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=
                       "l2": "input %.0f MiB per step > 126 MB L2, streamed from HBM every step" % (n * wl["in_bytes"] / 2 ** 20),
                       "parallelism": "replicas x%d (single-stream decimator does not shard)" % c.world},
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": c.hbm_peak, "unit": "GB/s", "frac": achieved / c.hbm_peak,
-                        "traffic": None, "peak_source": c.peak_src, "kernel": "hb64_cascade_kernel", "kernel_ms": kern_avg_ms,
+                        "traffic": measured_traffic(wl_name, n), "peak_source": c.peak_src, "kernel": "hb64_cascade_kernel", "kernel_ms": kern_avg_ms,
                         "algorithmic_bytes_per_sample": wl["in_bytes"] + wl["out_bytes"],
                         "issue": {"instr_per_sample": instr_per_sample, "roof_MSps_at_sampled_clk": issue_roof,
                                   "frac": (n / (kern_avg_ms * 1e-3) / 1e6) / issue_roof,
@@ -484,7 +494,8 @@ def bench_bank(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=T
                       "l2": "input %.0f MiB per step > 126 MB L2, streamed from HBM every step; tree levels are HBM-resident int16 arrays" % (n * 4 / 2 ** 20),
                       "parallelism": "channels sharded x%d (contiguous frequency blocks), baseband %s" % (c.world, "NCCL broadcast per step" if c.world > 1 else "local")},
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": c.hbm_peak, "unit": "GB/s", "frac": achieved / c.hbm_peak,
-                        "traffic": None, "peak_source": c.peak_src, "kernel": "hb48_level_kernel (one launch per tree level per chunk)",
+                        "traffic": measured_traffic(wl_name, n) if c.world == 1 else None, "traffic_note": "per hb48_level_kernel launch (one of %d tree levels per step)" % depth,
+                        "peak_source": c.peak_src, "kernel": "hb48_level_kernel (one launch per tree level per step)",
                         "kernel_ms": step_ms, "algorithmic_bytes_per_sample": 4 + out_bytes,
                         "issue": {"instr_per_sample": instr_per_sample, "roof_MSps_at_sampled_clk": issue_roof,
                                   "frac": (n / (step_ms * 1e-3) / 1e6) / issue_roof,
