@@ -461,20 +461,46 @@ def bench_bank(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=T
         parity = bool(ok)
     barrier(c)
 
-    state = {"i": 0}
+    state = {"i": 0, "overlap": True}
 
     def step():
         i = state["i"]
         cur = i % len(bufs)
         if c.world > 1 and not os.environ.get("B200_BENCH_NO_BCAST"):      # (developer switch: isolate the compute time)
-            if i == 0 or cur not in pending:
-                pending[cur] = dist.broadcast(bviews[cur], src=0, async_op=True)
-            pending.pop(cur).wait()                # stream-level wait: the compute stream waits for this step's baseband
-            nxt = (i + 1) % len(bufs)
-            # the next step's baseband starts moving now; its buffer was last read by step i-1, already ordered on `stream`
-            pending[nxt] = dist.broadcast(bviews[nxt], src=0, async_op=True)
+            if state["overlap"]:
+                if cur not in pending:
+                    pending[cur] = dist.broadcast(bviews[cur], src=0, async_op=True)
+                pending.pop(cur).wait()            # stream-level wait: the compute stream waits for this step's baseband
+                nxt = (i + 1) % len(bufs)
+                # the next step's baseband starts moving now; its buffer was last read by step i-1, already ordered on `stream`
+                pending[nxt] = dist.broadcast(bviews[nxt], src=0, async_op=True)
+            else:
+                for w in list(pending.values()):
+                    w.wait()
+                pending.clear()
+                dist.broadcast(bviews[cur], src=0)     # in stream order: broadcast, then the kernels
         bank.feed_dev(bufs[cur].data_ptr(), n, sptr)
         state["i"] = i + 1
+
+    bcast_mode = None
+    if c.world > 1 and not os.environ.get("B200_BENCH_NO_BCAST"):
+        # The NCCL broadcast of step k+1 can run under step k's kernels, but NCCL's ring CTAs then compete with the FIR kernels
+        # for SM slots; which wins depends on the rank count.  Try both orders for a few steps and keep the faster (all ranks
+        # agree through a MAX all-reduce of the trial times).
+        trial = {}
+        for mode in (True, False):
+            state["overlap"] = mode
+            with torch.cuda.stream(stream):
+                for _ in range(2):
+                    step()
+                barrier(c)
+                t0 = time.perf_counter()
+                for _ in range(4):
+                    step()
+                barrier(c)
+                trial[mode] = max_over_ranks(c, time.perf_counter() - t0)
+        state["overlap"] = trial[True] <= trial[False]
+        bcast_mode = "overlapped with the previous step's kernels" if state["overlap"] else "in stream order before the step's kernels"
 
     total_ms, kern_ms, clocks = timed_steps(c, stream, step, steps, warmup)
     value = n * steps / (total_ms * 1e-3) / 1e6
@@ -492,7 +518,7 @@ def bench_bank(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=T
            "config": {"workload": wl_name, "desc": wl["desc"], "samples_per_step": n, "input_rate": fs, "channels": len(fcs),
                       "channels_this_rank": len(mine), "tree_nodes_this_rank": nodes, "stage_inputs_per_sample_this_rank": stage_inputs,
                       "l2": "input %.0f MiB per step > 126 MB L2, streamed from HBM every step; tree levels are HBM-resident int16 arrays" % (n * 4 / 2 ** 20),
-                      "parallelism": "channels sharded x%d (contiguous frequency blocks), baseband %s" % (c.world, "NCCL broadcast per step" if c.world > 1 else "local")},
+                      "parallelism": "channels sharded x%d (contiguous frequency blocks), baseband %s" % (c.world, ("NCCL broadcast per step, " + str(bcast_mode)) if c.world > 1 else "local")},
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": c.hbm_peak, "unit": "GB/s", "frac": achieved / c.hbm_peak,
                         "traffic": measured_traffic(wl_name, n) if c.world == 1 else None, "traffic_note": "per hb48_level_kernel launch (one of %d tree levels per step)" % depth,
                         "peak_source": c.peak_src, "kernel": "hb48_level_kernel (one launch per tree level per step)",
