@@ -88,7 +88,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.005)
+            self._stop.wait(0.001)
 
     def start(self):
         if self.nv:
