@@ -126,6 +126,19 @@ int b200dsp_bank_fetch(b200dsp_bank_t* b, int chan_id, int stage, void* out, int
 int b200dsp_bank_fetch_dev(b200dsp_bank_t* b, int chan_id, int stage, const void** d_ptr, int64_t* n_samples);
 int b200dsp_bank_sync(b200dsp_bank_t* b);
 
+/* ---- stand-alone Interpolator (the polyphase resampler of K4 without the bank) -------------------------------------
+ * == Interpolator::create(phaseSteps, sampleRate, cutoff, nbTapsPerPhase)   sdrbase/dsp/interpolator.cpp:74-129
+ * b200dsp_interp_decimate is the block form of the loop every Rx plugin writes (plugins/channelrx/demodnfm/nfmdemod.cpp:150-155,315):
+ *     for each input c:  if (interp.decimate(&remain, c, &ci)) { out[m++] = ci; remain += distance; }
+ * `distance_remain` is the caller-owned Real the reference passes by pointer: read on entry, updated on return.
+ * Complex samples are interleaved float pairs.  At most 2^24-1 input samples per call. */
+typedef struct b200dsp_interp b200dsp_interp_t;
+int b200dsp_interp_create(b200dsp_interp_t** h, int phase_steps, double sample_rate, double cutoff, double taps_per_phase);
+int b200dsp_interp_destroy(b200dsp_interp_t* h);
+int b200dsp_interp_info(b200dsp_interp_t* h, int* taps_per_phase, float* taps, int taps_cap);
+int b200dsp_interp_decimate(b200dsp_interp_t* h, float* distance_remain, float distance, const float* in_c64, int64_t n_samples,
+                            float* out_c64, int64_t cap_samples, int64_t* n_out);
+
 /* ---- K5: SpectrumVis -------------------------------------------------------------------------------------
  * One handle == one reference SpectrumVis sink (sdrgui/dsp/spectrumvis.cpp:77-254,283-327) with its FFTWindow
  * (sdrbase/dsp/fftwindow.cpp:20-73), FFT engine (sdrbase/dsp/kissengine.cpp, kissfft.h) and per-bin averagers

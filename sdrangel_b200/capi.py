@@ -53,6 +53,10 @@ SIGNATURES = {
     "b200dsp_bank_fetch": (_i32, [_vp, _i32, _i32, _vp, _i64, _pi64]),
     "b200dsp_bank_fetch_dev": (_i32, [_vp, _i32, _i32, _pvp, _pi64]),
     "b200dsp_bank_sync": (_i32, [_vp]),
+    "b200dsp_interp_create": (_i32, [_pvp, _i32, C.c_double, C.c_double, C.c_double]),
+    "b200dsp_interp_destroy": (_i32, [_vp]),
+    "b200dsp_interp_info": (_i32, [_vp, _pi32, _vp, _i32]),
+    "b200dsp_interp_decimate": (_i32, [_vp, C.POINTER(C.c_float), _f32, _vp, _i64, _vp, _i64, _pi64]),
     "b200dsp_spectrum_create": (_i32, [_pvp, _f32]),
     "b200dsp_spectrum_destroy": (_i32, [_vp]),
     "b200dsp_spectrum_configure": (_i32, [_vp, _i32, _i32, C.c_uint, _i32, _i32, _i32]),

@@ -115,7 +115,32 @@ void interp_taps(int phase_steps, double rate, double cutoff, double taps_per_ph
     *per_phase = np;
 }
 
+// closed-form schedule when no sum r + ratio (< ratio + 1) can ever be rounded: ratio * 2^23 on the coarsest ulp lattice
+bool lattice_params(float ratio, int phase_steps, long long* A_out, int* phshift_out)
+{
+    *A_out = 0; *phshift_out = 0;
+    if (!(ratio >= 1.0f && ratio < 64.0f) || (phase_steps & (phase_steps - 1)) != 0) return false;
+    const long long A = (long long) ((double) ratio * 8388608.0);
+    long long smax = (long long) (((double) ratio + 1.0) * 8388608.0);
+    int bl = 0;
+    while (smax) { ++bl; smax >>= 1; }
+    const long long g = 1ll << (bl > 24 ? bl - 24 : 0);
+    int l2 = 0;
+    while ((1 << l2) < phase_steps) ++l2;
+    if ((double) A != (double) ratio * 8388608.0 || A % g != 0) return false;
+    *A_out = A; *phshift_out = 23 - l2;
+    return true;
+}
+
 } // namespace
+
+struct b200dsp_interp {
+    int device = 0; cudaStream_t stream = nullptr;
+    int phase_steps = 0, ntaps = 0, parity = 0;
+    std::vector<float> taps;
+    float* d_taps = nullptr; uint32_t* d_hist = nullptr; int* d_state = nullptr; long long* d_plan = nullptr; FrontendChan* d_chan = nullptr;
+    float2* d_in = nullptr; float2* d_out = nullptr; int* d_sched = nullptr; int* d_tile = nullptr; long long cap = 0;
+};
 
 struct b200dsp_bank {
     int device, sm_count;
@@ -333,7 +358,7 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
         for (size_t k = 0; k < b->fe_index.size(); ++k) {
             Channel& c = b->chans[b->fe_index[k]];
             FrontendChan& f = b->h_fe[k];
-            f.in = c.d_out; f.hist = c.d_hist; f.taps = c.d_taps; f.out = c.d_fe_out; f.sched = c.d_sched; f.tile_start = c.d_tile; f.state = c.d_state; f.plan = c.d_plan; f.A = c.A; f.lattice = c.lattice; f.phshift = c.phshift;
+            f.in = c.d_out; f.hist = c.d_hist; f.taps = c.d_taps; f.out = c.d_fe_out; f.sched = c.d_sched; f.tile_start = c.d_tile; f.state = c.d_state; f.plan = c.d_plan; f.A = c.A; f.lattice = c.lattice; f.phshift = c.phshift; f.in_f32 = 0; f.hist_stride = FE_HIST_WORDS;
             f.depth = c.S; f.inc = c.inc; f.ntaps = c.ntaps; f.phase_steps = c.phase_steps; f.ratio = c.ratio;
         }
         if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(b->d_leaf, b->h_leaf.data(), nc * sizeof(LeafChan), cudaMemcpyHostToDevice, st)))) return rc;
@@ -544,18 +569,7 @@ int b200dsp_bank_set_frontend(b200dsp_bank_t* b, int chan_id, float nco_freq_hz,
     c.ntaps = np;
     c.inc = (int) ((nco_freq_hz * 4096) / (float) c.out_rate);                 // NCO::setFreq: float arithmetic, truncation (nco.cpp:50)
     c.ratio = (float) c.out_rate / (float) out_rate_hz;                        // nfmdemod.cpp:469-470
-    // closed-form schedule when no sum r + ratio (< ratio + 1) can ever be rounded: ratio * 2^23 on the coarsest ulp lattice
-    c.lattice = 0; c.A = 0; c.phshift = 0;
-    if (c.ratio >= 1.0f && c.ratio < 64.0f && (phase_steps & (phase_steps - 1)) == 0) {
-        const long long A = (long long) ((double) c.ratio * 8388608.0);
-        long long smax = (long long) (((double) c.ratio + 1.0) * 8388608.0);
-        int bl = 0;
-        while (smax) { ++bl; smax >>= 1; }
-        const long long g = 1ll << (bl > 24 ? bl - 24 : 0);
-        int l2 = 0;
-        while ((1 << l2) < phase_steps) ++l2;
-        if ((double) A == (double) c.ratio * 8388608.0 && A % g == 0) { c.lattice = 1; c.A = A; c.phshift = 23 - l2; }
-    }
+    c.lattice = lattice_params(c.ratio, phase_steps, &c.A, &c.phshift) ? 1 : 0;
     if (b->built) { cudaSetDevice(b->device); cudaStreamSynchronize(b->stream); free_device(b); }
     return 0;
 }
@@ -652,6 +666,106 @@ int b200dsp_bank_sync(b200dsp_bank_t* b)
 {
     if (!b) return b200_fail(B200DSP_EINVAL, "null handle");
     return B200_CUDA_CHECK(cudaStreamSynchronize(b->stream));
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Stand-alone Interpolator (sdrbase/dsp/interpolator.h:19-36, interpolator.cpp:74-129): the block form of the loop every
+// Rx plugin writes around Interpolator::decimate (nfmdemod.cpp:150-155,315).  Same kernels as the bank's front-end,
+// complex64 input, no NCO.
+// ---------------------------------------------------------------------------------------------------------
+int b200dsp_interp_create(b200dsp_interp_t** out, int phase_steps, double sample_rate, double cutoff, double taps_per_phase)
+{
+    if (!out) return b200_fail(B200DSP_EINVAL, "interp_create: null handle pointer");
+    *out = nullptr;
+    if (phase_steps < 1 || phase_steps > 255 || sample_rate <= 0 || taps_per_phase <= 0) return b200_fail(B200DSP_EINVAL, "interp_create: bad parameters");
+    int rc = b200_require_device();
+    if (rc) return rc;
+    b200dsp_interp* h = new (std::nothrow) b200dsp_interp();
+    if (!h) return b200_fail(B200DSP_ENOMEM, "interp_create: out of host memory");
+    h->device = b200_current_device();
+    h->phase_steps = phase_steps;
+    interp_taps(phase_steps, sample_rate, cutoff, taps_per_phase, h->taps, &h->ntaps);
+    if (h->ntaps > FE_MAX_TAPS) { delete h; return b200_fail(B200DSP_EINVAL, "interp_create: %d taps per phase exceed the supported %d", h->ntaps, FE_MAX_TAPS); }
+    const size_t hist_bytes = 2 * (2 * FE_MAX_TAPS + 4) * 4;
+    if ((rc = B200_CUDA_CHECK(cudaSetDevice(h->device))) || (rc = B200_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking))) ||
+        (rc = B200_CUDA_CHECK(cudaMalloc(&h->d_taps, h->taps.size() * 4))) ||
+        (rc = B200_CUDA_CHECK(cudaMemcpy(h->d_taps, h->taps.data(), h->taps.size() * 4, cudaMemcpyHostToDevice))) ||
+        (rc = B200_CUDA_CHECK(cudaMalloc(&h->d_hist, hist_bytes))) || (rc = B200_CUDA_CHECK(cudaMemset(h->d_hist, 0, hist_bytes))) ||
+        (rc = B200_CUDA_CHECK(cudaMalloc(&h->d_state, 16))) || (rc = B200_CUDA_CHECK(cudaMemset(h->d_state, 0, 16))) ||
+        (rc = B200_CUDA_CHECK(cudaMalloc(&h->d_plan, 32))) || (rc = B200_CUDA_CHECK(cudaMalloc(&h->d_chan, sizeof(FrontendChan))))) { b200dsp_interp_destroy(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+int b200dsp_interp_destroy(b200dsp_interp_t* h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    void* ptrs[] = { h->d_taps, h->d_hist, h->d_state, h->d_plan, h->d_chan, h->d_in, h->d_out, h->d_sched, h->d_tile };
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+int b200dsp_interp_info(b200dsp_interp_t* h, int* taps_per_phase, float* taps, int taps_cap)
+{
+    if (!h) return b200_fail(B200DSP_EINVAL, "null handle");
+    if (taps_per_phase) *taps_per_phase = h->ntaps;
+    if (taps) for (int i = 0; i < (int) h->taps.size() && i < taps_cap; ++i) taps[i] = h->taps[i];
+    return 0;
+}
+
+int b200dsp_interp_decimate(b200dsp_interp_t* h, float* distance_remain, float distance, const float* in_c64, int64_t n, float* out_c64, int64_t cap, int64_t* n_out)
+{
+    if (!h || !distance_remain) return b200_fail(B200DSP_EINVAL, "interp_decimate: null argument");
+    if (n < 0 || n >= (1 << 24) || (n > 0 && (!in_c64 || !out_c64))) return b200_fail(B200DSP_EINVAL, "interp_decimate: bad buffer (at most 2^24-1 samples per call)");
+    if (!(distance > 0.0f)) return b200_fail(B200DSP_EINVAL, "interp_decimate: distance must be positive");
+    if (n_out) *n_out = 0;
+    if (n == 0) return 0;
+    int rc = B200_CUDA_CHECK(cudaSetDevice(h->device));
+    if (rc) return rc;
+    if (h->cap < n) {
+        void* old[] = { h->d_in, h->d_out, h->d_sched, h->d_tile };
+        for (void* p : old) if (p) cudaFree(p);
+        h->d_in = nullptr; h->d_out = nullptr; h->d_sched = nullptr; h->d_tile = nullptr; h->cap = 0;
+        if ((rc = B200_CUDA_CHECK(cudaMalloc(&h->d_in, (size_t) n * 8))) || (rc = B200_CUDA_CHECK(cudaMalloc(&h->d_out, (size_t) (n + 2) * 8))) ||
+            (rc = B200_CUDA_CHECK(cudaMalloc(&h->d_sched, (size_t) (n + 2) * 4))) || (rc = B200_CUDA_CHECK(cudaMalloc(&h->d_tile, (size_t) (n / FE_TILE + 4) * 4)))) return rc;
+        h->cap = n;
+    }
+    FrontendChan f;
+    memset(&f, 0, sizeof(f));
+    f.in = (const uint32_t*) h->d_in; f.hist = h->d_hist; f.taps = h->d_taps; f.out = h->d_out; f.sched = h->d_sched; f.tile_start = h->d_tile;
+    f.state = h->d_state; f.plan = h->d_plan; f.in_f32 = 1; f.hist_stride = 2 * FE_MAX_TAPS + 4;
+    f.depth = 0; f.inc = 0; f.ntaps = h->ntaps; f.phase_steps = h->phase_steps; f.ratio = distance;
+    f.lattice = lattice_params(distance, h->phase_steps, &f.A, &f.phshift) ? 1 : 0;
+    // the caller owns the distance (Real* distance in the reference): it travels in, and back out
+    int st[4] = { 0, 0, 0, 0 };
+    memcpy(&st[1], distance_remain, 4);
+    // an off-lattice remain (set by the caller) makes the closed form invalid: the serial replay is always exact
+    if (f.lattice && ((double) *distance_remain * 8388608.0 != floor((double) *distance_remain * 8388608.0) ||
+                      ((long long) ((double) *distance_remain * 8388608.0)) % (f.A & -f.A ? (f.A & -f.A) : 1) != 0)) f.lattice = 0;
+    PassInfo pi;
+    memset(&pi, 0, sizeof(pi));
+    pi.n_new[0] = (int) n; pi.first_pass = 1; pi.parity = h->parity;
+    const size_t smem = ((((size_t) ((h->ntaps + 2 * FE_PAD) | 1) * h->phase_steps + 3) & ~(size_t) 3)) * 4 + (size_t) (FE_MAX_TAPS + FE_TILE) * sizeof(float2);
+    if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(h->d_in, in_c64, (size_t) n * 8, cudaMemcpyHostToDevice, h->stream))) ||
+        (rc = B200_CUDA_CHECK(cudaMemcpyAsync(h->d_state, st, 16, cudaMemcpyHostToDevice, h->stream))) ||
+        (rc = B200_CUDA_CHECK(cudaMemcpyAsync(h->d_chan, &f, sizeof(f), cudaMemcpyHostToDevice, h->stream)))) return rc;
+    frontend_schedule_kernel<<<1, 32, 0, h->stream>>>(h->d_chan, 1, pi);
+    frontend_kernel<<<dim3((unsigned) ((n + FE_TILE - 1) / FE_TILE), 1), FE_THREADS, smem, h->stream>>>(h->d_chan, nullptr, pi);
+    if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
+    if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(st, h->d_state, 16, cudaMemcpyDeviceToHost, h->stream))) ||
+        (rc = B200_CUDA_CHECK(cudaStreamSynchronize(h->stream)))) return rc;
+    h->parity ^= 1;
+    memcpy(distance_remain, &st[1], 4);
+    const long long m = st[2];
+    if (n_out) *n_out = m;
+    if (m > cap) return b200_fail(B200DSP_EINVAL, "interp_decimate: output buffer too small (%lld needed)", m);
+    if (m > 0) return B200_CUDA_CHECK(cudaMemcpy(out_c64, h->d_out, (size_t) m * 8, cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 } // extern "C"

@@ -34,6 +34,8 @@ struct FrontendChan {            // one per channel with a front-end, device arr
     int*            state;       // [4]: unused, float distance remain (bits), outputs of the last pass, outputs of this feed
     long long*      plan;        // [4] written by the schedule kernel: k0 (outputs listed in sched), i0, D, closed-form output count
     long long       A;           // ratio * 2^23 (exact integer)
+    int             in_f32;      // 0: `in` is packed int16 IQ and the NCO mix applies; 1: `in` is complex64, no NCO (plain Interpolator)
+    int             hist_stride; // words per ping-pong half of `hist`
     int             lattice;     // 1: every sum of the distance recurrence is exactly representable => closed-form schedule
     int             phshift;     // 23 - log2(phase_steps)
     int             depth;       // S: selects the per-depth pass counts
@@ -160,8 +162,8 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(const FrontendChan
     const int m = pi.n_new[c.depth];
     const int t0 = blockIdx.x * FE_TILE;
     if (t0 >= m && !(blockIdx.x == 0)) return;
-    c.in += pi.out_count[c.depth];
-    const uint32_t* hin = c.hist + pi.parity * FE_HIST_WORDS;
+    c.in += pi.out_count[c.depth] * (c.in_f32 ? 2 : 1);
+    const uint32_t* hin = c.hist + pi.parity * c.hist_stride;
     const int nt = c.ntaps, nts = (c.ntaps + 2 * FE_PAD) | 1;   // zero-padded rows, odd stride: the phases start in distinct banks
     const int ntp = nts * c.phase_steps;
     float* taps = fe_smem;
@@ -170,11 +172,15 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(const FrontendChan
         const int ph = i / nts, k = i - ph * nts - FE_PAD;
         taps[i] = (k >= 0 && k < nt) ? c.taps[ph * nt + k] : 0.0f;
     }
-    const unsigned phase0 = hin[FE_MAX_TAPS];
+    const unsigned phase0 = c.in_f32 ? 0u : hin[FE_MAX_TAPS];
     const int t1 = (t0 + FE_TILE < m) ? t0 + FE_TILE : m;
     // z[k] holds mixed sample (t0 - FE_MAX_TAPS + k), k in [0, FE_MAX_TAPS + t1 - t0)
     for (int k = tid; k < FE_MAX_TAPS + (t1 - t0); k += FE_THREADS) {
         const int i = t0 - FE_MAX_TAPS + k;
+        if (c.in_f32) {
+            z[k] = (i >= 0) ? reinterpret_cast<const float2*>(c.in)[i] : reinterpret_cast<const float2*>(hin)[FE_MAX_TAPS + i];
+            continue;
+        }
         const uint32_t w = (i >= 0) ? c.in[i] : hin[FE_MAX_TAPS + i];
         const float x = (float) (short) (w & 0xffffu), y = (float) ((int) w >> 16);
         const int p = (int) ((phase0 + (unsigned) (i + 1) * (unsigned) c.inc) & 4095u);   // phase advanced before the lookup; wrap == mod 4096
@@ -243,12 +249,19 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(const FrontendChan
     }
     // the CTA of the last tile carries the newest FE_MAX_TAPS channel samples and the NCO phase to the next pass
     if (t1 == m && (t0 < m || blockIdx.x == 0)) {
-        uint32_t* hout = c.hist + (pi.parity ^ 1) * FE_HIST_WORDS;
-        for (int k = tid; k < FE_MAX_TAPS; k += FE_THREADS) {
-            const int i = m - FE_MAX_TAPS + k;
-            hout[k] = (i >= 0) ? c.in[i] : hin[FE_MAX_TAPS + i];
+        uint32_t* hout = c.hist + (pi.parity ^ 1) * c.hist_stride;
+        if (c.in_f32) {
+            for (int k = tid; k < FE_MAX_TAPS; k += FE_THREADS) {
+                const int i = m - FE_MAX_TAPS + k;
+                reinterpret_cast<float2*>(hout)[k] = (i >= 0) ? reinterpret_cast<const float2*>(c.in)[i] : reinterpret_cast<const float2*>(hin)[FE_MAX_TAPS + i];
+            }
+        } else {
+            for (int k = tid; k < FE_MAX_TAPS; k += FE_THREADS) {
+                const int i = m - FE_MAX_TAPS + k;
+                hout[k] = (i >= 0) ? c.in[i] : hin[FE_MAX_TAPS + i];
+            }
+            if (tid == 0) hout[FE_MAX_TAPS] = (phase0 + (unsigned) m * (unsigned) c.inc) & 4095u;
         }
-        if (tid == 0) hout[FE_MAX_TAPS] = (phase0 + (unsigned) m * (unsigned) c.inc) & 4095u;
     }
 }
 

@@ -243,3 +243,44 @@ class SpectrumVis:
         capi.check(capi.lib().b200dsp_spectrum_feed_dev(self._h, C.c_void_p(d_iq), int(n_samples), int(positive_only), C.c_void_p(d_out),
                                                         int(cap_frames), C.byref(got), C.c_void_p(stream or 0)))
         return got.value
+
+
+class Interpolator:
+    """Interpolator (sdrbase/dsp/interpolator.h:19-36): create() + the block form of the Rx plugins' decimate loop
+    (plugins/channelrx/demodnfm/nfmdemod.cpp:150-155,315).  `distance_remain` is caller-owned, like the Real* in the reference."""
+
+    def __init__(self, phase_steps, sample_rate, cutoff, taps_per_phase=4.5, device=None):
+        L = capi.lib()
+        if device is not None:
+            capi.init(device)
+        h = C.c_void_p()
+        capi.check(L.b200dsp_interp_create(C.byref(h), int(phase_steps), float(sample_rate), float(cutoff), float(taps_per_phase)))
+        self._h = h
+        self.phase_steps = int(phase_steps)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            capi.lib().b200dsp_interp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def taps(self):
+        nt = C.c_int32()
+        capi.check(capi.lib().b200dsp_interp_info(self._h, C.byref(nt), None, 0))
+        t = np.empty(nt.value * self.phase_steps, dtype=np.float32)
+        capi.check(capi.lib().b200dsp_interp_info(self._h, C.byref(nt), t.ctypes.data, t.size))
+        return t.reshape(self.phase_steps, nt.value)
+
+    def decimate(self, distance_remain, distance, samples):
+        """Returns (outputs complex64, new distance_remain)."""
+        x = np.ascontiguousarray(samples, dtype=np.complex64)
+        out = np.empty(x.size + 2, dtype=np.complex64)
+        rem = C.c_float(float(distance_remain))
+        n = C.c_int64(0)
+        capi.check(capi.lib().b200dsp_interp_decimate(self._h, C.byref(rem), float(distance), x.ctypes.data, x.size, out.ctypes.data, out.size, C.byref(n)))
+        return out[:n.value], rem.value

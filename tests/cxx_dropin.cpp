@@ -10,6 +10,7 @@
 #include "sdrangel_b200/dsp/decimatorsfi.h"
 #include "sdrangel_b200/dsp/downchannelizer.h"
 #include "sdrangel_b200/dsp/spectrumvis.h"
+#include "sdrangel_b200/dsp/interpolator.h"
 
 static uint64_t fnv(const void* p, size_t n_u16)
 {
@@ -63,6 +64,13 @@ int main()
         for (auto& s : sv) { s.setReal((qint16) ((g2() >> 20) - 2048)); s.setImag((qint16) ((g2() >> 20) - 2048)); }
         vis.feed(sv.begin(), sv.end(), false);
         printf("spectrumvis frames=%d\n", disp.frames);
+        Interpolator interp;
+        interp.create(16, 156250, 12500 / 2.2f);
+        std::vector<Complex> cin(20000), cout(20000);
+        for (size_t i = 0; i < cin.size(); i++) cin[i] = Complex((Real) ((int) (g2() >> 18) - 8192), (Real) ((int) (g2() >> 18) - 8192));
+        Real distance = 0, step = (Real) 156250 / (Real) 48000;
+        size_t m = interp.decimate(&distance, step, &cin[0], cin.size(), &cout[0], cout.size());
+        printf("interpolator n_out=%zu\n", m);
         delete[] buf;
     } catch (const std::exception& e) {
         fprintf(stderr, "exception: %s\n", e.what());

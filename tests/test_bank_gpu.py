@@ -147,3 +147,27 @@ def test_bank_with_frontends_vs_oracle(gpu_lib, port, golden_meta):
             got = b.fetch(cid, capi.STAGE_FRONTEND)
             assert got.shape == want.shape
             assert rel_rms(got, want) <= 1e-5
+
+
+@pytest.mark.parametrize("rate,outr", [(156250, 48000), (60000, 48000), (78125, 48000), (48000, 48000)])
+def test_standalone_interpolator_vs_oracle(gpu_lib, port, golden, rate, outr):
+    """b200dsp_interp_decimate == the plugin loop around Interpolator::decimate, fed in ragged blocks with the caller-owned
+    distance carried between calls.  Oracle: the reference front-end with a zero-frequency NCO (mix by exactly 1)."""
+    from sdrangel_b200 import Interpolator
+    rs = np.random.RandomState(rate)
+    n = 50_000
+    xi = rs.randint(-20000, 20000, size=(n, 2)).astype(np.int16)
+    x = (xi[:, 0].astype(np.float32) + 1j * xi[:, 1].astype(np.float32)).astype(np.complex64)
+    cutoff = np.float32(np.float32(12500) / np.float32(2.2))
+    it = Interpolator(16, rate, float(cutoff))
+    fe = port.PortFrontEnd(0, rate, outr, cutoff)
+    assert np.array_equal(it.taps(), fe.taps())
+    step = float(np.float32(np.float32(rate) / np.float32(outr)))
+    remain = 0.0
+    cuts = [0, 1, 2, 1000, 1001, 30_000, n]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        got, remain = it.decimate(remain, step, x[a:b])
+        want = fe.feed(xi[a:b])
+        assert got.shape[0] == want.shape[0], (a, b)
+        if got.size:
+            assert rel_rms(got.view(np.float32), want) <= 1e-5

@@ -39,3 +39,4 @@ def test_sdrbench_decimateii_through_cxx_wrappers(gpu_lib, golden_meta):
     assert "out=" + g["fnv"] in lines["decimate16_cen"]
     assert lines["downchannelizer"].startswith("rate=156250 ofs=-15433 n_out=937")
     assert lines["spectrumvis"] == "frames=2"
+    assert lines["interpolator"] == "n_out=6145"          # 20 000 inputs at 156 250 -> 48 000
