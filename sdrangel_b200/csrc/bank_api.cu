@@ -10,6 +10,7 @@
 #include "hb48_tree.cuh"
 #include "frontend.cuh"
 #include <math.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 
@@ -159,6 +160,8 @@ struct b200dsp_bank {
     std::vector<uint32_t*> d_level;  std::vector<long long> stride;   // per depth >= 1
     std::vector<uint32_t*> d_tail[2];            // per depth (parents), ping-pong
     std::vector<int*> d_fam;
+    std::vector<std::vector<int>> pfams; std::vector<int*> d_pfam;   // pair-kernel families per odd depth d (levels d, d+1)
+    bool fuse;                                   // use the two-level kernel where a call is aligned
     uint32_t* d_root; long long root_cap;        // staging for host feeds / odd-pending device feeds
     std::vector<long long> produced;             // P[d]
     int tcur;
@@ -177,6 +180,8 @@ void free_device(b200dsp_bank* b)
     for (auto p : b->d_level) if (p) cudaFree(p);
     for (int k = 0; k < 2; ++k) { for (auto p : b->d_tail[k]) if (p) cudaFree(p); b->d_tail[k].clear(); }
     for (auto p : b->d_fam) if (p) cudaFree(p);
+    for (auto p : b->d_pfam) if (p) cudaFree(p);
+    b->d_pfam.clear();
     b->d_level.clear(); b->d_fam.clear(); b->stride.clear();
     if (b->d_leaf) cudaFree(b->d_leaf);
     if (b->d_fe) cudaFree(b->d_fe);
@@ -232,7 +237,33 @@ int build(b200dsp_bank* b)
             b->fams[d].push_back(n.index);
             for (int m = 0; m < 3; ++m) b->fams[d].push_back(n.child[m] >= 0 ? b->nodes[n.child[m]].index : -1);
         }
+    // pair-kernel families for levels (d, d+1), d odd: root (depth d-1), its children, which of them are channel leaves,
+    // and the children's children
+    std::vector<char> is_leaf(b->nodes.size(), 0);
+    for (auto& c : b->chans) is_leaf[c.node] = 1;
+    b->pfams.assign(b->depth + 2, std::vector<int>());
+    for (int d = 1; d + 1 <= b->depth; d += 2)
+        for (int id : b->levels[d - 1]) {
+            const Node& r = b->nodes[id];
+            if (r.child[0] < 0 && r.child[1] < 0 && r.child[2] < 0) continue;
+            int e[16];
+            e[0] = r.index;
+            for (int m = 0; m < 3; ++m) {
+                const int cid = r.child[m];
+                e[1 + m] = cid >= 0 ? b->nodes[cid].index : -1;
+                e[4 + m] = (cid >= 0 && is_leaf[cid]) ? 1 : 0;
+                for (int g = 0; g < 3; ++g) e[7 + 3 * m + g] = (cid >= 0 && b->nodes[cid].child[g] >= 0) ? b->nodes[b->nodes[cid].child[g]].index : -1;
+            }
+            b->pfams[d].insert(b->pfams[d].end(), e, e + 16);
+        }
     int rc;
+    b->d_pfam.assign(b->depth + 2, nullptr);
+    for (int d = 1; d + 1 <= b->depth; d += 2) {
+        const size_t fb = b->pfams[d].size() * sizeof(int);
+        if (!fb) continue;
+        if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_pfam[d], fb))) ||
+            (rc = B200_CUDA_CHECK(cudaMemcpy(b->d_pfam[d], b->pfams[d].data(), fb, cudaMemcpyHostToDevice)))) return rc;
+    }
     b->d_level.assign(b->depth + 1, nullptr); b->stride.assign(b->depth + 1, 0);
     b->d_tail[0].assign(b->depth + 1, nullptr); b->d_tail[1].assign(b->depth + 1, nullptr);
     b->d_fam.assign(b->depth + 1, nullptr);
@@ -374,6 +405,39 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
     }
     const int tc = b->tcur, tn = tc ^ 1;
     for (int d = 1; d <= D; ++d) {
+        // levels (d, d+1) in one launch when the call is aligned at both (no pending samples, whole batch pairs)
+        if (b->fuse && (d & 1) && d + 1 <= D && b->d_pfam[d]) {
+            const long long n_in = 2 * (Pa[d] - Pb[d]);
+            const bool aligned = n_in > 0 && n_in % (2 * HB_IN) == 0 && (Pb[d - 1] == 2 * Pb[d]) && (Pa[d - 1] - Pb[d - 1] == n_in) &&
+                                 !(Pb[d] & 1) && (Pb[d] == 2 * Pb[d + 1]) && !(Pb[d + 1] & 1) && n_in < (1ll << 31);
+            if (aligned) {
+                PairParams q;
+                memset(&q, 0, sizeof(q));
+                q.in_base = (d == 1) ? rootB : b->d_level[d - 1];
+                q.in_stride = (d == 1) ? 0 : b->stride[d - 1];
+                q.mid_base = b->d_level[d]; q.mid_stride = b->stride[d];
+                q.out_base = b->d_level[d + 1]; q.out_stride = b->stride[d + 1];
+                q.root_tail_in = b->d_tail[tc][d - 1]; q.root_tail_out = b->d_tail[tn][d - 1];
+                q.child_tail_in = b->d_tail[tc][d]; q.child_tail_out = b->d_tail[tn][d];
+                q.fam = b->d_pfam[d]; q.n_fam = (int) (b->pfams[d].size() / 16);
+                q.n_in = (int) n_in;
+                q.opq_zero = 0; q.opq_one = 1; q.opq_mone = -1;
+                const long long npairs = n_in / (2 * HB_IN);
+                long long pps = 16;                                   // + 1 warm-up pair per slice: ~6 % recompute
+                const long long target = (long long) b->sm_count * 16;
+                while (pps > 2 && (long long) q.n_fam * ((npairs + pps - 1) / pps) < target) pps >>= 1;
+                q.pps = (int) pps; q.slices = (int) ((npairs + pps - 1) / pps);
+                const long long warps = (long long) q.n_fam * q.slices;
+                const int wpb = 8;      // 8 warps x (4 x 3.5 KB + 64 B) = 113.5 KB per block: two blocks = 16 warps per SM
+                static bool attr_done = false;
+                if (!attr_done) { cudaFuncSetAttribute((const void*) hb48_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wpb * (4 * HB_STAGE_BYTES + 64)); attr_done = true; }
+                hb48_pair_kernel<<<(unsigned) ((warps + wpb - 1) / wpb), wpb * 32, wpb * (4 * HB_STAGE_BYTES + 64), st>>>(q);
+                if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
+                // parents of level d+2 that exist only as leaves keep no tail; children tails were written by the kernel
+                ++d;
+                continue;
+            }
+        }
         const int n_fam = (int) (b->fams[d].size() / 4);
         if (n_fam == 0) continue;
         LevelParams p;
@@ -483,7 +547,8 @@ int b200dsp_bank_create(b200dsp_bank_t** out, int input_rate_hz)
     b->device = b200_current_device();
     b->sm_count = b200_sm_count_of(b->device);
     b->input_rate = input_rate_hz;
-    b->built = false; b->depth = 0; b->chunk = 3ll << 22; b->tables_dirty = true; b->d_root = nullptr; b->root_cap = 0;
+    b->built = false; b->depth = 0; b->chunk = 3ll << 22; b->tables_dirty = true;
+    b->fuse = (getenv("B200DSP_FUSE") != nullptr);      // measured on B200 (r01): halves the tree's HBM traffic but runs 16 % slower than two one-level launches; off by default b->d_root = nullptr; b->root_cap = 0;
     b->d_leaf = nullptr; b->d_fe = nullptr; b->d_nco = nullptr; b->tcur = 0;
     if ((rc = B200_CUDA_CHECK(cudaSetDevice(b->device))) || (rc = B200_CUDA_CHECK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking))) ||
         (rc = B200_CUDA_CHECK(cudaStreamCreateWithPriority(&b->side, cudaStreamNonBlocking, -5))) ||

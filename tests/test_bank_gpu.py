@@ -171,3 +171,47 @@ def test_standalone_interpolator_vs_oracle(gpu_lib, port, golden, rate, outr):
         assert got.shape[0] == want.shape[0], (a, b)
         if got.size:
             assert rel_rms(got.view(np.float32), want) <= 1e-5
+
+
+def test_bank_two_level_kernel_aligned_and_mixed_feeds(gpu_lib, port, golden_meta):
+    """Aligned feeds (whole batch pairs at every level) take the fused two-level kernel, anything else the one-level kernel;
+    a stream that alternates between both, with runs of -32768 and full-scale noise, must stay bit-exact against one oracle
+    chain per channel, call by call, and identical to a bank that never fuses."""
+    import os
+    from sdrangel_b200 import DownChannelizerBank
+    plan = golden_meta["chan_plans"]["bank64"]
+    rs = np.random.RandomState(77)
+    unit = 768 * 64                      # whole batch pairs down to the deepest pair of levels of the 7-level tree
+    sizes = [unit * 3, 1000, unit, 7, unit * 2, unit * 2 - 7 - 1000, unit * 4]
+    n = sum(sizes)
+    x = rs.randint(-32768, 32768, size=(n, 2)).astype(np.int16)
+    x[5000:5100] = -32768
+    x[unit * 3 + 500: unit * 3 + 600, 0] = -32768
+    x[unit * 5: unit * 5 + 3000] = -32768
+    chans = plan["channels"][::7]
+    plain = DownChannelizerBank(plan["input_rate"])
+    os.environ["B200DSP_FUSE"] = "1"          # the two-level kernel is opt-in (less HBM traffic, but slower on B200: DESIGN.md)
+    try:
+        fused = DownChannelizerBank(plan["input_rate"])
+    finally:
+        del os.environ["B200DSP_FUSE"]
+    ids = [fused.add_channel(48000, fc)[0] for fc, _, _, _ in chans]
+    for fc, _, _, _ in chans:
+        plain.add_channel(48000, fc)
+    oracles = []
+    for fc, _, _, _ in chans:
+        o = port.PortDownChannelizer()
+        o.configure(plan["input_rate"], 48000, fc)
+        oracles.append(o)
+    pos = 0
+    for sz in sizes:
+        blk = x[pos:pos + sz]
+        pos += sz
+        fused.feed(blk)
+        plain.feed(blk)
+        for cid, o in zip(ids, oracles):
+            want = o.feed(blk)
+            got = fused.fetch(cid)
+            assert got.shape == want.shape, (sz, cid)
+            assert np.array_equal(got, want), (sz, cid, int(np.argmax(np.any(got != want, axis=1))))
+            assert np.array_equal(plain.fetch(cid), want), (sz, cid)
