@@ -259,7 +259,10 @@ def setup():
     torch.cuda.set_device(c.local)
     c.dev = torch.device("cuda", c.local)
     if c.world > 1:
-        dist.init_process_group("nccl", device_id=c.dev)
+        # NCCL's kernels on a high-priority stream: when a broadcast overlaps the FIR kernels its ring CTAs are scheduled as
+        # soon as a block slot frees instead of queueing behind a whole wave (a late CTA stalls the ring on every rank)
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=not os.environ.get("B200_BENCH_NCCL_NORMAL_PRIO"))
+        dist.init_process_group("nccl", device_id=c.dev, pg_options=opts)
     capi.init(c.local)
     peaks = {}
     try:
@@ -640,6 +643,163 @@ def bench_spectrum(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_pari
     return res
 
 
+def bench_bank_coop(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=True):
+    """N > 1: the cooperative bank (sdrangel_b200/coop.py): scatter of time slices -> top tree levels on the slice ->
+    all-to-all of the depth-k node streams -> per-rank banks.  Every collective is NCCL over NVLink, in stream order."""
+    import sdrangel_b200 as S
+    from sdrangel_b200.coop import CoopPlan, CoopRank, HALO
+    torch, capi, dist = c.torch, c.capi, c.dist
+    fs, fcs = wl["plan"]()
+    n = args.samples or wl["n"]
+    cutoff = float(np.float32(np.float32(12500) / np.float32(2.2)))
+    stream = torch.cuda.Stream(device=c.dev)
+    sptr = stream.cuda_stream
+
+    class Pipe:
+        def __init__(self, n_samples, x=None):
+            self.plan = p = CoopPlan(fs, fcs, 48000, c.world, n_samples)
+            self.rk = CoopRank(p, c.rank, frontend=(cutoff, 48000))
+            self.slice = torch.empty(HALO + p.m, dtype=torch.int32, device=c.dev)
+            self.scatter_list = None
+            if c.rank == 0:
+                xi = x.view(torch.int32)
+                self.xcat = torch.cat([xi[-HALO:], xi])         # the stream is the buffer repeated: slice 0's halo is its end
+                self.scatter_list = [self.xcat[r * p.m: r * p.m + HALO + p.m] for r in range(c.world)]
+            self.my_nodes = p.rank_nodes[c.rank]
+            self.in_splits = [len(p.rank_nodes[q]) * p.mk for q in range(c.world)]
+            self.out_splits = [len(self.my_nodes) * p.mk] * c.world
+            self.send = torch.empty(sum(self.in_splits), dtype=torch.int32, device=c.dev)
+            self.recv = torch.empty(sum(self.out_splits), dtype=torch.int32, device=c.dev)
+            self.streams = torch.empty((len(self.my_nodes), c.world, p.mk), dtype=torch.int32, device=c.dev)
+            torch.cuda.synchronize()                            # tensors above were built on the default stream
+
+        def step(self):
+            p, rk = self.plan, self.rk
+            dist.scatter(self.slice, self.scatter_list, src=0)
+            rk.top.reset(sptr)
+            rk.top.feed_dev(self.slice.data_ptr(), HALO + p.m, sptr)
+            off = 0
+            for q in range(c.world):
+                for v in p.rank_nodes[q]:
+                    rk.top.copy_out_dev(rk.top_ids[v], p.skip, p.mk, self.send.data_ptr() + 4 * off, sptr)
+                    off += p.mk
+            dist.all_to_all_single(self.recv, self.send, self.out_splits, self.in_splits)
+            self.streams.copy_(self.recv.view(c.world, len(self.my_nodes), p.mk).permute(1, 0, 2))
+            for j, v in enumerate(self.my_nodes):
+                rk.subs[v].feed_dev(self.streams[j].data_ptr(), p.n >> p.k, sptr)
+
+    g = torch.Generator(device=c.dev)
+    g.manual_seed(1)
+    x = torch.randint(-2048, 2048, (2 * n,), dtype=torch.int16, device=c.dev, generator=g) if c.rank == 0 else None
+
+    parity = None
+    if want_parity:       # small instance, second step vs oracle chains fed the buffer twice (the stream is the buffer repeated)
+        ns = c.world * 768 * 8 * 16
+        xs = torch.randint(-2048, 2048, (2 * ns,), dtype=torch.int16, device=c.dev, generator=g) if c.rank == 0 else None
+        pp = Pipe(ns, xs)
+        with torch.cuda.stream(stream):
+            if c.rank == 0:
+                pp.xcat[:HALO].zero_()                          # first step: nothing precedes the stream (the oracle's zero history)
+            pp.step()
+            if c.rank == 0:
+                pp.xcat[:HALO].copy_(pp.xcat[-HALO:])
+            pp.step()
+        stream.synchronize()
+        if c.rank == 0:
+            _oracle_mod()
+            from oracle import portbind
+            hx = xs.cpu().numpy().reshape(-1, 2)
+            ok = True
+            lo, hi = pp.plan.ranges[0]
+            for i in (lo, (lo + hi) // 2, hi - 1):
+                rate, ofs, path = pp.plan.chains[i]
+                o = portbind.PortDownChannelizer()
+                o.configure(fs, 48000, fcs[i])
+                fe = portbind.PortFrontEnd(-ofs, rate, 48000, cutoff)
+                fe.feed(o.feed(hx))
+                ch = o.feed(hx)
+                want = fe.feed(ch)
+                node, cid = pp.rk.chan[i]
+                gc_ = pp.rk.subs[node].fetch(cid)
+                ok_c = gc_.shape == ch.shape and np.array_equal(gc_, ch)
+                got = pp.rk.subs[node].fetch(cid, capi.STAGE_FRONTEND)
+                ok_f = got.shape == want.shape and float(np.sqrt(np.mean((got - want) ** 2)) / np.sqrt(np.mean(want ** 2))) <= 1e-5
+                if not (ok_c and ok_f):
+                    bad = int(np.argmax(np.any(gc_ != ch, axis=1))) if gc_.shape == ch.shape else -1
+                    print("coop parity mismatch: channel %d node %s tree %s (first bad %d of %s, mk %d) front-end %s" %
+                          (i, node, ok_c, bad, gc_.shape, pp.plan.mk, ok_f), file=sys.stderr)
+                ok = ok and ok_c and ok_f
+            parity = bool(ok)
+        pp.rk.close()
+    barrier(c)
+
+    pipe = Pipe(n, x)
+    total_ms, kern_ms, clocks = timed_steps(c, stream, pipe.step, steps, warmup)
+    value = n * steps / (total_ms * 1e-3) / 1e6
+    step_ms = float(np.mean(kern_ms))
+    p = pipe.plan
+    lo, hi = p.ranges[c.rank]
+    stage_inputs = p.stage_inputs(c.rank)
+    out_bytes = (hi - lo) * 48000.0 / fs * 8
+    alg_bytes = n * (4.0 * (p.m + HALO) / n + 4.0 * len(pipe.my_nodes) / (1 << p.k) + out_bytes)
+    achieved = alg_bytes / (step_ms * 1e-3) / 1e9
+    instr_per_sample = stage_inputs * 27 + (hi - lo) * 48000.0 / fs * 160
+    f_clk = (clocks.get("sm_mhz") or 1965) * 1e6
+    issue_roof = c.sm_count * 128 * f_clk / instr_per_sample / 1e6
+    depth = max(len(ch[2]) for ch in p.chains)
+    res = {"value": value, "ms_per_step": total_ms / steps, "clocks": clocks, "parity": parity,
+           "launches": steps * (p.k + 1 + len(pipe.my_nodes) * (depth - p.k + 3)),
+           "config": {"workload": wl_name, "desc": wl["desc"], "samples_per_step": n, "input_rate": fs, "channels": len(fcs),
+                      "channels_this_rank": hi - lo, "stage_inputs_per_sample_this_rank": stage_inputs,
+                      "l2": "input %.0f MiB per step > 126 MB L2" % (n * 4 / 2 ** 20),
+                      "parallelism": "cooperative x%d: NCCL scatter of time slices (+%d-sample halo), top %d tree levels per slice, NCCL all-to-all of the "
+                                     "depth-%d node streams, channels below them sharded by frequency" % (c.world, HALO, p.k, p.k)},
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": c.hbm_peak, "unit": "GB/s", "frac": achieved / c.hbm_peak,
+                        "traffic": None, "peak_source": c.peak_src, "kernel": "hb48_level_kernel (one launch per tree level)", "kernel_ms": step_ms,
+                        "algorithmic_bytes_per_sample": alg_bytes / n,
+                        "issue": {"instr_per_sample": instr_per_sample, "roof_MSps_at_sampled_clk": issue_roof,
+                                  "frac": (n / (step_ms * 1e-3) / 1e6) / issue_roof,
+                                  "note": "per rank: 27 instructions per stage-input sample of its share of the tree + ~160 per front-end output"},
+                        "nvlink": {"bytes_in_per_step_this_rank": int(4 * (p.m + HALO) * (c.rank != 0) + 4 * len(pipe.my_nodes) * p.mk * (c.world - 1)),
+                                   "root_egress_bytes_per_step": int(4 * (p.m + HALO) * (c.world - 1))}},
+           "dtype": "s32", "scaling": "strong"}
+    if want_e2e:
+        # end to end: rank 0's baseband starts in pinned host memory, every rank reads its channels' outputs back
+        hx = torch.empty((2 * n,), dtype=torch.int16, pin_memory=True) if c.rank == 0 else None
+        if c.rank == 0:
+            hx.copy_(x)
+        outs = {i: torch.empty((int(n * 48000 / fs) + 64, 2), dtype=torch.float32, pin_memory=True) for i in range(lo, hi)}
+        L_ = capi.lib()
+        nn = C.c_int64(0)
+
+        def e2e_step():
+            if c.rank == 0:
+                x.copy_(hx, non_blocking=True)
+                pipe.xcat[HALO:].copy_(x.view(torch.int32))
+                pipe.xcat[:HALO].copy_(x.view(torch.int32)[-HALO:])
+            pipe.step()
+            stream.synchronize()
+            for i, o in outs.items():
+                node, cid = pipe.rk.chan[i]
+                capi.check(L_.b200dsp_bank_fetch(pipe.rk.subs[node]._h, cid, capi.STAGE_FRONTEND, o.data_ptr(), o.shape[0], C.byref(nn)))
+
+        with torch.cuda.stream(stream):
+            e2e_step()
+            barrier(c)
+            t0 = time.perf_counter()
+            ksteps = 3
+            for _ in range(ksteps):
+                e2e_step()
+            torch.cuda.synchronize()
+        dt = max_over_ranks(c, time.perf_counter() - t0)
+        res["e2e"] = {"value": n * ksteps / dt / 1e6, "unit": "input MS/s", "h2d_bytes_per_step": int(n * 4) if c.rank == 0 else 0,
+                      "d2h_bytes_per_step": int((hi - lo) * nn.value * 8), "steps": ksteps,
+                      "api": "pinned host baseband on rank 0 -> cooperative bank -> b200dsp_bank_fetch of every channel's front-end output on its rank",
+                      "samples_per_step": n}
+    pipe.rk.close()
+    return res
+
+
 def _node_depths(paths):
     seen = set()
     for p in paths:
@@ -651,7 +811,10 @@ def _node_depths(paths):
 def run_ours(args, wl_name, wl):
     c = setup()
     fns = {"decim": bench_decim, "bank": bench_bank, "spectrum": bench_spectrum}
-    res = fns[wl["type"]](c, args, wl_name, wl, args.steps, args.warmup, want_e2e=not args.no_e2e)
+    main_fn = fns[wl["type"]]
+    if wl["type"] == "bank" and c.world > 1 and os.environ.get("B200_BENCH_COOP"):
+        main_fn = bench_bank_coop          # developer switch: time-sliced top levels + all-to-all; measured slower
+    res = main_fn(c, args, wl_name, wl, args.steps, args.warmup, want_e2e=not args.no_e2e)
     also = {}
     if c.world == 1 and not args.no_also and not args.samples:
         for other in WORKLOADS:

@@ -109,6 +109,14 @@ int b200dsp_bank_set_chunk(b200dsp_bank_t* b, int64_t samples);
 /* == DSPConfigureChannelizer(requested_rate, center_offset) -> MsgChannelizerNotification(out_rate, residual_offset) */
 int b200dsp_bank_add_channel(b200dsp_bank_t* b, int requested_rate_hz, int center_offset_hz,
                              int* chan_id, int* out_rate_hz, int* residual_offset_hz);
+/* a channel given by its filter stages (0 centre, 1 lower half, 2 upper half) instead of (rate, offset); its output is
+ * trunc(stage output / 2^out_shift).  Building block for splitting one bank over several GPUs: a bank
+ * fed with the output of a depth-k tree node holds the channels below it by their path suffix with out_shift = k + n_modes;
+ * out_shift = 0 exposes a node's raw stage output. */
+int b200dsp_bank_add_channel_path(b200dsp_bank_t* b, const int* modes, int n_modes, int out_shift, int* chan_id);
+/* zero all filter state (as freshly constructed reference objects) without rebuilding the plan; in stream order on
+ * cuda_stream (NULL = the bank's own stream, the one the host-pointer calls use) */
+int b200dsp_bank_reset(b200dsp_bank_t* b, void* cuda_stream);
 /* filter stages chosen for the channel: 0 centre, 1 lower half, 2 upper half (downchannelizer.h:72-76); returns S */
 int b200dsp_bank_channel_path(b200dsp_bank_t* b, int chan_id, int* modes, int cap);
 /* number of distinct half-band stages (tree nodes) the bank evaluates for all its channels */
@@ -124,6 +132,8 @@ int b200dsp_bank_feed_dev(b200dsp_bank_t* b, const void* d_iq, int64_t n_samples
 /* outputs produced by the last feed for one channel; stage selects int16 IQ (4 bytes/sample) or complex64 (8 bytes) */
 int b200dsp_bank_fetch(b200dsp_bank_t* b, int chan_id, int stage, void* out, int64_t cap_samples, int64_t* n_samples);
 int b200dsp_bank_fetch_dev(b200dsp_bank_t* b, int chan_id, int stage, const void** d_ptr, int64_t* n_samples);
+/* device-to-device copy of samples [skip, skip + count) of a channel's channelizer output of the last feed */
+int b200dsp_bank_copy_out_dev(b200dsp_bank_t* b, int chan_id, int64_t skip, int64_t count, void* d_dst, void* cuda_stream);
 int b200dsp_bank_sync(b200dsp_bank_t* b);
 
 /* ---- stand-alone Interpolator (the polyphase resampler of K4 without the bank) -------------------------------------

@@ -44,6 +44,8 @@ SIGNATURES = {
     "b200dsp_bank_destroy": (_i32, [_vp]),
     "b200dsp_bank_set_chunk": (_i32, [_vp, _i64]),
     "b200dsp_bank_add_channel": (_i32, [_vp, _i32, _i32, _pi32, _pi32, _pi32]),
+    "b200dsp_bank_add_channel_path": (_i32, [_vp, _pi32, _i32, _i32, _pi32]),
+    "b200dsp_bank_reset": (_i32, [_vp, _vp]),
     "b200dsp_bank_channel_path": (_i32, [_vp, _i32, _pi32, _i32]),
     "b200dsp_bank_node_count": (_i32, [_vp]),
     "b200dsp_bank_set_frontend": (_i32, [_vp, _i32, _f32, _i32, C.c_double, C.c_double, _i32]),
@@ -52,6 +54,7 @@ SIGNATURES = {
     "b200dsp_bank_feed_dev": (_i32, [_vp, _vp, _i64, _vp]),
     "b200dsp_bank_fetch": (_i32, [_vp, _i32, _i32, _vp, _i64, _pi64]),
     "b200dsp_bank_fetch_dev": (_i32, [_vp, _i32, _i32, _pvp, _pi64]),
+    "b200dsp_bank_copy_out_dev": (_i32, [_vp, _i32, _i64, _i64, _vp, _vp]),
     "b200dsp_bank_sync": (_i32, [_vp]),
     "b200dsp_interp_create": (_i32, [_pvp, _i32, C.c_double, C.c_double, C.c_double]),
     "b200dsp_interp_destroy": (_i32, [_vp]),

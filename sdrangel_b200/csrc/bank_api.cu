@@ -21,7 +21,7 @@ namespace {
 // ---------------------------------------------------------------------------------------------------------
 // small kernels around the level kernel
 // ---------------------------------------------------------------------------------------------------------
-struct LeafChan { const uint32_t* src; uint32_t* dst; int depth; };     // static per channel (until a reallocation)
+struct LeafChan { const uint32_t* src; uint32_t* dst; int depth; int shift; };     // static per channel (until a reallocation)
 
 // channel output = trunc_toward_zero(y / 2^S) per component (downchannelizer.cpp:78-83)
 __global__ void hb48_finalize_kernel(const LeafChan* chans, const PassInfo pi)
@@ -31,12 +31,12 @@ __global__ void hb48_finalize_kernel(const LeafChan* chans, const PassInfo pi)
     const int n = pi.n_new[c.depth];
     const uint32_t* src = c.src + pi.wo[c.depth];
     uint32_t* dst = c.dst + pi.out_count[c.depth];
-    const int bias = (1 << c.depth) - 1;
+    const int bias = (1 << c.shift) - 1;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const uint32_t w = src[k];
         int re = (int) (short) (w & 0xffffu), im = (int) w >> 16;
-        re = (re + ((re >> 31) & bias)) >> c.depth;
-        im = (im + ((im >> 31) & bias)) >> c.depth;
+        re = (re + ((re >> 31) & bias)) >> c.shift;
+        im = (im + ((im >> 31) & bias)) >> c.shift;
         dst[k] = ((uint32_t) re & 0xffffu) | ((uint32_t) im << 16);
     }
 }
@@ -77,6 +77,7 @@ struct Channel {
     int requested_rate, center_offset;
     std::vector<int> modes;
     int node, S, out_rate, residual;
+    int out_shift;          // the channel output is trunc(y / 2^out_shift): S for a whole chain (downchannelizer.cpp:78-83)
     // front-end
     bool fe;
     float nco_freq; int phase_steps; double cutoff, taps_per_phase; int fe_out_rate;
@@ -310,6 +311,8 @@ int build(b200dsp_bank* b)
         if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_nco, 4096 * sizeof(float)))) ||
             (rc = B200_CUDA_CHECK(cudaMemcpy(b->d_nco, t.data(), 4096 * sizeof(float), cudaMemcpyHostToDevice)))) return rc;
     }
+    // the allocations above were zeroed/filled on the legacy default stream; the bank works on non-blocking streams
+    if ((rc = B200_CUDA_CHECK(cudaDeviceSynchronize()))) return rc;
     b->built = true;
     return 0;
 }
@@ -384,7 +387,7 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
         for (size_t i = 0; i < nc; ++i) {
             Channel& c = b->chans[i];
             b->h_leaf[i].src = (c.S == 0) ? nullptr : b->d_level[c.S] + (long long) b->nodes[c.node].index * b->stride[c.S];
-            b->h_leaf[i].dst = c.d_out; b->h_leaf[i].depth = c.S;
+            b->h_leaf[i].dst = c.d_out; b->h_leaf[i].depth = c.S; b->h_leaf[i].shift = c.out_shift;
         }
         for (size_t k = 0; k < b->fe_index.size(); ++k) {
             Channel& c = b->chans[b->fe_index[k]];
@@ -597,6 +600,7 @@ int b200dsp_bank_add_channel(b200dsp_bank_t* b, int requested_rate_hz, int cente
     const float ofs = filter_chain((float) (b->input_rate / -2), (float) (b->input_rate / 2),
                                    (float) (center_offset_hz - requested_rate_hz / 2), (float) (center_offset_hz + requested_rate_hz / 2), c.modes);
     c.S = (int) c.modes.size();
+    c.out_shift = c.S;
     c.out_rate = b->input_rate / (1 << c.S);
     c.residual = (int) ofs;
     if (b->built) { cudaSetDevice(b->device); cudaStreamSynchronize(b->stream); free_device(b); }   // plan changes: state restarts
@@ -604,6 +608,49 @@ int b200dsp_bank_add_channel(b200dsp_bank_t* b, int requested_rate_hz, int cente
     if (chan_id) *chan_id = (int) b->chans.size() - 1;
     if (out_rate_hz) *out_rate_hz = c.out_rate;
     if (residual_offset_hz) *residual_offset_hz = c.residual;
+    return 0;
+}
+
+// A channel given by its filter stages instead of (rate, offset).  Used to split a bank across GPUs: a bank fed with the
+// output of tree node P (depth k) holds the channels below P by their path suffix, with out_shift = k + len(suffix), and a
+// "top" bank exposes the depth-k nodes themselves as channels with out_shift = 0 (raw stage output).
+int b200dsp_bank_add_channel_path(b200dsp_bank_t* b, const int* modes, int n_modes, int out_shift, int* chan_id)
+{
+    if (!b || n_modes < 0 || n_modes > 30 || (n_modes > 0 && !modes) || out_shift < 0 || out_shift > 30) return b200_fail(B200DSP_EINVAL, "bank_add_channel_path: bad argument");
+    Channel c{};
+    for (int i = 0; i < n_modes; ++i) {
+        if (modes[i] < 0 || modes[i] > 2) return b200_fail(B200DSP_EINVAL, "bank_add_channel_path: stage mode must be 0, 1 or 2");
+        c.modes.push_back(modes[i]);
+    }
+    c.S = n_modes; c.out_shift = out_shift;
+    c.out_rate = b->input_rate / (1 << c.S);
+    if (b->built) { cudaSetDevice(b->device); cudaStreamSynchronize(b->stream); free_device(b); }
+    b->chans.push_back(c);
+    if (chan_id) *chan_id = (int) b->chans.size() - 1;
+    return 0;
+}
+
+// back to the state of freshly constructed reference objects (zero filter histories, phase 0) without rebuilding the plan
+int b200dsp_bank_reset(b200dsp_bank_t* b, void* cuda_stream)
+{
+    if (!b) return b200_fail(B200DSP_EINVAL, "null handle");
+    if (!b->built) return 0;
+    int rc = B200_CUDA_CHECK(cudaSetDevice(b->device));
+    if (rc) return rc;
+    cudaStream_t st = cuda_stream ? (cudaStream_t) cuda_stream : b->stream;
+    for (int d = 0; d < b->depth; ++d)
+        for (int k = 0; k < 2; ++k)
+            if ((rc = B200_CUDA_CHECK(cudaMemsetAsync(b->d_tail[k][d], 0, (size_t) b->levels[d].size() * TAIL_WORDS * 4, st)))) return rc;
+    for (auto& c : b->chans) {
+        c.out_count = 0;
+        if (!c.fe) continue;
+        if ((rc = B200_CUDA_CHECK(cudaMemsetAsync(c.d_state, 0, 4 * sizeof(int), st))) ||
+            (rc = B200_CUDA_CHECK(cudaMemsetAsync(c.d_hist, 0, 2 * FE_HIST_WORDS * 4, st))) ||
+            (rc = B200_CUDA_CHECK(cudaMemsetAsync(c.d_plan, 0, 4 * sizeof(long long), st)))) return rc;
+    }
+    b->produced.assign(b->depth + 1, 0);
+    b->out_count_depth.assign(32, 0);
+    b->tcur = 0; b->fe_parity = 0;
     return 0;
 }
 
@@ -727,6 +774,19 @@ int b200dsp_bank_fetch_dev(b200dsp_bank_t* b, int chan_id, int stage, const void
     return b200_fail(B200DSP_EINVAL, "bank_fetch_dev: bad stage");
 }
 
+// device-to-device copy of part of a channel's output of the last feed (asynchronous on the stream): the building block of
+// the cooperative multi-GPU bank, where one bank's node outputs are exchanged and become another bank's input
+int b200dsp_bank_copy_out_dev(b200dsp_bank_t* b, int chan_id, int64_t skip, int64_t count, void* d_dst, void* cuda_stream)
+{
+    if (!b || chan_id < 0 || chan_id >= (int) b->chans.size() || skip < 0 || count < 0 || (count > 0 && !d_dst)) return b200_fail(B200DSP_EINVAL, "bank_copy_out_dev: bad argument");
+    Channel& c = b->chans[chan_id];
+    if (skip + count > c.out_count) return b200_fail(B200DSP_EINVAL, "bank_copy_out_dev: range beyond the %lld samples of the last feed", c.out_count);
+    if (count == 0) return 0;
+    int rc = B200_CUDA_CHECK(cudaSetDevice(b->device));
+    if (rc) return rc;
+    return B200_CUDA_CHECK(cudaMemcpyAsync(d_dst, c.d_out + skip, (size_t) count * 4, cudaMemcpyDeviceToDevice, cuda_stream ? (cudaStream_t) cuda_stream : b->stream));
+}
+
 int b200dsp_bank_sync(b200dsp_bank_t* b)
 {
     if (!b) return b200_fail(B200DSP_EINVAL, "null handle");
@@ -758,7 +818,8 @@ int b200dsp_interp_create(b200dsp_interp_t** out, int phase_steps, double sample
         (rc = B200_CUDA_CHECK(cudaMemcpy(h->d_taps, h->taps.data(), h->taps.size() * 4, cudaMemcpyHostToDevice))) ||
         (rc = B200_CUDA_CHECK(cudaMalloc(&h->d_hist, hist_bytes))) || (rc = B200_CUDA_CHECK(cudaMemset(h->d_hist, 0, hist_bytes))) ||
         (rc = B200_CUDA_CHECK(cudaMalloc(&h->d_state, 16))) || (rc = B200_CUDA_CHECK(cudaMemset(h->d_state, 0, 16))) ||
-        (rc = B200_CUDA_CHECK(cudaMalloc(&h->d_plan, 32))) || (rc = B200_CUDA_CHECK(cudaMalloc(&h->d_chan, sizeof(FrontendChan))))) { b200dsp_interp_destroy(h); return rc; }
+        (rc = B200_CUDA_CHECK(cudaMalloc(&h->d_plan, 32))) || (rc = B200_CUDA_CHECK(cudaMalloc(&h->d_chan, sizeof(FrontendChan)))) ||
+        (rc = B200_CUDA_CHECK(cudaDeviceSynchronize()))) { b200dsp_interp_destroy(h); return rc; }
     *out = h;
     return 0;
 }

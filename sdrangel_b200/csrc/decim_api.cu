@@ -373,6 +373,7 @@ int b200dsp_decim_create(b200dsp_decim_t** out, int in_fmt, int out_fmt, int inp
             (rc = B200_CUDA_CHECK(cudaMalloc(&h->d_state[i], B200DSP_DECIM_STATE_ELEMS * 4))) ||
             (rc = B200_CUDA_CHECK(cudaMemset(h->d_state[i], 0, B200DSP_DECIM_STATE_ELEMS * 4)))) { b200dsp_decim_destroy(h); return rc; }
     }
+    if ((rc = B200_CUDA_CHECK(cudaDeviceSynchronize()))) { b200dsp_decim_destroy(h); return rc; }   // memsets ran on the default stream
     *out = h;
     return 0;
 }

@@ -565,6 +565,7 @@ int b200dsp_spectrum_configure(b200dsp_spectrum_t* s, int fft_size, int overlap_
     s->fill = 0; s->fix_idx = 0; s->pcur = 0;
     if ((rc = B200_CUDA_CHECK(cudaMemset(s->d_fix_sum, 0, SPEC_MAX_N * sizeof(double))))) return rc;
     if (s->d_power) { cudaFree(s->d_power); s->d_power = nullptr; s->power_cap = 0; }
+    if ((rc = B200_CUDA_CHECK(cudaDeviceSynchronize()))) return rc;      // the copies above ran on the default stream
     s->configured = true;
     return 0;
 }

@@ -162,6 +162,25 @@ class DownChannelizerBank:
         self.channels.append((cid.value, rate.value, ofs.value, path))
         return cid.value, rate.value, ofs.value, path
 
+    def add_channel_path(self, path, out_shift):
+        """Channel by explicit stages ('C','L','U' string); output = trunc(stage output / 2^out_shift).  Returns chan_id."""
+        modes = (C.c_int32 * max(len(path), 1))(*["CLU".index(ch) for ch in path])
+        cid = C.c_int32()
+        capi.check(capi.lib().b200dsp_bank_add_channel_path(self._h, modes, len(path), int(out_shift), C.byref(cid)))
+        return cid.value
+
+    def reset(self, stream=None):
+        capi.check(capi.lib().b200dsp_bank_reset(self._h, C.c_void_p(stream or 0)))
+
+    def fetch_dev(self, chan_id, stage=capi.STAGE_CHANNELIZER):
+        """(device pointer, n_samples) of the channel's output of the last feed (n is -1 for the front-end stage)."""
+        ptr, n = C.c_void_p(), C.c_int64(0)
+        capi.check(capi.lib().b200dsp_bank_fetch_dev(self._h, chan_id, stage, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def copy_out_dev(self, chan_id, skip, count, d_dst, stream=None):
+        capi.check(capi.lib().b200dsp_bank_copy_out_dev(self._h, chan_id, int(skip), int(count), C.c_void_p(d_dst), C.c_void_p(stream or 0)))
+
     def node_count(self):
         n = capi.lib().b200dsp_bank_node_count(self._h)
         if n < 0:

@@ -215,3 +215,118 @@ def test_bank_two_level_kernel_aligned_and_mixed_feeds(gpu_lib, port, golden_met
             assert got.shape == want.shape, (sz, cid)
             assert np.array_equal(got, want), (sz, cid, int(np.argmax(np.any(got != want, axis=1))))
             assert np.array_equal(plain.fetch(cid), want), (sz, cid)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_cooperative_bank_emulated_ranks_bit_exact(gpu_lib, port, golden_meta, world):
+    """The cooperative multi-GPU scheme (time-sliced top levels with halos -> all-to-all of node streams -> per-rank banks by
+    path suffix), with the ranks emulated one after the other on one GPU and the exchange done by array copies: every
+    channel's output must equal one oracle chain over the whole stream, step by step (tree bit-exact, front-end <= 1e-5)."""
+    from sdrangel_b200 import capi
+    from sdrangel_b200.coop import CoopPlan, CoopRank, HALO
+    plan1024 = golden_meta["chan_plans"]["bank1024"]
+    fs = plan1024["input_rate"]
+    rows = plan1024["channels"][3::32]                      # 32 channels spread over the band
+    fcs = [r[0] for r in rows]
+    n = 8 * 768 * 8 * 4
+    steps = 3
+    rs = np.random.RandomState(world)
+    X = rs.randint(-32768, 32768, size=(steps * n, 2)).astype(np.int16)
+    X[n - 50:n + 50] = -32768                               # a -32768 run across a step boundary
+    cutoff = float(np.float32(np.float32(12500) / np.float32(2.2)))
+    plan = CoopPlan(fs, fcs, 48000, world, n)
+    assert [c[2] for c in plan.chains] == [r[3] for r in rows]
+    ranks = [CoopRank(plan, r, frontend=(cutoff, 48000)) for r in range(world)]
+    oracles = []
+    for fc, rate, ofs, path in rows:
+        o = port.PortDownChannelizer()
+        o.configure(fs, 48000, fc)
+        oracles.append((o, port.PortFrontEnd(-ofs, rate, 48000, cutoff)))
+    Xpad = np.concatenate([np.zeros((HALO, 2), np.int16), X])
+    for t in range(steps):
+        node_out = []
+        for r, rk in enumerate(ranks):
+            a = t * n + r * plan.m                           # slice start in X; Xpad is shifted by HALO
+            rk.top.reset()
+            rk.top.feed(Xpad[a:a + HALO + plan.m])
+            outs = {}
+            for v, cid in rk.top_ids.items():
+                o = rk.top.fetch(cid)
+                assert o.shape[0] == (HALO + plan.m) >> plan.k
+                outs[v] = o[plan.skip:].copy()
+            node_out.append(outs)
+        for q, rk in enumerate(ranks):
+            for v, bank in rk.subs.items():
+                bank.feed(np.concatenate([node_out[r][v] for r in range(world)]))
+        for i, (o, fe) in enumerate(oracles):
+            q = next(r for r, (lo, hi) in enumerate(plan.ranges) if lo <= i < hi)
+            node, cid = ranks[q].chan[i]
+            want = o.feed(X[t * n:(t + 1) * n])
+            got = ranks[q].subs[node].fetch(cid)
+            assert got.shape == want.shape, (t, i)
+            assert np.array_equal(got, want), (t, i, int(np.argmax(np.any(got != want, axis=1))))
+            wf = fe.feed(want)
+            gf = ranks[q].subs[node].fetch(cid, capi.STAGE_FRONTEND)
+            assert gf.shape == wf.shape and rel_rms(gf, wf) <= 1e-5, (t, i)
+    for rk in ranks:
+        rk.close()
+
+
+@pytest.mark.gpu
+def test_cooperative_bank_device_path_wrapped_halo(gpu_lib, port, golden_meta):
+    """The same scheme through the device-pointer calls bench.py uses at N > 1 (reset / feed_dev / copy_out_dev on a caller
+    stream), two emulated ranks, the stream being one buffer repeated (slice 0's halo is the buffer's end): the second
+    step must equal oracle chains fed the buffer twice."""
+    import torch
+    from sdrangel_b200 import capi
+    from sdrangel_b200.coop import CoopPlan, CoopRank, HALO
+    world = 2
+    plan1024 = golden_meta["chan_plans"]["bank1024"]
+    fs = plan1024["input_rate"]
+    rows = plan1024["channels"][5::64]
+    fcs = [r[0] for r in rows]
+    n = world * 768 * 8 * 16
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    x = torch.randint(-2048, 2048, (2 * n,), dtype=torch.int16, device=dev, generator=g)
+    hx = x.cpu().numpy().reshape(-1, 2)
+    cutoff = float(np.float32(np.float32(12500) / np.float32(2.2)))
+    p = CoopPlan(fs, fcs, 48000, world, n)
+    ranks = [CoopRank(p, r, frontend=(cutoff, 48000)) for r in range(world)]
+    xi = x.view(torch.int32)
+    xcat = torch.cat([xi[-HALO:], xi])
+    stream = torch.cuda.Stream(device=dev)
+    sptr = stream.cuda_stream
+    torch.cuda.synchronize()
+    node_buf = {v: torch.empty((world, p.mk), dtype=torch.int32, device=dev) for v in p.nodes}
+    with torch.cuda.stream(stream):
+        for step in range(2):
+            # first step: nothing precedes the stream (zero history, as the oracle); then the buffer's end precedes its start
+            xcat[:HALO] = 0 if step == 0 else xi[-HALO:]
+            for r, rk in enumerate(ranks):
+                sl = xcat[r * p.m: r * p.m + HALO + p.m].clone()
+                rk.top.reset(sptr)
+                rk.top.feed_dev(sl.data_ptr(), HALO + p.m, sptr)
+                for v in p.nodes:
+                    rk.top.copy_out_dev(rk.top_ids[v], p.skip, p.mk, node_buf[v][r].data_ptr(), sptr)
+            for rk in ranks:
+                for v, bank in rk.subs.items():
+                    bank.feed_dev(node_buf[v].data_ptr(), p.n >> p.k, sptr)
+    stream.synchronize()
+    for i, (fc, rate, ofs, path) in enumerate(rows):
+        o = port.PortDownChannelizer()
+        o.configure(fs, 48000, fc)
+        fe = port.PortFrontEnd(-ofs, rate, 48000, cutoff)
+        fe.feed(o.feed(hx))
+        ch = o.feed(hx)
+        want = fe.feed(ch)
+        q = next(r for r, (lo, hi) in enumerate(p.ranges) if lo <= i < hi)
+        node, cid = ranks[q].chan[i]
+        got = ranks[q].subs[node].fetch(cid)
+        assert got.shape == ch.shape, i
+        assert np.array_equal(got, ch), (i, int(np.argmax(np.any(got != ch, axis=1))))
+        gf = ranks[q].subs[node].fetch(cid, capi.STAGE_FRONTEND)
+        assert gf.shape == want.shape and rel_rms(gf, want) <= 1e-5, i
+    for rk in ranks:
+        rk.close()

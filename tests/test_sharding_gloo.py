@@ -100,3 +100,23 @@ def test_reference_arm_under_two_ranks_prints_one_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port")
+
+
+def test_coop_plan_host_logic(golden_meta):
+    """Cooperative plan: every channel is owned by exactly one rank below one depth-k node, and the per-rank tree work is
+    close to 1/N of the single-GPU tree (21.0 stage inputs for the 1024-channel plan)."""
+    sys.path.insert(0, ROOT)
+    from sdrangel_b200.coop import CoopPlan, HALO
+    plan = golden_meta["chan_plans"]["bank1024"]
+    fcs = [r[0] for r in plan["channels"]]
+    n = 3 << 24
+    for world in (1, 2, 4, 8):
+        p = CoopPlan(plan["input_rate"], fcs, 48000, world, n)
+        assert p.k == {1: 0, 2: 1, 4: 2, 8: 3}[world]
+        owned = sorted(i for r in range(world) for v in p.rank_nodes[r] for i in p.channels_of(r, v))
+        assert owned == list(range(len(fcs)))
+        assert p.m * world == n and p.mk << p.k == p.m and p.skip << p.k == HALO
+        work = [p.stage_inputs(r) for r in range(world)]
+        assert max(work) <= 21.0 / world * 1.25 + 0.01, (world, work)
+    with pytest.raises(ValueError):
+        CoopPlan(plan["input_rate"], fcs, 48000, 8, 12345)
