@@ -531,30 +531,42 @@ def bench_bank(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=T
                                   "note": "binding roof: 27 instructions per stage-input sample over the shared-prefix tree + ~160 per front-end output"}},
            "dtype": "s32", "scaling": "strong"}
     if want_e2e:
-        n_e = min(n, 3 << 20)
-        hx = torch.empty((2 * n_e,), dtype=torch.int16, pin_memory=True)
+        # end to end through the plugin-facing calls: the baseband starts in pinned host memory (on rank 0: the ingest GPU's
+        # host), H2D, NCCL broadcast (N > 1), the bank, and ONE pooled device-to-host fetch of every channel's front-end output
+        hx = torch.empty((2 * n,), dtype=torch.int16, pin_memory=True) if c.rank == 0 else None
         if c.rank == 0:
-            hx.copy_(x[: 2 * n_e])
-        L_ = capi.lib()
-        outs = [torch.empty((int(n_e * 48000 / rate * (rate / fs)) + 64, 2), dtype=torch.float32, pin_memory=True) for _, rate, _, _ in info]
-        nn = C.c_int64(0)
+            hx.copy_(x)
+        stride = int(n * 48000.0 / fs) + 64
+        hout = torch.empty((max(len(info), 1), stride, 2), dtype=torch.float32, pin_memory=True)
+        for w in list(pending.values()):
+            w.wait()
+        pending.clear()
+        counts = {}
 
         def e2e_step():
-            capi.check(L_.b200dsp_bank_feed(bank._h, hx.data_ptr(), n_e))
-            for (cid, _, _, _), o in zip(info, outs):
-                capi.check(L_.b200dsp_bank_fetch(bank._h, cid, capi.STAGE_FRONTEND, o.data_ptr(), o.shape[0], C.byref(nn)))
+            if c.rank == 0:
+                x.copy_(hx, non_blocking=True)
+            if c.world > 1:
+                dist.broadcast(bviews[0], src=0)
+            bank.feed_dev(x.data_ptr(), n, sptr)
+            counts["n"] = bank.fetch_all(capi.STAGE_FRONTEND, stride=stride, out_ptr=hout.data_ptr(), stream=sptr)
 
-        e2e_step()
-        barrier(c)
-        t0 = time.perf_counter()
-        ksteps = 3
-        for _ in range(ksteps):
+        with torch.cuda.stream(stream):
             e2e_step()
-        torch.cuda.synchronize()
-        dt = max_over_ranks(c, time.perf_counter() - t0)
-        res["e2e"] = {"value": n_e * ksteps / dt / 1e6, "unit": "input MS/s", "h2d_bytes_per_step": int(n_e * 4),
-                      "d2h_bytes_per_step": int(len(mine) * nn.value * 8), "steps": ksteps,
-                      "api": "b200dsp_bank_feed (host pointer, pinned) + b200dsp_bank_fetch of every channel's front-end output", "samples_per_step": n_e}
+            barrier(c)
+            t0 = time.perf_counter()
+            ksteps = 3
+            for _ in range(ksteps):
+                e2e_step()
+            torch.cuda.synchronize()
+            dt = max_over_ranks(c, time.perf_counter() - t0)
+            tot = torch.tensor([float(counts["n"].sum()) * 8], device=c.dev, dtype=torch.float64)
+            if c.world > 1:
+                dist.all_reduce(tot)
+        res["e2e"] = {"value": n * ksteps / dt / 1e6, "unit": "input MS/s", "h2d_bytes_per_step": int(n * 4),
+                      "d2h_bytes_per_step": int(tot.item()), "steps": ksteps,
+                      "api": "pinned host baseband -> H2D%s -> b200dsp_bank_feed_dev -> b200dsp_bank_fetch_all (every channel's front-end output, "
+                             "pinned host)" % (" on rank 0 -> NCCL broadcast" if c.world > 1 else ""), "samples_per_step": n}
     bank.close()
     return res
 

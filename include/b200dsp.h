@@ -132,6 +132,11 @@ int b200dsp_bank_feed_dev(b200dsp_bank_t* b, const void* d_iq, int64_t n_samples
 /* outputs produced by the last feed for one channel; stage selects int16 IQ (4 bytes/sample) or complex64 (8 bytes) */
 int b200dsp_bank_fetch(b200dsp_bank_t* b, int chan_id, int stage, void* out, int64_t cap_samples, int64_t* n_samples);
 int b200dsp_bank_fetch_dev(b200dsp_bank_t* b, int chan_id, int stage, const void** d_ptr, int64_t* n_samples);
+/* every channel's outputs of the last feed in one transfer (what DSPDeviceSourceEngine::work's loop over the channel sinks
+ * hands out, dspdevicesourceengine.cpp:325-408): channel c's samples land at out + c * stride_samples (samples of 4 or 8
+ * bytes by stage), counts[c] = its sample count (0 for a channel without that stage); waits for the stream (NULL: the
+ * bank's own) before returning.  Pinned `out` makes it one DMA. */
+int b200dsp_bank_fetch_all(b200dsp_bank_t* b, int stage, void* out, int64_t stride_samples, int64_t* counts, void* cuda_stream);
 /* device-to-device copy of samples [skip, skip + count) of a channel's channelizer output of the last feed */
 int b200dsp_bank_copy_out_dev(b200dsp_bank_t* b, int chan_id, int64_t skip, int64_t count, void* d_dst, void* cuda_stream);
 int b200dsp_bank_sync(b200dsp_bank_t* b);

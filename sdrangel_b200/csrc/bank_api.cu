@@ -21,6 +21,8 @@ namespace {
 // ---------------------------------------------------------------------------------------------------------
 // small kernels around the level kernel
 // ---------------------------------------------------------------------------------------------------------
+struct GatherSrc { const void* src; const int* state; long long count; };     // state != null: count = state[3] (front-end)
+
 struct LeafChan { const uint32_t* src; uint32_t* dst; int depth; int shift; };     // static per channel (until a reallocation)
 
 // channel output = trunc_toward_zero(y / 2^S) per component (downchannelizer.cpp:78-83)
@@ -39,6 +41,19 @@ __global__ void hb48_finalize_kernel(const LeafChan* chans, const PassInfo pi)
         im = (im + ((im >> 31) & bias)) >> c.shift;
         dst[k] = ((uint32_t) re & 0xffffu) | ((uint32_t) im << 16);
     }
+}
+
+// pooled fetch: channel c's outputs of the last feed -> pool[c * stride ...], its count -> counts[c]
+template <typename T>
+__global__ void gather_outputs_kernel(const GatherSrc* srcs, T* pool, long long stride, long long* counts)
+{
+    const GatherSrc g = srcs[blockIdx.y];
+    long long n = g.state ? (long long) g.state[3] : g.count;
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts[blockIdx.y] = n;
+    if (n > stride) n = stride;                 // reported through counts; the host call turns it into an error
+    const T* src = static_cast<const T*>(g.src);
+    T* dst = pool + (long long) blockIdx.y * stride;
+    for (long long k = (long long) blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long) gridDim.x * blockDim.x) dst[k] = src[k];
 }
 
 __global__ void copy_words_kernel(const uint32_t* src, uint32_t* dst, long long n)
@@ -172,6 +187,9 @@ struct b200dsp_bank {
     bool tables_dirty;                           // channel pointer tables must be re-uploaded (after a (re)allocation)
     std::vector<long long> out_count_depth;      // channel outputs per depth produced in the current feed
     std::vector<int> fe_index;                   // channel ids with a front-end
+    // pooled fetch (b200dsp_bank_fetch_all): [channel][stride] staging + per-channel source table and counts
+    void* d_pool; size_t pool_bytes;
+    GatherSrc* d_gsrc; long long* d_gcnt; size_t gcap;
 };
 
 namespace {
@@ -187,6 +205,10 @@ void free_device(b200dsp_bank* b)
     if (b->d_leaf) cudaFree(b->d_leaf);
     if (b->d_fe) cudaFree(b->d_fe);
     b->d_leaf = nullptr; b->d_fe = nullptr;
+    if (b->d_pool) cudaFree(b->d_pool);
+    if (b->d_gsrc) cudaFree(b->d_gsrc);
+    if (b->d_gcnt) cudaFree(b->d_gcnt);
+    b->d_pool = nullptr; b->pool_bytes = 0; b->d_gsrc = nullptr; b->d_gcnt = nullptr; b->gcap = 0;
     for (auto& c : b->chans) {
         if (c.d_out) cudaFree(c.d_out);
         if (c.d_hist) cudaFree(c.d_hist);
@@ -772,6 +794,54 @@ int b200dsp_bank_fetch_dev(b200dsp_bank_t* b, int chan_id, int stage, const void
     if (stage == B200DSP_STAGE_CHANNELIZER) { *d_ptr = c.d_out; if (n) *n = c.out_count; return 0; }
     if (stage == B200DSP_STAGE_FRONTEND && c.fe) { *d_ptr = c.d_fe_out; if (n) *n = -1; return 0; }
     return b200_fail(B200DSP_EINVAL, "bank_fetch_dev: bad stage");
+}
+
+// Every channel's outputs of the last feed with one gather kernel and one device-to-host transfer (the per-channel
+// b200dsp_bank_fetch costs a synchronous small copy per channel: latency-bound for a 1024-channel bank).
+int b200dsp_bank_fetch_all(b200dsp_bank_t* b, int stage, void* out, int64_t stride_samples, int64_t* counts, void* cuda_stream)
+{
+    if (!b || !out || !counts || stride_samples <= 0) return b200_fail(B200DSP_EINVAL, "bank_fetch_all: bad argument");
+    if (stage != B200DSP_STAGE_CHANNELIZER && stage != B200DSP_STAGE_FRONTEND) return b200_fail(B200DSP_EINVAL, "bank_fetch_all: bad stage");
+    const size_t nc = b->chans.size();
+    if (nc == 0) return 0;
+    int rc = B200_CUDA_CHECK(cudaSetDevice(b->device));
+    if (rc) return rc;
+    cudaStream_t st = cuda_stream ? (cudaStream_t) cuda_stream : b->stream;
+    const size_t elem = (stage == B200DSP_STAGE_FRONTEND) ? sizeof(float2) : sizeof(uint32_t);
+    const size_t need = nc * (size_t) stride_samples * elem;
+    if (b->pool_bytes < need || b->gcap < nc) {
+        if ((rc = B200_CUDA_CHECK(cudaStreamSynchronize(st)))) return rc;
+        if (b->d_pool) cudaFree(b->d_pool);
+        if (b->d_gsrc) cudaFree(b->d_gsrc);
+        if (b->d_gcnt) cudaFree(b->d_gcnt);
+        b->d_pool = nullptr; b->d_gsrc = nullptr; b->d_gcnt = nullptr; b->pool_bytes = 0; b->gcap = 0;
+        if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_pool, need))) || (rc = B200_CUDA_CHECK(cudaMalloc(&b->d_gsrc, nc * sizeof(GatherSrc)))) ||
+            (rc = B200_CUDA_CHECK(cudaMalloc(&b->d_gcnt, nc * sizeof(long long))))) return rc;
+        b->pool_bytes = need; b->gcap = nc;
+    }
+    std::vector<GatherSrc> g(nc);
+    long long max_count = 0;
+    for (size_t i = 0; i < nc; ++i) {
+        const Channel& c = b->chans[i];
+        if (stage == B200DSP_STAGE_CHANNELIZER) { g[i].src = c.d_out; g[i].state = nullptr; g[i].count = b->built ? c.out_count : 0; }
+        else if (c.fe && b->built && c.d_fe_out) { g[i].src = c.d_fe_out; g[i].state = c.d_state; g[i].count = 0; }
+        else { g[i].src = nullptr; g[i].state = nullptr; g[i].count = 0; }
+        if (c.out_count > max_count) max_count = c.out_count;       // front-end outputs never exceed the channel's input count when decimating
+    }
+    if (max_count > stride_samples) max_count = stride_samples;
+    if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(b->d_gsrc, g.data(), nc * sizeof(GatherSrc), cudaMemcpyHostToDevice, st)))) return rc;
+    int gx = (int) ((max_count + 1023) / 1024);
+    if (gx < 1) gx = 1;
+    if (gx > 256) gx = 256;
+    if (stage == B200DSP_STAGE_FRONTEND) gather_outputs_kernel<float2><<<dim3(gx, (unsigned) nc), 256, 0, st>>>(b->d_gsrc, (float2*) b->d_pool, stride_samples, b->d_gcnt);
+    else gather_outputs_kernel<uint32_t><<<dim3(gx, (unsigned) nc), 256, 0, st>>>(b->d_gsrc, (uint32_t*) b->d_pool, stride_samples, b->d_gcnt);
+    if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
+    if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(out, b->d_pool, need, cudaMemcpyDeviceToHost, st))) ||
+        (rc = B200_CUDA_CHECK(cudaMemcpyAsync(counts, b->d_gcnt, nc * sizeof(long long), cudaMemcpyDeviceToHost, st))) ||
+        (rc = B200_CUDA_CHECK(cudaStreamSynchronize(st)))) return rc;
+    for (size_t i = 0; i < nc; ++i)
+        if (counts[i] > stride_samples) return b200_fail(B200DSP_EINVAL, "bank_fetch_all: stride too small (channel %d has %lld samples)", (int) i, (long long) counts[i]);
+    return 0;
 }
 
 // device-to-device copy of part of a channel's output of the last feed (asynchronous on the stream): the building block of

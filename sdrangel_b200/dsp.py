@@ -137,6 +137,7 @@ class DownChannelizerBank:
         self._h = h
         self.input_rate = int(input_rate)
         self.channels = []
+        self._n_channels = 0
 
     def close(self):
         if getattr(self, "_h", None):
@@ -160,6 +161,7 @@ class DownChannelizerBank:
         n = capi.lib().b200dsp_bank_channel_path(self._h, cid.value, modes, 32)
         path = "".join("CLU"[modes[i]] for i in range(n))
         self.channels.append((cid.value, rate.value, ofs.value, path))
+        self._n_channels = max(self._n_channels, cid.value + 1)
         return cid.value, rate.value, ofs.value, path
 
     def add_channel_path(self, path, out_shift):
@@ -167,6 +169,7 @@ class DownChannelizerBank:
         modes = (C.c_int32 * max(len(path), 1))(*["CLU".index(ch) for ch in path])
         cid = C.c_int32()
         capi.check(capi.lib().b200dsp_bank_add_channel_path(self._h, modes, len(path), int(out_shift), C.byref(cid)))
+        self._n_channels = max(self._n_channels, cid.value + 1)
         return cid.value
 
     def reset(self, stream=None):
@@ -214,6 +217,23 @@ class DownChannelizerBank:
         out = np.empty((max(n.value, 1), 2), dtype=dt)
         capi.check(capi.lib().b200dsp_bank_fetch(self._h, chan_id, stage, out.ctypes.data, out.shape[0], C.byref(n)))
         return out[:n.value]
+
+    def fetch_all(self, stage=capi.STAGE_CHANNELIZER, stride=None, out_ptr=None, stream=None, n_channels=None):
+        """Every channel's outputs of the last feed in one transfer.  Returns (array [n_channels, stride, 2], counts);
+        with `out_ptr` (e.g. pinned memory of n_channels * stride samples) only the counts array is returned."""
+        nc = int(n_channels if n_channels is not None else self._n_channels)
+        counts = np.zeros(nc, dtype=np.int64)
+        if nc == 0:
+            return (np.empty((0, 0, 2), np.int16 if stage == capi.STAGE_CHANNELIZER else np.float32), counts) if out_ptr is None else counts
+        if stride is None:
+            stride = max(1, max(self.fetch_dev(c, capi.STAGE_CHANNELIZER)[1] for c in range(nc)))
+        L = capi.lib()
+        if out_ptr is not None:
+            capi.check(L.b200dsp_bank_fetch_all(self._h, stage, C.c_void_p(out_ptr), int(stride), counts.ctypes.data, C.c_void_p(stream or 0)))
+            return counts
+        out = np.empty((nc, int(stride), 2), dtype=np.int16 if stage == capi.STAGE_CHANNELIZER else np.float32)
+        capi.check(L.b200dsp_bank_fetch_all(self._h, stage, out.ctypes.data, int(stride), counts.ctypes.data, C.c_void_p(stream or 0)))
+        return out, counts
 
 
 class SpectrumVis:

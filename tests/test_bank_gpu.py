@@ -147,6 +147,16 @@ def test_bank_with_frontends_vs_oracle(gpu_lib, port, golden_meta):
             got = b.fetch(cid, capi.STAGE_FRONTEND)
             assert got.shape == want.shape
             assert rel_rms(got, want) <= 1e-5
+        # the pooled fetch hands out exactly what the per-channel fetch does, for both stages
+        ch_all, ch_cnt = b.fetch_all(capi.STAGE_CHANNELIZER)
+        fe_all, fe_cnt = b.fetch_all(capi.STAGE_FRONTEND, stride=ch_all.shape[1])
+        for cid in ids:
+            one = b.fetch(cid)
+            assert ch_cnt[cid] == one.shape[0] and np.array_equal(ch_all[cid, :ch_cnt[cid]], one)
+            onef = b.fetch(cid, capi.STAGE_FRONTEND)
+            assert fe_cnt[cid] == onef.shape[0] and np.array_equal(fe_all[cid, :fe_cnt[cid]], onef)
+    with pytest.raises(RuntimeError):
+        b.fetch_all(capi.STAGE_FRONTEND, stride=1)             # stride too small: loud, not truncated
 
 
 @pytest.mark.parametrize("rate,outr", [(156250, 48000), (60000, 48000), (78125, 48000), (48000, 48000)])
