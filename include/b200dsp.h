@@ -33,6 +33,8 @@ extern "C" {
 /* sample formats */
 #define B200DSP_FMT_I16   0   /* int16 interleaved I,Q  (reference: qint16 buffers / Sample, dsptypes.h:44-65) */
 #define B200DSP_FMT_F32   1   /* float interleaved I,Q  (reference: FSample, dsptypes.h:67-93) */
+#define B200DSP_FMT_I8    2   /* int8 interleaved I,Q   (reference: qint8 device buffers, hackrfinputthread.h:57) */
+#define B200DSP_FMT_U8    3   /* uint8 interleaved I,Q  (reference: quint8 device buffers, rtlsdrthread.h:55) */
 /* fc position, same meaning as the reference's m_fcPos switch (plugins/samplesource/airspy/airspythread.cpp:118-202) */
 #define B200DSP_MODE_INF  0
 #define B200DSP_MODE_SUP  1
@@ -51,12 +53,17 @@ int         b200dsp_sm_count(void);
  *   in F32, out I16 : DecimatorsFI                               sdrbase/dsp/decimatorsfi.h:26-55
  *   in F32, out F32 : DecimatorsFF                               sdrbase/dsp/decimatorsff.h
  *   in I16, out F32 : DecimatorsIF<qint16,input_bits>            sdrbase/dsp/decimatorsif.h:53-83
+ *   in I8,  out I16 : Decimators<qint32,qint8,16,8>              plugins/samplesource/hackrfinput/hackrfinputthread.h:57
+ *   in U8,  out I16 : DecimatorsU<qint32,quint8,16,8,Shift>      sdrbase/dsp/decimatorsu.h:175-215 (Shift 127: rtlsdrthread.h:55)
  * input_bits in {8,12,16} selects decimation_shifts<16,input_bits> (decimators.h:79-167) / the IF scale.
  */
 typedef struct b200dsp_decim b200dsp_decim_t;
 
 int b200dsp_decim_create(b200dsp_decim_t** h, int in_fmt, int out_fmt, int input_bits);
 int b200dsp_decim_destroy(b200dsp_decim_t* h);
+
+/* DecimatorsU's Shift template argument (sample = byte - Shift, decimatorsu.h:225-226,241-249); U8 handles only, default 127 */
+int b200dsp_decim_set_shift(b200dsp_decim_t* h, int shift);
 
 /* float arithmetic flavour: 0 (default) = fused multiply-add accumulation (within 1e-5 rel. RMS of the
  * reference), 1 = separately rounded add/mul/add in the reference's order (bit-identical to the reference

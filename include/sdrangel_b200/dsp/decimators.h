@@ -50,12 +50,14 @@ protected:
     void decimate64_cen(ItVec::iterator* it, const TIn* buf, qint32 len) { this->run(6, B200DSP_MODE_CEN, it, buf, len); }
 
 /** Decimators with integer input and integer output (decimators.h:277-341).  StorageType is the reference's filter
- *  accumulator type (qint32 in 16-bit Rx mode); T must be qint16 here (the 8-bit/unsigned device variants are SURVEY.md 8f). */
+ *  accumulator type (qint32 in 16-bit Rx mode); T is qint16 (Airspy, LimeSDR, PlutoSDR, BladeRF, SDRplay, TestSource) or
+ *  qint8 with InputBits 8 (HackRF, hackrfinputthread.h:57).  The unsigned variant is DecimatorsU (decimatorsu.h). */
 template<typename StorageType, typename T, uint SdrBits, uint InputBits>
-class Decimators : public b200dsp_cxx::DecimatorsImpl<B200DSP_FMT_I16, B200DSP_FMT_I16, T, SampleVector> {
-    static_assert(sizeof(T) == 2 && SdrBits == 16 && sizeof(StorageType) == 4, "16-bit Rx mode: Decimators<qint32, qint16, 16, {8,12,16}>");
+class Decimators : public b200dsp_cxx::DecimatorsImpl<(sizeof(T) == 1 ? B200DSP_FMT_I8 : B200DSP_FMT_I16), B200DSP_FMT_I16, T, SampleVector> {
+    static_assert((sizeof(T) == 2 || (sizeof(T) == 1 && InputBits == 8)) && SdrBits == 16 && sizeof(StorageType) == 4,
+                  "16-bit Rx mode: Decimators<qint32, qint16, 16, {8,12,16}> or Decimators<qint32, qint8, 16, 8>");
 public:
-    Decimators() : b200dsp_cxx::DecimatorsImpl<B200DSP_FMT_I16, B200DSP_FMT_I16, T, SampleVector>(InputBits) {}
+    Decimators() : b200dsp_cxx::DecimatorsImpl<(sizeof(T) == 1 ? B200DSP_FMT_I8 : B200DSP_FMT_I16), B200DSP_FMT_I16, T, SampleVector>(InputBits) {}
     B200DSP_DECIM_ENTRY_POINTS(SampleVector, T)
 };
 #endif

@@ -189,6 +189,35 @@ int orc_decim_ii_run(void* h, int log2, int mode, const int16_t* buf, int len, i
     return (int) ((o - out) / 2);
 }
 
+/* 8-bit device samples: Decimators<qint32,qint8,16,8> (hackrfinputthread.h:57; decimators.h entry points with T = qint8)
+ * and DecimatorsU<qint32,quint8,16,8,Shift> (decimatorsu.h:218-231,241-249: every scalar enters as (buf[i] - Shift) << pre,
+ * otherwise the text of decimators.h).  Both are the <16,8> integer cascade on the widened scalars. */
+typedef struct { void* ii; int is_unsigned, shift; int16_t* tmp; int cap; } decim_x8;
+
+void* orc_decim_x8_create(int is_unsigned, int shift)
+{
+    decim_x8* d = (decim_x8*) calloc(1, sizeof(decim_x8));
+    d->ii = orc_decim_ii_create(8);
+    d->is_unsigned = is_unsigned; d->shift = is_unsigned ? shift : 0;
+    return d;
+}
+void orc_decim_x8_destroy(void* h)
+{
+    decim_x8* d = (decim_x8*) h;
+    if (!d) return;
+    orc_decim_ii_destroy(d->ii);
+    free(d->tmp);
+    free(d);
+}
+int orc_decim_x8_run(void* h, int log2, int mode, const uint8_t* buf, int len, int16_t* out)
+{
+    decim_x8* d = (decim_x8*) h;
+    if (len > d->cap) { free(d->tmp); d->tmp = (int16_t*) malloc((size_t) len * sizeof(int16_t)); d->cap = len; }
+    for (int i = 0; i < len; i++)
+        d->tmp[i] = d->is_unsigned ? (int16_t) ((int) buf[i] - d->shift) : (int16_t) (int8_t) buf[i];
+    return orc_decim_ii_run(d->ii, log2, mode, d->tmp, len, out);
+}
+
 /* ------------------------------------------------------------------------------------------------
  * HB64 float stage: y = ((..(0 + hF0*(a0+b0)) + hF1*(a1+b1)) ..) + 0.5f*centre, float throughout.
  * inthalfbandfiltereof.h:63-71,141-188.

@@ -27,6 +27,12 @@ void* orc_decim_ii_create(int input_bits);
 void  orc_decim_ii_destroy(void* h);
 int   orc_decim_ii_run(void* h, int log2, int mode, const int16_t* buf, int len, int16_t* out);
 
+/* 8-bit inputs: Decimators<qint32,qint8,16,8> (is_unsigned 0) / DecimatorsU<qint32,quint8,16,8,shift> (is_unsigned 1):
+ * hackrfinputthread.h:57, rtlsdrthread.h:55, sdrbase/dsp/decimatorsu.h:175-249 */
+void* orc_decim_x8_create(int is_unsigned, int shift);
+void  orc_decim_x8_destroy(void* h);
+int   orc_decim_x8_run(void* h, int log2, int mode, const uint8_t* buf, int len, int16_t* out);
+
 /* DecimatorsFI / DecimatorsFF / DecimatorsIF: sdrbase/dsp/decimatorsfi.cpp, decimatorsff.cpp, decimatorsif.h */
 void* orc_decim_f_create(int in_fmt, int out_fmt, int input_bits);
 void  orc_decim_f_destroy(void* h);

@@ -40,6 +40,8 @@ def load():
         "orc_sdrbench_gen_s16": (None, [pi16, i32]), "orc_sdrbench_gen_f32": (None, [pf32, i32]),
         "orc_decim_ii_create": (vp, [i32]), "orc_decim_ii_destroy": (None, [vp]),
         "orc_decim_ii_run": (i32, [vp, i32, i32, pi16, i32, pi16]),
+        "orc_decim_x8_create": (vp, [i32, i32]), "orc_decim_x8_destroy": (None, [vp]),
+        "orc_decim_x8_run": (i32, [vp, i32, i32, vp, i32, pi16]),
         "orc_decim_f_create": (vp, [i32, i32, i32]), "orc_decim_f_destroy": (None, [vp]),
         "orc_decim_f_run": (i32, [vp, i32, i32, vp, i32, vp]),
         "orc_chan_create": (vp, []), "orc_chan_destroy": (None, [vp]),
@@ -75,12 +77,14 @@ class _Handle:
 
 
 class PortDecimators(_Handle):
-    def __init__(self, kind="ii", input_bits=12):
+    def __init__(self, kind="ii", input_bits=12, shift=127):
         L = load()
         self.kind = kind
-        self.in_dt = np.int16 if kind[0] == "i" else np.float32
-        self.out_dt = np.int16 if kind[1] == "i" else np.float32
-        if kind == "ii":
+        self.in_dt = {"i8": np.int8, "u8": np.uint8}.get(kind, np.int16 if kind[0] == "i" else np.float32)
+        self.out_dt = np.int16 if kind[1] in "i8" else np.float32
+        if kind in ("i8", "u8"):            # input_bits is 8 by construction; `shift` only matters for 'u8'
+            super().__init__(L.orc_decim_x8_create(int(kind == "u8"), shift), L.orc_decim_x8_destroy)
+        elif kind == "ii":
             super().__init__(L.orc_decim_ii_create(input_bits), L.orc_decim_ii_destroy)
         else:
             super().__init__(L.orc_decim_f_create(FMT_I16 if kind[0] == "i" else FMT_F32,
@@ -91,7 +95,9 @@ class PortDecimators(_Handle):
         L = load()
         buf = np.ascontiguousarray(buf, dtype=self.in_dt)
         out = np.empty((buf.size // 2 + 8, 2), dtype=self.out_dt)
-        if self.kind == "ii":
+        if self.kind in ("i8", "u8"):
+            n = L.orc_decim_x8_run(self.h, log2, mode, buf.ctypes.data, buf.size, _p(out, C.c_int16))
+        elif self.kind == "ii":
             n = L.orc_decim_ii_run(self.h, log2, mode, _p(buf, C.c_int16), buf.size, _p(out, C.c_int16))
         else:
             n = L.orc_decim_f_run(self.h, log2, mode, buf.ctypes.data, buf.size, out.ctypes.data)

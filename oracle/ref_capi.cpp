@@ -82,6 +82,8 @@ struct DecimII {
     SampleVector out;
 };
 
+// 8-bit signed device format: HackRF (hackrfinputthread.h:57); the unsigned one (DecimatorsU) lives in ref_capi_u8.cpp
+struct DecimI8 { Decimators<qint32, qint8, SDR_RX_SAMP_SZ, 8> d; SampleVector out; };
 struct DecimFI { DecimatorsFI d; SampleVector out; };
 struct DecimFF { DecimatorsFF d; FSampleVector out; };
 struct DecimIF {
@@ -166,6 +168,20 @@ int ref_decim_ii_run(void* p, int log2, int mode, const int16_t* buf, int len, i
     return n;
 }
 
+// ---------------------------------------------------------------- 8-bit inputs (int8 / uint8-127 -> int16)
+void* ref_decim_i8_create() { return new DecimI8; }
+void ref_decim_i8_destroy(void* p) { delete (DecimI8*) p; }
+int ref_decim_i8_run(void* p, int log2, int mode, const int8_t* buf, int len, int16_t* out)
+{
+    DecimI8* h = (DecimI8*) p;
+    std::size_t need = (std::size_t) (len / 2) + 8;
+    if (h->out.size() < need) h->out.resize(need);
+    SampleVector::iterator it = h->out.begin();
+    if (!dispatch(h->d, log2, mode, &it, (const qint8*) buf, len)) return -1;
+    int n = (int) (it - h->out.begin());
+    if (n > 0) memcpy(out, &h->out[0], (std::size_t) n * sizeof(Sample));
+    return n;
+}
 // ---------------------------------------------------------------- DecimatorsFI (float -> int16)
 void* ref_decim_fi_create() { return new DecimFI; }
 void ref_decim_fi_destroy(void* p) { delete (DecimFI*) p; }

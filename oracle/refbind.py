@@ -36,6 +36,10 @@ def load(strict=False):
     sig = {
         "ref_decim_ii_create": (vp, [i32]), "ref_decim_ii_destroy": (None, [vp]),
         "ref_decim_ii_run": (i32, [vp, i32, i32, pi16, i32, pi16]),
+        "ref_decim_i8_create": (vp, []), "ref_decim_i8_destroy": (None, [vp]),
+        "ref_decim_i8_run": (i32, [vp, i32, i32, C.POINTER(C.c_int8), i32, pi16]),
+        "ref_decim_u8_create": (vp, []), "ref_decim_u8_destroy": (None, [vp]),
+        "ref_decim_u8_run": (i32, [vp, i32, i32, C.POINTER(C.c_uint8), i32, pi16]),
         "ref_decim_fi_create": (vp, []), "ref_decim_fi_destroy": (None, [vp]),
         "ref_decim_fi_run": (i32, [vp, i32, i32, pf32, i32, pi16]),
         "ref_decim_ff_create": (vp, []), "ref_decim_ff_destroy": (None, [vp]),
@@ -78,7 +82,8 @@ class _Handle:
 
 
 class RefDecimators(_Handle):
-    """kind: 'ii' (int16->int16), 'fi' (float->int16), 'ff' (float->float), 'if' (int16->float)."""
+    """kind: 'ii' (int16->int16), 'fi' (float->int16), 'ff' (float->float), 'if' (int16->float),
+    'i8' (int8->int16, Decimators<qint32,qint8,16,8>), 'u8' (uint8->int16, DecimatorsU<qint32,quint8,16,8,127>)."""
 
     def __init__(self, kind="ii", input_bits=12, strict=False):
         L = load(strict)
@@ -89,13 +94,13 @@ class RefDecimators(_Handle):
             h = getattr(L, f"ref_decim_{kind}_create")()
         super().__init__(L, h, getattr(L, f"ref_decim_{kind}_destroy"))
         self._run = getattr(L, f"ref_decim_{kind}_run")
-        self.in_dt = np.int16 if kind[0] == "i" else np.float32
-        self.out_dt = np.int16 if kind[1] == "i" else np.float32
+        self.in_dt = {"i8": np.int8, "u8": np.uint8}.get(kind, np.int16 if kind[0] == "i" else np.float32)
+        self.out_dt = np.int16 if kind[1] in "i8" else np.float32
 
     def run(self, log2, mode, buf):
         buf = np.ascontiguousarray(buf, dtype=self.in_dt)
         out = np.empty((buf.size // 2 + 8, 2), dtype=self.out_dt)
-        ct_in = C.c_int16 if self.in_dt == np.int16 else C.c_float
+        ct_in = {np.int16: C.c_int16, np.float32: C.c_float, np.int8: C.c_int8, np.uint8: C.c_uint8}[self.in_dt]
         ct_out = C.c_int16 if self.out_dt == np.int16 else C.c_float
         n = self._run(self.h, log2, mode, _p(buf, ct_in), buf.size, _p(out, ct_out))
         if n < 0:

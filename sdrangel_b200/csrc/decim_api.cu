@@ -20,7 +20,7 @@ enum { EW_COPY = 0, EW_HALF = 1, EW_DIV4 = 2 };
 struct EwParams {
     const void* in; void* out;
     long long n_units;     // COPY: IQ samples, HALF/DIV4: groups of 8 scalars
-    int kind, sup, pre;
+    int kind, sup, pre, shift;
     float out_scale;
 };
 
@@ -80,6 +80,23 @@ __global__ void ew_int_copy_kernel(const EwParams p)
     }
 }
 
+// 8-bit inputs: Decimators<qint32,qint8,16,8>::decimate1 / DecimatorsU<...,Shift>::decimate1 (decimatorsu.h:218-231):
+// (qint16) ((byte - Shift) << pre1)
+template<bool UNSIGNED>
+__global__ void ew_int8_copy_kernel(const EwParams p)
+{
+    const uint16_t* in = reinterpret_cast<const uint16_t*>(p.in);
+    uint32_t* out = reinterpret_cast<uint32_t*>(p.out);
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (long long u = (long long) blockIdx.x * blockDim.x + threadIdx.x; u < p.n_units; u += stride) {
+        const uint32_t v = in[u];
+        const int32_t x = UNSIGNED ? (int32_t) (v & 0xffu) : (int32_t) (signed char) (v & 0xffu);
+        const int32_t y = UNSIGNED ? (int32_t) (v >> 8) : (int32_t) (signed char) (v >> 8);
+        const uint32_t re = (uint32_t) (x - p.shift) << p.pre, im = (uint32_t) (y - p.shift) << p.pre;
+        out[u] = (re & 0xffffu) | (im << 16);
+    }
+}
+
 // decimation_shifts<16, InputBits> (decimators.h:79-95 / 115-131 / 151-167), index = log2
 const int PRE8[7]  = { 8, 7, 6, 5, 4, 3, 2 }, POST8[7]  = { 0, 0, 0, 0, 0, 0, 0 };
 const int PRE12[7] = { 4, 3, 2, 1, 0, 0, 0 }, POST12[7] = { 0, 0, 0, 0, 0, 1, 2 };
@@ -90,8 +107,12 @@ typedef void (*cascade_fn)(const CascadeParams);
 template<typename T, int IN, int OUT, bool HASROT, bool EXACT>
 cascade_fn kfn() { return hb64_cascade_kernel<T, IN, OUT, HASROT, EXACT>; }
 
+bool is_int8(int fmt) { return fmt == B200DSP_FMT_I8 || fmt == B200DSP_FMT_U8; }
+
 cascade_fn pick_kernel(int in_fmt, int out_fmt, bool div4, bool hasrot, bool exact, bool pre)
 {
+    if (in_fmt == B200DSP_FMT_I8) return hasrot ? kfn<int32_t, IN_I8, OUT_I16_SHIFT, true, false>() : kfn<int32_t, IN_I8, OUT_I16_SHIFT, false, false>();
+    if (in_fmt == B200DSP_FMT_U8) return hasrot ? kfn<int32_t, IN_U8, OUT_I16_SHIFT, true, false>() : kfn<int32_t, IN_U8, OUT_I16_SHIFT, false, false>();
     if (in_fmt == B200DSP_FMT_I16 && out_fmt == B200DSP_FMT_I16) {
         if (pre) return hasrot ? kfn<int32_t, IN_I16_PRE, OUT_I16_SHIFT, true, false>() : kfn<int32_t, IN_I16_PRE, OUT_I16_SHIFT, false, false>();
         return hasrot ? kfn<int32_t, IN_I16, OUT_I16_SHIFT, true, false>() : kfn<int32_t, IN_I16, OUT_I16_SHIFT, false, false>();
@@ -111,6 +132,8 @@ cascade_fn pick_kernel(int in_fmt, int out_fmt, bool div4, bool hasrot, bool exa
 // kernels of a split cascade (stages [0,3) then [3,L)): the hand-off is raw T pairs in an HBM scratch buffer
 cascade_fn pick_split_a(int in_fmt, int out_fmt, bool hasrot, bool exact, bool pre)
 {
+    if (in_fmt == B200DSP_FMT_I8) return hasrot ? kfn<int32_t, IN_I8, OUT_I32, true, false>() : kfn<int32_t, IN_I8, OUT_I32, false, false>();
+    if (in_fmt == B200DSP_FMT_U8) return hasrot ? kfn<int32_t, IN_U8, OUT_I32, true, false>() : kfn<int32_t, IN_U8, OUT_I32, false, false>();
     if (in_fmt == B200DSP_FMT_I16 && out_fmt == B200DSP_FMT_I16) {
         if (pre) return hasrot ? kfn<int32_t, IN_I16_PRE, OUT_I32, true, false>() : kfn<int32_t, IN_I16_PRE, OUT_I32, false, false>();
         return hasrot ? kfn<int32_t, IN_I16, OUT_I32, true, false>() : kfn<int32_t, IN_I16, OUT_I32, false, false>();
@@ -120,7 +143,7 @@ cascade_fn pick_split_a(int in_fmt, int out_fmt, bool hasrot, bool exact, bool p
 }
 cascade_fn pick_split_b(int in_fmt, int out_fmt, bool hasrot, bool exact)
 {
-    if (in_fmt == B200DSP_FMT_I16 && out_fmt == B200DSP_FMT_I16)
+    if ((in_fmt == B200DSP_FMT_I16 || is_int8(in_fmt)) && out_fmt == B200DSP_FMT_I16)
         return hasrot ? kfn<int32_t, IN_I32, OUT_I16_SHIFT, true, false>() : kfn<int32_t, IN_I32, OUT_I16_SHIFT, false, false>();
     if (out_fmt == B200DSP_FMT_I16) return exact ? kfn<float, IN_F32, OUT_I16_SCALE, false, true>() : kfn<float, IN_F32, OUT_I16_SCALE, false, false>();
     return exact ? kfn<float, IN_F32, OUT_F32, false, true>() : kfn<float, IN_F32, OUT_F32, false, false>();
@@ -132,6 +155,7 @@ struct LaunchGeom { int wpb; int warps_per_sm; };
 
 struct b200dsp_decim {
     int in_fmt, out_fmt, bits, exact;
+    int shift;                            // DecimatorsU's Shift template argument (unsigned 8-bit input only)
     int device, sm_count;
     cudaStream_t stream, copy_stream;
     cudaEvent_t ev_h2d[2], ev_done[2];
@@ -162,7 +186,7 @@ int make_plan(int in_fmt, int out_fmt, int bits, int log2, int mode, long long l
 {
     if (log2 < 0 || log2 > 6 || mode < 0 || mode > 2 || len < 0) return B200DSP_EINVAL;
     memset(pl, 0, sizeof(*pl));
-    const bool is_int = (in_fmt == B200DSP_FMT_I16 && out_fmt == B200DSP_FMT_I16);
+    const bool is_int = ((in_fmt == B200DSP_FMT_I16 || is_int8(in_fmt)) && out_fmt == B200DSP_FMT_I16);
     const int N = 1 << log2;
     pl->out_scale = 1.0f;
     if (in_fmt == B200DSP_FMT_I16 && out_fmt == B200DSP_FMT_F32)     // decimation_scale<InputBits>::scaleIn
@@ -266,6 +290,7 @@ int launch_segment(b200dsp_decim* h, cascade_fn fn, const Plan& pl, int base, in
     p.state_out = (char*) h->d_state[h->cur ^ 1] + (size_t) base * 128 * esz;
     p.n0 = n0; p.n_out = n0 >> L; p.L = L;
     p.pre = first ? pl.pre : 0; p.post = final ? pl.post : 0;
+    p.in_mul = 1 << pl.pre; p.in_add = -(h->shift << pl.pre);
     p.out_scale = final ? pl.out_scale : 1.0f; p.div4 = pl.div4_kind;
     for (int s = 1; s <= L && s + base < 8; ++s) p.rot[s] = pl.rot[s + base];
     p.opq_zero = 0; p.opq_one = 1; p.opq_mone = -1;
@@ -293,14 +318,16 @@ int launch_plan(b200dsp_decim* h, const Plan& pl, const void* d_in, void* d_out,
     if (pl.n_out <= 0) return 0;
     if (pl.elementwise) {
         EwParams ep;
-        ep.in = d_in; ep.out = d_out; ep.kind = pl.ew_kind; ep.pre = pl.pre; ep.out_scale = pl.out_scale;
+        ep.in = d_in; ep.out = d_out; ep.kind = pl.ew_kind; ep.pre = pl.pre; ep.out_scale = pl.out_scale; ep.shift = h->shift;
         ep.sup = pl.div4_kind;   // HALF/DIV4: 0 inf, 1 sup
         ep.n_units = pl.ew_kind == EW_COPY ? pl.n_out : pl.consumed_scalars / 8;
         const int threads = 256;
         long long blocks = (ep.n_units + threads - 1) / threads;
         if (blocks > (long long) h->sm_count * 16) blocks = (long long) h->sm_count * 16;
         if (blocks < 1) blocks = 1;
-        if (h->in_fmt == B200DSP_FMT_I16 && h->out_fmt == B200DSP_FMT_I16) ew_int_copy_kernel<<<(unsigned) blocks, threads, 0, st>>>(ep);
+        if (h->in_fmt == B200DSP_FMT_I8) ew_int8_copy_kernel<false><<<(unsigned) blocks, threads, 0, st>>>(ep);
+        else if (h->in_fmt == B200DSP_FMT_U8) ew_int8_copy_kernel<true><<<(unsigned) blocks, threads, 0, st>>>(ep);
+        else if (h->in_fmt == B200DSP_FMT_I16 && h->out_fmt == B200DSP_FMT_I16) ew_int_copy_kernel<<<(unsigned) blocks, threads, 0, st>>>(ep);
         else if (h->in_fmt == B200DSP_FMT_F32 && h->out_fmt == B200DSP_FMT_I16) ew_float_kernel<float, OUT_I16_SCALE><<<(unsigned) blocks, threads, 0, st>>>(ep);
         else if (h->in_fmt == B200DSP_FMT_F32) ew_float_kernel<float, OUT_F32><<<(unsigned) blocks, threads, 0, st>>>(ep);
         else ew_float_kernel<int16_t, OUT_F32><<<(unsigned) blocks, threads, 0, st>>>(ep);
@@ -331,7 +358,13 @@ int launch_plan(b200dsp_decim* h, const Plan& pl, const void* d_in, void* d_out,
     return rc;
 }
 
-size_t in_elem_bytes(int fmt) { return fmt == B200DSP_FMT_I16 ? 2 : 4; }
+bool valid_formats(int in_fmt, int out_fmt)
+{
+    if (is_int8(in_fmt)) return out_fmt == B200DSP_FMT_I16;
+    return (in_fmt == B200DSP_FMT_I16 || in_fmt == B200DSP_FMT_F32) && (out_fmt == B200DSP_FMT_I16 || out_fmt == B200DSP_FMT_F32);
+}
+
+size_t in_elem_bytes(int fmt) { return is_int8(fmt) ? 1 : fmt == B200DSP_FMT_I16 ? 2 : 4; }
 
 } // namespace
 
@@ -343,8 +376,8 @@ extern "C" {
 int64_t b200dsp_decim_out_count(int in_fmt, int out_fmt, int log2_decim, int mode, int64_t len_scalars)
 {
     Plan pl;
-    if ((in_fmt != B200DSP_FMT_I16 && in_fmt != B200DSP_FMT_F32) || (out_fmt != B200DSP_FMT_I16 && out_fmt != B200DSP_FMT_F32)) return -1;
-    if (make_plan(in_fmt, out_fmt, 12, log2_decim, mode, len_scalars, &pl) != 0) return -1;
+    if (!valid_formats(in_fmt, out_fmt)) return -1;
+    if (make_plan(in_fmt, out_fmt, is_int8(in_fmt) ? 8 : 12, log2_decim, mode, len_scalars, &pl) != 0) return -1;
     return pl.n_out;
 }
 
@@ -352,16 +385,19 @@ int b200dsp_decim_create(b200dsp_decim_t** out, int in_fmt, int out_fmt, int inp
 {
     if (!out) return b200_fail(B200DSP_EINVAL, "decim_create: null handle pointer");
     *out = nullptr;
-    if ((in_fmt != B200DSP_FMT_I16 && in_fmt != B200DSP_FMT_F32) || (out_fmt != B200DSP_FMT_I16 && out_fmt != B200DSP_FMT_F32))
-        return b200_fail(B200DSP_EINVAL, "decim_create: bad sample format");
+    if (!valid_formats(in_fmt, out_fmt))
+        return b200_fail(B200DSP_EINVAL, "decim_create: bad sample format (8-bit inputs decimate to int16 only)");
     if (input_bits != 8 && input_bits != 12 && input_bits != 16)
         return b200_fail(B200DSP_EINVAL, "decim_create: input_bits must be 8, 12 or 16");
+    if (is_int8(in_fmt) && input_bits != 8)
+        return b200_fail(B200DSP_EINVAL, "decim_create: 8-bit sample formats take input_bits = 8");
     int rc = b200_require_device();
     if (rc) return rc;
     b200dsp_decim* h = new (std::nothrow) b200dsp_decim();
     if (!h) return b200_fail(B200DSP_ENOMEM, "decim_create: out of host memory");
     memset(h, 0, sizeof(*h));
     h->in_fmt = in_fmt; h->out_fmt = out_fmt; h->bits = input_bits;
+    h->shift = (in_fmt == B200DSP_FMT_U8) ? 127 : 0;     // rtlsdrthread.h:55
     h->device = b200_current_device();
     h->sm_count = b200_sm_count_of(h->device);
     if ((rc = B200_CUDA_CHECK(cudaSetDevice(h->device))) ||
@@ -395,6 +431,15 @@ int b200dsp_decim_destroy(b200dsp_decim_t* h)
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     delete h;
+    return 0;
+}
+
+int b200dsp_decim_set_shift(b200dsp_decim_t* h, int shift)
+{
+    if (!h) return b200_fail(B200DSP_EINVAL, "null handle");
+    if (h->in_fmt != B200DSP_FMT_U8) return b200_fail(B200DSP_ESTATE, "decim_set_shift: only the unsigned 8-bit input format has a shift");
+    if (shift < 0 || shift > 255) return b200_fail(B200DSP_EINVAL, "decim_set_shift: shift must be in [0, 255]");
+    h->shift = shift;
     return 0;
 }
 

@@ -45,7 +45,7 @@ constexpr int HB_STAGE_BYTES = HB_STAGE_WORDS * 4;
 constexpr int HB_MAX_STAGES  = 6;
 constexpr int HB_STATE_ELEMS = 64;            // per stage, per component (canonical carried state)
 
-enum : int { IN_I16 = 0, IN_F32 = 1, IN_I16F = 2, IN_F32_DIV4 = 3, IN_I16F_DIV4 = 4, IN_I16_PRE = 5, IN_I32 = 6 };
+enum : int { IN_I16 = 0, IN_F32 = 1, IN_I16F = 2, IN_F32_DIV4 = 3, IN_I16F_DIV4 = 4, IN_I16_PRE = 5, IN_I32 = 6, IN_I8 = 7, IN_U8 = 8 };
 enum : int { DIV4_INF = 0, DIV4_SUP = 1, DIV4_SUP16 = 2 };   // /4 front-end flavours (decimatorsfi.cpp:95-367)
 enum : int { OUT_I16_SHIFT = 0, OUT_I16_SCALE = 1, OUT_F32 = 2, OUT_I32 = 3 };
 
@@ -60,6 +60,7 @@ struct CascadeParams {
     int         slice_sp;    // superphases per slice
     int         n_slices;
     int         pre, post;   // integer pre/post shifts (decimation_shifts<>)
+    int         in_mul, in_add;   // 8-bit inputs: sample = byte * in_mul + in_add == (byte - Shift) << pre  (decimatorsu.h:241-249)
     float       out_scale;   // float output scale (IF: 1/2^(bits-1))
     int         div4;        // DIV4_* flavour for the /4 front-end loaders
     int         opq_zero, opq_one, opq_mone;   // 0, 1, -1 passed as data so ptxas keeps the 3-input / multiply forms
@@ -310,6 +311,50 @@ template<bool PRE> struct LoaderI16 {
 };
 template<> struct Loader<IN_I16, int32_t>     : LoaderI16<false> {};
 template<> struct Loader<IN_I16_PRE, int32_t> : LoaderI16<true> {};
+
+// 8-bit IQ -> int32: Decimators<qint32,qint8,16,8> (signed, HackRF: hackrfinputthread.h:57) and
+// DecimatorsU<qint32,quint8,16,8,Shift> (unsigned minus Shift, RTL-SDR: rtlsdrthread.h:55, decimatorsu.h:241-249).
+// (byte - Shift) << pre is one multiply-add per scalar: byte * 2^pre - (Shift << pre).
+__device__ __forceinline__ int2 ldg_nc_v2(const void* p)
+{
+    int2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+template<bool UNSIGNED, int B> __device__ __forceinline__ int32_t ext_byte(int32_t v)
+{
+    int32_t r;
+    if (UNSIGNED) asm("prmt.b32 %0, %1, 0, %2;" : "=r"(r) : "r"(v), "n"(0x4440 + B));             // zero-extend byte B
+    else          asm("prmt.b32 %0, %1, 0, %2;" : "=r"(r) : "r"(v), "n"(0x8880 + 0x1111 * B));    // sign-extend byte B
+    return r;
+}
+template<bool UNSIGNED> struct LoaderI8 {
+    static constexpr int NV = 3;                // one 8-byte load (4 IQ samples) per register set; .z/.w stay unused
+    __device__ static __forceinline__ void fetch(const CascadeParams& p, long long pos, int lane, int4 (&v)[NV])
+    {
+        const int16_t* in = reinterpret_cast<const int16_t*>(p.in) + pos + 4 * lane;      // one IQ sample = 2 bytes
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            int2 t = make_int2(0, 0);
+            if (pos + HB_IN <= p.n0 || pos + 4 * (lane + 32 * q) < p.n0) t = ldg_nc_v2(in + 128 * q);
+            v[q].x = t.x; v[q].y = t.y;
+        }
+    }
+    __device__ static __forceinline__ void store(const CascadeParams& p, int32_t* X0, int lane, const int4 (&v)[NV])
+    {
+        const int m = p.in_mul, c = p.in_add;
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            int32_t* a = X0 + HB_HIST + 2 * (lane + 32 * q);
+            *reinterpret_cast<int2*>(a)              = make_int2(ext_byte<UNSIGNED, 0>(v[q].x) * m + c, ext_byte<UNSIGNED, 0>(v[q].y) * m + c);
+            *reinterpret_cast<int2*>(a + HB_ARR)     = make_int2(ext_byte<UNSIGNED, 2>(v[q].x) * m + c, ext_byte<UNSIGNED, 2>(v[q].y) * m + c);
+            *reinterpret_cast<int2*>(a + 2 * HB_ARR) = make_int2(ext_byte<UNSIGNED, 1>(v[q].x) * m + c, ext_byte<UNSIGNED, 1>(v[q].y) * m + c);
+            *reinterpret_cast<int2*>(a + 3 * HB_ARR) = make_int2(ext_byte<UNSIGNED, 3>(v[q].x) * m + c, ext_byte<UNSIGNED, 3>(v[q].y) * m + c);
+        }
+    }
+};
+template<> struct Loader<IN_I8, int32_t> : LoaderI8<false> {};
+template<> struct Loader<IN_U8, int32_t> : LoaderI8<true> {};
 
 // float IQ -> float (DecimatorsFI/FF *_cen, decimatorsfi.cpp:33-53,369-1172)
 template<> struct Loader<IN_F32, float> {

@@ -26,9 +26,9 @@ class _DecimatorsBase:
         capi.check(L.b200dsp_decim_create(C.byref(h), self.IN_FMT, self.OUT_FMT, input_bits))
         self._h = h
         self.input_bits = input_bits
-        self.in_dtype = np.int16 if self.IN_FMT == capi.FMT_I16 else np.float32
+        self.in_dtype = {capi.FMT_I16: np.int16, capi.FMT_F32: np.float32, capi.FMT_I8: np.int8, capi.FMT_U8: np.uint8}[self.IN_FMT]
         self.out_dtype = np.int16 if self.OUT_FMT == capi.FMT_I16 else np.float32
-        self.state_dtype = np.int32 if (self.IN_FMT, self.OUT_FMT) == (capi.FMT_I16, capi.FMT_I16) else np.float32
+        self.state_dtype = np.int32 if (self.IN_FMT != capi.FMT_F32 and self.OUT_FMT == capi.FMT_I16) else np.float32
 
     def close(self):
         if getattr(self, "_h", None):
@@ -101,6 +101,28 @@ def _add_entry_points(cls):
 class Decimators(_DecimatorsBase):
     """Decimators<qint32, qint16, 16, input_bits> (sdrbase/dsp/decimators.h:277-341)."""
     IN_FMT, OUT_FMT = capi.FMT_I16, capi.FMT_I16
+
+
+@_add_entry_points
+class Decimators8(_DecimatorsBase):
+    """Decimators<qint32, qint8, 16, 8> (plugins/samplesource/hackrfinput/hackrfinputthread.h:57): int8 in, int16 out."""
+    IN_FMT, OUT_FMT = capi.FMT_I8, capi.FMT_I16
+
+    def __init__(self, device=None):
+        super().__init__(8, device)
+
+
+@_add_entry_points
+class DecimatorsU(_DecimatorsBase):
+    """DecimatorsU<qint32, quint8, 16, 8, shift> (sdrbase/dsp/decimatorsu.h:175-215; RTL-SDR: shift 127): uint8 in,
+    sample = byte - shift, int16 out."""
+    IN_FMT, OUT_FMT = capi.FMT_U8, capi.FMT_I16
+
+    def __init__(self, shift=127, device=None):
+        super().__init__(8, device)
+        if shift != 127:
+            capi.check(capi.lib().b200dsp_decim_set_shift(self._h, int(shift)))
+        self.shift = shift
 
 
 @_add_entry_points

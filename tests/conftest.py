@@ -30,6 +30,14 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_x8():
+    """8-bit device decimators (oracle/gen_golden_x8.py): (arrays, meta)."""
+    z = np.load(os.path.join(GOLDEN_DIR, "golden_x8.npz"))
+    with open(os.path.join(GOLDEN_DIR, "golden_x8.json")) as f:
+        return {k: z[k] for k in z.files}, json.load(f)
+
+
+@pytest.fixture(scope="session")
 def port():
     """The C restatement oracle (oracle/port), built on demand with gcc."""
     import subprocess

@@ -7,6 +7,7 @@
 #include <functional>
 #include <algorithm>
 #include "sdrangel_b200/dsp/decimators.h"
+#include "sdrangel_b200/dsp/decimatorsu.h"
 #include "sdrangel_b200/dsp/decimatorsfi.h"
 #include "sdrangel_b200/dsp/downchannelizer.h"
 #include "sdrangel_b200/dsp/spectrumvis.h"
@@ -46,6 +47,22 @@ int main()
         const size_t n_out = it - m_convertBuffer.begin();
         printf("decimate16_cen n_out=%zu in=%016llx out=%016llx\n", n_out, (unsigned long long) fnv(buf, 2 * (size_t) nbSamples),
                (unsigned long long) fnv(&m_convertBuffer[0], 2 * n_out));
+        // 8-bit device plugins (rtlsdrthread.h:55 / rtlsdrthread.cpp:167, hackrfinputthread.h:57 / hackrfinputthread.cpp:155)
+        // on the low bytes of the same buffer
+        {
+            std::vector<quint8> u8(nbSamples * 2);
+            for (int i = 0; i < nbSamples * 2; i++) u8[i] = (quint8) (buf[i] & 0xff);
+            DecimatorsU<qint32, quint8, SDR_RX_SAMP_SZ, 8, 127> m_decimatorsU;
+            it = m_convertBuffer.begin();
+            m_decimatorsU.decimate16_cen(&it, &u8[0], nbSamples * 2);
+            size_t nu = it - m_convertBuffer.begin();
+            printf("decimatorsu16_cen n_out=%zu out=%016llx\n", nu, (unsigned long long) fnv(&m_convertBuffer[0], 2 * nu));
+            Decimators<qint32, qint8, SDR_RX_SAMP_SZ, 8> m_decimators8;
+            it = m_convertBuffer.begin();
+            m_decimators8.decimate64_inf(&it, (const qint8*) &u8[0], nbSamples * 2);
+            nu = it - m_convertBuffer.begin();
+            printf("decimators8_64_inf n_out=%zu out=%016llx\n", nu, (unsigned long long) fnv(&m_convertBuffer[0], 2 * nu));
+        }
         // DownChannelizer as a plugin wires it (nfmdemod.cpp:93-95): 10 MS/s, 48 kS/s at +1234567 Hz
         CaptureSink sink;
         DownChannelizer chan(&sink);

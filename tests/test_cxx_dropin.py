@@ -28,7 +28,7 @@ def test_wrapper_headers_compile_and_link():
 
 
 @pytest.mark.gpu
-def test_sdrbench_decimateii_through_cxx_wrappers(gpu_lib, golden_meta):
+def test_sdrbench_decimateii_through_cxx_wrappers(gpu_lib, golden_meta, golden_x8):
     build_exe()
     r = subprocess.run([EXE], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
@@ -37,6 +37,9 @@ def test_sdrbench_decimateii_through_cxx_wrappers(gpu_lib, golden_meta):
     assert "n_out=%d" % g["n_out"] in lines["decimate16_cen"]
     assert "in=" + golden_meta["sdrbench_s16"]["fnv"] in lines["decimate16_cen"]      # same libstdc++ generator as the reference run
     assert "out=" + g["fnv"] in lines["decimate16_cen"]
+    rows = golden_x8[1]["long"]["rows"]
+    assert lines["decimatorsu16_cen"] == "n_out=%d out=%s" % (rows["u8/4/cen"]["n_out"], rows["u8/4/cen"]["fnv"])
+    assert lines["decimators8_64_inf"] == "n_out=%d out=%s" % (rows["i8/6/inf"]["n_out"], rows["i8/6/inf"]["fnv"])
     assert lines["downchannelizer"].startswith("rate=156250 ofs=-15433 n_out=937")
     assert lines["spectrumvis"] == "frames=2"
     assert lines["interpolator"] == "n_out=6145"          # 20 000 inputs at 156 250 -> 48 000

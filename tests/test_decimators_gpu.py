@@ -38,6 +38,62 @@ def test_decimators_mode_switching_golden(gpu_lib, golden, golden_meta):
     assert np.array_equal(np.concatenate(outs), golden["decim_ii_switch/out"])
 
 
+@pytest.mark.parametrize("kind", ["i8", "u8"])
+def test_decimators_8bit_inputs_golden_bit_exact(gpu_lib, port, golden_x8, kind):
+    """Decimators<qint32,qint8,16,8> (HackRF) and DecimatorsU<qint32,quint8,16,8,127> (RTL-SDR) on the
+    same kernel: streaming golden vectors for every entry point, then every 2^20-sample hash row of the reference."""
+    from sdrangel_b200 import Decimators8, DecimatorsU
+    arrays, meta = golden_x8
+    mk = Decimators8 if kind == "i8" else DecimatorsU
+    x = arrays["stream/raw"].view(np.int8 if kind == "i8" else np.uint8)
+    cuts = meta["stream"]["cuts"]
+    for log2 in range(7):
+        for mname, mode in MODES.items():
+            d = mk()
+            outs = [d.run(log2, mode, x[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+            assert [o.shape[0] for o in outs] == arrays[f"stream_counts/{kind}/{log2}/{mname}"].tolist()
+            got, want = np.concatenate(outs), arrays[f"stream/{kind}/{log2}/{mname}"]
+            assert np.array_equal(got, want), (kind, log2, mname, int(np.argmax(np.any(got != want, axis=1))))
+            d.close()
+    lo = (port.sdrbench_s16(1 << 20).astype(np.int32) & 0xff).astype(np.uint8).view(x.dtype)
+    for key, g in meta["long"]["rows"].items():
+        k, log2, mname = key.split("/")
+        if k != kind:
+            continue
+        d = mk()
+        out = d.run(int(log2), MODES[mname], lo)
+        assert out.shape[0] == g["n_out"] and out[100].tolist() == g["at100"], key
+        assert fnv1a64_u16(out) == g["fnv"], key
+        d.close()
+
+
+def test_decimators_u8_shift_and_large_ragged_calls_vs_oracle(gpu_lib, port):
+    """DecimatorsU with a non-default Shift template argument (128) and multi-megabyte ragged calls (split cascade for
+    log2 >= 5, many slices, carry-over) against the oracle port."""
+    from sdrangel_b200 import DecimatorsU, Decimators8
+    rs = np.random.RandomState(808)
+    x = rs.randint(0, 256, size=2 * 2_100_003).astype(np.uint8)
+    cuts = [0, 2, 4098, 1_000_003, 1_000_004, 3_000_000, x.size]
+    for log2, mname in ((6, "inf"), (5, "cen"), (3, "sup"), (1, "cen")):
+        d, o = DecimatorsU(shift=128), port.PortDecimators("u8", shift=128)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            got, want = d.run(log2, MODES[mname], x[a:b]), o.run(log2, MODES[mname], x[a:b])
+            assert got.shape == want.shape and np.array_equal(got, want), (log2, mname, a, b)
+        d.close()
+    d, o = Decimators8(), port.PortDecimators("i8")
+    xi = x.view(np.int8)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        got, want = d.run(6, MODES["sup"], xi[a:b]), o.run(6, MODES["sup"], xi[a:b])
+        assert got.shape == want.shape and np.array_equal(got, want), (a, b)
+    with pytest.raises(RuntimeError):
+        capi_check_shift_on_signed(Decimators8())
+
+
+def capi_check_shift_on_signed(d):
+    from sdrangel_b200 import capi
+    capi.check(capi.lib().b200dsp_decim_set_shift(d._h, 127))     # only the unsigned format has a Shift: loud error
+
+
 def test_decimateii_config1_sdrbench_hash(gpu_lib, port, golden_meta):
     """BASELINE config 1: 2^20 int16 IQ, log2=4 centred, 12 bit: the reference's hash."""
     from sdrangel_b200 import Decimators

@@ -50,6 +50,28 @@ def test_decim_ii_sdrbench_config1(port, golden_meta):
     assert fnv1a64_u16(out) == g["fnv"] == "f06c9917a38677e6"
 
 
+@pytest.mark.parametrize("kind", ["i8", "u8"])
+def test_decim_8bit_inputs_golden(port, golden_x8, kind):
+    """Decimators<qint32,qint8,16,8> (HackRF) and DecimatorsU<qint32,quint8,16,8,127> (RTL-SDR): streaming golden vectors
+    (ragged calls, extreme-code runs) and the 2^20-sample hash rows, all entry points."""
+    arrays, meta = golden_x8
+    raw = arrays["stream/raw"]
+    x = raw.view(np.int8 if kind == "i8" else np.uint8)
+    cuts = meta["stream"]["cuts"]
+    for log2 in range(7):
+        for mname, mode in MODES.items():
+            d = port.PortDecimators(kind)
+            outs = [d.run(log2, mode, x[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+            assert [o.shape[0] for o in outs] == arrays[f"stream_counts/{kind}/{log2}/{mname}"].tolist()
+            assert np.array_equal(np.concatenate(outs), arrays[f"stream/{kind}/{log2}/{mname}"]), (kind, log2, mname)
+    lo = (port.sdrbench_s16(1 << 20).astype(np.int32) & 0xff).astype(np.uint8)
+    for key in (f"{kind}/4/cen", f"{kind}/6/inf", f"{kind}/1/sup"):
+        k, log2, mname = key.split("/")
+        out = port.PortDecimators(kind).run(int(log2), MODES[mname], lo.view(x.dtype))
+        g = meta["long"]["rows"][key]
+        assert out.shape[0] == g["n_out"] and out[100].tolist() == g["at100"] and fnv1a64_u16(out) == g["fnv"]
+
+
 @pytest.mark.parametrize("kind", ["fi", "ff", "if"])
 def test_decim_float_strict_bit_exact_and_fast_within_tolerance(port, golden, golden_meta, kind):
     src = port.sdrbench_s16(1 << 14) if kind[0] == "i" else port.sdrbench_f32(1 << 14)
