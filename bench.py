@@ -60,9 +60,13 @@ WORKLOADS = {
 class ClockSampler:
     """Samples SM clock and throttle reasons with NVML while the timed region runs."""
 
-    def __init__(self, index):
+    def __init__(self, index, interval=0.001, enabled=True):
         self.samples, self.reasons, self._stop, self._t = [], set(), threading.Event(), None
         self.max_mhz = None
+        self.interval = interval
+        self.nv = None
+        if not enabled:
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -88,7 +92,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.001)
+            self._stop.wait(self.interval)
 
     def start(self):
         if self.nv:
@@ -301,14 +305,18 @@ def max_over_ranks(c, v):
 
 def timed_steps(c, stream, step, steps, warmup):
     """W warm-up steps, then K steps timed with CUDA events on the launching stream, barrier + synchronize on both
-    sides, max over ranks.  Returns (total_ms, per-step kernel ms list, clocks)."""
+    sides, max over ranks.  Returns (total_ms, per-step kernel ms list, clocks).
+
+    N = 1: NVML samples SM clock / throttle reasons every millisecond inside the timed region.  N > 1: NVML queries serialise
+    on the driver across ranks and stall the querying rank's kernel launches (8 ranks sampling: 0.58 -> 2.3 ms per step;
+    rank 0 alone: 0.58 -> 0.81), so the K steps are timed unperturbed and the clocks are sampled by rank 0 during an immediate
+    repeat of the same K steps, whose own time is reported next to them."""
     torch = c.torch
-    with torch.cuda.stream(stream):
-        for _ in range(max(warmup, 3)):
-            step()
+
+    def region(sampler):
         barrier(c)
-        sampler = ClockSampler(c.local)
-        sampler.start()
+        if sampler:
+            sampler.start()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -318,9 +326,19 @@ def timed_steps(c, stream, step, steps, warmup):
             b.record(stream)
         e1.record(stream)
         barrier(c)
-        clocks = sampler.stop()
-    total_ms = max_over_ranks(c, e0.elapsed_time(e1))
-    return total_ms, [a.elapsed_time(b) for a, b in evs], clocks
+        clocks = sampler.stop() if sampler else None
+        return max_over_ranks(c, e0.elapsed_time(e1)), [a.elapsed_time(b) for a, b in evs], clocks
+
+    with torch.cuda.stream(stream):
+        for _ in range(max(warmup, 3)):
+            step()
+        if c.world == 1:
+            return region(ClockSampler(c.local))
+        total_ms, kern_ms, _ = region(None)
+        rep_ms, _, clocks = region(ClockSampler(c.local, interval=0.002, enabled=(c.rank == 0)))
+        clocks["sampled"] = "by rank 0 during an immediate repeat of the K timed steps (NVML queries stall kernel launches at N > 1)"
+        clocks["ms_per_step_while_sampling"] = rep_ms / steps
+    return total_ms, kern_ms, clocks
 
 
 def bench_decim(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=True):
@@ -464,7 +482,7 @@ def bench_bank(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=T
         parity = bool(ok)
     barrier(c)
 
-    state = {"i": 0, "overlap": True}
+    state = {"i": 0, "overlap": True, "group": None}
 
     def step():
         i = state["i"]
@@ -472,38 +490,85 @@ def bench_bank(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=T
         if c.world > 1 and not os.environ.get("B200_BENCH_NO_BCAST"):      # (developer switch: isolate the compute time)
             if state["overlap"]:
                 if cur not in pending:
-                    pending[cur] = dist.broadcast(bviews[cur], src=0, async_op=True)
+                    pending[cur] = dist.broadcast(bviews[cur], src=0, async_op=True, group=state["group"])
                 pending.pop(cur).wait()            # stream-level wait: the compute stream waits for this step's baseband
                 nxt = (i + 1) % len(bufs)
                 # the next step's baseband starts moving now; its buffer was last read by step i-1, already ordered on `stream`
-                pending[nxt] = dist.broadcast(bviews[nxt], src=0, async_op=True)
+                pending[nxt] = dist.broadcast(bviews[nxt], src=0, async_op=True, group=state["group"])
             else:
                 for w in list(pending.values()):
                     w.wait()
                 pending.clear()
-                dist.broadcast(bviews[cur], src=0)     # in stream order: broadcast, then the kernels
+                dist.broadcast(bviews[cur], src=0, group=state["group"])     # in stream order: broadcast, then the kernels
         bank.feed_dev(bufs[cur].data_ptr(), n, sptr)
         state["i"] = i + 1
 
     bcast_mode = None
+    reserved = 0
     if c.world > 1 and not os.environ.get("B200_BENCH_NO_BCAST"):
-        # The NCCL broadcast of step k+1 can run under step k's kernels, but NCCL's ring CTAs then compete with the FIR kernels
-        # for SM slots; which wins depends on the rank count.  Try both orders for a few steps and keep the faster (all ranks
-        # agree through a MAX all-reduce of the trial times).
+        # The NCCL broadcast of step k+1 can run under step k's kernels, but its ring CTAs need (nearly) a whole SM's registers
+        # each: while a tree kernel has blocks queued they are only placed in the gaps between kernels, and every late CTA
+        # stalls the ring on all ranks.  Reserving R SMs (the ones the block scheduler fills first: b200dsp_probe_sm_order) for
+        # the collective lets it start at once; the tree kernels then run as a work queue on the other SMs.  Which of
+        # {in stream order, overlapped, overlapped + R reserved} wins depends on the rank count: try each for a few steps
+        # and keep the fastest (all ranks agree through a MAX all-reduce of the trial times).
+        order = np.zeros(48, dtype=np.int32)
+        capi.check(capi.lib().b200dsp_probe_sm_order(48, 640, order.ctypes.data))
+        # NCCL communicators with fewer CTAs (ncclConfig maxCTAs): fewer SMs to give up, at some cost in ring bandwidth
+        groups = {0: None}
+        for ctas in (16,):
+            o = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            o.config.max_ctas = ctas
+            groups[ctas] = dist.new_group(ranks=list(range(c.world)), backend="nccl", pg_options=o)
+        cands = [(False, 0, 0), (True, 0, 0), (True, 0, 16), (True, 0, 32), (True, 16, 0), (True, 16, 16)]
+        if os.environ.get("B200_BENCH_BCAST_MODE"):            # developer switch: "overlap,ctas,reserved"
+            o_, g_, r_ = os.environ["B200_BENCH_BCAST_MODE"].split(",")
+            cands = [(o_ == "1", int(g_), int(r_))]
         trial = {}
-        for mode in (True, False):
-            state["overlap"] = mode
+        for mode, g, r in cands:
+            for w in list(pending.values()):
+                w.wait()
+            pending.clear()
+            state["overlap"], state["group"] = mode, groups[g]
+            bank.set_reserved_sms(order[:r])
             with torch.cuda.stream(stream):
-                for _ in range(2):
+                for _ in range(3):
                     step()
                 barrier(c)
-                t0 = time.perf_counter()
-                for _ in range(4):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(8):
                     step()
+                e1.record(stream)
                 barrier(c)
-                trial[mode] = max_over_ranks(c, time.perf_counter() - t0)
-        state["overlap"] = trial[True] <= trial[False]
-        bcast_mode = "overlapped with the previous step's kernels" if state["overlap"] else "in stream order before the step's kernels"
+                trial[(mode, g, r)] = max_over_ranks(c, e0.elapsed_time(e1) / 8)
+        best = min(trial, key=lambda k: trial[k])
+        for w in list(pending.values()):
+            w.wait()
+        pending.clear()
+        state["overlap"], reserved = best[0], best[2]
+        state["group"] = groups[best[1]]
+        bank.set_reserved_sms(order[:reserved])
+        bcast_mode = "in stream order before the step's kernels"
+        if state["overlap"]:
+            bcast_mode = "overlapped with the previous step's kernels" + (", NCCL limited to %d CTAs" % best[1] if best[1] else "") + \
+                         (", %d SMs reserved for the collective" % reserved if reserved else "")
+        bcast_trials = {("%s/ctas%s/rsv%d" % ("overlap" if m else "serial", g or "dflt", r)): round(t, 4) for (m, g, r), t in trial.items()}
+        if reserved:
+            # the work-queue form of the tree kernels must give the very same samples: same feed from a reset state, both ways
+            outs = []
+            for r in (0, reserved):
+                bank.set_reserved_sms(order[:r])
+                bank.reset(sptr)
+                bank.feed_dev(bufs[0].data_ptr(), min(n, 3 << 20), sptr)
+                stream.synchronize()
+                outs.append((bank.fetch(info[0][0]), bank.fetch(info[-1][0], capi.STAGE_FRONTEND)))
+            same = all(np.array_equal(a, b) for a, b in zip(outs[0], outs[1]))
+            if parity is not None or c.rank != 0:
+                parity = bool(same) if parity is None else bool(parity and same)
+            ok_all = max_over_ranks(c, 0.0 if same else 1.0)
+            if c.rank == 0:
+                parity = bool(parity and ok_all == 0.0)
 
     total_ms, kern_ms, clocks = timed_steps(c, stream, step, steps, warmup)
     value = n * steps / (total_ms * 1e-3) / 1e6
@@ -521,7 +586,8 @@ def bench_bank(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=T
            "config": {"workload": wl_name, "desc": wl["desc"], "samples_per_step": n, "input_rate": fs, "channels": len(fcs),
                       "channels_this_rank": len(mine), "tree_nodes_this_rank": nodes, "stage_inputs_per_sample_this_rank": stage_inputs,
                       "l2": "input %.0f MiB per step > 126 MB L2, streamed from HBM every step; tree levels are HBM-resident int16 arrays" % (n * 4 / 2 ** 20),
-                      "parallelism": "channels sharded x%d (contiguous frequency blocks), baseband %s" % (c.world, ("NCCL broadcast per step, " + str(bcast_mode)) if c.world > 1 else "local")},
+                      "parallelism": "channels sharded x%d (contiguous frequency blocks), baseband %s" % (c.world, ("NCCL broadcast per step, " + str(bcast_mode)) if c.world > 1 else "local"),
+                      "broadcast_trials_ms_per_step": bcast_trials if bcast_mode else None},
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": c.hbm_peak, "unit": "GB/s", "frac": achieved / c.hbm_peak,
                         "traffic": measured_traffic(wl_name, n) if c.world == 1 else None, "traffic_note": "per hb48_level_kernel launch (one of %d tree levels per step)" % depth,
                         "peak_source": c.peak_src, "kernel": "hb48_level_kernel (one launch per tree level per step)",
@@ -541,6 +607,7 @@ def bench_bank(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=T
         for w in list(pending.values()):
             w.wait()
         pending.clear()
+        bank.set_reserved_sms([])
         counts = {}
 
         def e2e_step():

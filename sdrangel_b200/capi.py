@@ -58,6 +58,8 @@ SIGNATURES = {
     "b200dsp_bank_fetch_all": (_i32, [_vp, _i32, _vp, _i64, _vp, _vp]),
     "b200dsp_bank_copy_out_dev": (_i32, [_vp, _i32, _i64, _i64, _vp, _vp]),
     "b200dsp_bank_sync": (_i32, [_vp]),
+    "b200dsp_bank_set_reserved_sms": (_i32, [_vp, _vp, _i32]),
+    "b200dsp_probe_sm_order": (_i32, [_i32, _i32, _vp]),
     "b200dsp_interp_create": (_i32, [_pvp, _i32, C.c_double, C.c_double, C.c_double]),
     "b200dsp_interp_destroy": (_i32, [_vp]),
     "b200dsp_interp_info": (_i32, [_vp, _pi32, _vp, _i32]),

@@ -189,6 +189,8 @@ struct b200dsp_bank {
     std::vector<int> fe_index;                   // channel ids with a front-end
     // pooled fetch (b200dsp_bank_fetch_all): [channel][stride] staging + per-channel source table and counts
     void* d_pool; size_t pool_bytes;
+    // SMs left to a concurrent collective (b200dsp_bank_set_reserved_sms): level kernels run in work-queue mode
+    uint32_t rsv[5]; int n_rsv; int* d_queue; int level_occ;
     GatherSrc* d_gsrc; long long* d_gcnt; size_t gcap;
 };
 
@@ -208,7 +210,8 @@ void free_device(b200dsp_bank* b)
     if (b->d_pool) cudaFree(b->d_pool);
     if (b->d_gsrc) cudaFree(b->d_gsrc);
     if (b->d_gcnt) cudaFree(b->d_gcnt);
-    b->d_pool = nullptr; b->pool_bytes = 0; b->d_gsrc = nullptr; b->d_gcnt = nullptr; b->gcap = 0;
+    if (b->d_queue) cudaFree(b->d_queue);
+    b->d_pool = nullptr; b->pool_bytes = 0; b->d_gsrc = nullptr; b->d_gcnt = nullptr; b->gcap = 0; b->d_queue = nullptr;
     for (auto& c : b->chans) {
         if (c.d_out) cudaFree(c.d_out);
         if (c.d_hist) cudaFree(c.d_hist);
@@ -429,6 +432,15 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
         if ((rc = B200_CUDA_CHECK(cudaGetLastError())) || (rc = B200_CUDA_CHECK(cudaEventRecord(b->ev_sched, b->side)))) return rc;
     }
     const int tc = b->tcur, tn = tc ^ 1;
+    if (b->n_rsv > 0) {
+        if (!b->d_queue) {
+            if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_queue, 64 * sizeof(int))))) return rc;
+            int occ = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*) hb48_level_queue_kernel, 4 * 32, 4 * HB_STAGE_BYTES) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 4; }
+            b->level_occ = occ;
+        }
+        if ((rc = B200_CUDA_CHECK(cudaMemsetAsync(b->d_queue, 0, 64 * sizeof(int), st)))) return rc;
+    }
     for (int d = 1; d <= D; ++d) {
         // levels (d, d+1) in one launch when the call is aligned at both (no pending samples, whole batch pairs)
         if (b->fuse && (d & 1) && d + 1 <= D && b->d_pfam[d]) {
@@ -495,7 +507,17 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
             p.slices = (int) slices; p.bps = bps;
             const long long warps = (long long) n_fam * slices;
             const int wpb = 4;
-            hb48_level_kernel<<<(unsigned) ((warps + wpb - 1) / wpb), wpb * 32, wpb * HB_STAGE_BYTES, st>>>(p);
+            long long blocks = (warps + wpb - 1) / wpb;
+            if (b->n_rsv > 0 && d < 64) {
+                // work-queue mode: one resident wave; blocks landing on reserved SMs exit, the others pull items until none is left
+                p.queue = b->d_queue + d;
+                for (int i = 0; i < 5; ++i) p.rsv[i] = b->rsv[i];
+                // always a full resident wave: a small grid would land exactly on the SMs the scheduler fills first -- the reserved ones
+                blocks = (long long) b->sm_count * b->level_occ;
+                hb48_level_queue_kernel<<<(unsigned) blocks, wpb * 32, wpb * HB_STAGE_BYTES, st>>>(p);
+            } else {
+                hb48_level_kernel<<<(unsigned) blocks, wpb * 32, wpb * HB_STAGE_BYTES, st>>>(p);
+            }
             if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
         }
     }
@@ -673,6 +695,22 @@ int b200dsp_bank_reset(b200dsp_bank_t* b, void* cuda_stream)
     b->produced.assign(b->depth + 1, 0);
     b->out_count_depth.assign(32, 0);
     b->tcur = 0; b->fe_parity = 0;
+    return 0;
+}
+
+// Leave the listed SMs to a concurrent kernel (the NCCL broadcast of the next baseband block): the tree-level kernels,
+// which are most of a feed, then run as one resident wave of work-queue warps that never occupies those SMs.
+int b200dsp_bank_set_reserved_sms(b200dsp_bank_t* b, const int* smids, int n)
+{
+    if (!b || n < 0 || (n > 0 && !smids)) return b200_fail(B200DSP_EINVAL, "bank_set_reserved_sms: bad argument");
+    if (n >= b->sm_count) return b200_fail(B200DSP_EINVAL, "bank_set_reserved_sms: cannot reserve every SM");
+    uint32_t m[5] = { 0, 0, 0, 0, 0 };
+    for (int i = 0; i < n; ++i) {
+        if (smids[i] < 0 || smids[i] >= 160) return b200_fail(B200DSP_EINVAL, "bank_set_reserved_sms: SM id out of range");
+        m[smids[i] >> 5] |= 1u << (smids[i] & 31);
+    }
+    for (int i = 0; i < 5; ++i) b->rsv[i] = m[i];
+    b->n_rsv = n;
     return 0;
 }
 

@@ -39,6 +39,11 @@ struct LevelParams {
     int flip;          // (C_before / 2) & 1 : parity of the absolute pair index of B[0]
     int slices, bps;   // slices per family, batches per slice
     int opq_zero, opq_one, opq_mone;
+    // work-queue mode (queue != null): resident warps pull (family, slice) items from *queue; blocks that land on an SM
+    // whose bit is set in rsv[] exit at once, leaving those SMs to a concurrent collective (NCCL's ring CTAs need a whole
+    // SM's registers and otherwise only get placed between kernels)
+    int* queue;
+    uint32_t rsv[5];
 };
 
 __device__ __forceinline__ constexpr int hb48_h(int i)
@@ -180,15 +185,11 @@ __device__ __noinline__ void hb48_slow_child(const int32_t* X, int comp, int j, 
     hb48_item<false, false>(wr, cr, 0, opq, y);
 }
 
-__global__ void __launch_bounds__(256, 2) hb48_level_kernel(const LevelParams p)
+// one work item: warp `w` = (family, time slice) of this level
+__device__ __forceinline__ void hb48_level_warp(const LevelParams& p, int w, int32_t* X, int lane)
 {
-    extern __shared__ __align__(16) unsigned char hb48_smem[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int w = blockIdx.x * (blockDim.x >> 5) + wib;
-    if (w >= p.n_fam * p.slices) return;
     const int f = w / p.slices, slice = w - f * p.slices;
     const int4 fam = reinterpret_cast<const int4*>(p.fam)[f];      // parent, child C, child L, child U
-    int32_t* X = reinterpret_cast<int32_t*>(hb48_smem) + (size_t) wib * HB_STAGE_WORDS;
     const int comp = lane >> 4, j = lane & 15;
     const IntOpaque opq = { p.opq_zero, p.opq_one, p.opq_mone };
     const uint32_t* B = p.in_base + (long long) fam.x * p.in_stride;
@@ -282,6 +283,35 @@ __global__ void __launch_bounds__(256, 2) hb48_level_kernel(const LevelParams p)
         }
         __syncwarp();
         hb64_tail_store<int32_t>(X, lane, tl);
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(256, 2) hb48_level_kernel(const LevelParams p)
+{
+    extern __shared__ __align__(16) unsigned char hb48_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int w = blockIdx.x * (blockDim.x >> 5) + wib;
+    if (w >= p.n_fam * p.slices) return;
+    hb48_level_warp(p, w, reinterpret_cast<int32_t*>(hb48_smem) + (size_t) wib * HB_STAGE_WORDS, lane);
+}
+
+// work-queue form: one resident wave; blocks on reserved SMs exit, the other warps pull items until none is left
+__global__ void __launch_bounds__(256, 2) hb48_level_queue_kernel(const LevelParams p)
+{
+    extern __shared__ __align__(16) unsigned char hb48_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    int32_t* X = reinterpret_cast<int32_t*>(hb48_smem) + (size_t) wib * HB_STAGE_WORDS;
+    const int total = p.n_fam * p.slices;
+    unsigned smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (smid < 160u && ((p.rsv[smid >> 5] >> (smid & 31)) & 1u)) return;
+    for (;;) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(p.queue, 1);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= total) break;
+        hb48_level_warp(p, w, X, lane);
         __syncwarp();
     }
 }

@@ -206,6 +206,11 @@ class DownChannelizerBank:
     def copy_out_dev(self, chan_id, skip, count, d_dst, stream=None):
         capi.check(capi.lib().b200dsp_bank_copy_out_dev(self._h, chan_id, int(skip), int(count), C.c_void_p(d_dst), C.c_void_p(stream or 0)))
 
+    def set_reserved_sms(self, smids):
+        """Keep the tree kernels off these SMs (left to a concurrent NCCL broadcast); [] turns it off."""
+        a = np.ascontiguousarray(smids, dtype=np.int32)
+        capi.check(capi.lib().b200dsp_bank_set_reserved_sms(self._h, a.ctypes.data if a.size else None, int(a.size)))
+
     def node_count(self):
         n = capi.lib().b200dsp_bank_node_count(self._h)
         if n < 0:
