@@ -51,6 +51,8 @@ WORKLOADS = {
                    desc="64 NFM 12.5 kHz channels off a synthetic 10 MS/s int16 baseband: DownChannelizer tree + NCO + Interpolator to 48 kS/s"),
     "spectrum": dict(type="spectrum", n=1 << 26, fft=4096, avg_nb=10, avg_mode=2,
                      desc="SpectrumVis: 4096-pt Blackman-Harris windowed FFT, log power, fixed averaging over 10 frames, synthetic int16 IQ (61.44 MS/s LimeSDR-rate stream)"),
+    "iqcorr": dict(type="iqcorr", n=1 << 27,
+                   desc="DSPDeviceSourceEngine::iqCorrections, DC branch (1024-sample moving average removed per component), synthetic int16 IQ"),
     "bank1024": dict(type="bank", plan=plan1024, n=3 << 24,
                      desc="1024 channels over a synthetic 122.88 MS/s int16 stream: DownChannelizer tree + NCO + Interpolator to 48 kS/s, channels sharded"),
 }
@@ -215,7 +217,29 @@ def cpu_reference_spectrum(wl, seconds, threads=None):
             "sample": "%d x 64-frame feeds per thread, one stream per thread, %.1f s wall" % (max(counts), wall)}
 
 
+def cpu_reference_iqcorr(wl, seconds, threads=None):
+    """The reference's iqCorrections loop around its own MovingAverageUtil (oracle/_ref), one engine object per host thread."""
+    kind, mod = _oracle_mod()
+    threads = threads or (os.cpu_count() or 1)
+    n = 1 << 20
+    x = np.random.RandomState(3).randint(-2048, 2048, size=(n, 2)).astype(np.int16)
+    objs = [(mod.RefIQCorrections() if kind == "reference" else mod.PortIQCorrections()) for _ in range(threads)]
+    counts = [0] * threads
+    t_end = time.perf_counter() + seconds
+
+    def work(i):
+        while time.perf_counter() < t_end:
+            objs[i].run(x)
+            counts[i] += 1
+
+    wall = _run_threads(work, threads)
+    return {"value": sum(counts) * n / wall / 1e6, "unit": "input MS/s", "cores": threads, "kind": kind,
+            "sample": "%d x 2^20-sample buffer per thread, state carried, %.1f s wall" % (max(counts), wall)}
+
+
 def cpu_reference(wl, seconds):
+    if wl["type"] == "iqcorr":
+        return cpu_reference_iqcorr(wl, seconds)
     if wl["type"] == "decim":
         return cpu_reference_decim(wl, seconds)
     if wl["type"] == "spectrum":
@@ -427,6 +451,65 @@ def bench_decim(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=
                       "api": "b200dsp_decim_run (host pointers, pinned; chunked H2D/compute overlap)", "samples_per_step": n_e}
         d2.close()
     dec.close()
+    return res
+
+
+def bench_iqcorr(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=True):
+    """the engine's DC correction on a device-resident int16 IQ stream (replicas at N > 1)."""
+    import sdrangel_b200 as S
+    torch, capi = c.torch, c.capi
+    n = args.samples or wl["n"]
+    g = torch.Generator(device=c.dev)
+    g.manual_seed(3)
+    x = torch.randint(-2048, 2048, (n, 2), dtype=torch.int16, device=c.dev, generator=g)
+    y = torch.empty_like(x)
+    stream = torch.cuda.Stream(device=c.dev)
+    sptr = stream.cuda_stream
+    q = S.IQCorrections()
+    parity = None
+    if c.rank == 0 and want_parity:
+        _oracle_mod()
+        from oracle import portbind
+        m = 1 << 20
+        chk = S.IQCorrections()
+        chk.run_dev(x.data_ptr(), y.data_ptr(), m, sptr)
+        stream.synchronize()
+        parity = bool(np.array_equal(y[:m].cpu().numpy(), portbind.PortIQCorrections().run(x[:m].cpu().numpy())))
+        chk.close()
+
+    def step():
+        q.run_dev(x.data_ptr(), y.data_ptr(), n, sptr)
+
+    total_ms, kern_ms, clocks = timed_steps(c, stream, step, steps, warmup)
+    k_ms = float(np.mean(kern_ms))
+    achieved = n * 8.0 / (k_ms * 1e-3) / 1e9
+    res = {"value": c.world * n * steps / (total_ms * 1e-3) / 1e6, "ms_per_step": total_ms / steps, "clocks": clocks, "parity": parity, "launches": steps,
+           "config": {"workload": wl_name, "desc": wl["desc"], "samples_per_step": n,
+                      "l2": "input %.0f MiB per step > 126 MB L2" % (n * 4 / 2 ** 20), "parallelism": "replicas x%d" % c.world},
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": c.hbm_peak, "unit": "GB/s", "frac": achieved / c.hbm_peak, "traffic": None,
+                        "peak_source": c.peak_src, "kernel": "dc_correct_kernel", "kernel_ms": k_ms, "algorithmic_bytes_per_sample": 8.0,
+                        "issue": {"instr_per_sample": None, "roof_MSps_at_sampled_clk": None, "frac": None, "note": "HBM-bound by design: 4 B in + 4 B out per sample"}},
+           "dtype": "s32", "scaling": "weak"}
+    if want_e2e:
+        hx = torch.empty((n, 2), dtype=torch.int16, pin_memory=True)
+        hx.copy_(x)
+        q2 = S.IQCorrections()
+        L_ = capi.lib()
+
+        def e2e_step():
+            capi.check(L_.b200dsp_iqcorr_run(q2._h, hx.data_ptr(), n, 0))
+
+        e2e_step()
+        barrier(c)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = max_over_ranks(c, time.perf_counter() - t0)
+        res["e2e"] = {"value": c.world * n * 3 / dt / 1e6, "unit": "input MS/s", "h2d_bytes_per_step": int(n * 4), "d2h_bytes_per_step": int(n * 4),
+                      "steps": 3, "api": "b200dsp_iqcorr_run (pinned host buffer, corrected in place)", "samples_per_step": n}
+        q2.close()
+    q.close()
     return res
 
 
@@ -889,7 +972,7 @@ def _node_depths(paths):
 
 def run_ours(args, wl_name, wl):
     c = setup()
-    fns = {"decim": bench_decim, "bank": bench_bank, "spectrum": bench_spectrum}
+    fns = {"decim": bench_decim, "bank": bench_bank, "spectrum": bench_spectrum, "iqcorr": bench_iqcorr}
     main_fn = fns[wl["type"]]
     if wl["type"] == "bank" and c.world > 1 and os.environ.get("B200_BENCH_COOP"):
         main_fn = bench_bank_coop          # developer switch: time-sliced top levels + all-to-all; measured slower

@@ -153,6 +153,18 @@ int b200dsp_bank_sync(b200dsp_bank_t* b);
  * baseband block) gets whole SMs at once instead of waiting for a gap between kernels; n = 0 turns it off */
 int b200dsp_bank_set_reserved_sms(b200dsp_bank_t* b, const int* smids, int n);
 
+/* ---- engine-side sample corrections ----------------------------------------------------------------
+ * == DSPDeviceSourceEngine::iqCorrections(begin, end, imbalanceCorrection)  sdrbase/dsp/dspdevicesourceengine.cpp:175-262,
+ *    the step DSPDeviceSourceEngine::work applies between the device Decimators<> and the channel sinks (:343-347).
+ * One handle == one engine's m_iBeta / m_qBeta state (MovingAverageUtil<int32_t,int64_t,1024>, dspdevicesourceengine.h:106-107).
+ * imbalance must be 0 (DC correction, :254-259); the I/Q imbalance branch returns B200DSP_ESTATE. */
+typedef struct b200dsp_iqcorr b200dsp_iqcorr_t;
+int b200dsp_iqcorr_create(b200dsp_iqcorr_t** h);
+int b200dsp_iqcorr_destroy(b200dsp_iqcorr_t* h);
+int b200dsp_iqcorr_reset(b200dsp_iqcorr_t* h);
+int b200dsp_iqcorr_run(b200dsp_iqcorr_t* h, int16_t* iq, int64_t n_samples, int imbalance);      /* in place, host buffer */
+int b200dsp_iqcorr_run_dev(b200dsp_iqcorr_t* h, const void* d_in, void* d_out, int64_t n_samples, int imbalance, void* cuda_stream);
+
 /* ---- stand-alone Interpolator (the polyphase resampler of K4 without the bank) -------------------------------------
  * == Interpolator::create(phaseSteps, sampleRate, cutoff, nbTapsPerPhase)   sdrbase/dsp/interpolator.cpp:74-129
  * b200dsp_interp_decimate is the block form of the loop every Rx plugin writes (plugins/channelrx/demodnfm/nfmdemod.cpp:150-155,315):

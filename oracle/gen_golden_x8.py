@@ -52,6 +52,18 @@ def main():
             for mname, mode in MODES.items():
                 out = R.RefDecimators(kind).run(log2, mode, lo.view(dt))
                 meta["long"]["rows"][f"{kind}/{log2}/{mname}"] = {"n_out": int(out.shape[0]), "fnv": R.fnv1a64_u16(out), "at100": out[100].tolist()}
+    # DSPDeviceSourceEngine::iqCorrections, DC branch: ragged calls across the 1024-sample fill-up, offsets, extreme runs
+    rs = np.random.RandomState(20181020)
+    xq = (rs.randint(-3000, 3000, size=(6000, 2)) + np.array([700, -1234])).astype(np.int16)
+    xq[2500:2600] = 32767
+    xq[4000:4100] = -32768
+    qcuts = [0, 7, 1000, 1030, 1031, 3333, 6000]
+    q = R.RefIQCorrections()
+    outs = [q.run(xq[a:b]) for a, b in zip(qcuts[:-1], qcuts[1:])]
+    arrays["iqcorr/in"] = xq
+    arrays["iqcorr/out"] = np.concatenate(outs)
+    meta["iqcorr"] = {"seed": 20181020, "cuts": qcuts, "input": "iqcorr/in", "output": "iqcorr/out", "mode": "DC only (imbalanceCorrection false)",
+                      "fnv": R.fnv1a64_u16(arrays["iqcorr/out"])}
     np.savez_compressed(os.path.join(OUT, "golden_x8.npz"), **arrays)
     with open(os.path.join(OUT, "golden_x8.json"), "w") as f:
         json.dump(meta, f, indent=1)

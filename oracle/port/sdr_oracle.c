@@ -218,6 +218,28 @@ int orc_decim_x8_run(void* h, int log2, int mode, const uint8_t* buf, int len, i
     return orc_decim_ii_run(d->ii, log2, mode, d->tmp, len, out);
 }
 
+/* DSPDeviceSourceEngine::iqCorrections, DC branch (dspdevicesourceengine.cpp:175-183,254-261) with
+ * MovingAverageUtil<int32_t,int64_t,1024> (util/movingaverage.h: fill-up then roll; operator T() = total / N). */
+typedef struct { int32_t s[2][1024]; int num[2]; unsigned idx[2]; int64_t total[2]; } iqcorr;
+
+void* orc_iqcorr_create(void) { return calloc(1, sizeof(iqcorr)); }
+void  orc_iqcorr_destroy(void* h) { free(h); }
+static int32_t mavg_push(iqcorr* q, int c, int32_t v)
+{
+    if (q->num[c] < 1024) { q->s[c][q->num[c]++] = v; q->total[c] += v; }
+    else { q->total[c] += v - q->s[c][q->idx[c]]; q->s[c][q->idx[c]] = v; q->idx[c] = (q->idx[c] + 1) % 1024; }
+    return (int32_t) (q->total[c] / 1024);
+}
+void orc_iqcorr_dc(void* h, int16_t* iq, int n)
+{
+    iqcorr* q = (iqcorr*) h;
+    for (int i = 0; i < n; i++) {
+        int32_t bi = mavg_push(q, 0, iq[2 * i]), bq = mavg_push(q, 1, iq[2 * i + 1]);
+        iq[2 * i] = (int16_t) (iq[2 * i] - bi);
+        iq[2 * i + 1] = (int16_t) (iq[2 * i + 1] - bq);
+    }
+}
+
 /* ------------------------------------------------------------------------------------------------
  * HB64 float stage: y = ((..(0 + hF0*(a0+b0)) + hF1*(a1+b1)) ..) + 0.5f*centre, float throughout.
  * inthalfbandfiltereof.h:63-71,141-188.

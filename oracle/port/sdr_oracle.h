@@ -33,6 +33,11 @@ void* orc_decim_x8_create(int is_unsigned, int shift);
 void  orc_decim_x8_destroy(void* h);
 int   orc_decim_x8_run(void* h, int log2, int mode, const uint8_t* buf, int len, int16_t* out);
 
+/* DSPDeviceSourceEngine::iqCorrections(begin, end, false): sdrbase/dsp/dspdevicesourceengine.cpp:175-183,254-261 */
+void* orc_iqcorr_create(void);
+void  orc_iqcorr_destroy(void* h);
+void  orc_iqcorr_dc(void* h, int16_t* iq, int n_samples);
+
 /* DecimatorsFI / DecimatorsFF / DecimatorsIF: sdrbase/dsp/decimatorsfi.cpp, decimatorsff.cpp, decimatorsif.h */
 void* orc_decim_f_create(int in_fmt, int out_fmt, int input_bits);
 void  orc_decim_f_destroy(void* h);

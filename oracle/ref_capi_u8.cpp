@@ -7,6 +7,7 @@
 #include <string.h>
 #include <cstddef>
 #include "dsp/decimatorsu.h"
+#include "util/movingaverage.h"
 
 namespace {
 
@@ -37,7 +38,30 @@ bool dispatch_u8(DecimU8* h, int log2, int mode, SampleVector::iterator* it, con
 
 } // namespace
 
+// DSPDeviceSourceEngine::iqCorrections, DC branch.  dspdevicesourceengine.cpp pulls QThread / the plugin API and is not
+// buildable here, so its loop (:175-183,254-261) is restated around the reference's own MovingAverageUtil and Sample types.
+struct IqCorr {
+    MovingAverageUtil<int32_t, int64_t, 1024> m_iBeta;      // dspdevicesourceengine.h:106-107
+    MovingAverageUtil<int32_t, int64_t, 1024> m_qBeta;
+};
+
 extern "C" {
+
+void* ref_iqcorr_create() { return new IqCorr; }
+void ref_iqcorr_destroy(void* p) { delete (IqCorr*) p; }
+// in place on n Samples (int16 I,Q interleaved)
+void ref_iqcorr_dc(void* p, int16_t* iq, int n)
+{
+    IqCorr* h = (IqCorr*) p;
+    Sample* begin = (Sample*) iq;
+    for (Sample* it = begin; it < begin + n; it++)
+    {
+        h->m_iBeta(it->real());
+        h->m_qBeta(it->imag());
+        it->m_real -= (int32_t) h->m_iBeta;
+        it->m_imag -= (int32_t) h->m_qBeta;
+    }
+}
 
 void* ref_decim_u8_create() { return new DecimU8; }
 void ref_decim_u8_destroy(void* p) { delete (DecimU8*) p; }

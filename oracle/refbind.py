@@ -40,6 +40,7 @@ def load(strict=False):
         "ref_decim_i8_run": (i32, [vp, i32, i32, C.POINTER(C.c_int8), i32, pi16]),
         "ref_decim_u8_create": (vp, []), "ref_decim_u8_destroy": (None, [vp]),
         "ref_decim_u8_run": (i32, [vp, i32, i32, C.POINTER(C.c_uint8), i32, pi16]),
+        "ref_iqcorr_create": (vp, []), "ref_iqcorr_destroy": (None, [vp]), "ref_iqcorr_dc": (None, [vp, pi16, i32]),
         "ref_decim_fi_create": (vp, []), "ref_decim_fi_destroy": (None, [vp]),
         "ref_decim_fi_run": (i32, [vp, i32, i32, pf32, i32, pi16]),
         "ref_decim_ff_create": (vp, []), "ref_decim_ff_destroy": (None, [vp]),
@@ -106,6 +107,19 @@ class RefDecimators(_Handle):
         if n < 0:
             raise ValueError("bad log2/mode")
         return out[:n].copy()
+
+
+class RefIQCorrections(_Handle):
+    """DSPDeviceSourceEngine::iqCorrections(begin, end, false): DC correction in place."""
+
+    def __init__(self, strict=False):
+        L = load(strict)
+        super().__init__(L, L.ref_iqcorr_create(), L.ref_iqcorr_destroy)
+
+    def run(self, iq):
+        a = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1, 2).copy()
+        self.lib.ref_iqcorr_dc(self.h, _p(a, C.c_int16), a.shape[0])
+        return a
 
 
 class RefDownChannelizer(_Handle):

@@ -60,6 +60,11 @@ SIGNATURES = {
     "b200dsp_bank_sync": (_i32, [_vp]),
     "b200dsp_bank_set_reserved_sms": (_i32, [_vp, _vp, _i32]),
     "b200dsp_probe_sm_order": (_i32, [_i32, _i32, _vp]),
+    "b200dsp_iqcorr_create": (_i32, [_pvp]),
+    "b200dsp_iqcorr_destroy": (_i32, [_vp]),
+    "b200dsp_iqcorr_reset": (_i32, [_vp]),
+    "b200dsp_iqcorr_run": (_i32, [_vp, _vp, _i64, _i32]),
+    "b200dsp_iqcorr_run_dev": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp]),
     "b200dsp_interp_create": (_i32, [_pvp, _i32, C.c_double, C.c_double, C.c_double]),
     "b200dsp_interp_destroy": (_i32, [_vp]),
     "b200dsp_interp_info": (_i32, [_vp, _pi32, _vp, _i32]),

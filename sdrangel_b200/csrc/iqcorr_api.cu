@@ -1,0 +1,236 @@
+// iqcorr_api.cu — C ABI of the engine-side sample corrections: b200dsp_iqcorr_*
+//
+// Reference: DSPDeviceSourceEngine::iqCorrections (sdrbase/dsp/dspdevicesourceengine.cpp:175-262), the step between the
+// device Decimators<> and the channel sinks (called from DSPDeviceSourceEngine::work, :343-347,375-379).  DC branch
+// (imbalanceCorrection == false, :254-259):
+//     m_iBeta(it->real()); m_qBeta(it->imag());                 MovingAverageUtil<int32_t, int64_t, 1024>  (dspdevicesourceengine.h:106-107)
+//     it->m_real -= (int32_t) m_iBeta; it->m_imag -= (int32_t) m_qBeta;
+// MovingAverageUtil (sdrbase/util/movingaverage.h): running total of the last 1024 pushed samples (fewer while filling
+// up, but the divisor is always N), operator T() = total / N with C++ truncation toward zero.  So
+//     y[i] = (int16) (x[i] - trunc(S_i / 1024)),   S_i = sum of the (raw) samples x[max(0, i-1023) .. i] of the stream.
+// The sequential running total becomes a windowed sum of raw inputs: a block-wide prefix scan over a tile plus a
+// 1024-sample halo; the carried state is the last 1024 raw samples (zeros at start == the fill-up phase).
+#include "common.cuh"
+
+using namespace b200dsp;
+
+namespace {
+
+constexpr int DC_N = 1024;            // MovingAverageUtil<..., 1024>
+constexpr int DC_TILE = 3072;         // samples per block
+constexpr int DC_THREADS = 256;
+constexpr int DC_PER = (DC_TILE + DC_N) / DC_THREADS;     // 16 consecutive elements of (halo + tile) per thread
+
+struct DcParams {
+    const uint32_t* in;        // packed int16 IQ
+    uint32_t* out;
+    const uint32_t* hist_in;   // last DC_N raw samples before this call (oldest first)
+    uint32_t* hist_out;
+    long long n;
+};
+
+// shared arrays are padded by one word per 16 so that "thread t owns elements 16t .. 16t+15" is bank-conflict-free
+__device__ __forceinline__ int dc_pad(int e) { return e + (e >> 4); }
+constexpr int DC_WORDS = DC_TILE + DC_N + ((DC_TILE + DC_N) >> 4);
+
+template<bool VEC>
+__global__ void __launch_bounds__(DC_THREADS) dc_correct_kernel(const DcParams p)
+{
+    __shared__ int sA[DC_WORDS], sB[DC_WORDS];      // sA: packed raw samples, then the I prefix; sB: the Q prefix
+    __shared__ int wre[DC_THREADS / 32], wim[DC_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long t0 = (long long) blockIdx.x * DC_TILE;
+    const long long w0 = t0 - DC_N;                 // stream index of window element 0 (a multiple of 1024)
+    // 1. coalesced load of the window (halo + tile): element e is stream sample w0 + e
+    if (VEC) {
+#pragma unroll
+        for (int k = 0; k < DC_PER / 4; ++k) {
+            const int e = 4 * (k * DC_THREADS + tid);
+            const long long i = w0 + e;
+            uint4 v;
+            if (i >= 0 && i + 4 <= p.n) v = *reinterpret_cast<const uint4*>(p.in + i);
+            else if (i < 0) v = *reinterpret_cast<const uint4*>(p.hist_in + (DC_N + i));      // the halo of block 0: all of it history
+            else {
+                v.x = (i < p.n) ? p.in[i] : 0u;         v.y = (i + 1 < p.n) ? p.in[i + 1] : 0u;
+                v.z = (i + 2 < p.n) ? p.in[i + 2] : 0u; v.w = (i + 3 < p.n) ? p.in[i + 3] : 0u;
+            }
+            const int q = dc_pad(e);                 // e is a multiple of 4: the four words stay inside one group of 16
+            sA[q] = (int) v.x; sA[q + 1] = (int) v.y; sA[q + 2] = (int) v.z; sA[q + 3] = (int) v.w;
+        }
+    } else {
+        for (int e = tid; e < DC_TILE + DC_N; e += DC_THREADS) {
+            const long long i = w0 + e;
+            uint32_t w = 0;
+            if (i < 0) w = p.hist_in[DC_N + i];
+            else if (i < p.n) w = p.in[i];
+            sA[dc_pad(e)] = (int) w;
+        }
+    }
+    __syncthreads();
+    // 2. thread-local inclusive prefix over 16 consecutive elements, block-wide exclusive prefix of the thread sums
+    int vr[DC_PER], vi[DC_PER];
+    int sr = 0, si = 0;
+    const int base = tid * DC_PER + tid;            // dc_pad(16 tid)
+#pragma unroll
+    for (int k = 0; k < DC_PER; ++k) {
+        const int w = sA[base + k];
+        sr += (int) (short) (w & 0xffff); si += w >> 16;
+        vr[k] = sr; vi[k] = si;
+    }
+    int xr = sr, xi = si;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, xr, d), b = __shfl_up_sync(0xffffffffu, xi, d);
+        if (lane >= d) { xr += a; xi += b; }
+    }
+    if (lane == 31) { wre[wid] = xr; wim[wid] = xi; }
+    __syncthreads();                                 // also: every thread has read its raw words
+    int br = 0, bi = 0;
+    for (int w2 = 0; w2 < wid; ++w2) { br += wre[w2]; bi += wim[w2]; }
+    const int offr = br + xr - sr, offi = bi + xi - si;
+#pragma unroll
+    for (int k = 0; k < DC_PER; ++k) { sA[base + k] = vr[k] + offr; sB[base + k] = vi[k] + offi; }
+    __syncthreads();
+    // 3. outputs: window sum S = P[e] - P[e - 1024]; own raw sample = P[e] - P[e - 1]
+    for (int o = tid; o < DC_TILE; o += DC_THREADS) {
+        const long long i = t0 + o;
+        if (i >= p.n) break;
+        const int e = o + DC_N;
+        const int pe = dc_pad(e), pw = dc_pad(e - DC_N), p1 = dc_pad(e - 1);
+        const int Pr = sA[pe], Pi = sB[pe];
+        const int Sr = Pr - sA[pw], Si = Pi - sB[pw];
+        const int x = Pr - sA[p1], y = Pi - sB[p1];
+        const int re = x - Sr / DC_N, im = y - Si / DC_N;         // C++ integer division: toward zero, like total / N
+        p.out[i] = ((uint32_t) re & 0xffffu) | ((uint32_t) im << 16);
+    }
+    // carry: the last DC_N raw samples of the stream so far (block 0 also covers calls shorter than DC_N)
+    if (blockIdx.x == 0) {
+        for (int t = tid; t < DC_N; t += DC_THREADS) {
+            const long long i = p.n - DC_N + t;
+            p.hist_out[t] = (i < 0) ? p.hist_in[DC_N + i] : p.in[i];
+        }
+    }
+}
+
+} // namespace
+
+struct b200dsp_iqcorr {
+    int device;
+    cudaStream_t stream;
+    uint32_t* d_hist[2];
+    int cur;
+    uint32_t* d_in;  uint32_t* d_out; long long cap;       // staging for the host-pointer / in-place forms
+};
+
+namespace {
+
+int ensure_staging(b200dsp_iqcorr* h, long long n, cudaStream_t st)
+{
+    if (h->cap >= n) return 0;
+    int rc;
+    if ((rc = B200_CUDA_CHECK(cudaStreamSynchronize(st)))) return rc;
+    if (h->d_in) cudaFree(h->d_in);
+    if (h->d_out) cudaFree(h->d_out);
+    h->d_in = nullptr; h->d_out = nullptr; h->cap = 0;
+    if ((rc = B200_CUDA_CHECK(cudaMalloc(&h->d_in, (size_t) n * 4))) || (rc = B200_CUDA_CHECK(cudaMalloc(&h->d_out, (size_t) n * 4)))) return rc;
+    h->cap = n;
+    return 0;
+}
+
+int launch_dc(b200dsp_iqcorr* h, const uint32_t* d_in, uint32_t* d_out, long long n, cudaStream_t st)
+{
+    DcParams p;
+    p.in = d_in; p.out = d_out; p.hist_in = h->d_hist[h->cur]; p.hist_out = h->d_hist[h->cur ^ 1]; p.n = n;
+    const long long blocks = (n + DC_TILE - 1) / DC_TILE;
+    if (((uintptr_t) d_in & 15) == 0) dc_correct_kernel<true><<<(unsigned) blocks, DC_THREADS, 0, st>>>(p);
+    else                              dc_correct_kernel<false><<<(unsigned) blocks, DC_THREADS, 0, st>>>(p);
+    int rc = B200_CUDA_CHECK(cudaGetLastError());
+    if (rc == 0) h->cur ^= 1;
+    return rc;
+}
+
+} // namespace
+
+extern "C" {
+
+int b200dsp_iqcorr_create(b200dsp_iqcorr_t** out)
+{
+    if (!out) return b200_fail(B200DSP_EINVAL, "iqcorr_create: null handle pointer");
+    *out = nullptr;
+    int rc = b200_require_device();
+    if (rc) return rc;
+    b200dsp_iqcorr* h = new (std::nothrow) b200dsp_iqcorr();
+    if (!h) return b200_fail(B200DSP_ENOMEM, "iqcorr_create: out of host memory");
+    memset(h, 0, sizeof(*h));
+    h->device = b200_current_device();
+    if ((rc = B200_CUDA_CHECK(cudaSetDevice(h->device))) ||
+        (rc = B200_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)))) { delete h; return rc; }
+    for (int i = 0; i < 2; ++i)
+        if ((rc = B200_CUDA_CHECK(cudaMalloc(&h->d_hist[i], DC_N * 4))) || (rc = B200_CUDA_CHECK(cudaMemset(h->d_hist[i], 0, DC_N * 4)))) { b200dsp_iqcorr_destroy(h); return rc; }
+    if ((rc = B200_CUDA_CHECK(cudaDeviceSynchronize()))) { b200dsp_iqcorr_destroy(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+int b200dsp_iqcorr_destroy(b200dsp_iqcorr_t* h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < 2; ++i) if (h->d_hist[i]) cudaFree(h->d_hist[i]);
+    if (h->d_in) cudaFree(h->d_in);
+    if (h->d_out) cudaFree(h->d_out);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+int b200dsp_iqcorr_reset(b200dsp_iqcorr_t* h)
+{
+    if (!h) return b200_fail(B200DSP_EINVAL, "null handle");
+    int rc = B200_CUDA_CHECK(cudaSetDevice(h->device));
+    if (rc) return rc;
+    for (int i = 0; i < 2; ++i) if ((rc = B200_CUDA_CHECK(cudaMemsetAsync(h->d_hist[i], 0, DC_N * 4, h->stream)))) return rc;
+    return B200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+}
+
+static int check_mode(int imbalance)
+{
+    if (imbalance) return b200_fail(B200DSP_ESTATE, "iqcorr: the I/Q imbalance branch (dspdevicesourceengine.cpp:184-252) is not implemented; only DC correction");
+    return 0;
+}
+
+int b200dsp_iqcorr_run_dev(b200dsp_iqcorr_t* h, const void* d_in, void* d_out, int64_t n_samples, int imbalance, void* cuda_stream)
+{
+    if (!h) return b200_fail(B200DSP_EINVAL, "null handle");
+    int rc = check_mode(imbalance);
+    if (rc) return rc;
+    if (n_samples < 0 || (n_samples > 0 && (!d_in || !d_out))) return b200_fail(B200DSP_EINVAL, "iqcorr_run_dev: bad buffer");
+    if (n_samples == 0) return 0;
+    if ((rc = B200_CUDA_CHECK(cudaSetDevice(h->device)))) return rc;
+    cudaStream_t st = cuda_stream ? (cudaStream_t) cuda_stream : h->stream;
+    const uint32_t* src = (const uint32_t*) d_in;
+    if (d_in == d_out) {          // in place (as the reference works): the halo of a tile must stay raw, so read from a copy
+        if ((rc = ensure_staging(h, n_samples, st))) return rc;
+        if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(h->d_in, d_in, (size_t) n_samples * 4, cudaMemcpyDeviceToDevice, st)))) return rc;
+        src = h->d_in;
+    }
+    return launch_dc(h, src, (uint32_t*) d_out, n_samples, st);
+}
+
+int b200dsp_iqcorr_run(b200dsp_iqcorr_t* h, int16_t* iq, int64_t n_samples, int imbalance)
+{
+    if (!h) return b200_fail(B200DSP_EINVAL, "null handle");
+    int rc = check_mode(imbalance);
+    if (rc) return rc;
+    if (n_samples < 0 || (n_samples > 0 && !iq)) return b200_fail(B200DSP_EINVAL, "iqcorr_run: bad buffer");
+    if (n_samples == 0) return 0;
+    if ((rc = B200_CUDA_CHECK(cudaSetDevice(h->device)))) return rc;
+    if ((rc = ensure_staging(h, n_samples, h->stream))) return rc;
+    if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(h->d_in, iq, (size_t) n_samples * 4, cudaMemcpyHostToDevice, h->stream))) ||
+        (rc = launch_dc(h, h->d_in, h->d_out, n_samples, h->stream)) ||
+        (rc = B200_CUDA_CHECK(cudaMemcpyAsync(iq, h->d_out, (size_t) n_samples * 4, cudaMemcpyDeviceToHost, h->stream)))) return rc;
+    return B200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+}
+
+} // extern "C"

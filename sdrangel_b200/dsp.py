@@ -350,3 +350,40 @@ class Interpolator:
         n = C.c_int64(0)
         capi.check(capi.lib().b200dsp_interp_decimate(self._h, C.byref(rem), float(distance), x.ctypes.data, x.size, out.ctypes.data, out.size, C.byref(n)))
         return out[:n.value], rem.value
+
+
+class IQCorrections:
+    """DSPDeviceSourceEngine::iqCorrections (sdrbase/dsp/dspdevicesourceengine.cpp:175-262): the engine's DC (and I/Q
+    imbalance) correction of the decimated baseband before it reaches the sinks.  One object == one engine's state."""
+
+    def __init__(self, device=None):
+        if device is not None:
+            capi.init(device)
+        h = C.c_void_p()
+        capi.check(capi.lib().b200dsp_iqcorr_create(C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            capi.lib().b200dsp_iqcorr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        capi.check(capi.lib().b200dsp_iqcorr_reset(self._h))
+
+    def iqCorrections(self, iq, imbalanceCorrection=False):
+        """Corrects the (n, 2) int16 samples in place, like the reference does on the FIFO's vector; returns the array."""
+        a = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1, 2)
+        capi.check(capi.lib().b200dsp_iqcorr_run(self._h, a.ctypes.data, a.shape[0], int(bool(imbalanceCorrection))))
+        if a is not iq and isinstance(iq, np.ndarray) and iq.dtype == np.int16 and iq.size == a.size:
+            iq.reshape(-1, 2)[...] = a
+        return a
+
+    def run_dev(self, d_in, d_out, n_samples, stream=None):
+        capi.check(capi.lib().b200dsp_iqcorr_run_dev(self._h, C.c_void_p(d_in), C.c_void_p(d_out), int(n_samples), 0, C.c_void_p(stream or 0)))

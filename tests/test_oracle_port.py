@@ -72,6 +72,15 @@ def test_decim_8bit_inputs_golden(port, golden_x8, kind):
         assert out.shape[0] == g["n_out"] and out[100].tolist() == g["at100"] and fnv1a64_u16(out) == g["fnv"]
 
 
+def test_iqcorrections_dc_golden(port, golden_x8):
+    """DSPDeviceSourceEngine::iqCorrections(begin, end, false) (dspdevicesourceengine.cpp:175-183,254-261)."""
+    arrays, meta = golden_x8
+    x, cuts = arrays["iqcorr/in"], meta["iqcorr"]["cuts"]
+    q = port.PortIQCorrections()
+    out = np.concatenate([q.run(x[a:b]) for a, b in zip(cuts[:-1], cuts[1:])])
+    assert np.array_equal(out, arrays["iqcorr/out"]) and fnv1a64_u16(out) == meta["iqcorr"]["fnv"]
+
+
 @pytest.mark.parametrize("kind", ["fi", "ff", "if"])
 def test_decim_float_strict_bit_exact_and_fast_within_tolerance(port, golden, golden_meta, kind):
     src = port.sdrbench_s16(1 << 14) if kind[0] == "i" else port.sdrbench_f32(1 << 14)
