@@ -425,7 +425,9 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
         b->tables_dirty = false;
     }
     // front-end schedules depend only on counts: replay them on the side stream while the tree runs
-    if (!b->fe_index.empty() && max_new > 0) {
+    // (the first pass of a feed always runs it, even with nothing new at the channels' depths: it zeroes the per-feed output counts)
+    const bool run_sched = !b->fe_index.empty() && (max_new > 0 || first_pass);
+    if (run_sched) {
         if ((rc = B200_CUDA_CHECK(cudaEventRecord(b->ev_begin, st))) || (rc = B200_CUDA_CHECK(cudaStreamWaitEvent(b->side, b->ev_begin, 0)))) return rc;
         const int nfe = (int) b->h_fe.size();
         frontend_schedule_kernel<<<(nfe + 3) / 4, 128, 0, b->side>>>(b->d_fe, nfe, pi);      // one warp per channel
@@ -534,11 +536,11 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
         hb48_finalize_kernel<<<dim3(gx, (unsigned) nc), 256, 0, st>>>(b->d_leaf, pi);
         if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
     }
+    if (run_sched && (rc = B200_CUDA_CHECK(cudaStreamWaitEvent(st, b->ev_sched, 0)))) return rc;
     if (!b->fe_index.empty() && max_new > 0) {
         size_t smem = 0;
         for (int ci : b->fe_index) { const Channel& cc = b->chans[ci]; const size_t s2 = (((size_t) ((cc.ntaps + 2 * FE_PAD) | 1) * cc.phase_steps + 3) & ~(size_t) 3) * sizeof(float); if (s2 > smem) smem = s2; }
         smem += (size_t) (FE_MAX_TAPS + FE_TILE) * sizeof(float2);
-        if ((rc = B200_CUDA_CHECK(cudaStreamWaitEvent(st, b->ev_sched, 0)))) return rc;
         frontend_kernel<<<dim3((unsigned) ((max_new + FE_TILE - 1) / FE_TILE), (unsigned) b->h_fe.size()), FE_THREADS, smem, st>>>(b->d_fe, b->d_nco, pi);
         if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
         b->fe_parity ^= 1;
@@ -550,6 +552,20 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
     return 0;
 }
 
+// a feed of zero samples (DownChannelizer::feed with begin == end): nothing moves, every channel's outputs of "the last
+// feed" are empty -- the front-ends' per-feed counts live on the device and are zeroed by an empty schedule pass
+int empty_feed(b200dsp_bank* b, cudaStream_t st)
+{
+    if (b->fe_index.empty()) return 0;
+    PassInfo pi;
+    memset(&pi, 0, sizeof(pi));
+    pi.first_pass = 1;
+    const int nfe = (int) b->h_fe.size();
+    if (b->tables_dirty) return 0;            // never fed: the device tables do not exist yet and every count is still zero
+    frontend_schedule_kernel<<<(nfe + 3) / 4, 128, 0, st>>>(b->d_fe, nfe, pi);
+    return B200_CUDA_CHECK(cudaGetLastError());
+}
+
 int feed_common(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t st)
 {
     int rc;
@@ -557,6 +573,7 @@ int feed_common(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t
     if ((rc = reserve_outputs(b, n))) return rc;
     for (auto& c : b->chans) c.out_count = 0;
     b->out_count_depth.assign(32, 0);
+    if (n == 0) return empty_feed(b, st);
     long long done = 0;
     while (done < n) {
         const long long m = (n - done) < b->chunk ? (n - done) : b->chunk;
@@ -775,6 +792,7 @@ int b200dsp_bank_feed(b200dsp_bank_t* b, const int16_t* iq, int64_t n_samples)
     if ((rc = reserve_outputs(b, n_samples))) return rc;
     for (auto& c : b->chans) c.out_count = 0;
     b->out_count_depth.assign(32, 0);
+    if (n_samples == 0) return empty_feed(b, b->stream);
     long long done = 0;
     while (done < n_samples) {
         const long long m = (n_samples - done) < b->chunk ? (n_samples - done) : b->chunk;
