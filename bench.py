@@ -681,25 +681,53 @@ def bench_bank(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=T
            "dtype": "s32", "scaling": "strong"}
     if want_e2e:
         # end to end through the plugin-facing calls: the baseband starts in pinned host memory (on rank 0: the ingest GPU's
-        # host), H2D, NCCL broadcast (N > 1), the bank, and ONE pooled device-to-host fetch of every channel's front-end output
+        # host) and is processed in K blocks so that the H2D copy of block k+1, the kernels of block k (NCCL broadcast first
+        # when N > 1) and the pooled device-to-host copy of block k-1's channel outputs overlap (three streams)
+        K = 4
+        nb_ = n // K
         hx = torch.empty((2 * n,), dtype=torch.int16, pin_memory=True) if c.rank == 0 else None
         if c.rank == 0:
             hx.copy_(x)
-        stride = int(n * 48000.0 / fs) + 64
-        hout = torch.empty((max(len(info), 1), stride, 2), dtype=torch.float32, pin_memory=True)
+        stride = int(nb_ * 48000.0 / fs) + 64
+        nch = max(len(info), 1)
+        pools = [torch.empty((nch, stride, 2), dtype=torch.float32, device=c.dev) for _ in range(2)]
+        dcnt = [torch.zeros((nch,), dtype=torch.int64, device=c.dev) for _ in range(2)]
+        hout = torch.empty((K, nch, stride, 2), dtype=torch.float32, pin_memory=True)
+        hcnt = torch.zeros((K, nch), dtype=torch.int64, pin_memory=True)
+        s_in, s_out = torch.cuda.Stream(device=c.dev), torch.cuda.Stream(device=c.dev)
         for w in list(pending.values()):
             w.wait()
         pending.clear()
+        state["group"] = None
         bank.set_reserved_sms([])
-        counts = {}
+        torch.cuda.synchronize()
 
         def e2e_step():
-            if c.rank == 0:
-                x.copy_(hx, non_blocking=True)
-            if c.world > 1:
-                dist.broadcast(bviews[0], src=0)
-            bank.feed_dev(x.data_ptr(), n, sptr)
-            counts["n"] = bank.fetch_all(capi.STAGE_FRONTEND, stride=stride, out_ptr=hout.data_ptr(), stream=sptr)
+            ev_out = [None] * K
+            for k in range(K):
+                xs = x[2 * k * nb_: 2 * (k + 1) * nb_]
+                if c.rank == 0:
+                    with torch.cuda.stream(s_in):
+                        xs.copy_(hx[2 * k * nb_: 2 * (k + 1) * nb_], non_blocking=True)
+                        e_in = torch.cuda.Event()
+                        e_in.record(s_in)
+                    stream.wait_event(e_in)
+                if c.world > 1:
+                    dist.broadcast(xs.view(torch.int32), src=0)
+                bank.feed_dev(xs.data_ptr(), nb_, sptr)
+                if k >= 2:
+                    stream.wait_event(ev_out[k - 2])           # the pool being gathered into has left for the host
+                bank.gather_dev(capi.STAGE_FRONTEND, pools[k % 2].data_ptr(), stride, dcnt[k % 2].data_ptr(), sptr)
+                e_g = torch.cuda.Event()
+                e_g.record(stream)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(e_g)
+                    hout[k].copy_(pools[k % 2], non_blocking=True)
+                    hcnt[k].copy_(dcnt[k % 2], non_blocking=True)
+                    ev_out[k] = torch.cuda.Event()
+                    ev_out[k].record(s_out)
+            s_out.synchronize()
+            stream.synchronize()
 
         with torch.cuda.stream(stream):
             e2e_step()
@@ -710,13 +738,14 @@ def bench_bank(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=T
                 e2e_step()
             torch.cuda.synchronize()
             dt = max_over_ranks(c, time.perf_counter() - t0)
-            tot = torch.tensor([float(counts["n"].sum()) * 8], device=c.dev, dtype=torch.float64)
+            tot = torch.tensor([float(hcnt.sum()) * 8], device=c.dev, dtype=torch.float64)
             if c.world > 1:
                 dist.all_reduce(tot)
         res["e2e"] = {"value": n * ksteps / dt / 1e6, "unit": "input MS/s", "h2d_bytes_per_step": int(n * 4),
                       "d2h_bytes_per_step": int(tot.item()), "steps": ksteps,
-                      "api": "pinned host baseband -> H2D%s -> b200dsp_bank_feed_dev -> b200dsp_bank_fetch_all (every channel's front-end output, "
-                             "pinned host)" % (" on rank 0 -> NCCL broadcast" if c.world > 1 else ""), "samples_per_step": n}
+                      "api": "pinned host baseband -> H2D%s -> b200dsp_bank_feed_dev -> b200dsp_bank_gather_dev + D2H of every channel's front-end output "
+                             "(pinned host), in %d blocks pipelined over three streams" % (" on rank 0 -> NCCL broadcast" if c.world > 1 else "", K),
+                      "samples_per_step": n}
     bank.close()
     return res
 

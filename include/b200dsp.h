@@ -146,6 +146,9 @@ int b200dsp_bank_fetch_dev(b200dsp_bank_t* b, int chan_id, int stage, const void
  * bytes by stage), counts[c] = its sample count (0 for a channel without that stage); waits for the stream (NULL: the
  * bank's own) before returning.  Pinned `out` makes it one DMA. */
 int b200dsp_bank_fetch_all(b200dsp_bank_t* b, int stage, void* out, int64_t stride_samples, int64_t* counts, void* cuda_stream);
+/* the device half of fetch_all: gathers into a caller-owned device array [channel][stride_samples] and device counts,
+ * asynchronously on the stream (for callers that overlap the device-to-host copy with the next block's kernels) */
+int b200dsp_bank_gather_dev(b200dsp_bank_t* b, int stage, void* d_out, int64_t stride_samples, int64_t* d_counts, void* cuda_stream);
 /* device-to-device copy of samples [skip, skip + count) of a channel's channelizer output of the last feed */
 int b200dsp_bank_copy_out_dev(b200dsp_bank_t* b, int chan_id, int64_t skip, int64_t count, void* d_dst, void* cuda_stream);
 int b200dsp_bank_sync(b200dsp_bank_t* b);

@@ -56,6 +56,7 @@ SIGNATURES = {
     "b200dsp_bank_fetch": (_i32, [_vp, _i32, _i32, _vp, _i64, _pi64]),
     "b200dsp_bank_fetch_dev": (_i32, [_vp, _i32, _i32, _pvp, _pi64]),
     "b200dsp_bank_fetch_all": (_i32, [_vp, _i32, _vp, _i64, _vp, _vp]),
+    "b200dsp_bank_gather_dev": (_i32, [_vp, _i32, _vp, _i64, _vp, _vp]),
     "b200dsp_bank_copy_out_dev": (_i32, [_vp, _i32, _i64, _i64, _vp, _vp]),
     "b200dsp_bank_sync": (_i32, [_vp]),
     "b200dsp_bank_set_reserved_sms": (_i32, [_vp, _vp, _i32]),

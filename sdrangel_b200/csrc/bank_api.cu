@@ -191,7 +191,7 @@ struct b200dsp_bank {
     void* d_pool; size_t pool_bytes;
     // SMs left to a concurrent collective (b200dsp_bank_set_reserved_sms): level kernels run in work-queue mode
     uint32_t rsv[5]; int n_rsv; int* d_queue; int level_occ;
-    GatherSrc* d_gsrc; long long* d_gcnt; size_t gcap;
+    GatherSrc* d_gsrc; long long* d_gcnt; size_t gcap; int gslot; std::vector<GatherSrc> h_gsrc;
 };
 
 namespace {
@@ -852,6 +852,49 @@ int b200dsp_bank_fetch_dev(b200dsp_bank_t* b, int chan_id, int stage, const void
     return b200_fail(B200DSP_EINVAL, "bank_fetch_dev: bad stage");
 }
 
+// Every channel's outputs of the last feed gathered into one [channel][stride] device array (+ per-channel counts), on the
+// stream: the device half of b200dsp_bank_fetch_all, for callers that pipeline the device-to-host copy themselves.
+int b200dsp_bank_gather_dev(b200dsp_bank_t* b, int stage, void* d_out, int64_t stride_samples, int64_t* d_counts, void* cuda_stream)
+{
+    if (!b || !d_out || !d_counts || stride_samples <= 0) return b200_fail(B200DSP_EINVAL, "bank_gather_dev: bad argument");
+    if (stage != B200DSP_STAGE_CHANNELIZER && stage != B200DSP_STAGE_FRONTEND) return b200_fail(B200DSP_EINVAL, "bank_gather_dev: bad stage");
+    const size_t nc = b->chans.size();
+    if (nc == 0) return 0;
+    int rc = B200_CUDA_CHECK(cudaSetDevice(b->device));
+    if (rc) return rc;
+    cudaStream_t st = cuda_stream ? (cudaStream_t) cuda_stream : b->stream;
+    if (b->gcap < nc) {
+        if ((rc = B200_CUDA_CHECK(cudaStreamSynchronize(st)))) return rc;
+        if (b->d_gsrc) cudaFree(b->d_gsrc);
+        if (b->d_gcnt) cudaFree(b->d_gcnt);
+        b->d_gsrc = nullptr; b->d_gcnt = nullptr; b->gcap = 0;
+        if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_gsrc, 2 * nc * sizeof(GatherSrc)))) || (rc = B200_CUDA_CHECK(cudaMalloc(&b->d_gcnt, nc * sizeof(long long))))) return rc;
+        b->gcap = nc;
+    }
+    // the source table changes only with a reallocation or a new feed's channelizer counts: two slots, alternating, so a
+    // table still being read by an earlier gather on another stream is not overwritten
+    b->gslot ^= 1;
+    GatherSrc* d_tab = b->d_gsrc + (size_t) b->gslot * nc;
+    b->h_gsrc.resize(nc);
+    long long max_count = 0;
+    for (size_t i = 0; i < nc; ++i) {
+        const Channel& c = b->chans[i];
+        GatherSrc& g = b->h_gsrc[i];
+        if (stage == B200DSP_STAGE_CHANNELIZER) { g.src = c.d_out; g.state = nullptr; g.count = b->built ? c.out_count : 0; }
+        else if (c.fe && b->built && c.d_fe_out) { g.src = c.d_fe_out; g.state = c.d_state; g.count = 0; }
+        else { g.src = nullptr; g.state = nullptr; g.count = 0; }
+        if (c.out_count > max_count) max_count = c.out_count;       // front-end outputs never exceed the channel's input count when decimating
+    }
+    if (max_count > stride_samples) max_count = stride_samples;
+    if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(d_tab, b->h_gsrc.data(), nc * sizeof(GatherSrc), cudaMemcpyHostToDevice, st)))) return rc;
+    int gx = (int) ((max_count + 1023) / 1024);
+    if (gx < 1) gx = 1;
+    if (gx > 256) gx = 256;
+    if (stage == B200DSP_STAGE_FRONTEND) gather_outputs_kernel<float2><<<dim3(gx, (unsigned) nc), 256, 0, st>>>(d_tab, (float2*) d_out, stride_samples, (long long*) d_counts);
+    else gather_outputs_kernel<uint32_t><<<dim3(gx, (unsigned) nc), 256, 0, st>>>(d_tab, (uint32_t*) d_out, stride_samples, (long long*) d_counts);
+    return B200_CUDA_CHECK(cudaGetLastError());
+}
+
 // Every channel's outputs of the last feed with one gather kernel and one device-to-host transfer (the per-channel
 // b200dsp_bank_fetch costs a synchronous small copy per channel: latency-bound for a 1024-channel bank).
 int b200dsp_bank_fetch_all(b200dsp_bank_t* b, int stage, void* out, int64_t stride_samples, int64_t* counts, void* cuda_stream)
@@ -865,33 +908,22 @@ int b200dsp_bank_fetch_all(b200dsp_bank_t* b, int stage, void* out, int64_t stri
     cudaStream_t st = cuda_stream ? (cudaStream_t) cuda_stream : b->stream;
     const size_t elem = (stage == B200DSP_STAGE_FRONTEND) ? sizeof(float2) : sizeof(uint32_t);
     const size_t need = nc * (size_t) stride_samples * elem;
-    if (b->pool_bytes < need || b->gcap < nc) {
+    if (b->pool_bytes < need) {
         if ((rc = B200_CUDA_CHECK(cudaStreamSynchronize(st)))) return rc;
         if (b->d_pool) cudaFree(b->d_pool);
+        b->d_pool = nullptr; b->pool_bytes = 0;
+        if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_pool, need)))) return rc;
+        b->pool_bytes = need;
+    }
+    if (b->gcap < nc) {       // (gather_dev allocates d_gcnt; make sure it exists before it is used as the counts target)
+        if ((rc = B200_CUDA_CHECK(cudaStreamSynchronize(st)))) return rc;
         if (b->d_gsrc) cudaFree(b->d_gsrc);
         if (b->d_gcnt) cudaFree(b->d_gcnt);
-        b->d_pool = nullptr; b->d_gsrc = nullptr; b->d_gcnt = nullptr; b->pool_bytes = 0; b->gcap = 0;
-        if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_pool, need))) || (rc = B200_CUDA_CHECK(cudaMalloc(&b->d_gsrc, nc * sizeof(GatherSrc)))) ||
-            (rc = B200_CUDA_CHECK(cudaMalloc(&b->d_gcnt, nc * sizeof(long long))))) return rc;
-        b->pool_bytes = need; b->gcap = nc;
+        b->d_gsrc = nullptr; b->d_gcnt = nullptr; b->gcap = 0;
+        if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_gsrc, 2 * nc * sizeof(GatherSrc)))) || (rc = B200_CUDA_CHECK(cudaMalloc(&b->d_gcnt, nc * sizeof(long long))))) return rc;
+        b->gcap = nc;
     }
-    std::vector<GatherSrc> g(nc);
-    long long max_count = 0;
-    for (size_t i = 0; i < nc; ++i) {
-        const Channel& c = b->chans[i];
-        if (stage == B200DSP_STAGE_CHANNELIZER) { g[i].src = c.d_out; g[i].state = nullptr; g[i].count = b->built ? c.out_count : 0; }
-        else if (c.fe && b->built && c.d_fe_out) { g[i].src = c.d_fe_out; g[i].state = c.d_state; g[i].count = 0; }
-        else { g[i].src = nullptr; g[i].state = nullptr; g[i].count = 0; }
-        if (c.out_count > max_count) max_count = c.out_count;       // front-end outputs never exceed the channel's input count when decimating
-    }
-    if (max_count > stride_samples) max_count = stride_samples;
-    if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(b->d_gsrc, g.data(), nc * sizeof(GatherSrc), cudaMemcpyHostToDevice, st)))) return rc;
-    int gx = (int) ((max_count + 1023) / 1024);
-    if (gx < 1) gx = 1;
-    if (gx > 256) gx = 256;
-    if (stage == B200DSP_STAGE_FRONTEND) gather_outputs_kernel<float2><<<dim3(gx, (unsigned) nc), 256, 0, st>>>(b->d_gsrc, (float2*) b->d_pool, stride_samples, b->d_gcnt);
-    else gather_outputs_kernel<uint32_t><<<dim3(gx, (unsigned) nc), 256, 0, st>>>(b->d_gsrc, (uint32_t*) b->d_pool, stride_samples, b->d_gcnt);
-    if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
+    if ((rc = b200dsp_bank_gather_dev(b, stage, b->d_pool, stride_samples, (int64_t*) b->d_gcnt, (void*) st))) return rc;
     if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(out, b->d_pool, need, cudaMemcpyDeviceToHost, st))) ||
         (rc = B200_CUDA_CHECK(cudaMemcpyAsync(counts, b->d_gcnt, nc * sizeof(long long), cudaMemcpyDeviceToHost, st))) ||
         (rc = B200_CUDA_CHECK(cudaStreamSynchronize(st)))) return rc;

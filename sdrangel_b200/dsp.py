@@ -206,6 +206,10 @@ class DownChannelizerBank:
     def copy_out_dev(self, chan_id, skip, count, d_dst, stream=None):
         capi.check(capi.lib().b200dsp_bank_copy_out_dev(self._h, chan_id, int(skip), int(count), C.c_void_p(d_dst), C.c_void_p(stream or 0)))
 
+    def gather_dev(self, stage, d_out, stride, d_counts, stream=None):
+        """Device half of fetch_all: [channel][stride] samples into d_out and int64 counts into d_counts, asynchronously."""
+        capi.check(capi.lib().b200dsp_bank_gather_dev(self._h, stage, C.c_void_p(d_out), int(stride), C.c_void_p(d_counts), C.c_void_p(stream or 0)))
+
     def set_reserved_sms(self, smids):
         """Keep the tree kernels off these SMs (left to a concurrent NCCL broadcast); [] turns it off."""
         a = np.ascontiguousarray(smids, dtype=np.int32)

@@ -373,3 +373,40 @@ def test_bank_reserved_sms_work_queue_bit_exact(gpu_lib, port, golden_meta):
         b_bank.set_reserved_sms(list(range(148)))            # cannot reserve every SM
     a_bank.close()
     b_bank.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("plan_name,chunk", [("bank64", 2304), ("bank1024", 768 * 5), ("bank64", 100_000)])
+def test_bank_frontends_many_internal_passes(gpu_lib, port, golden_meta, plan_name, chunk):
+    """A feed larger than the bank's chunk runs as several internal passes: the front-end's per-feed output count, its
+    schedule state (exact replay for bank64's ratios, closed form for bank1024's 1.25), the NCO phase and the 128-sample
+    history must carry from pass to pass exactly as they do from feed to feed."""
+    from sdrangel_b200 import DownChannelizerBank, capi
+    plan = golden_meta["chan_plans"][plan_name]
+    fs = plan["input_rate"]
+    rows = plan["channels"][2::max(1, len(plan["channels"]) // 6)][:6]
+    rs = np.random.RandomState(chunk)
+    n = 260_000
+    x = rs.randint(-20000, 20000, size=(n, 2)).astype(np.int16)
+    cutoff = float(np.float32(np.float32(12500) / np.float32(2.2)))
+    b = DownChannelizerBank(fs)
+    b.set_chunk(chunk)
+    ids, refs = [], []
+    for fc, rate, ofs, path in rows:
+        cid = b.add_channel(48000, fc)[0]
+        b.set_frontend(cid, -ofs, cutoff, 48000)
+        ids.append(cid)
+        o = port.PortDownChannelizer()
+        o.configure(fs, 48000, fc)
+        refs.append((o, port.PortFrontEnd(-ofs, rate, 48000, cutoff)))
+    for a, e in ((0, 130_001), (130_001, 130_002), (130_002, n)):
+        b.feed(x[a:e])
+        for cid, (o, fe) in zip(ids, refs):
+            ch = o.feed(x[a:e])
+            assert np.array_equal(b.fetch(cid), ch), (a, cid)
+            want = fe.feed(ch)
+            got = b.fetch(cid, capi.STAGE_FRONTEND)
+            assert got.shape == want.shape, (a, cid, got.shape, want.shape)
+            if want.size:
+                assert rel_rms(got, want) <= 1e-5, (a, cid)
+    b.close()
