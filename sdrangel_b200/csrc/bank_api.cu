@@ -641,7 +641,7 @@ int b200dsp_bank_destroy(b200dsp_bank_t* b)
 
 int b200dsp_bank_set_chunk(b200dsp_bank_t* b, int64_t samples)
 {
-    if (!b || samples < 768) return b200_fail(B200DSP_EINVAL, "bank_set_chunk: bad argument");
+    if (!b || samples < 768 || samples > (1ll << 30)) return b200_fail(B200DSP_EINVAL, "bank_set_chunk: chunk must be within [768, 2^30] samples (kernels index a pass with 32-bit integers)");
     cudaSetDevice(b->device);
     cudaStreamSynchronize(b->stream);
     b->chunk = (samples + 767) / 768 * 768;

@@ -12,6 +12,7 @@
 #include "sdrangel_b200/dsp/downchannelizer.h"
 #include "sdrangel_b200/dsp/spectrumvis.h"
 #include "sdrangel_b200/dsp/interpolator.h"
+#include "sdrangel_b200/dsp/iqcorrections.h"
 
 static uint64_t fnv(const void* p, size_t n_u16)
 {
@@ -62,6 +63,18 @@ int main()
             m_decimators8.decimate64_inf(&it, (const qint8*) &u8[0], nbSamples * 2);
             nu = it - m_convertBuffer.begin();
             printf("decimators8_64_inf n_out=%zu out=%016llx\n", nu, (unsigned long long) fnv(&m_convertBuffer[0], 2 * nu));
+        }
+        // engine-side DC correction on the decimated vector, in two parts like DSPDeviceSourceEngine::work's FIFO halves (:343-379)
+        {
+            IQCorrections corr;
+            SampleVector v(1 << 16);
+            for (size_t i = 0; i < v.size(); i++) { v[i].setReal(buf[2 * i]); v[i].setImag(buf[2 * i + 1]); }
+            corr.iqCorrections(v.begin(), v.begin() + 40000, false);
+            corr.iqCorrections(v.begin() + 40000, v.end(), false);
+            printf("iqcorrections out=%016llx\n", (unsigned long long) fnv(&v[0], 2 * v.size()));
+            bool threw = false;
+            try { corr.iqCorrections(v.begin(), v.begin() + 8, true); } catch (const std::runtime_error&) { threw = true; }
+            printf("iqcorrections_imbalance %s\n", threw ? "throws" : "silent");
         }
         // DownChannelizer as a plugin wires it (nfmdemod.cpp:93-95): 10 MS/s, 48 kS/s at +1234567 Hz
         CaptureSink sink;

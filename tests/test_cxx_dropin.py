@@ -4,6 +4,8 @@ reproduces the reference's output hash."""
 import os
 import subprocess
 
+import numpy as np
+
 import pytest
 
 from conftest import ROOT
@@ -28,7 +30,7 @@ def test_wrapper_headers_compile_and_link():
 
 
 @pytest.mark.gpu
-def test_sdrbench_decimateii_through_cxx_wrappers(gpu_lib, golden_meta, golden_x8):
+def test_sdrbench_decimateii_through_cxx_wrappers(gpu_lib, port, golden_meta, golden_x8):
     build_exe()
     r = subprocess.run([EXE], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
@@ -40,6 +42,12 @@ def test_sdrbench_decimateii_through_cxx_wrappers(gpu_lib, golden_meta, golden_x
     rows = golden_x8[1]["long"]["rows"]
     assert lines["decimatorsu16_cen"] == "n_out=%d out=%s" % (rows["u8/4/cen"]["n_out"], rows["u8/4/cen"]["fnv"])
     assert lines["decimators8_64_inf"] == "n_out=%d out=%s" % (rows["i8/6/inf"]["n_out"], rows["i8/6/inf"]["fnv"])
+    from conftest import fnv1a64_u16
+    q = port.PortIQCorrections()
+    xs = port.sdrbench_s16(1 << 20)[: 2 << 16].reshape(-1, 2)      # the C++ program corrects the first 2^16 samples of its 2^20 buffer
+    want = np.concatenate([q.run(xs[:40000]), q.run(xs[40000:])])
+    assert lines["iqcorrections"] == "out=" + fnv1a64_u16(want)
+    assert lines["iqcorrections_imbalance"] == "throws"
     assert lines["downchannelizer"].startswith("rate=156250 ofs=-15433 n_out=937")
     assert lines["spectrumvis"] == "frames=2"
     assert lines["interpolator"] == "n_out=6145"          # 20 000 inputs at 156 250 -> 48 000
