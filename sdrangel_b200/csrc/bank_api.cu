@@ -164,6 +164,8 @@ struct b200dsp_bank {
     int input_rate;
     cudaStream_t stream, side;
     cudaEvent_t ev_begin, ev_sched;
+    cudaStream_t copy; cudaEvent_t ev_h2d[2], ev_done[2];     // host-pointer feeds: H2D of pass p+1 under the kernels of pass p
+    uint32_t* d_root_alt; long long root_alt_cap;              // second root staging buffer
     std::vector<Channel> chans;
     bool built;
     // tree
@@ -617,7 +619,11 @@ int b200dsp_bank_create(b200dsp_bank_t** out, int input_rate_hz)
     if ((rc = B200_CUDA_CHECK(cudaSetDevice(b->device))) || (rc = B200_CUDA_CHECK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking))) ||
         (rc = B200_CUDA_CHECK(cudaStreamCreateWithPriority(&b->side, cudaStreamNonBlocking, -5))) ||
         (rc = B200_CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_begin, cudaEventDisableTiming))) ||
-        (rc = B200_CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_sched, cudaEventDisableTiming)))) { delete b; return rc; }
+        (rc = B200_CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_sched, cudaEventDisableTiming))) ||
+        (rc = B200_CUDA_CHECK(cudaStreamCreateWithFlags(&b->copy, cudaStreamNonBlocking)))) { delete b; return rc; }
+    for (int i = 0; i < 2; ++i)
+        if ((rc = B200_CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_h2d[i], cudaEventDisableTiming))) ||
+            (rc = B200_CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_done[i], cudaEventDisableTiming)))) { delete b; return rc; }
     *out = b;
     return 0;
 }
@@ -629,8 +635,12 @@ int b200dsp_bank_destroy(b200dsp_bank_t* b)
     cudaStreamSynchronize(b->stream);
     cudaStreamSynchronize(b->side);
     free_device(b);
+    if (b->copy) cudaStreamSynchronize(b->copy);
     if (b->d_root) cudaFree(b->d_root);
+    if (b->d_root_alt) cudaFree(b->d_root_alt);
     if (b->d_nco) cudaFree(b->d_nco);
+    if (b->copy) cudaStreamDestroy(b->copy);
+    for (int i = 0; i < 2; ++i) { if (b->ev_h2d[i]) cudaEventDestroy(b->ev_h2d[i]); if (b->ev_done[i]) cudaEventDestroy(b->ev_done[i]); }
     cudaStreamDestroy(b->stream);
     cudaStreamDestroy(b->side);
     cudaEventDestroy(b->ev_begin);
@@ -793,23 +803,42 @@ int b200dsp_bank_feed(b200dsp_bank_t* b, const int16_t* iq, int64_t n_samples)
     for (auto& c : b->chans) c.out_count = 0;
     b->out_count_depth.assign(32, 0);
     if (n_samples == 0) return empty_feed(b, b->stream);
-    long long done = 0;
-    while (done < n_samples) {
-        const long long m = (n_samples - done) < b->chunk ? (n_samples - done) : b->chunk;
-        const int pend = (b->depth >= 1) ? (int) (b->produced[0] - 2 * b->produced[1]) : 0;
-        if (b->root_cap < m + 8) {
-            if ((rc = B200_CUDA_CHECK(cudaStreamSynchronize(b->stream)))) return rc;
+    // Passes of `chunk` samples through two staging buffers: the H2D copy of pass p+1 (copy stream) runs under the kernels of
+    // pass p (bank stream); a buffer is refilled only after the pass that read it has finished (ev_done).
+    const long long first_m = n_samples < b->chunk ? n_samples : b->chunk;
+    if (b->root_cap < first_m + 8 || b->root_alt_cap < first_m + 8) {
+        if ((rc = B200_CUDA_CHECK(cudaStreamSynchronize(b->stream))) || (rc = B200_CUDA_CHECK(cudaStreamSynchronize(b->copy)))) return rc;
+        const long long cap = (b->chunk > first_m ? b->chunk : first_m) + 8;
+        if (b->root_cap < cap) {
             if (b->d_root) cudaFree(b->d_root);
             b->d_root = nullptr; b->root_cap = 0;
-            const long long cap = (b->chunk > m ? b->chunk : m) + 8;
             if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_root, (size_t) cap * 4)))) return rc;
             b->root_cap = cap;
         }
-        // the previous pass may still be reading d_root
-        if ((rc = B200_CUDA_CHECK(cudaStreamSynchronize(b->stream)))) return rc;
-        if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(b->d_root + pend, iq + 2 * done, (size_t) m * 4, cudaMemcpyHostToDevice, b->stream)))) return rc;
+        if (b->root_alt_cap < cap) {
+            if (b->d_root_alt) cudaFree(b->d_root_alt);
+            b->d_root_alt = nullptr; b->root_alt_cap = 0;
+            if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_root_alt, (size_t) cap * 4)))) return rc;
+            b->root_alt_cap = cap;
+        }
+    }
+    long long done = 0;
+    int pass = 0;
+    while (done < n_samples) {
+        const long long m = (n_samples - done) < b->chunk ? (n_samples - done) : b->chunk;
+        const int pend = (b->depth >= 1) ? (int) (b->produced[0] - 2 * b->produced[1]) : 0;
+        const int slot = pass & 1;
+        // ev_done[slot] is only waited on once pass-2 has recorded it in this call; an earlier call's passes were synchronised at its end
+        if (pass >= 2 && (rc = B200_CUDA_CHECK(cudaStreamWaitEvent(b->copy, b->ev_done[slot], 0)))) return rc;
+        if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(b->d_root + pend, iq + 2 * done, (size_t) m * 4, cudaMemcpyHostToDevice, b->copy))) ||
+            (rc = B200_CUDA_CHECK(cudaEventRecord(b->ev_h2d[slot], b->copy))) ||
+            (rc = B200_CUDA_CHECK(cudaStreamWaitEvent(b->stream, b->ev_h2d[slot], 0)))) return rc;
         if ((rc = feed_chunk(b, b->d_root + pend, m, b->stream, done == 0))) return rc;
+        if ((rc = B200_CUDA_CHECK(cudaEventRecord(b->ev_done[slot], b->stream)))) return rc;
+        std::swap(b->d_root, b->d_root_alt);          // the next pass stages into the other buffer
+        std::swap(b->root_cap, b->root_alt_cap);
         done += m;
+        ++pass;
     }
     return B200_CUDA_CHECK(cudaStreamSynchronize(b->stream));
 }
