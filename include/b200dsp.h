@@ -152,6 +152,8 @@ int b200dsp_bank_gather_dev(b200dsp_bank_t* b, int stage, void* d_out, int64_t s
 /* device-to-device copy of samples [skip, skip + count) of a channel's channelizer output of the last feed */
 int b200dsp_bank_copy_out_dev(b200dsp_bank_t* b, int chan_id, int64_t skip, int64_t count, void* d_dst, void* cuda_stream);
 int b200dsp_bank_sync(b200dsp_bank_t* b);
+/* device time (ms) and count of the tree-level kernel launches of the last internal pass (instrumentation for bench.py) */
+int b200dsp_bank_tree_time(b200dsp_bank_t* b, float* ms, int* launches);
 /* K6 support: keep the bank's tree kernels off the listed SMs so a concurrent collective (the NCCL broadcast of the next
  * baseband block) gets whole SMs at once instead of waiting for a gap between kernels; n = 0 turns it off */
 int b200dsp_bank_set_reserved_sms(b200dsp_bank_t* b, const int* smids, int n);

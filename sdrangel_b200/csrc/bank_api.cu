@@ -166,6 +166,7 @@ struct b200dsp_bank {
     cudaEvent_t ev_begin, ev_sched;
     cudaStream_t copy; cudaEvent_t ev_h2d[2], ev_done[2];     // host-pointer feeds: H2D of pass p+1 under the kernels of pass p
     uint32_t* d_root_alt; long long root_alt_cap;              // second root staging buffer
+    cudaEvent_t ev_tree0, ev_tree1; int tree_launches;         // timing of the tree-level launches of the last pass (b200dsp_bank_tree_time)
     std::vector<Channel> chans;
     bool built;
     // tree
@@ -445,6 +446,8 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
         }
         if ((rc = B200_CUDA_CHECK(cudaMemsetAsync(b->d_queue, 0, 64 * sizeof(int), st)))) return rc;
     }
+    if ((rc = B200_CUDA_CHECK(cudaEventRecord(b->ev_tree0, st)))) return rc;
+    b->tree_launches = 0;
     for (int d = 1; d <= D; ++d) {
         // levels (d, d+1) in one launch when the call is aligned at both (no pending samples, whole batch pairs)
         if (b->fuse && (d & 1) && d + 1 <= D && b->d_pfam[d]) {
@@ -474,6 +477,7 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
                 if (!attr_done) { cudaFuncSetAttribute((const void*) hb48_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wpb * (4 * HB_STAGE_BYTES + 64)); attr_done = true; }
                 hb48_pair_kernel<<<(unsigned) ((warps + wpb - 1) / wpb), wpb * 32, wpb * (4 * HB_STAGE_BYTES + 64), st>>>(q);
                 if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
+                ++b->tree_launches;
                 // parents of level d+2 that exist only as leaves keep no tail; children tails were written by the kernel
                 ++d;
                 continue;
@@ -523,8 +527,10 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
                 hb48_level_kernel<<<(unsigned) blocks, wpb * 32, wpb * HB_STAGE_BYTES, st>>>(p);
             }
             if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
+            ++b->tree_launches;
         }
     }
+    if ((rc = B200_CUDA_CHECK(cudaEventRecord(b->ev_tree1, st)))) return rc;
     // stage-less channels (S == 0) are forwarded unchanged (downchannelizer.cpp:57-60): plain copy of the input
     for (size_t i = 0; i < nc; ++i) {
         Channel& c = b->chans[i];
@@ -621,6 +627,7 @@ int b200dsp_bank_create(b200dsp_bank_t** out, int input_rate_hz)
         (rc = B200_CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_begin, cudaEventDisableTiming))) ||
         (rc = B200_CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_sched, cudaEventDisableTiming))) ||
         (rc = B200_CUDA_CHECK(cudaStreamCreateWithFlags(&b->copy, cudaStreamNonBlocking)))) { delete b; return rc; }
+    if ((rc = B200_CUDA_CHECK(cudaEventCreate(&b->ev_tree0))) || (rc = B200_CUDA_CHECK(cudaEventCreate(&b->ev_tree1)))) { delete b; return rc; }
     for (int i = 0; i < 2; ++i)
         if ((rc = B200_CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_h2d[i], cudaEventDisableTiming))) ||
             (rc = B200_CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_done[i], cudaEventDisableTiming)))) { delete b; return rc; }
@@ -643,6 +650,8 @@ int b200dsp_bank_destroy(b200dsp_bank_t* b)
     for (int i = 0; i < 2; ++i) { if (b->ev_h2d[i]) cudaEventDestroy(b->ev_h2d[i]); if (b->ev_done[i]) cudaEventDestroy(b->ev_done[i]); }
     cudaStreamDestroy(b->stream);
     cudaStreamDestroy(b->side);
+    if (b->ev_tree0) cudaEventDestroy(b->ev_tree0);
+    if (b->ev_tree1) cudaEventDestroy(b->ev_tree1);
     cudaEventDestroy(b->ev_begin);
     cudaEventDestroy(b->ev_sched);
     delete b;
@@ -738,6 +747,19 @@ int b200dsp_bank_set_reserved_sms(b200dsp_bank_t* b, const int* smids, int n)
     }
     for (int i = 0; i < 5; ++i) b->rsv[i] = m[i];
     b->n_rsv = n;
+    return 0;
+}
+
+// Device time of the tree-level launches (hb48_level_kernel, one per level) of the last internal pass, between two events on
+// the feed's stream: bench.py's per-launch roofline of the dominant kernel.  Waits for that pass to finish.
+int b200dsp_bank_tree_time(b200dsp_bank_t* b, float* ms, int* launches)
+{
+    if (!b || !ms) return b200_fail(B200DSP_EINVAL, "bank_tree_time: bad argument");
+    if (!b->built || b->tree_launches == 0) return b200_fail(B200DSP_ESTATE, "bank_tree_time: no feed with tree levels yet");
+    int rc = B200_CUDA_CHECK(cudaSetDevice(b->device));
+    if (rc) return rc;
+    if ((rc = B200_CUDA_CHECK(cudaEventSynchronize(b->ev_tree1))) || (rc = B200_CUDA_CHECK(cudaEventElapsedTime(ms, b->ev_tree0, b->ev_tree1)))) return rc;
+    if (launches) *launches = b->tree_launches;
     return 0;
 }
 

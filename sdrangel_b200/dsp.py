@@ -210,6 +210,12 @@ class DownChannelizerBank:
         """Device half of fetch_all: [channel][stride] samples into d_out and int64 counts into d_counts, asynchronously."""
         capi.check(capi.lib().b200dsp_bank_gather_dev(self._h, stage, C.c_void_p(d_out), int(stride), C.c_void_p(d_counts), C.c_void_p(stream or 0)))
 
+    def tree_time(self):
+        """(ms, launches) of the tree-level kernels of the last internal pass (waits for it)."""
+        ms, k = C.c_float(0), C.c_int32(0)
+        capi.check(capi.lib().b200dsp_bank_tree_time(self._h, C.byref(ms), C.byref(k)))
+        return ms.value, k.value
+
     def set_reserved_sms(self, smids):
         """Keep the tree kernels off these SMs (left to a concurrent NCCL broadcast); [] turns it off."""
         a = np.ascontiguousarray(smids, dtype=np.int32)
