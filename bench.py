@@ -1042,7 +1042,7 @@ def run_ours(args, wl_name, wl):
             except Exception as e:      # an auxiliary measurement must not take the headline down
                 also[other] = {"error": repr(e)}
     if c.rank == 0:
-        cpu = None if args.no_cpu else cpu_reference(wl, args.cpu_seconds)
+        cpu = None if (args.no_cpu or c.world > 1) else cpu_reference(wl, args.cpu_seconds)       # reported at N = 1 only
         line = {"metric": METRIC, "value": res["value"], "unit": "input MS/s", "n_gpus": c.world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": res["scaling"], "vs_baseline": None,
                 "dtype": res["dtype"], "data": "synthetic", "config": res["config"], "roofline": res["roofline"], "cpu_baseline": cpu,
