@@ -548,8 +548,13 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
     if (!b->fe_index.empty() && max_new > 0) {
         size_t smem = 0;
         for (int ci : b->fe_index) { const Channel& cc = b->chans[ci]; const size_t s2 = (((size_t) ((cc.ntaps + 2 * FE_PAD) | 1) * cc.phase_steps + 3) & ~(size_t) 3) * sizeof(float); if (s2 > smem) smem = s2; }
-        smem += (size_t) (FE_MAX_TAPS + FE_TILE) * sizeof(float2);
-        frontend_kernel<<<dim3((unsigned) ((max_new + FE_TILE - 1) / FE_TILE), (unsigned) b->h_fe.size()), FE_THREADS, smem, st>>>(b->d_fe, b->d_nco, pi);
+        smem += (size_t) (FE_MAX_TAPS + FE_TILE + FE_Z_EXTRA) * sizeof(float2);
+        // every channel a 5/4 closed-form resampler with 72 taps per phase (the 1024-channel plan): register-tiled variant
+        bool lat54 = true;
+        for (int ci : b->fe_index) { const Channel& cc = b->chans[ci]; if (!cc.lattice || 4 * cc.A != (5ll << 23) || cc.ntaps != 72) { lat54 = false; break; } }
+        const dim3 grid((unsigned) ((max_new + FE_TILE - 1) / FE_TILE), (unsigned) b->h_fe.size());
+        if (lat54) frontend_kernel_t<true><<<grid, FE_THREADS, smem, st>>>(b->d_fe, b->d_nco, pi);
+        else       frontend_kernel_t<false><<<grid, FE_THREADS, smem, st>>>(b->d_fe, b->d_nco, pi);
         if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
         b->fe_parity ^= 1;
     }
@@ -1085,12 +1090,12 @@ int b200dsp_interp_decimate(b200dsp_interp_t* h, float* distance_remain, float d
     PassInfo pi;
     memset(&pi, 0, sizeof(pi));
     pi.n_new[0] = (int) n; pi.first_pass = 1; pi.parity = h->parity;
-    const size_t smem = ((((size_t) ((h->ntaps + 2 * FE_PAD) | 1) * h->phase_steps + 3) & ~(size_t) 3)) * 4 + (size_t) (FE_MAX_TAPS + FE_TILE) * sizeof(float2);
+    const size_t smem = ((((size_t) ((h->ntaps + 2 * FE_PAD) | 1) * h->phase_steps + 3) & ~(size_t) 3)) * 4 + (size_t) (FE_MAX_TAPS + FE_TILE + FE_Z_EXTRA) * sizeof(float2);
     if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(h->d_in, in_c64, (size_t) n * 8, cudaMemcpyHostToDevice, h->stream))) ||
         (rc = B200_CUDA_CHECK(cudaMemcpyAsync(h->d_state, st, 16, cudaMemcpyHostToDevice, h->stream))) ||
         (rc = B200_CUDA_CHECK(cudaMemcpyAsync(h->d_chan, &f, sizeof(f), cudaMemcpyHostToDevice, h->stream)))) return rc;
     frontend_schedule_kernel<<<1, 32, 0, h->stream>>>(h->d_chan, 1, pi);
-    frontend_kernel<<<dim3((unsigned) ((n + FE_TILE - 1) / FE_TILE), 1), FE_THREADS, smem, h->stream>>>(h->d_chan, nullptr, pi);
+    frontend_kernel_t<false><<<dim3((unsigned) ((n + FE_TILE - 1) / FE_TILE), 1), FE_THREADS, smem, h->stream>>>(h->d_chan, nullptr, pi);
     if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
     if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(st, h->d_state, 16, cudaMemcpyDeviceToHost, h->stream))) ||
         (rc = B200_CUDA_CHECK(cudaStreamSynchronize(h->stream)))) return rc;
