@@ -137,6 +137,9 @@ int b200dsp_bank_set_frontend(b200dsp_bank_t* b, int chan_id, float nco_freq_hz,
 int b200dsp_bank_frontend_info(b200dsp_bank_t* b, int chan_id, int* nco_increment, int* taps_per_phase, float* taps, int taps_cap);
 /* == DownChannelizer::feed(begin, end, positiveOnly) for every channel of the bank (+ the front-ends) */
 int b200dsp_bank_feed(b200dsp_bank_t* b, const int16_t* iq, int64_t n_samples);
+/* device-pointer form, asynchronous on cuda_stream (NULL = the bank's own stream).  A bank is single-writer: successive
+ * feeds must be ordered on one stream (or by events); fetch / fetch_all synchronise only the stream they are given (fetch:
+ * the bank's own), so after a feed_dev on a caller stream synchronise that stream, or pass it to fetch_all, first. */
 int b200dsp_bank_feed_dev(b200dsp_bank_t* b, const void* d_iq, int64_t n_samples, void* cuda_stream);
 /* outputs produced by the last feed for one channel; stage selects int16 IQ (4 bytes/sample) or complex64 (8 bytes) */
 int b200dsp_bank_fetch(b200dsp_bank_t* b, int chan_id, int stage, void* out, int64_t cap_samples, int64_t* n_samples);

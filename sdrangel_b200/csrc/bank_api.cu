@@ -625,7 +625,10 @@ int b200dsp_bank_create(b200dsp_bank_t** out, int input_rate_hz)
     b->sm_count = b200_sm_count_of(b->device);
     b->input_rate = input_rate_hz;
     b->built = false; b->depth = 0; b->chunk = 3ll << 22; b->tables_dirty = true;
-    b->fuse = (getenv("B200DSP_FUSE") != nullptr);      // measured on B200 (r01): halves the tree's HBM traffic but runs 16 % slower than two one-level launches; off by default b->d_root = nullptr; b->root_cap = 0;
+    // two-level fused kernel: measured on B200 (r01) it halves the tree's HBM traffic but runs 16 % slower than two one-level
+    // launches (the kernels are issue-bound), so it is off unless B200DSP_FUSE is set
+    b->fuse = (getenv("B200DSP_FUSE") != nullptr);
+    b->d_root = nullptr; b->root_cap = 0;
     b->d_leaf = nullptr; b->d_fe = nullptr; b->d_nco = nullptr; b->tcur = 0;
     if ((rc = B200_CUDA_CHECK(cudaSetDevice(b->device))) || (rc = B200_CUDA_CHECK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking))) ||
         (rc = B200_CUDA_CHECK(cudaStreamCreateWithPriority(&b->side, cudaStreamNonBlocking, -5))) ||
