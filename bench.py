@@ -658,7 +658,7 @@ def bench_bank(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=T
     step_ms = float(np.mean(kern_ms))
     tree_ms, tree_launches = bank.tree_time()         # the level launches of the last timed step, between events on its stream
     out_bytes = sum(48000.0 / fs * 8 for _ in mine)
-    instr_per_sample = stage_inputs * 27 + len(mine) * 48000.0 / fs * 160
+    instr_per_sample = _tree_instr_per_sample([p for _, _, _, p in info]) + len(mine) * 48000.0 / fs * 160
     f_clk = (clocks.get("sm_mhz") or 1965) * 1e6
     issue_roof = c.sm_count * 128 * f_clk / instr_per_sample / 1e6
     passes = 1                            # bank.set_chunk(n): one pass per step
@@ -693,7 +693,7 @@ def bench_bank(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=T
                                          "this design's own HBM traffic, not algorithmic minimum"},
                         "issue": {"instr_per_sample": instr_per_sample, "roof_MSps_at_sampled_clk": issue_roof,
                                   "frac": (n / (step_ms * 1e-3) / 1e6) / issue_roof,
-                                  "note": "binding roof: 27 instructions per stage-input sample over the shared-prefix tree + ~160 per front-end output"}},
+                                  "note": "binding roof: 27 instructions per child per parent sample over the shared-prefix tree (31 for a lower/upper pair, which shares its tap sum) + ~160 per front-end output"}},
            "dtype": "s32", "scaling": "strong"}
     if want_e2e:
         # end to end through the plugin-facing calls: the baseband starts in pinned host memory (on rank 0: the ingest GPU's
@@ -1005,6 +1005,22 @@ def bench_bank_coop(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_par
                       "samples_per_step": n}
     pipe.rk.close()
     return res
+
+
+def _tree_instr_per_sample(paths):
+    """Issued-instruction model of the shared-prefix tree per baseband sample: a child costs 27
+    instructions per sample of its parent's stream (12 pre-subtractions/additions + 13 multiply-adds + shift + pack); a
+    parent's lower-half and upper-half children share the tap sum: 31 for the two."""
+    nodes = set()
+    for p in paths:
+        for k in range(1, len(p) + 1):
+            nodes.add(p[:k])
+    total = 0.0
+    for parent in {n[:-1] for n in nodes}:
+        kids = {n[-1] for n in nodes if n[:-1] == parent}
+        units = (27.0 if "C" in kids else 0.0) + (31.0 if ("L" in kids and "U" in kids) else 27.0 if ("L" in kids or "U" in kids) else 0.0)
+        total += units * 2.0 ** -len(parent)
+    return total
 
 
 def _node_depths(paths):

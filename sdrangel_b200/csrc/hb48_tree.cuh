@@ -83,6 +83,33 @@ __device__ __forceinline__ void hb48_item(const int32_t (&w)[36], const int32_t 
     }
 }
 
+// Lower-half and upper-half children of one parent share everything but the centre term: the odd-phase samples a
+// half-band stage taps sit at odd indices n, where the stage rotation (+-j)^((n+1)&3) is the real factor (-1)^((n+1)/2) for
+// BOTH directions; only the centre sample (even n) is multiplied by +-j.  So with F = sum_i g_i (a_i - b_i) (the rotated
+// tap sum, identical for both children) and Cc = the lower-half child's centre term,
+//     y_lower = (F + Cc) >> 11,   y_upper = (F - Cc) >> 11        (all modulo 2^32, exactly what hb48_item<true> computes)
+// and a two-child family costs 12 subtractions + 13 multiply-adds + 2 additions per output instead of 2 x (12 + 13).
+template<bool FLIP>
+__device__ __forceinline__ void hb48_pair_terms(const int32_t (&w)[36], const int32_t (&co)[16], int comp, const IntOpaque& q,
+                                                uint32_t (&F)[HB_R], uint32_t (&Cc)[HB_R])
+{
+    const int csgn = comp ? 1 : -1;            // the lower-half child (sigma = +1): hb48_item's csgn = comp ? sigma : -sigma
+#pragma unroll
+    for (int r = 0; r < HB_R; ++r) {
+        const int sk = ((r & 1) ? 1 : -1) * (FLIP ? -1 : 1);
+        Cc[r] = (uint32_t) co[1 + r] * (uint32_t) (csgn * sk * 2048);
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            const int g = ((i & 1) ? -sk : sk) * hb48_h(i);
+            const uint32_t a = (uint32_t) w[24 + r - i], b = (uint32_t) w[1 + r + i];
+            const uint32_t d = (i < HB_XH) ? mad_fma(b, q.mone, a) : sub_alu(a, b, q.zero);
+            acc += (uint32_t) g * d;
+        }
+        F[r] = acc;
+    }
+}
+
 __device__ __forceinline__ int32_t wrap16(int32_t v) { return sext_lo16(v); }
 
 // Explicit rotation of the register windows (slow path, exact for every int16 value incl. -32768):
@@ -268,18 +295,31 @@ __device__ __forceinline__ void hb48_level_warp(const LevelParams& p, int w, int
             hb48_item<false, false>(wv, cv, 0, opq, y);
             hb48_store_child(p.out_base + (long long) fam.y * p.out_stride, y, comp, j, kbase, p.wo, n_out);
         }
+        if (fam.z >= 0 && fam.w >= 0 && !slow) {
+            // both rotated children: one shared tap sum, the centre term added for the lower half, subtracted for the upper
+            uint32_t F[HB_R], Cc[HB_R];
+            if (p.flip) hb48_pair_terms<true>(wv, co, comp, opq, F, Cc);
+            else        hb48_pair_terms<false>(wv, co, comp, opq, F, Cc);
 #pragma unroll
-        for (int m = 1; m <= 2; ++m) {          // lower-half (+j) and upper-half (-j) children
-            const int child = (m == 1) ? fam.z : fam.w;
-            if (child < 0) continue;
-            const int sigma = (m == 1) ? 1 : -1;
-            if (!slow) {
-                if (p.flip) hb48_item<true, true>(wv, co, comp ? sigma : -sigma, opq, y);
-                else        hb48_item<true, false>(wv, co, comp ? sigma : -sigma, opq, y);
-            } else {
-                hb48_slow_child(X, comp, j, sigma, p.flip, opq, y);
+            for (int r = 0; r < HB_R; ++r) y[r] = (int32_t) add_alu(F[r], Cc[r], opq.zero) >> 11;
+            hb48_store_child(p.out_base + (long long) fam.z * p.out_stride, y, comp, j, kbase, p.wo, n_out);
+#pragma unroll
+            for (int r = 0; r < HB_R; ++r) y[r] = (int32_t) sub_alu(F[r], Cc[r], opq.zero) >> 11;
+            hb48_store_child(p.out_base + (long long) fam.w * p.out_stride, y, comp, j, kbase, p.wo, n_out);
+        } else {
+#pragma unroll
+            for (int m = 1; m <= 2; ++m) {          // lower-half (+j) and upper-half (-j) children
+                const int child = (m == 1) ? fam.z : fam.w;
+                if (child < 0) continue;
+                const int sigma = (m == 1) ? 1 : -1;
+                if (!slow) {
+                    if (p.flip) hb48_item<true, true>(wv, co, comp ? sigma : -sigma, opq, y);
+                    else        hb48_item<true, false>(wv, co, comp ? sigma : -sigma, opq, y);
+                } else {
+                    hb48_slow_child(X, comp, j, sigma, p.flip, opq, y);
+                }
+                hb48_store_child(p.out_base + (long long) child * p.out_stride, y, comp, j, kbase, p.wo, n_out);
             }
-            hb48_store_child(p.out_base + (long long) child * p.out_stride, y, comp, j, kbase, p.wo, n_out);
         }
         __syncwarp();
         hb64_tail_store<int32_t>(X, lane, tl);
