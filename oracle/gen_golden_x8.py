@@ -64,6 +64,22 @@ def main():
     arrays["iqcorr/out"] = np.concatenate(outs)
     meta["iqcorr"] = {"seed": 20181020, "cuts": qcuts, "input": "iqcorr/in", "output": "iqcorr/out", "mode": "DC only (imbalanceCorrection false)",
                       "fnv": R.fnv1a64_u16(arrays["iqcorr/out"])}
+    # ... and its I/Q imbalance branch (floating-point flavour): a tone with gain and phase imbalance, DC and noise
+    rs = np.random.RandomState(20181021)
+    t = np.arange(8000)
+    xi_ = 3000 * np.cos(2 * np.pi * 0.0137 * t) + 500 + rs.randn(t.size) * 50
+    xq_ = 0.8 * 3000 * np.sin(2 * np.pi * 0.0137 * t + 0.2) - 300 + rs.randn(t.size) * 50
+    xm = np.stack([xi_, xq_], 1).astype(np.int16)
+    mcuts = [0, 7, 1000, 1030, 1031, 4444, 8000]
+    q = R.RefIQCorrections()
+    outs = [q.run(xm[a:b], True) for a, b in zip(mcuts[:-1], mcuts[1:])]
+    qs = R.RefIQCorrections(strict=True)
+    outs_s = [qs.run(xm[a:b], True) for a, b in zip(mcuts[:-1], mcuts[1:])]
+    arrays["iqcorr_imb/in"] = xm
+    arrays["iqcorr_imb/out"] = np.concatenate(outs)
+    arrays["iqcorr_imb/out_strict"] = np.concatenate(outs_s)
+    meta["iqcorr_imb"] = {"seed": 20181021, "cuts": mcuts, "input": "iqcorr_imb/in", "output": "iqcorr_imb/out (reference flags), iqcorr_imb/out_strict (-O2, no -ffast-math)",
+                          "mode": "imbalanceCorrection true, floating-point flavour (IMBALANCE_INT undefined)", "fnv": R.fnv1a64_u16(arrays["iqcorr_imb/out"])}
     np.savez_compressed(os.path.join(OUT, "golden_x8.npz"), **arrays)
     with open(os.path.join(OUT, "golden_x8.json"), "w") as f:
         json.dump(meta, f, indent=1)

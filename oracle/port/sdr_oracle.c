@@ -220,7 +220,26 @@ int orc_decim_x8_run(void* h, int log2, int mode, const uint8_t* buf, int len, i
 
 /* DSPDeviceSourceEngine::iqCorrections, DC branch (dspdevicesourceengine.cpp:175-183,254-261) with
  * MovingAverageUtil<int32_t,int64_t,1024> (util/movingaverage.h: fill-up then roll; operator T() = total / N). */
-typedef struct { int32_t s[2][1024]; int num[2]; unsigned idx[2]; int64_t total[2]; } iqcorr;
+/* MovingAverageUtil<float,double,128> and <double,double,128> (util/movingaverage.h): note `m_total += sample - oldest`
+ * subtracts in T (float for the power averages) before the double accumulation. */
+typedef struct { float s[128]; int num; unsigned idx; double total; } mavg_f;
+typedef struct { double s[128]; int num; unsigned idx; double total; } mavg_d;
+static void mavg_f_push(mavg_f* m, float v)
+{
+    if (m->num < 128) { m->s[m->num++] = v; m->total += v; }
+    else { float d = v - m->s[m->idx]; m->total += d; m->s[m->idx] = v; m->idx = (m->idx + 1) % 128; }
+}
+static void mavg_d_push(mavg_d* m, double v)
+{
+    if (m->num < 128) { m->s[m->num++] = v; m->total += v; }
+    else { m->total += v - m->s[m->idx]; m->s[m->idx] = v; m->idx = (m->idx + 1) % 128; }
+}
+
+typedef struct {
+    int32_t s[2][1024]; int num[2]; unsigned idx[2]; int64_t total[2];
+    mavg_f avgII, avgIQ, avgII2, avgQQ2;
+    mavg_d avgPhi, avgAmp;
+} iqcorr;
 
 void* orc_iqcorr_create(void) { return calloc(1, sizeof(iqcorr)); }
 void  orc_iqcorr_destroy(void* h) { free(h); }
@@ -237,6 +256,29 @@ void orc_iqcorr_dc(void* h, int16_t* iq, int n)
         int32_t bi = mavg_push(q, 0, iq[2 * i]), bq = mavg_push(q, 1, iq[2 * i + 1]);
         iq[2 * i] = (int16_t) (iq[2 * i] - bi);
         iq[2 * i + 1] = (int16_t) (iq[2 * i + 1] - bq);
+    }
+}
+/* imbalance branch, floating-point flavour (IMBALANCE_INT undefined): dspdevicesourceengine.cpp:219-252.
+ * float -> qint16 stores are C conversions (truncation toward zero); values stay in range for in-range inputs. */
+void orc_iqcorr_imbalance(void* h, int16_t* iq, int n)
+{
+    iqcorr* q = (iqcorr*) h;
+    for (int i = 0; i < n; i++) {
+        int32_t bi = mavg_push(q, 0, iq[2 * i]), bq = mavg_push(q, 1, iq[2 * i + 1]);
+        float xi = (float) (iq[2 * i] - bi) / 32768.0f;
+        float xq = (float) (iq[2 * i + 1] - bq) / 32768.0f;
+        mavg_f_push(&q->avgII, xi * xi);
+        mavg_f_push(&q->avgIQ, xi * xq);
+        if (q->avgII.total / 128 != 0) mavg_d_push(&q->avgPhi, (q->avgIQ.total / 128) / (q->avgII.total / 128));
+        float yi = xi;
+        float yq = (float) ((double) xq - (q->avgPhi.total / 128) * (double) xi);
+        mavg_f_push(&q->avgII2, yi * yi);
+        mavg_f_push(&q->avgQQ2, yq * yq);
+        if (q->avgQQ2.total / 128 != 0) mavg_d_push(&q->avgAmp, sqrt((q->avgII2.total / 128) / (q->avgQQ2.total / 128)));
+        float zi = yi;
+        float zq = (float) ((q->avgAmp.total / 128) * (double) yq);
+        iq[2 * i] = (int16_t) (zi * 32768.0f);
+        iq[2 * i + 1] = (int16_t) (zq * 32768.0f);
     }
 }
 

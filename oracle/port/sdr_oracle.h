@@ -37,6 +37,8 @@ int   orc_decim_x8_run(void* h, int log2, int mode, const uint8_t* buf, int len,
 void* orc_iqcorr_create(void);
 void  orc_iqcorr_destroy(void* h);
 void  orc_iqcorr_dc(void* h, int16_t* iq, int n_samples);
+/* ... (begin, end, true), floating-point flavour: dspdevicesourceengine.cpp:219-252 */
+void  orc_iqcorr_imbalance(void* h, int16_t* iq, int n_samples);
 
 /* DecimatorsFI / DecimatorsFF / DecimatorsIF: sdrbase/dsp/decimatorsfi.cpp, decimatorsff.cpp, decimatorsif.h */
 void* orc_decim_f_create(int in_fmt, int out_fmt, int input_bits);

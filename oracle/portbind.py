@@ -40,7 +40,7 @@ def load():
         "orc_sdrbench_gen_s16": (None, [pi16, i32]), "orc_sdrbench_gen_f32": (None, [pf32, i32]),
         "orc_decim_ii_create": (vp, [i32]), "orc_decim_ii_destroy": (None, [vp]),
         "orc_decim_ii_run": (i32, [vp, i32, i32, pi16, i32, pi16]),
-        "orc_iqcorr_create": (vp, []), "orc_iqcorr_destroy": (None, [vp]), "orc_iqcorr_dc": (None, [vp, pi16, i32]),
+        "orc_iqcorr_create": (vp, []), "orc_iqcorr_destroy": (None, [vp]), "orc_iqcorr_dc": (None, [vp, pi16, i32]), "orc_iqcorr_imbalance": (None, [vp, pi16, i32]),
         "orc_decim_x8_create": (vp, [i32, i32]), "orc_decim_x8_destroy": (None, [vp]),
         "orc_decim_x8_run": (i32, [vp, i32, i32, vp, i32, pi16]),
         "orc_decim_f_create": (vp, [i32, i32, i32]), "orc_decim_f_destroy": (None, [vp]),
@@ -112,9 +112,9 @@ class PortIQCorrections(_Handle):
         L = load()
         super().__init__(L.orc_iqcorr_create(), L.orc_iqcorr_destroy)
 
-    def run(self, iq):
+    def run(self, iq, imbalance=False):
         a = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1, 2).copy()
-        load().orc_iqcorr_dc(self.h, _p(a, C.c_int16), a.shape[0])
+        (load().orc_iqcorr_imbalance if imbalance else load().orc_iqcorr_dc)(self.h, _p(a, C.c_int16), a.shape[0])
         return a
 
 

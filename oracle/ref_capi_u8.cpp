@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <string.h>
 #include <cstddef>
+#include <cmath>
 #include "dsp/decimatorsu.h"
 #include "util/movingaverage.h"
 
@@ -43,6 +44,13 @@ bool dispatch_u8(DecimU8* h, int log2, int mode, SampleVector::iterator* it, con
 struct IqCorr {
     MovingAverageUtil<int32_t, int64_t, 1024> m_iBeta;      // dspdevicesourceengine.h:106-107
     MovingAverageUtil<int32_t, int64_t, 1024> m_qBeta;
+    // floating-point imbalance correction (IMBALANCE_INT is not defined in the reference build): dspdevicesourceengine.h:119-125
+    MovingAverageUtil<float, double, 128> m_avgII;
+    MovingAverageUtil<float, double, 128> m_avgIQ;
+    MovingAverageUtil<float, double, 128> m_avgII2;
+    MovingAverageUtil<float, double, 128> m_avgQQ2;
+    MovingAverageUtil<double, double, 128> m_avgPhi;
+    MovingAverageUtil<double, double, 128> m_avgAmp;
 };
 
 extern "C" {
@@ -60,6 +68,36 @@ void ref_iqcorr_dc(void* p, int16_t* iq, int n)
         h->m_qBeta(it->imag());
         it->m_real -= (int32_t) h->m_iBeta;
         it->m_imag -= (int32_t) h->m_qBeta;
+    }
+}
+
+// the imbalance branch of the same loop (dspdevicesourceengine.cpp:175-183,219-252), restated statement by statement
+void ref_iqcorr_imbalance(void* p, int16_t* iq, int n)
+{
+    IqCorr* h = (IqCorr*) p;
+    Sample* begin = (Sample*) iq;
+    for (Sample* it = begin; it < begin + n; it++)
+    {
+        h->m_iBeta(it->real());
+        h->m_qBeta(it->imag());
+        float xi = (it->m_real - (int32_t) h->m_iBeta) / SDR_RX_SCALEF;
+        float xq = (it->m_imag - (int32_t) h->m_qBeta) / SDR_RX_SCALEF;
+        h->m_avgII(xi*xi);
+        h->m_avgIQ(xi*xq);
+        if (h->m_avgII.asDouble() != 0) {
+            h->m_avgPhi(h->m_avgIQ.asDouble()/h->m_avgII.asDouble());
+        }
+        float& yi = xi;
+        float yq = xq - h->m_avgPhi.asDouble()*xi;
+        h->m_avgII2(yi*yi);
+        h->m_avgQQ2(yq*yq);
+        if (h->m_avgQQ2.asDouble() != 0) {
+            h->m_avgAmp(sqrt(h->m_avgII2.asDouble() / h->m_avgQQ2.asDouble()));
+        }
+        float& zi = yi;
+        float zq = h->m_avgAmp.asDouble() * yq;
+        it->m_real = zi * SDR_RX_SCALEF;
+        it->m_imag = zq * SDR_RX_SCALEF;
     }
 }
 

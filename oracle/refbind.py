@@ -40,7 +40,7 @@ def load(strict=False):
         "ref_decim_i8_run": (i32, [vp, i32, i32, C.POINTER(C.c_int8), i32, pi16]),
         "ref_decim_u8_create": (vp, []), "ref_decim_u8_destroy": (None, [vp]),
         "ref_decim_u8_run": (i32, [vp, i32, i32, C.POINTER(C.c_uint8), i32, pi16]),
-        "ref_iqcorr_create": (vp, []), "ref_iqcorr_destroy": (None, [vp]), "ref_iqcorr_dc": (None, [vp, pi16, i32]),
+        "ref_iqcorr_create": (vp, []), "ref_iqcorr_destroy": (None, [vp]), "ref_iqcorr_dc": (None, [vp, pi16, i32]), "ref_iqcorr_imbalance": (None, [vp, pi16, i32]),
         "ref_decim_fi_create": (vp, []), "ref_decim_fi_destroy": (None, [vp]),
         "ref_decim_fi_run": (i32, [vp, i32, i32, pf32, i32, pi16]),
         "ref_decim_ff_create": (vp, []), "ref_decim_ff_destroy": (None, [vp]),
@@ -116,9 +116,9 @@ class RefIQCorrections(_Handle):
         L = load(strict)
         super().__init__(L, L.ref_iqcorr_create(), L.ref_iqcorr_destroy)
 
-    def run(self, iq):
+    def run(self, iq, imbalance=False):
         a = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1, 2).copy()
-        self.lib.ref_iqcorr_dc(self.h, _p(a, C.c_int16), a.shape[0])
+        (self.lib.ref_iqcorr_imbalance if imbalance else self.lib.ref_iqcorr_dc)(self.h, _p(a, C.c_int16), a.shape[0])
         return a
 
 

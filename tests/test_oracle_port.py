@@ -81,6 +81,18 @@ def test_iqcorrections_dc_golden(port, golden_x8):
     assert np.array_equal(out, arrays["iqcorr/out"]) and fnv1a64_u16(out) == meta["iqcorr"]["fnv"]
 
 
+def test_iqcorrections_imbalance_golden(port, golden_x8):
+    """The imbalance branch of iqCorrections (dspdevicesourceengine.cpp:219-252, floating-point flavour): the C port against
+    the vectors of both reference builds (int16 outputs: <= 1 LSB vs the -ffast-math build, exact vs the strict one).
+    The CUDA path does not implement this branch yet (it fails loudly); the pinned oracle is ready for it."""
+    arrays, meta = golden_x8
+    x, cuts = arrays["iqcorr_imb/in"], meta["iqcorr_imb"]["cuts"]
+    q = port.PortIQCorrections()
+    out = np.concatenate([q.run(x[a:b], True) for a, b in zip(cuts[:-1], cuts[1:])])
+    assert np.array_equal(out, arrays["iqcorr_imb/out_strict"])
+    assert np.max(np.abs(out.astype(np.int32) - arrays["iqcorr_imb/out"].astype(np.int32))) <= 1
+
+
 @pytest.mark.parametrize("kind", ["fi", "ff", "if"])
 def test_decim_float_strict_bit_exact_and_fast_within_tolerance(port, golden, golden_meta, kind):
     src = port.sdrbench_s16(1 << 14) if kind[0] == "i" else port.sdrbench_f32(1 << 14)
