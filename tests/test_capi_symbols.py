@@ -60,3 +60,35 @@ def test_out_count_matches_oracle_block_rounding(port):
                     assert got == want, (kind, log2, mode, n, got, want)
     assert L.b200dsp_decim_out_count(0, 0, 7, 0, 100) == -1
     assert L.b200dsp_decim_out_count(0, 0, 3, 5, 100) == -1
+
+
+def test_filter_chain_host_arithmetic_matches_reference_plans(golden_meta):
+    """b200dsp_filter_chain is pure host arithmetic (createFilterChain's float32/double mix, downchannelizer.cpp:250-287): every
+    golden plan of the reference -- the 64- and 1024-channel plans and 200 random (rate, request, offset) triples -- without
+    a device."""
+    from sdrangel_b200.sharding import filter_chain
+    plans = golden_meta["chan_plans"]
+    n = 0
+    for name in ("bank64", "bank1024"):
+        fs = plans[name]["input_rate"]
+        for fc, rate, ofs, path in plans[name]["channels"]:
+            assert filter_chain(fs, 48000, fc) == (rate, ofs, path), (name, fc)
+            n += 1
+    for fs, req, fc, rate, ofs, path in plans["random"]:
+        assert filter_chain(fs, req, fc) == (rate, ofs, path), (fs, req, fc)
+        n += 1
+    assert n >= 1288
+
+
+def test_out_count_8bit_formats_and_bad_arguments(port):
+    from sdrangel_b200 import capi
+    L = capi.lib()
+    for kind, fmt, dt in (("i8", capi.FMT_I8, np.int8), ("u8", capi.FMT_U8, np.uint8)):
+        for log2 in range(7):
+            for mode in MODES.values():
+                for n in (0, 1, 7, 8, 31, 32, 255, 256, 257, 1000, 4097, 12345):
+                    want = port.PortDecimators(kind).run(log2, mode, np.zeros(n, dtype=dt)).shape[0]
+                    assert L.b200dsp_decim_out_count(fmt, capi.FMT_I16, log2, mode, n) == want, (kind, log2, mode, n)
+        assert L.b200dsp_decim_out_count(fmt, capi.FMT_F32, 4, 2, 1024) == -1        # 8-bit -> float does not exist in the reference
+    assert L.b200dsp_decim_out_count(0, 0, 7, 2, 1024) == -1 and L.b200dsp_decim_out_count(0, 0, 4, 5, 1024) == -1
+    assert L.b200dsp_decim_out_count(9, 0, 4, 2, 1024) == -1
