@@ -8,6 +8,7 @@
 //   the NFM plugin's front-end wiring                         plugins/channelrx/demodnfm/nfmdemod.cpp:453-476
 #include "common.cuh"
 #include "hb48_tree.cuh"
+#include "hb48_fused.cuh"
 #include "frontend.cuh"
 #include <math.h>
 #include <stdlib.h>
@@ -181,6 +182,10 @@ struct b200dsp_bank {
     std::vector<int*> d_fam;
     std::vector<std::vector<int>> pfams; std::vector<int*> d_pfam;   // pair-kernel families per odd depth d (levels d, d+1)
     bool fuse;                                   // use the two-level kernel where a call is aligned
+    // fused multi-level launches (hb48_fused.cuh): the tree cut into depth ranges [b, b+k]
+    struct FusedLaunch { int b, k, T; size_t smem; int n_groups, n_fams; FusedGroup* d_groups; FusedFam* d_fams; int lvl_off[FZ_MAXK]; };
+    std::vector<FusedLaunch> flaunch;
+    bool fused_on;                               // B200DSP_NO_FUSED_TREE unset: aligned passes take hb48_fused_kernel
     uint32_t* d_root; long long root_cap;        // staging for host feeds / odd-pending device feeds
     std::vector<long long> produced;             // P[d]
     int tcur;
@@ -206,6 +211,8 @@ void free_device(b200dsp_bank* b)
     for (auto p : b->d_fam) if (p) cudaFree(p);
     for (auto p : b->d_pfam) if (p) cudaFree(p);
     b->d_pfam.clear();
+    for (auto& fl : b->flaunch) { if (fl.d_groups) cudaFree(fl.d_groups); if (fl.d_fams) cudaFree(fl.d_fams); }
+    b->flaunch.clear();
     b->d_level.clear(); b->d_fam.clear(); b->stride.clear();
     if (b->d_leaf) cudaFree(b->d_leaf);
     if (b->d_fe) cudaFree(b->d_fe);
@@ -228,6 +235,124 @@ void free_device(b200dsp_bank* b)
         c.out_cap = c.fe_cap = 0;
     }
     b->built = false;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Fused plan: cut the tree into depth ranges [b, b+k], k <= FZ_MAXK; every node of depth b that has children roots a group
+// (hb48_fused.cuh).  k shrinks until the shared-memory pyramid of the widest group fits twice per SM.
+// ---------------------------------------------------------------------------------------------------------
+constexpr size_t FZ_SMEM_LIMIT = (size_t) (216 / FZ_CTAS_PER_SM) * 1024;      // the pyramid of a CTA: FZ_CTAS_PER_SM of them share an SM
+inline int fused_tile0(int k) { const int a = HB_IN << (k - 1), b = HB_IN * FZ_WARPS; return a > b ? a : b; }   // smallest tile: whole items at the deepest level, one item per warp at the top
+
+struct FusedBuild { std::vector<FusedGroup> groups; std::vector<FusedFam> fams; int max_slots[FZ_MAXK]; int min_items; };
+
+void fused_collect(const b200dsp_bank* b, const std::vector<char>& is_leaf, int b0, int k, FusedBuild& out)
+{
+    out.groups.clear(); out.fams.clear();
+    for (int j = 0; j < FZ_MAXK; ++j) out.max_slots[j] = 0;
+    out.min_items = 1 << 30;
+    const int T0 = fused_tile0(k);
+    for (int rid : b->levels[b0]) {
+        const Node& r = b->nodes[rid];
+        if (r.child[0] < 0 && r.child[1] < 0 && r.child[2] < 0) continue;
+        FusedGroup g;
+        memset(&g, 0, sizeof(g));
+        g.root_index = r.index; g.k = 0;
+        std::vector<int> cur(1, rid), next;
+        for (int j = 0; j < k; ++j) {
+            g.fam_begin[j] = (int) out.fams.size();
+            g.nslots[j] = (int) cur.size();
+            next.clear();
+            int nfam = 0;
+            for (size_t s = 0; s < cur.size(); ++s) {
+                const Node& n = b->nodes[cur[s]];
+                if (n.child[0] < 0 && n.child[1] < 0 && n.child[2] < 0) continue;
+                FusedFam f;
+                f.pslot = (int) s; f.pindex = n.index; f.pbase = (int) s;       // pbase / cbase: slot numbers here, scaled by fused_scale_offsets
+                for (int m = 0; m < 3; ++m) {
+                    f.cbase[m] = -1; f.cbit[m] = 0; f.cindex[m] = -1;
+                    const int c = n.child[m];
+                    if (c < 0) continue;
+                    const Node& cn = b->nodes[c];
+                    const bool kids = cn.child[0] >= 0 || cn.child[1] >= 0 || cn.child[2] >= 0;
+                    if (kids && j + 1 < k) { f.cbase[m] = (int) next.size(); f.cbit[m] = 1 << next.size(); next.push_back(c); }
+                    if (is_leaf[c] || (kids && j + 1 == k)) f.cindex[m] = cn.index;
+                }
+                out.fams.push_back(f);
+                ++nfam;
+            }
+            if (nfam) {
+                g.k = j + 1;
+                const int items = nfam * ((T0 >> j) / HB_IN);
+                if (items < out.min_items) out.min_items = items;
+            }
+            cur.swap(next);
+            if (cur.empty()) { for (int jj = j + 1; jj <= k; ++jj) g.fam_begin[jj] = (int) out.fams.size(); break; }
+        }
+        g.fam_begin[k] = (int) out.fams.size();
+        for (int jj = g.k + 1; jj <= FZ_MAXK; ++jj) g.fam_begin[jj] = (int) out.fams.size();
+        for (int j = 0; j < g.k; ++j) if (g.nslots[j] > out.max_slots[j]) out.max_slots[j] = g.nslots[j];
+        out.groups.push_back(g);
+    }
+}
+
+// slot numbers -> word offsets within the pyramid levels, for the launch's tile size
+void fused_scale_offsets(FusedBuild& fb, int T)
+{
+    for (const FusedGroup& g : fb.groups)
+        for (int j = 0; j < g.k; ++j)
+            for (int f = g.fam_begin[j]; f < g.fam_begin[j + 1]; ++f) {
+                FusedFam& x = fb.fams[f];
+                x.pbase = x.pslot * 4 * (HB_HIST + (T >> (j + 1)));
+                for (int m = 0; m < 3; ++m) if (x.cbase[m] >= 0) x.cbase[m] *= 4 * (HB_HIST + (T >> (j + 2)));
+            }
+}
+
+size_t fused_smem(const FusedBuild& fb, int k, int T, int* lvl_off)
+{
+    size_t words = 0;
+    for (int j = 0; j < k; ++j) {
+        if (lvl_off) lvl_off[j] = (int) words;
+        words += (size_t) fb.max_slots[j] * 4 * (HB_HIST + (T >> (j + 1)));
+    }
+    return words * 4;
+}
+
+int build_fused_plan(b200dsp_bank* b, const std::vector<char>& is_leaf)
+{
+    int rc;
+    const int D = b->depth;
+    int b0 = 0;
+    while (b0 < D) {
+        const int left = D - b0;
+        const int parts = (left + FZ_MAXK - 1) / FZ_MAXK;
+        int k = (left + parts - 1) / parts;
+        FusedBuild fb;
+        for (;; --k) {
+            fused_collect(b, is_leaf, b0, k, fb);
+            bool wide = false;
+            for (int j = 0; j < k; ++j) if (fb.max_slots[j] > 32) wide = true;
+            if ((!wide && fused_smem(fb, k, fused_tile0(k), nullptr) <= FZ_SMEM_LIMIT) || k == 1) break;
+        }
+        b200dsp_bank::FusedLaunch fl;
+        memset(&fl, 0, sizeof(fl));
+        fl.b = b0; fl.k = k; fl.T = fused_tile0(k);
+        // sparse groups (chains) have few items per level at the smallest tile: a larger tile keeps the warps busy
+        while (fl.T < 12288 && fb.min_items * (fl.T / fused_tile0(k)) < FZ_WARPS && fused_smem(fb, k, 2 * fl.T, nullptr) <= FZ_SMEM_LIMIT) fl.T *= 2;
+        fl.smem = fused_smem(fb, k, fl.T, fl.lvl_off);
+        fused_scale_offsets(fb, fl.T);
+        fl.n_groups = (int) fb.groups.size(); fl.n_fams = (int) fb.fams.size();
+        if (fl.smem > 200 * 1024) { b->flaunch.clear(); return 0; }        // a tree this wide stays on the one-level kernel
+        if (fl.n_groups) {
+            if ((rc = B200_CUDA_CHECK(cudaMalloc(&fl.d_groups, fb.groups.size() * sizeof(FusedGroup)))) ||
+                (rc = B200_CUDA_CHECK(cudaMemcpy(fl.d_groups, fb.groups.data(), fb.groups.size() * sizeof(FusedGroup), cudaMemcpyHostToDevice))) ||
+                (rc = B200_CUDA_CHECK(cudaMalloc(&fl.d_fams, fb.fams.size() * sizeof(FusedFam)))) ||
+                (rc = B200_CUDA_CHECK(cudaMemcpy(fl.d_fams, fb.fams.data(), fb.fams.size() * sizeof(FusedFam), cudaMemcpyHostToDevice)))) return rc;
+        }
+        b->flaunch.push_back(fl);
+        b0 += k;
+    }
+    return 0;
 }
 
 // Build the shared-prefix tree and all device state (filter histories zero, like freshly constructed reference objects).
@@ -304,6 +429,7 @@ int build(b200dsp_bank* b)
         if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_fam[d], fb))) ||
             (rc = B200_CUDA_CHECK(cudaMemcpy(b->d_fam[d], b->fams[d].data(), fb, cudaMemcpyHostToDevice)))) return rc;
     }
+    if ((rc = build_fused_plan(b, is_leaf))) return rc;
     for (int d = 0; d < b->depth; ++d)
         for (int k = 0; k < 2; ++k) {
             const size_t bytes = (size_t) b->levels[d].size() * TAIL_WORDS * 4;
@@ -448,7 +574,39 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
     }
     if ((rc = B200_CUDA_CHECK(cudaEventRecord(b->ev_tree0, st)))) return rc;
     b->tree_launches = 0;
-    for (int d = 1; d <= D; ++d) {
+    // fused path: the pass starts aligned at every level (no pending sample, even pair index) and is a multiple of 2^depth long
+    bool fused = b->fused_on && !b->flaunch.empty() && D >= 1 && n > 0 && (n % (1ll << D)) == 0 && n < (1ll << 31) && b->n_rsv == 0;
+    for (int d = 1; d <= D && fused; ++d) fused = (Pb[d - 1] == 2 * Pb[d]) && !(Pb[d] & 1);
+    if (fused) {
+        for (const auto& fl : b->flaunch) {
+            if (fl.n_groups == 0) continue;
+            FusedParams q;
+            memset(&q, 0, sizeof(q));
+            q.in_base = (fl.b == 0) ? rootB : b->d_level[fl.b];
+            q.in_stride = (fl.b == 0) ? 0 : b->stride[fl.b];
+            for (int j = 0; j < fl.k; ++j) {
+                q.out_base[j] = b->d_level[fl.b + j + 1]; q.out_stride[j] = b->stride[fl.b + j + 1];
+                q.tail_in[j] = b->d_tail[tc][fl.b + j]; q.tail_out[j] = b->d_tail[tn][fl.b + j];
+                q.lvl_off[j] = fl.lvl_off[j];
+            }
+            q.groups = fl.d_groups; q.fams = fl.d_fams; q.n_groups = fl.n_groups;
+            q.lvl_off[fl.k] = 0;
+            q.T = fl.T; q.l2items = 0;
+            while ((HB_IN << q.l2items) < fl.T) ++q.l2items;
+            q.n_root = (int) (n >> fl.b); q.tpr = (q.n_root + fl.T - 1) / fl.T;
+            q.opq_zero = 0; q.opq_one = 1; q.opq_mone = -1;
+            const long long tot = (long long) q.n_groups * q.tpr;
+            // persistent CTAs over contiguous (group, tile) ranges; a range that starts inside a stream pays one warm-up tile
+            long long ctas = (long long) b->sm_count * ((fl.smem <= FZ_SMEM_LIMIT) ? FZ_CTAS_PER_SM : 1);
+            if (ctas > (tot + 3) / 4) ctas = (tot + 3) / 4;
+            if (ctas < 1) ctas = 1;
+            if ((rc = B200_CUDA_CHECK(cudaFuncSetAttribute((const void*) hb48_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fl.smem)))) return rc;
+            hb48_fused_kernel<<<(unsigned) ctas, FZ_THREADS, fl.smem, st>>>(q);
+            if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
+            ++b->tree_launches;
+        }
+    }
+    for (int d = 1; d <= D && !fused; ++d) {
         // levels (d, d+1) in one launch when the call is aligned at both (no pending samples, whole batch pairs)
         if (b->fuse && (d & 1) && d + 1 <= D && b->d_pfam[d]) {
             const long long n_in = 2 * (Pa[d] - Pb[d]);
@@ -565,6 +723,20 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
     return 0;
 }
 
+// length of the next internal pass: at most `chunk`; while the stream is aligned at every level, long passes are cut to a
+// multiple of 2^(depth+1) so that they take the fused kernel and leave the stream aligned (a ragged rest follows as its
+// own short pass through the one-level kernel)
+long long next_pass_len(const b200dsp_bank* b, long long remaining)
+{
+    long long m = remaining < b->chunk ? remaining : b->chunk;
+    const int D = b->depth;
+    if (!b->fused_on || b->flaunch.empty() || D < 1 || D > 28) return m;
+    const long long unit = 2ll << D;
+    if (m < unit || m % unit == 0) return m;
+    for (int d = 1; d <= D; ++d) if (b->produced[d - 1] != 2 * b->produced[d] || (b->produced[d] & 1)) return m;
+    return m - m % unit;
+}
+
 // a feed of zero samples (DownChannelizer::feed with begin == end): nothing moves, every channel's outputs of "the last
 // feed" are empty -- the front-ends' per-feed counts live on the device and are zeroed by an empty schedule pass
 int empty_feed(b200dsp_bank* b, cudaStream_t st)
@@ -589,7 +761,7 @@ int feed_common(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t
     if (n == 0) return empty_feed(b, st);
     long long done = 0;
     while (done < n) {
-        const long long m = (n - done) < b->chunk ? (n - done) : b->chunk;
+        const long long m = next_pass_len(b, n - done);
         if ((rc = feed_chunk(b, d_in + done, m, st, done == 0))) return rc;
         done += m;
     }
@@ -628,6 +800,7 @@ int b200dsp_bank_create(b200dsp_bank_t** out, int input_rate_hz)
     // two-level fused kernel: measured on B200 (r01) it halves the tree's HBM traffic but runs 16 % slower than two one-level
     // launches (the kernels are issue-bound), so it is off unless B200DSP_FUSE is set
     b->fuse = (getenv("B200DSP_FUSE") != nullptr);
+    b->fused_on = (getenv("B200DSP_NO_FUSED_TREE") == nullptr);
     b->d_root = nullptr; b->root_cap = 0;
     b->d_leaf = nullptr; b->d_fe = nullptr; b->d_nco = nullptr; b->tcur = 0;
     if ((rc = B200_CUDA_CHECK(cudaSetDevice(b->device))) || (rc = B200_CUDA_CHECK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking))) ||
@@ -855,7 +1028,7 @@ int b200dsp_bank_feed(b200dsp_bank_t* b, const int16_t* iq, int64_t n_samples)
     long long done = 0;
     int pass = 0;
     while (done < n_samples) {
-        const long long m = (n_samples - done) < b->chunk ? (n_samples - done) : b->chunk;
+        const long long m = next_pass_len(b, n_samples - done);
         const int pend = (b->depth >= 1) ? (int) (b->produced[0] - 2 * b->produced[1]) : 0;
         const int slot = pass & 1;
         // ev_done[slot] is only waited on once pass-2 has recorded it in this call; an earlier call's passes were synchronised at its end

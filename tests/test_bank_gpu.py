@@ -183,28 +183,36 @@ def test_standalone_interpolator_vs_oracle(gpu_lib, port, golden, rate, outr):
             assert rel_rms(got.view(np.float32), want) <= 1e-5
 
 
-def test_bank_two_level_kernel_aligned_and_mixed_feeds(gpu_lib, port, golden_meta):
-    """Aligned feeds (whole batch pairs at every level) take the fused two-level kernel, anything else the one-level kernel;
-    a stream that alternates between both, with runs of -32768 and full-scale noise, must stay bit-exact against one oracle
-    chain per channel, call by call, and identical to a bank that never fuses."""
+def _plain_bank(input_rate):
+    """A bank that never takes the fused multi-level kernel (every pass through hb48_level_kernel)."""
     import os
+    from sdrangel_b200 import DownChannelizerBank
+    os.environ["B200DSP_NO_FUSED_TREE"] = "1"
+    try:
+        return DownChannelizerBank(input_rate)
+    finally:
+        del os.environ["B200DSP_NO_FUSED_TREE"]
+
+
+def test_bank_fused_tree_aligned_and_mixed_feeds(gpu_lib, port, golden_meta):
+    """Passes that start aligned at every level and are a multiple of 2^depth long take the fused multi-level kernel
+    (hb48_fused_kernel: levels of a group in shared memory), anything else the one-level kernel; both share the carried
+    tails.  A stream that alternates between them, with runs of -32768 and full-scale noise, must stay bit-exact against
+    one oracle chain per channel, call by call, and identical to a bank that never fuses."""
     from sdrangel_b200 import DownChannelizerBank
     plan = golden_meta["chan_plans"]["bank64"]
     rs = np.random.RandomState(77)
-    unit = 768 * 64                      # whole batch pairs down to the deepest pair of levels of the 7-level tree
-    sizes = [unit * 3, 1000, unit, 7, unit * 2, unit * 2 - 7 - 1000, unit * 4]
+    unit = 256 * 768                     # a multiple of 2^(depth+1) for the 7-level tree; 64 tiles of the top group
+    sizes = [unit * 3, 256, unit, 1000, unit * 2, 7, unit * 2 - 7 - 1000, unit * 4 + 128, 128, unit]
     n = sum(sizes)
     x = rs.randint(-32768, 32768, size=(n, 2)).astype(np.int16)
     x[5000:5100] = -32768
     x[unit * 3 + 500: unit * 3 + 600, 0] = -32768
     x[unit * 5: unit * 5 + 3000] = -32768
+    x[n - unit - 40: n - unit + 40, 1] = -32768            # across a pass boundary: the carried tails hold -32768
     chans = plan["channels"][::7]
-    plain = DownChannelizerBank(plan["input_rate"])
-    os.environ["B200DSP_FUSE"] = "1"          # the two-level kernel is opt-in (less HBM traffic, but slower on B200: DESIGN.md)
-    try:
-        fused = DownChannelizerBank(plan["input_rate"])
-    finally:
-        del os.environ["B200DSP_FUSE"]
+    plain = _plain_bank(plan["input_rate"])
+    fused = DownChannelizerBank(plan["input_rate"])
     ids = [fused.add_channel(48000, fc)[0] for fc, _, _, _ in chans]
     for fc, _, _, _ in chans:
         plain.add_channel(48000, fc)
@@ -225,6 +233,52 @@ def test_bank_two_level_kernel_aligned_and_mixed_feeds(gpu_lib, port, golden_met
             assert got.shape == want.shape, (sz, cid)
             assert np.array_equal(got, want), (sz, cid, int(np.argmax(np.any(got != want, axis=1))))
             assert np.array_equal(plain.fetch(cid), want), (sz, cid)
+    fused.close()
+    plain.close()
+
+
+@pytest.mark.parametrize("chunk", [3 << 22, 768 * 64])
+def test_bank1024_every_channel_vs_oracle(gpu_lib, port, golden_meta, chunk):
+    """The whole 1024-channel plan (BASELINE config 5), every channel: two feeds (2^18 then 2^17 + 2^12 samples) against one
+    oracle DownChannelizer per channel (downchannelizer.cpp:50-91), tree bit-exact; the front-end of every 16th channel
+    within 1e-5.  With the small chunk the second feed runs as several internal passes."""
+    from sdrangel_b200 import DownChannelizerBank, capi
+    plan = golden_meta["chan_plans"]["bank1024"]
+    fs = plan["input_rate"]
+    rows = plan["channels"]
+    assert len(rows) == 1024
+    rs = np.random.RandomState(1024)
+    n1, n2 = 1 << 18, (1 << 17) + (1 << 12)
+    x = rs.randint(-32768, 32768, size=(n1 + n2, 2)).astype(np.int16)
+    x[100_000:100_300] = -32768
+    cutoff = float(np.float32(np.float32(12500) / np.float32(2.2)))
+    b = DownChannelizerBank(fs)
+    b.set_chunk(chunk)
+    for fc, rate, ofs, path in rows:
+        cid = b.add_channel(48000, fc)[0]
+        b.set_frontend(cid, -ofs, cutoff, 48000)
+    assert b.node_count() == 3070
+    oracles = []
+    for fc, rate, ofs, path in rows:
+        o = port.PortDownChannelizer()
+        o.configure(fs, 48000, fc)
+        oracles.append(o)
+    fes = {i: port.PortFrontEnd(-rows[i][2], rows[i][1], 48000, cutoff) for i in range(0, 1024, 16)}
+    for a, e in ((0, n1), (n1, n1 + n2)):
+        b.feed(x[a:e])
+        ch_all, ch_cnt = b.fetch_all(capi.STAGE_CHANNELIZER)
+        fe_all, fe_cnt = b.fetch_all(capi.STAGE_FRONTEND, stride=ch_all.shape[1])
+        bad = []
+        for i, o in enumerate(oracles):
+            want = o.feed(x[a:e])
+            if ch_cnt[i] != want.shape[0] or not np.array_equal(ch_all[i, :ch_cnt[i]], want):
+                bad.append(i)
+            if i in fes:
+                wf = fes[i].feed(want)
+                assert fe_cnt[i] == wf.shape[0], (a, i)
+                assert rel_rms(fe_all[i, :fe_cnt[i]], wf) <= 1e-5, (a, i)
+        assert not bad, (a, len(bad), bad[:8])
+    b.close()
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
