@@ -24,13 +24,12 @@ namespace {
 // ---------------------------------------------------------------------------------------------------------
 struct GatherSrc { const void* src; const int* state; long long count; };     // state != null: count = state[3] (front-end)
 
-struct LeafChan { const uint32_t* src; uint32_t* dst; int depth; int shift; };     // static per channel (until a reallocation)
-
 // channel output = trunc_toward_zero(y / 2^S) per component (downchannelizer.cpp:78-83)
 __global__ void hb48_finalize_kernel(const LeafChan* chans, const PassInfo pi)
 {
     const LeafChan c = chans[blockIdx.y];
     if (c.depth == 0) return;                  // stage-less channel: forwarded by a plain copy
+    if (c.direct && pi.fused_pass) return;     // written by the fused tree kernel itself
     const int n = pi.n_new[c.depth];
     const uint32_t* src = c.src + pi.wo[c.depth];
     uint32_t* dst = c.dst + pi.out_count[c.depth];
@@ -186,6 +185,9 @@ struct b200dsp_bank {
     struct FusedLaunch { int b, k, T; size_t smem; int n_groups, n_fams; FusedGroup* d_groups; FusedFam* d_fams; int lvl_off[FZ_MAXK]; };
     std::vector<FusedLaunch> flaunch;
     bool fused_on;                               // B200DSP_NO_FUSED_TREE unset: aligned passes take hb48_fused_kernel
+    std::vector<int> node_chan;                  // per node: the one channel ending there (-1 none, -2 several)
+    std::vector<char> chan_direct;               // per channel: the fused kernel writes its output itself
+    int n_indirect;                              // channels with stages that still need hb48_finalize_kernel after a fused pass
     uint32_t* d_root; long long root_cap;        // staging for host feeds / odd-pending device feeds
     std::vector<long long> produced;             // P[d]
     int tcur;
@@ -276,7 +278,8 @@ void fused_collect(const b200dsp_bank* b, const std::vector<char>& is_leaf, int 
                     const Node& cn = b->nodes[c];
                     const bool kids = cn.child[0] >= 0 || cn.child[1] >= 0 || cn.child[2] >= 0;
                     if (kids && j + 1 < k) { f.cbase[m] = (int) next.size(); f.cbit[m] = 1 << next.size(); next.push_back(c); }
-                    if (is_leaf[c] || (kids && j + 1 == k)) f.cindex[m] = cn.index;
+                    if (kids && j + 1 == k) f.cindex[m] = cn.index;              // another launch reads the raw stage output
+                    else if (is_leaf[c]) f.cindex[m] = (b->node_chan[c] >= 0) ? -2 - b->node_chan[c] : cn.index;
                 }
                 out.fams.push_back(f);
                 ++nfam;
@@ -322,6 +325,13 @@ int build_fused_plan(b200dsp_bank* b, const std::vector<char>& is_leaf)
 {
     int rc;
     const int D = b->depth;
+    // a node where exactly one channel ends, and which no later launch reads, is finalised by the fused kernel itself
+    b->node_chan.assign(b->nodes.size(), -1);
+    for (size_t i = 0; i < b->chans.size(); ++i) {
+        int& nc = b->node_chan[b->chans[i].node];
+        nc = (nc == -1) ? (int) i : -2;
+    }
+    b->chan_direct.assign(b->chans.size(), 0);
     int b0 = 0;
     while (b0 < D) {
         const int left = D - b0;
@@ -342,13 +352,15 @@ int build_fused_plan(b200dsp_bank* b, const std::vector<char>& is_leaf)
         fl.smem = fused_smem(fb, k, fl.T, fl.lvl_off);
         fused_scale_offsets(fb, fl.T);
         fl.n_groups = (int) fb.groups.size(); fl.n_fams = (int) fb.fams.size();
-        if (fl.smem > 200 * 1024) { b->flaunch.clear(); return 0; }        // a tree this wide stays on the one-level kernel
+        if (fl.smem > 200 * 1024) { b->flaunch.clear(); b->chan_direct.assign(b->chans.size(), 0); return 0; }        // a tree this wide stays on the one-level kernel
         if (fl.n_groups) {
             if ((rc = B200_CUDA_CHECK(cudaMalloc(&fl.d_groups, fb.groups.size() * sizeof(FusedGroup)))) ||
                 (rc = B200_CUDA_CHECK(cudaMemcpy(fl.d_groups, fb.groups.data(), fb.groups.size() * sizeof(FusedGroup), cudaMemcpyHostToDevice))) ||
                 (rc = B200_CUDA_CHECK(cudaMalloc(&fl.d_fams, fb.fams.size() * sizeof(FusedFam)))) ||
                 (rc = B200_CUDA_CHECK(cudaMemcpy(fl.d_fams, fb.fams.data(), fb.fams.size() * sizeof(FusedFam), cudaMemcpyHostToDevice)))) return rc;
         }
+        for (const FusedFam& f : fb.fams)
+            for (int m = 0; m < 3; ++m) if (f.cindex[m] <= -2) b->chan_direct[-2 - f.cindex[m]] = 1;
         b->flaunch.push_back(fl);
         b0 += k;
     }
@@ -542,6 +554,7 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
             Channel& c = b->chans[i];
             b->h_leaf[i].src = (c.S == 0) ? nullptr : b->d_level[c.S] + (long long) b->nodes[c.node].index * b->stride[c.S];
             b->h_leaf[i].dst = c.d_out; b->h_leaf[i].depth = c.S; b->h_leaf[i].shift = c.out_shift;
+            b->h_leaf[i].direct = (i < b->chan_direct.size() && b->chan_direct[i]) ? 1 : 0; b->h_leaf[i].pad = 0;
         }
         for (size_t k = 0; k < b->fe_index.size(); ++k) {
             Channel& c = b->chans[b->fe_index[k]];
@@ -590,6 +603,8 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
                 q.lvl_off[j] = fl.lvl_off[j];
             }
             q.groups = fl.d_groups; q.fams = fl.d_fams; q.n_groups = fl.n_groups;
+            q.leaf = b->d_leaf;
+            for (int j = 0; j < fl.k; ++j) q.leaf_count[j] = b->out_count_depth[fl.b + j + 1];
             q.lvl_off[fl.k] = 0;
             q.T = fl.T; q.l2items = 0;
             while ((HB_IN << q.l2items) < fl.T) ++q.l2items;
@@ -696,7 +711,10 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
             if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(c.d_out + b->out_count_depth[0], d_in, (size_t) n * 4, cudaMemcpyDeviceToDevice, st)))) return rc;
         }
     }
-    if (nc && max_new > 0 && D >= 1) {
+    pi.fused_pass = fused ? 1 : 0;
+    bool need_finalize = !fused;
+    if (fused) for (size_t i = 0; i < nc; ++i) if (b->chans[i].S > 0 && !b->chan_direct[i]) { need_finalize = true; break; }
+    if (nc && max_new > 0 && D >= 1 && need_finalize) {
         int gx = (max_new + 255) / 256;
         if (gx > 64) gx = 64;
         hb48_finalize_kernel<<<dim3(gx, (unsigned) nc), 256, 0, st>>>(b->d_leaf, pi);
@@ -710,9 +728,16 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
         // every channel a 5/4 closed-form resampler with 72 taps per phase (the 1024-channel plan): register-tiled variant
         bool lat54 = true;
         for (int ci : b->fe_index) { const Channel& cc = b->chans[ci]; if (!cc.lattice || 4 * cc.A != (5ll << 23) || cc.ntaps != 72) { lat54 = false; break; } }
-        const dim3 grid((unsigned) ((max_new + FE_TILE - 1) / FE_TILE), (unsigned) b->h_fe.size());
-        if (lat54) frontend_kernel_t<true><<<grid, FE_THREADS, smem, st>>>(b->d_fe, b->d_nco, pi);
-        else       frontend_kernel_t<false><<<grid, FE_THREADS, smem, st>>>(b->d_fe, b->d_nco, pi);
+        if (lat54) {
+            // closed-form outputs per channel <= 0.8 * inputs + 1
+            const long long max_out = (long long) max_new * 4 / 5 + 2;
+            const dim3 grid((unsigned) ((max_out + F54_OPB - 1) / F54_OPB), (unsigned) b->h_fe.size());
+            if ((rc = B200_CUDA_CHECK(cudaFuncSetAttribute((const void*) frontend54_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F54_SMEM)))) return rc;
+            frontend54_kernel<<<grid, 128, F54_SMEM, st>>>(b->d_fe, b->d_nco, pi);
+        } else {
+            const dim3 grid((unsigned) ((max_new + FE_TILE - 1) / FE_TILE), (unsigned) b->h_fe.size());
+            frontend_kernel_t<false><<<grid, FE_THREADS, smem, st>>>(b->d_fe, b->d_nco, pi);
+        }
         if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
         b->fe_parity ^= 1;
     }

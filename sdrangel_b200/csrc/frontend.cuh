@@ -51,6 +51,7 @@ struct PassInfo {
     long long out_count[32];     // channel outputs of depth-d channels already produced in this feed
     int       first_pass;
     int       parity;            // which half of the ping-pong history is current
+    int       fused_pass;        // the tree ran as hb48_fused_kernel: channels marked direct already hold their outputs
 };
 
 // Schedule.  The reference's float32 recurrence (interpolator.h:23-36 + nfmdemod.cpp:315): per input d -= 1; if d < 1 emit
@@ -297,6 +298,151 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel_t(const FrontendCh
                 hout[k] = (i >= 0) ? c.in[i] : hin[FE_MAX_TAPS + i];
             }
             if (tid == 0) hout[FE_MAX_TAPS] = (phase0 + (unsigned) m * (unsigned) c.inc) & 4095u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// frontend54_kernel: every channel a 5/4 closed-form resampler with 72 taps per phase (ratio 1.25: the 60 kS/s -> 48 kS/s
+// channels of the 1024-channel plan).  Output k' of the closed form sits at E = D + k' A (units of 2^-23 inputs), A = 5 * 2^21:
+// four outputs later it is exactly five inputs later at the same phase, so only four of the sixteen phases occur in a pass.
+//   * grid = (blocks of 4608 outputs, channels); a block mixes the 5760 (+ 72) channel samples its outputs span with the
+//     table NCO into shared memory once;
+//   * warp w of the block owns phase residue w: its 72 taps live in registers for the whole block (loaded once);
+//   * a lane computes NINE consecutive outputs of that phase (45 inputs apart from the next lane's: an odd stride, so
+//     the 64-bit shared loads of a warp hit 32 distinct banks) in one sweep over the 112 samples they span: one shared
+//     load per 11.6 FFMA, accumulation in ascending tap order like the generic kernel;
+//   * results go through a small padded staging tile so that the global stores are contiguous.
+// Outputs listed by the schedule kernel before the closed form takes over (the stream's first output) and the carried
+// state (newest 128 channel samples + NCO phase) are block 0's.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int F54_NOUT = 9;
+constexpr int F54_ROUNDS = 4;
+constexpr int F54_G = 32 * F54_ROUNDS;                  // lanes x rounds: groups of 36 outputs per block
+constexpr int F54_OPB = 4 * F54_NOUT * F54_G;           // 4608 outputs per block
+constexpr int F54_IPB = 5 * F54_NOUT * F54_G;           // 5760 inputs
+constexpr int F54_ZN = F54_IPB + 72 + 8;                // mixed samples a block may touch
+constexpr int F54_SROW = 4 * F54_NOUT + 1;              // staging row of one lane group, padded to an odd number of float2
+constexpr int F54_STAGE = 32 * F54_SROW;
+constexpr int F54_SMEM = (F54_ZN + 2 * F54_STAGE) * (int) sizeof(float2) + 4096 * (int) sizeof(float);
+
+__device__ __forceinline__ float2 fe_mix(uint32_t w, unsigned phase0, int i, int inc, const float* __restrict__ nco_table)
+{
+    const float x = (float) (short) (w & 0xffffu), y = (float) ((int) w >> 16);
+    const int p = (int) ((phase0 + (unsigned) (i + 1) * (unsigned) inc) & 4095u);   // phase advanced before the lookup; wrap == mod 4096
+    const float u = nco_table[p], v = -nco_table[(p + 1024) & 4095];
+    return make_float2(x * u - y * v, x * v + y * u);
+}
+
+__global__ void __launch_bounds__(128, 2) frontend54_kernel(const FrontendChan* __restrict__ chans, const float* __restrict__ nco_table, const PassInfo pi)
+{
+    extern __shared__ float2 f54_smem[];
+    float2* z = f54_smem;
+    float2* stage = f54_smem + F54_ZN;
+    float* nco = reinterpret_cast<float*>(f54_smem + F54_ZN + 2 * F54_STAGE);      // the NCO table: the mix gathers two entries per sample
+    const FrontendChan c = chans[blockIdx.y];
+    const int tid = threadIdx.x, lane = tid & 31, cc = tid >> 5;
+    const int m = pi.n_new[c.depth];
+    const uint32_t* __restrict__ in = c.in + pi.out_count[c.depth];
+    const uint32_t* __restrict__ hin = c.hist + pi.parity * c.hist_stride;
+    const unsigned phase0 = hin[FE_MAX_TAPS];
+    const int k0 = (int) c.plan[0], ncf = (int) c.plan[3];
+    const long long i0 = c.plan[1], D0 = c.plan[2];
+    const int out_base = c.state[3] - c.state[2];
+    if (blockIdx.x == 0) {
+        uint32_t* hout = c.hist + (pi.parity ^ 1) * c.hist_stride;
+        {
+            const int i = m - FE_MAX_TAPS + tid;
+            hout[tid] = (i >= 0) ? in[i] : hin[FE_MAX_TAPS + i];
+            if (tid == 0) hout[FE_MAX_TAPS] = (phase0 + (unsigned) m * (unsigned) c.inc) & 4095u;
+        }
+        for (int o = tid; o < k0; o += 128) {                  // before the closed form: straight from global memory (a handful per stream)
+            const unsigned s = (unsigned) c.sched[o];
+            const int idx = (int) (s >> 8);
+            const float* row = c.taps + (s & 0xffu) * c.ntaps;
+            float ra = 0.0f, ia = 0.0f;
+            for (int k = 0; k < c.ntaps; ++k) {
+                const int i = idx - k;
+                const float2 v = fe_mix((i >= 0) ? in[i] : hin[FE_MAX_TAPS + i], phase0, i, c.inc, nco_table);
+                ra = fmaf(row[k], v.x, ra);
+                ia = fmaf(row[k], v.y, ia);
+            }
+            c.out[out_base + o] = make_float2(ra, ia);
+        }
+    }
+    const int kb = blockIdx.x * F54_OPB;
+    if (kb >= ncf) return;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(nco)[tid + 128 * q] = __ldg(reinterpret_cast<const float4*>(nco_table) + tid + 128 * q);
+    const long long Eb = D0 + (long long) kb * c.A;
+    const int zlo = (int) (i0 + (Eb >> 23) - 1) - 71;          // oldest sample any output of this block taps (>= -71: inside the history)
+    // samples up to the newest one the block's last output taps (a channel's last block is usually partly empty)
+    int zn = F54_ZN;
+    {
+        const int klast = ((ncf - kb < F54_OPB) ? ncf - kb : F54_OPB) - 1;
+        const int need = (int) (i0 + ((Eb + (long long) klast * c.A) >> 23) - 1) - zlo + 1 + 8;
+        if (need < zn) zn = need;
+    }
+    const float4* taprow;
+    int idx_c;
+    {
+        const long long Ec = Eb + (long long) cc * c.A;
+        idx_c = (int) (i0 + (Ec >> 23) - 1);
+        taprow = reinterpret_cast<const float4*>(c.taps + (int) ((Ec & 0x7fffffll) >> c.phshift) * 72);      // 72 floats per phase: 16-byte aligned rows
+    }
+    __syncthreads();
+    // mix: all loads of eight samples in flight, no branches (out-of-range indices are clamped, their result zeroed)
+    for (int kk = tid; kk < zn; kk += 128 * 8) {
+        uint32_t w[8];
+        float u[8], v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int i = zlo + kk + 128 * q;
+            const int ii = (i < m) ? i : m - 1;
+            const uint32_t* src = (ii >= 0) ? in + ii : hin + FE_MAX_TAPS + ii;
+            w[q] = __ldg(src);
+            const int p = (int) ((phase0 + (unsigned) (i + 1) * (unsigned) c.inc) & 4095u);
+            u[q] = nco[p]; v[q] = -nco[(p + 1024) & 4095];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int k = kk + 128 * q, i = zlo + k;
+            const float x = (float) (short) (w[q] & 0xffffu), y = (float) ((int) w[q] >> 16);
+            if (k < F54_ZN) z[k] = (i < m) ? make_float2(x * u[q] - y * v[q], x * v[q] + y * u[q]) : make_float2(0.0f, 0.0f);
+        }
+    }
+    float t[72];
+#pragma unroll
+    for (int k = 0; k < 18; ++k) { const float4 f = __ldg(taprow + k); t[4 * k] = f.x; t[4 * k + 1] = f.y; t[4 * k + 2] = f.z; t[4 * k + 3] = f.w; }
+    __syncthreads();
+#pragma unroll 1
+    for (int round = 0; round < F54_ROUNDS; ++round) {
+        const int kr = kb + 32 * 4 * F54_NOUT * round;
+        if (kr >= ncf) break;                                   // block-uniform
+        const int g = lane + 32 * round;
+        float ra[F54_NOUT], ia[F54_NOUT];
+#pragma unroll
+        for (int n = 0; n < F54_NOUT; ++n) { ra[n] = 0.0f; ia[n] = 0.0f; }
+        if (kb + 4 * F54_NOUT * g + cc < ncf) {
+            const float2* zz = z + (idx_c + 5 * F54_NOUT * g + 5 * (F54_NOUT - 1) - zlo);      // newest sample of this lane's last output
+#pragma unroll
+            for (int s = 0; s < 72 + 5 * (F54_NOUT - 1); ++s) {
+                const float2 v = zz[-s];
+#pragma unroll
+                for (int n = 0; n < F54_NOUT; ++n) {
+                    const int k = 5 * n - 5 * (F54_NOUT - 1) + s;            // tap of output n at this sample (compile-time)
+                    if (k >= 0 && k < 72) { ra[n] = fmaf(t[k], v.x, ra[n]); ia[n] = fmaf(t[k], v.y, ia[n]); }
+                }
+            }
+        }
+        float2* st = stage + (round & 1) * F54_STAGE + lane * F54_SROW + cc;
+#pragma unroll
+        for (int n = 0; n < F54_NOUT; ++n) st[4 * n] = make_float2(ra[n], ia[n]);
+        __syncthreads();
+        const float2* sr = stage + (round & 1) * F54_STAGE;
+        for (int o = tid; o < 32 * 4 * F54_NOUT; o += 128) {
+            const int r = o / (4 * F54_NOUT);
+            if (kr + o < ncf) c.out[out_base + k0 + kr + o] = sr[r * F54_SROW + (o - r * 4 * F54_NOUT)];
         }
     }
 }

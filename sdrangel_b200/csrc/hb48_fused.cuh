@@ -41,8 +41,11 @@ struct FusedFam {            // a parent at group level j and its children at le
     int pbase, pslot, pindex;    // parent: word offset of its slot within pyramid level j, slot number, index within its tree level (tails)
     int cbase[3];                // children C, L, U: word offset of the slot within pyramid level j+1 (-1: not a parent inside this group)
     int cbit[3];                 // 1 << slot of that child (0 when cbase < 0)
-    int cindex[3];               // children: index within their tree level when the node is written to HBM, else -1
+    int cindex[3];               // children written to HBM: >= 0 index within their tree level (raw stage output for another launch
+                                 // or the finalize kernel); <= -2: channel -2 - cindex ends here and takes trunc(y / 2^shift) straight
+                                 // into its output buffer (downchannelizer.cpp:78-83); -1: not written
 };
+struct LeafChan { const uint32_t* src; uint32_t* dst; int depth; int shift; int direct; int pad; };     // static per channel (until a reallocation)
 struct FusedGroup {
     int root_index, k;
     int fam_begin[FZ_MAXK + 1];     // families of level j: [fam_begin[j], fam_begin[j+1]) of the launch's family table
@@ -57,6 +60,7 @@ struct FusedParams {
     uint32_t*       out_base[FZ_MAXK]; long long out_stride[FZ_MAXK];   // level buffers of depths b+1 .. b+k
     const uint32_t* tail_in[FZ_MAXK];  uint32_t* tail_out[FZ_MAXK];     // carried tails of depths b .. b+k-1
     const FusedGroup* groups; const FusedFam* fams;
+    const LeafChan* leaf; long long leaf_count[FZ_MAXK];            // channel table; outputs of depth b+j+1 channels already produced in this feed
     int n_groups, T, tpr;        // tile size in root samples (384 * 2^n), tiles per root stream this pass
     int l2items;                 // log2(T / 384)
     int n_root;                  // root samples per group this pass (a multiple of 2^k)
@@ -146,7 +150,8 @@ __device__ __forceinline__ int32_t fz_store_smem(int32_t* xe, int A, const uint3
 
 __device__ __forceinline__ void fz_store12(uint32_t* o, const uint32_t (&wds)[HB_R], int k0, int n_valid)
 {
-    if (k0 + HB_R <= n_valid) {
+    // (a channel's output buffer is written at its running count within the feed: any word alignment)
+    if (k0 + HB_R <= n_valid && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
 #pragma unroll
         for (int t = 0; t < 3; ++t) *reinterpret_cast<uint4*>(o + 4 * t) = make_uint4(wds[4 * t], wds[4 * t + 1], wds[4 * t + 2], wds[4 * t + 3]);
     } else {
@@ -155,32 +160,73 @@ __device__ __forceinline__ void fz_store12(uint32_t* o, const uint32_t (&wds)[HB
     }
 }
 
+struct FzDst { uint32_t* ptr; int shift; };      // shift < 0: the raw int16 stage output; else the channel output trunc(y / 2^shift)
+
+__device__ __forceinline__ FzDst fz_dst(const FusedParams& p, int j, int ci, long long tile_out)
+{
+    FzDst d;
+    if (ci >= 0) { d.ptr = p.out_base[j] + (long long) ci * p.out_stride[j] + tile_out; d.shift = -1; }
+    else {
+        const LeafChan* lc = p.leaf + (-2 - ci);
+        d.ptr = lc->dst + p.leaf_count[j] + tile_out; d.shift = lc->shift;
+    }
+    return d;
+}
+
+// The channel output is the C++ truncating division of the int16 stage output by 2^shift (downchannelizer.cpp:78-83).  On the
+// accumulator (value in the high half): add 2^shift - 1 at bit 16 when negative, then shift by 16 + shift.  Each lane does
+// this for its own component BEFORE the exchange; the words are then packed from the low halves.
+__device__ __forceinline__ void fz_finalize12(uint32_t (&y)[HB_R], int shift)
+{
+    const int nb = -(((1 << shift) - 1) << 16);
+#pragma unroll
+    for (int t = 0; t < HB_R; ++t) {
+        const int v = (int) y[t];
+        y[t] = (uint32_t) (((v >> 31) * nb + v) >> (16 + shift));
+    }
+}
+__device__ __forceinline__ uint32_t fz_pack(uint32_t re, uint32_t im, bool low)
+{
+    uint32_t w;
+    if (low) asm("prmt.b32 %0, %1, %2, 0x5410;" : "=r"(w) : "r"(re), "r"(im));       // finalised values: low halves
+    else     asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(w) : "r"(re), "r"(im));       // raw accumulators: the int16-wrapped stage outputs are the high halves
+    return w;
+}
+
 // packed int16 IQ to HBM: lane (comp 0, lj) packs its re with the im of lane (comp 1, lj) and stores 12 words
-__device__ __forceinline__ void fz_store_global(uint32_t* out, const uint32_t (&y)[HB_R], int comp, int k0, int n_valid)
+__device__ __forceinline__ void fz_store_global(const FzDst& d, uint32_t (&y)[HB_R], int comp, int k0, int n_valid)
 {
     uint32_t wds[HB_R];
+    const bool fin = d.shift >= 0;
+    if (fin) fz_finalize12(y, d.shift);
 #pragma unroll
     for (int t = 0; t < HB_R; ++t) {
         const uint32_t im = __shfl_down_sync(0xffffffffu, y[t], 16);
-        asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(wds[t]) : "r"(y[t]), "r"(im));       // high halves: the int16-wrapped stage outputs
+        wds[t] = fz_pack(y[t], im, fin);
     }
     if (comp != 0 || k0 >= n_valid) return;
-    fz_store12(out + k0, wds, k0, n_valid);
+    fz_store12(d.ptr + k0, wds, k0, n_valid);
 }
 
 // both rotated children at once.  yA is the lane's own child (lower half on the comp-0 lanes, upper half on the comp-1
-// lanes), yB the other one: each lane sends yB to its partner lane and stores its own child's 12 words.
-__device__ __forceinline__ void fz_store_global_pair(uint32_t* outA, const uint32_t (&yA)[HB_R], const uint32_t (&yB)[HB_R], int comp, int k0, int n_valid)
+// lanes), yB the other one: each lane sends yB to its partner lane and stores its own child's 12 words.  (Raw or
+// finalised is the same for both children -- the caller checks -- but the two channels' shifts may differ.)
+__device__ __forceinline__ void fz_store_global_pair(const FzDst& dA, uint32_t (&yA)[HB_R], uint32_t (&yB)[HB_R], int comp, int k0, int n_valid)
 {
     uint32_t wds[HB_R];
-    const uint32_t sel = comp ? 0x3276u : 0x7632u;       // comp 0: (re = own, im = partner's); comp 1: (re = partner's, im = own)
+    const bool fin = dA.shift >= 0;
+    if (fin) {
+        fz_finalize12(yA, dA.shift);
+        fz_finalize12(yB, __shfl_xor_sync(0xffffffffu, dA.shift, 16));       // yB belongs to the partner lane's channel
+    }
 #pragma unroll
     for (int t = 0; t < HB_R; ++t) {
         const uint32_t got = __shfl_xor_sync(0xffffffffu, yB[t], 16);
-        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(wds[t]) : "r"(yA[t]), "r"(got), "r"(sel));
+        // comp 0: (re = own, im = partner's); comp 1: (re = partner's, im = own)
+        wds[t] = fz_pack(comp ? got : yA[t], comp ? yA[t] : got, fin);
     }
     if (k0 >= n_valid) return;
-    fz_store12(outA + k0, wds, k0, n_valid);
+    fz_store12(dA.ptr + k0, wds, k0, n_valid);
 }
 
 constexpr int FZ_MAX_FAMS = 40;      // per group: at most 1 + 3 + 9 + 27 parents
@@ -223,7 +269,7 @@ __device__ __forceinline__ void fz_item(const FusedParams& p, FzShared& sh, cons
     int32_t wv[36];
     fz_load_w(P + ph.woff, wv);
     unsigned newbad = 0;
-    if (fam.cbase[0] >= 0 || fam.cindex[0] >= 0) {
+    if (fam.cbase[0] >= 0 || fam.cindex[0] != -1) {
         int32_t cv[16];
         uint32_t y[HB_R];
         fz_load_c(P + ph.coff_own, cv);
@@ -232,15 +278,15 @@ __device__ __forceinline__ void fz_item(const FusedParams& p, FzShared& sh, cons
             const int32_t m = fz_store_smem(Sc + fam.cbase[0], A1, y);
             if (__any_sync(0xffffffffu, m == -32768)) newbad |= (unsigned) fam.cbit[0];
         }
-        if (fam.cindex[0] >= 0 && emit)
-            fz_store_global(p.out_base[j] + (long long) fam.cindex[0] * p.out_stride[j] + ph.tile_out, y, comp, k0, ph.nv_child);
+        if (fam.cindex[0] != -1 && emit) fz_store_global(fz_dst(p, j, fam.cindex[0], ph.tile_out), y, comp, k0, ph.nv_child);
     }
-    const bool hasL = fam.cbase[1] >= 0 || fam.cindex[1] >= 0, hasU = fam.cbase[2] >= 0 || fam.cindex[2] >= 0;
+    const bool hasL = fam.cbase[1] >= 0 || fam.cindex[1] != -1, hasU = fam.cbase[2] >= 0 || fam.cindex[2] != -1;
     if (hasL || hasU) {
         const bool slow = ((ph.badmask >> fam.pslot) & 1u) != 0;
         // the pair path needs both children treated alike (both or neither kept in the pyramid / written to HBM): its
         // stores pick the child by half-warp, so anything else would diverge inside a warp
-        const bool alike = ((fam.cbase[1] >= 0) == (fam.cbase[2] >= 0)) && ((fam.cindex[1] >= 0) == (fam.cindex[2] >= 0));
+        const bool alike = ((fam.cbase[1] >= 0) == (fam.cbase[2] >= 0)) && ((fam.cindex[1] >= 0) == (fam.cindex[2] >= 0)) &&
+                           ((fam.cindex[1] == -1) == (fam.cindex[2] == -1));
         if (hasL && hasU && alike && !slow) {
             // Both rotated children from one tap sum F.  With yL = F + co*m, yU = F - co*m and m = +-65536 by (component,
             // output parity), the lane's OWN child (lower half on comp-0 lanes, upper half on comp-1 lanes) is
@@ -264,17 +310,15 @@ __device__ __forceinline__ void fz_item(const FusedParams& p, FzShared& sh, cons
                 if ((bal & 0xffffu) | (bbl >> 16)) newbad |= (unsigned) fam.cbit[1];
                 if ((bal >> 16) | (bbl & 0xffffu)) newbad |= (unsigned) fam.cbit[2];
             }
-            if (emit && fam.cindex[1] >= 0) {
-                const int iA = comp ? fam.cindex[2] : fam.cindex[1];
-                fz_store_global_pair(p.out_base[j] + (long long) iA * p.out_stride[j] + ph.tile_out, yA, yB, comp, k0, ph.nv_child);
-            }
+            if (emit && fam.cindex[1] != -1)
+                fz_store_global_pair(fz_dst(p, j, comp ? fam.cindex[2] : fam.cindex[1], ph.tile_out), yA, yB, comp, k0, ph.nv_child);
         } else {
 #pragma unroll 1
             for (int m = 1; m <= 2; ++m) {
                 // (selected, not indexed: a runtime index would move the family descriptor to local memory)
                 const int cb = (m == 1) ? fam.cbase[1] : fam.cbase[2], ci = (m == 1) ? fam.cindex[1] : fam.cindex[2];
                 const int bit = (m == 1) ? fam.cbit[1] : fam.cbit[2];
-                if (cb < 0 && ci < 0) continue;
+                if (cb < 0 && ci == -1) continue;
                 const int sigma = (m == 1) ? 1 : -1;
                 uint32_t y[HB_R];
                 if (!slow) {
@@ -295,8 +339,7 @@ __device__ __forceinline__ void fz_item(const FusedParams& p, FzShared& sh, cons
                     const int32_t mn = fz_store_smem(Sc + cb, A1, y);
                     if (__any_sync(0xffffffffu, mn == -32768)) newbad |= (unsigned) bit;
                 }
-                if (ci >= 0 && emit)
-                    fz_store_global(p.out_base[j] + (long long) ci * p.out_stride[j] + ph.tile_out, y, comp, k0, ph.nv_child);
+                if (ci != -1 && emit) fz_store_global(fz_dst(p, j, ci, ph.tile_out), y, comp, k0, ph.nv_child);
             }
         }
     }
