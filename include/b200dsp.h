@@ -46,8 +46,6 @@ int         b200dsp_device_count(void);            /* 0 when no usable CUDA devi
 const char* b200dsp_last_error(void);
 const char* b200dsp_version(void);
 int         b200dsp_sm_count(void);
-/* the SMs the block scheduler gives the first n_blocks large blocks of a kernel launched on an idle GPU (smids[n_blocks]) */
-int         b200dsp_probe_sm_order(int n_blocks, int threads_per_block, int* smids);
 
 /* ---- K1/K2: half-band decimation cascades ---------------------------------------------------------------
  * One handle == one reference decimator object with its six half-band stages of state:
@@ -157,9 +155,6 @@ int b200dsp_bank_copy_out_dev(b200dsp_bank_t* b, int chan_id, int64_t skip, int6
 int b200dsp_bank_sync(b200dsp_bank_t* b);
 /* device time (ms) and count of the tree-level kernel launches of the last internal pass (instrumentation for bench.py) */
 int b200dsp_bank_tree_time(b200dsp_bank_t* b, float* ms, int* launches);
-/* K6 support: keep the bank's tree kernels off the listed SMs so a concurrent collective (the NCCL broadcast of the next
- * baseband block) gets whole SMs at once instead of waiting for a gap between kernels; n = 0 turns it off */
-int b200dsp_bank_set_reserved_sms(b200dsp_bank_t* b, const int* smids, int n);
 
 /* ---- engine-side sample corrections ----------------------------------------------------------------
  * == DSPDeviceSourceEngine::iqCorrections(begin, end, imbalanceCorrection)  sdrbase/dsp/dspdevicesourceengine.cpp:175-262,

@@ -60,8 +60,6 @@ SIGNATURES = {
     "b200dsp_bank_copy_out_dev": (_i32, [_vp, _i32, _i64, _i64, _vp, _vp]),
     "b200dsp_bank_sync": (_i32, [_vp]),
     "b200dsp_bank_tree_time": (_i32, [_vp, _vp, _vp]),
-    "b200dsp_bank_set_reserved_sms": (_i32, [_vp, _vp, _i32]),
-    "b200dsp_probe_sm_order": (_i32, [_i32, _i32, _vp]),
     "b200dsp_iqcorr_create": (_i32, [_pvp]),
     "b200dsp_iqcorr_destroy": (_i32, [_vp]),
     "b200dsp_iqcorr_reset": (_i32, [_vp]),

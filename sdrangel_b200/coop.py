@@ -25,6 +25,9 @@ class CoopPlan:
         self.chains = [filter_chain(input_rate, requested_rate, fc) for fc in offsets]      # (out_rate, residual, path)
         min_len = min(len(p) for _, _, p in self.chains)
         self.k = min(int(math.ceil(math.log2(world))) if world > 1 else 0, min_len)
+        if 46 * ((1 << self.k) - 1) > HALO:
+            raise ValueError("CoopPlan: %d cooperative levels need %d samples of history per slice, the halo is %d (world > 32 is not supported)"
+                             % (self.k, 46 * ((1 << self.k) - 1), HALO))
         self.nodes = sorted({p[:self.k] for _, _, p in self.chains})                         # depth-k nodes (path prefixes)
         self.ranges = [shard_channels(len(offsets), world, r) for r in range(world)]
         self.rank_nodes = [sorted({self.chains[i][2][:self.k] for i in range(lo, hi)}) for lo, hi in self.ranges]

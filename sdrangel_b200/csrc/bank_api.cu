@@ -179,8 +179,6 @@ struct b200dsp_bank {
     std::vector<uint32_t*> d_level;  std::vector<long long> stride;   // per depth >= 1
     std::vector<uint32_t*> d_tail[2];            // per depth (parents), ping-pong
     std::vector<int*> d_fam;
-    std::vector<std::vector<int>> pfams; std::vector<int*> d_pfam;   // pair-kernel families per odd depth d (levels d, d+1)
-    bool fuse;                                   // use the two-level kernel where a call is aligned
     // fused multi-level launches (hb48_fused.cuh): the tree cut into depth ranges [b, b+k]
     struct FusedLaunch { int b, k, T; size_t smem; int n_groups, n_fams; FusedGroup* d_groups; FusedFam* d_fams; int lvl_off[FZ_MAXK]; };
     std::vector<FusedLaunch> flaunch;
@@ -199,8 +197,6 @@ struct b200dsp_bank {
     std::vector<int> fe_index;                   // channel ids with a front-end
     // pooled fetch (b200dsp_bank_fetch_all): [channel][stride] staging + per-channel source table and counts
     void* d_pool; size_t pool_bytes;
-    // SMs left to a concurrent collective (b200dsp_bank_set_reserved_sms): level kernels run in work-queue mode
-    uint32_t rsv[5]; int n_rsv; int* d_queue; int level_occ;
     GatherSrc* d_gsrc; long long* d_gcnt; size_t gcap; int gslot; std::vector<GatherSrc> h_gsrc;
 };
 
@@ -211,8 +207,6 @@ void free_device(b200dsp_bank* b)
     for (auto p : b->d_level) if (p) cudaFree(p);
     for (int k = 0; k < 2; ++k) { for (auto p : b->d_tail[k]) if (p) cudaFree(p); b->d_tail[k].clear(); }
     for (auto p : b->d_fam) if (p) cudaFree(p);
-    for (auto p : b->d_pfam) if (p) cudaFree(p);
-    b->d_pfam.clear();
     for (auto& fl : b->flaunch) { if (fl.d_groups) cudaFree(fl.d_groups); if (fl.d_fams) cudaFree(fl.d_fams); }
     b->flaunch.clear();
     b->d_level.clear(); b->d_fam.clear(); b->stride.clear();
@@ -222,8 +216,7 @@ void free_device(b200dsp_bank* b)
     if (b->d_pool) cudaFree(b->d_pool);
     if (b->d_gsrc) cudaFree(b->d_gsrc);
     if (b->d_gcnt) cudaFree(b->d_gcnt);
-    if (b->d_queue) cudaFree(b->d_queue);
-    b->d_pool = nullptr; b->pool_bytes = 0; b->d_gsrc = nullptr; b->d_gcnt = nullptr; b->gcap = 0; b->d_queue = nullptr;
+    b->d_pool = nullptr; b->pool_bytes = 0; b->d_gsrc = nullptr; b->d_gcnt = nullptr; b->gcap = 0;
     for (auto& c : b->chans) {
         if (c.d_out) cudaFree(c.d_out);
         if (c.d_hist) cudaFree(c.d_hist);
@@ -403,33 +396,9 @@ int build(b200dsp_bank* b)
             b->fams[d].push_back(n.index);
             for (int m = 0; m < 3; ++m) b->fams[d].push_back(n.child[m] >= 0 ? b->nodes[n.child[m]].index : -1);
         }
-    // pair-kernel families for levels (d, d+1), d odd: root (depth d-1), its children, which of them are channel leaves,
-    // and the children's children
     std::vector<char> is_leaf(b->nodes.size(), 0);
     for (auto& c : b->chans) is_leaf[c.node] = 1;
-    b->pfams.assign(b->depth + 2, std::vector<int>());
-    for (int d = 1; d + 1 <= b->depth; d += 2)
-        for (int id : b->levels[d - 1]) {
-            const Node& r = b->nodes[id];
-            if (r.child[0] < 0 && r.child[1] < 0 && r.child[2] < 0) continue;
-            int e[16];
-            e[0] = r.index;
-            for (int m = 0; m < 3; ++m) {
-                const int cid = r.child[m];
-                e[1 + m] = cid >= 0 ? b->nodes[cid].index : -1;
-                e[4 + m] = (cid >= 0 && is_leaf[cid]) ? 1 : 0;
-                for (int g = 0; g < 3; ++g) e[7 + 3 * m + g] = (cid >= 0 && b->nodes[cid].child[g] >= 0) ? b->nodes[b->nodes[cid].child[g]].index : -1;
-            }
-            b->pfams[d].insert(b->pfams[d].end(), e, e + 16);
-        }
     int rc;
-    b->d_pfam.assign(b->depth + 2, nullptr);
-    for (int d = 1; d + 1 <= b->depth; d += 2) {
-        const size_t fb = b->pfams[d].size() * sizeof(int);
-        if (!fb) continue;
-        if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_pfam[d], fb))) ||
-            (rc = B200_CUDA_CHECK(cudaMemcpy(b->d_pfam[d], b->pfams[d].data(), fb, cudaMemcpyHostToDevice)))) return rc;
-    }
     b->d_level.assign(b->depth + 1, nullptr); b->stride.assign(b->depth + 1, 0);
     b->d_tail[0].assign(b->depth + 1, nullptr); b->d_tail[1].assign(b->depth + 1, nullptr);
     b->d_fam.assign(b->depth + 1, nullptr);
@@ -576,19 +545,10 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
         if ((rc = B200_CUDA_CHECK(cudaGetLastError())) || (rc = B200_CUDA_CHECK(cudaEventRecord(b->ev_sched, b->side)))) return rc;
     }
     const int tc = b->tcur, tn = tc ^ 1;
-    if (b->n_rsv > 0) {
-        if (!b->d_queue) {
-            if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_queue, 64 * sizeof(int))))) return rc;
-            int occ = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*) hb48_level_queue_kernel, 4 * 32, 4 * HB_STAGE_BYTES) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 4; }
-            b->level_occ = occ;
-        }
-        if ((rc = B200_CUDA_CHECK(cudaMemsetAsync(b->d_queue, 0, 64 * sizeof(int), st)))) return rc;
-    }
     if ((rc = B200_CUDA_CHECK(cudaEventRecord(b->ev_tree0, st)))) return rc;
     b->tree_launches = 0;
     // fused path: the pass starts aligned at every level (no pending sample, even pair index) and is a multiple of 2^depth long
-    bool fused = b->fused_on && !b->flaunch.empty() && D >= 1 && n > 0 && (n % (1ll << D)) == 0 && n < (1ll << 31) && b->n_rsv == 0;
+    bool fused = b->fused_on && !b->flaunch.empty() && D >= 1 && n > 0 && (n % (1ll << D)) == 0 && n < (1ll << 31);
     for (int d = 1; d <= D && fused; ++d) fused = (Pb[d - 1] == 2 * Pb[d]) && !(Pb[d] & 1);
     if (fused) {
         for (const auto& fl : b->flaunch) {
@@ -622,40 +582,6 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
         }
     }
     for (int d = 1; d <= D && !fused; ++d) {
-        // levels (d, d+1) in one launch when the call is aligned at both (no pending samples, whole batch pairs)
-        if (b->fuse && (d & 1) && d + 1 <= D && b->d_pfam[d]) {
-            const long long n_in = 2 * (Pa[d] - Pb[d]);
-            const bool aligned = n_in > 0 && n_in % (2 * HB_IN) == 0 && (Pb[d - 1] == 2 * Pb[d]) && (Pa[d - 1] - Pb[d - 1] == n_in) &&
-                                 !(Pb[d] & 1) && (Pb[d] == 2 * Pb[d + 1]) && !(Pb[d + 1] & 1) && n_in < (1ll << 31);
-            if (aligned) {
-                PairParams q;
-                memset(&q, 0, sizeof(q));
-                q.in_base = (d == 1) ? rootB : b->d_level[d - 1];
-                q.in_stride = (d == 1) ? 0 : b->stride[d - 1];
-                q.mid_base = b->d_level[d]; q.mid_stride = b->stride[d];
-                q.out_base = b->d_level[d + 1]; q.out_stride = b->stride[d + 1];
-                q.root_tail_in = b->d_tail[tc][d - 1]; q.root_tail_out = b->d_tail[tn][d - 1];
-                q.child_tail_in = b->d_tail[tc][d]; q.child_tail_out = b->d_tail[tn][d];
-                q.fam = b->d_pfam[d]; q.n_fam = (int) (b->pfams[d].size() / 16);
-                q.n_in = (int) n_in;
-                q.opq_zero = 0; q.opq_one = 1; q.opq_mone = -1;
-                const long long npairs = n_in / (2 * HB_IN);
-                long long pps = 16;                                   // + 1 warm-up pair per slice: ~6 % recompute
-                const long long target = (long long) b->sm_count * 16;
-                while (pps > 2 && (long long) q.n_fam * ((npairs + pps - 1) / pps) < target) pps >>= 1;
-                q.pps = (int) pps; q.slices = (int) ((npairs + pps - 1) / pps);
-                const long long warps = (long long) q.n_fam * q.slices;
-                const int wpb = 8;      // 8 warps x (4 x 3.5 KB + 64 B) = 113.5 KB per block: two blocks = 16 warps per SM
-                static bool attr_done = false;
-                if (!attr_done) { cudaFuncSetAttribute((const void*) hb48_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wpb * (4 * HB_STAGE_BYTES + 64)); attr_done = true; }
-                hb48_pair_kernel<<<(unsigned) ((warps + wpb - 1) / wpb), wpb * 32, wpb * (4 * HB_STAGE_BYTES + 64), st>>>(q);
-                if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
-                ++b->tree_launches;
-                // parents of level d+2 that exist only as leaves keep no tail; children tails were written by the kernel
-                ++d;
-                continue;
-            }
-        }
         const int n_fam = (int) (b->fams[d].size() / 4);
         if (n_fam == 0) continue;
         LevelParams p;
@@ -689,16 +615,7 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
             const long long warps = (long long) n_fam * slices;
             const int wpb = 4;
             long long blocks = (warps + wpb - 1) / wpb;
-            if (b->n_rsv > 0 && d < 64) {
-                // work-queue mode: one resident wave; blocks landing on reserved SMs exit, the others pull items until none is left
-                p.queue = b->d_queue + d;
-                for (int i = 0; i < 5; ++i) p.rsv[i] = b->rsv[i];
-                // always a full resident wave: a small grid would land exactly on the SMs the scheduler fills first -- the reserved ones
-                blocks = (long long) b->sm_count * b->level_occ;
-                hb48_level_queue_kernel<<<(unsigned) blocks, wpb * 32, wpb * HB_STAGE_BYTES, st>>>(p);
-            } else {
-                hb48_level_kernel<<<(unsigned) blocks, wpb * 32, wpb * HB_STAGE_BYTES, st>>>(p);
-            }
+            hb48_level_kernel<<<(unsigned) blocks, wpb * 32, wpb * HB_STAGE_BYTES, st>>>(p);
             if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
             ++b->tree_launches;
         }
@@ -733,9 +650,10 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
             const long long max_out = (long long) max_new * 4 / 5 + 2;
             const dim3 grid((unsigned) ((max_out + F54_OPB - 1) / F54_OPB), (unsigned) b->h_fe.size());
             if ((rc = B200_CUDA_CHECK(cudaFuncSetAttribute((const void*) frontend54_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F54_SMEM)))) return rc;
-            frontend54_kernel<<<grid, 128, F54_SMEM, st>>>(b->d_fe, b->d_nco, pi);
+            frontend54_kernel<<<grid, F54_THREADS, F54_SMEM, st>>>(b->d_fe, b->d_nco, pi);
         } else {
             const dim3 grid((unsigned) ((max_new + FE_TILE - 1) / FE_TILE), (unsigned) b->h_fe.size());
+            if (smem > 48 * 1024 && (rc = B200_CUDA_CHECK(cudaFuncSetAttribute((const void*) frontend_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)))) return rc;
             frontend_kernel_t<false><<<grid, FE_THREADS, smem, st>>>(b->d_fe, b->d_nco, pi);
         }
         if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
@@ -822,9 +740,6 @@ int b200dsp_bank_create(b200dsp_bank_t** out, int input_rate_hz)
     b->sm_count = b200_sm_count_of(b->device);
     b->input_rate = input_rate_hz;
     b->built = false; b->depth = 0; b->chunk = 3ll << 22; b->tables_dirty = true;
-    // two-level fused kernel: measured on B200 (r01) it halves the tree's HBM traffic but runs 16 % slower than two one-level
-    // launches (the kernels are issue-bound), so it is off unless B200DSP_FUSE is set
-    b->fuse = (getenv("B200DSP_FUSE") != nullptr);
     b->fused_on = (getenv("B200DSP_NO_FUSED_TREE") == nullptr);
     b->d_root = nullptr; b->root_cap = 0;
     b->d_leaf = nullptr; b->d_fe = nullptr; b->d_nco = nullptr; b->tcur = 0;
@@ -869,7 +784,10 @@ int b200dsp_bank_set_chunk(b200dsp_bank_t* b, int64_t samples)
     if (!b || samples < 768 || samples > (1ll << 30)) return b200_fail(B200DSP_EINVAL, "bank_set_chunk: chunk must be within [768, 2^30] samples (kernels index a pass with 32-bit integers)");
     cudaSetDevice(b->device);
     cudaStreamSynchronize(b->stream);
-    b->chunk = (samples + 767) / 768 * 768;
+    const long long chunk = (samples + 767) / 768 * 768;
+    for (const auto& c : b->chans)
+        if (c.fe && !c.lattice && (chunk >> c.S) >= (1ll << 24)) return b200_fail(B200DSP_EINVAL, "bank_set_chunk: a channel's replayed schedule indexes a pass with 24 bits; chunk too large for it");
+    b->chunk = chunk;
     free_device(b);
     return 0;
 }
@@ -940,22 +858,6 @@ int b200dsp_bank_reset(b200dsp_bank_t* b, void* cuda_stream)
     return 0;
 }
 
-// Leave the listed SMs to a concurrent kernel (the NCCL broadcast of the next baseband block): the tree-level kernels,
-// which are most of a feed, then run as one resident wave of work-queue warps that never occupies those SMs.
-int b200dsp_bank_set_reserved_sms(b200dsp_bank_t* b, const int* smids, int n)
-{
-    if (!b || n < 0 || (n > 0 && !smids)) return b200_fail(B200DSP_EINVAL, "bank_set_reserved_sms: bad argument");
-    if (n >= b->sm_count) return b200_fail(B200DSP_EINVAL, "bank_set_reserved_sms: cannot reserve every SM");
-    uint32_t m[5] = { 0, 0, 0, 0, 0 };
-    for (int i = 0; i < n; ++i) {
-        if (smids[i] < 0 || smids[i] >= 160) return b200_fail(B200DSP_EINVAL, "bank_set_reserved_sms: SM id out of range");
-        m[smids[i] >> 5] |= 1u << (smids[i] & 31);
-    }
-    for (int i = 0; i < 5; ++i) b->rsv[i] = m[i];
-    b->n_rsv = n;
-    return 0;
-}
-
 // Device time of the tree-level launches (hb48_level_kernel, one per level) of the last internal pass, between two events on
 // the feed's stream: bench.py's per-launch roofline of the dominant kernel.  Waits for that pass to finish.
 int b200dsp_bank_tree_time(b200dsp_bank_t* b, float* ms, int* launches)
@@ -989,14 +891,24 @@ int b200dsp_bank_set_frontend(b200dsp_bank_t* b, int chan_id, float nco_freq_hz,
     if (!b || chan_id < 0 || chan_id >= (int) b->chans.size()) return b200_fail(B200DSP_EINVAL, "bank_set_frontend: bad channel");
     if (phase_steps < 1 || phase_steps > 255 || out_rate_hz <= 0 || taps_per_phase <= 0) return b200_fail(B200DSP_EINVAL, "bank_set_frontend: bad parameters");
     Channel& c = b->chans[chan_id];
+    // computed aside and committed only once everything is validated: a failed call leaves the channel as it was
     int np = 0;
-    interp_taps(phase_steps, (double) c.out_rate, cutoff_hz, taps_per_phase, c.taps, &np);
+    std::vector<float> taps;
+    interp_taps(phase_steps, (double) c.out_rate, cutoff_hz, taps_per_phase, taps, &np);
     if (np > FE_MAX_TAPS) return b200_fail(B200DSP_EINVAL, "bank_set_frontend: %d taps per phase exceed the supported %d", np, FE_MAX_TAPS);
+    const size_t smem = ((((size_t) ((np + 2 * FE_PAD) | 1) * phase_steps + 3) & ~(size_t) 3)) * sizeof(float) + (size_t) (FE_MAX_TAPS + FE_TILE + FE_Z_EXTRA) * sizeof(float2);
+    if (smem > 200 * 1024) return b200_fail(B200DSP_EINVAL, "bank_set_frontend: %d phases x %d taps need %zu bytes of shared memory (limit 200 KiB)", phase_steps, np, smem);
+    const float ratio = (float) c.out_rate / (float) out_rate_hz;                  // nfmdemod.cpp:469-470
+    long long A = 0; int phshift = 0;
+    const int lattice = lattice_params(ratio, phase_steps, &A, &phshift) ? 1 : 0;
+    // the replayed schedule packs the input index of an output into 24 bits (frontend.cuh): a pass must stay below 2^24 channel samples
+    if (!lattice && (b->chunk >> c.S) >= (1ll << 24))
+        return b200_fail(B200DSP_EINVAL, "bank_set_frontend: a pass of %lld samples at this channel's rate exceeds 2^24; lower the chunk (b200dsp_bank_set_chunk)", (long long) (b->chunk >> c.S));
+    c.taps.swap(taps);
     c.fe = true; c.nco_freq = nco_freq_hz; c.phase_steps = phase_steps; c.cutoff = cutoff_hz; c.taps_per_phase = taps_per_phase; c.fe_out_rate = out_rate_hz;
     c.ntaps = np;
     c.inc = (int) ((nco_freq_hz * 4096) / (float) c.out_rate);                 // NCO::setFreq: float arithmetic, truncation (nco.cpp:50)
-    c.ratio = (float) c.out_rate / (float) out_rate_hz;                        // nfmdemod.cpp:469-470
-    c.lattice = lattice_params(c.ratio, phase_steps, &c.A, &c.phshift) ? 1 : 0;
+    c.ratio = ratio; c.lattice = lattice; c.A = A; c.phshift = phshift;
     if (b->built) { cudaSetDevice(b->device); cudaStreamSynchronize(b->stream); free_device(b); }
     return 0;
 }

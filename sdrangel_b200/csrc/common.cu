@@ -53,40 +53,7 @@ int b200_sm_count_of(int device)
 
 using namespace b200dsp;
 
-namespace {
-// each block notes the SM it runs on and lingers a few microseconds so the blocks of the probe are co-resident
-__global__ void sm_probe_kernel(int* smids)
-{
-    extern __shared__ unsigned char probe_smem[];
-    unsigned smid;
-    asm("mov.u32 %0, %%smid;" : "=r"(smid));
-    if (threadIdx.x == 0) { probe_smem[0] = 1; smids[blockIdx.x] = (int) smid; }
-    const long long t0 = clock64();
-    while (clock64() - t0 < 40000) { }
-}
-} // namespace
-
 extern "C" {
-
-// Which SMs does the block scheduler hand to the first `n_blocks` big blocks of a kernel launched on an idle GPU?  (A
-// collective's CTAs launched into a gap land there; b200dsp_bank_set_reserved_sms keeps the bank's kernels off them.)
-int b200dsp_probe_sm_order(int n_blocks, int threads_per_block, int* smids)
-{
-    int rc = b200_require_device();
-    if (rc) return rc;
-    if (n_blocks < 1 || n_blocks > 1024 || threads_per_block < 32 || threads_per_block > 1024 || !smids) return b200_fail(B200DSP_EINVAL, "probe_sm_order: bad argument");
-    if ((rc = B200_CUDA_CHECK(cudaSetDevice(b200_current_device())))) return rc;
-    int* d = nullptr;
-    const size_t smem = 120 * 1024;                       // more than half an SM's shared memory: one block per SM
-    if ((rc = B200_CUDA_CHECK(cudaMalloc(&d, n_blocks * sizeof(int)))) ||
-        (rc = B200_CUDA_CHECK(cudaFuncSetAttribute((const void*) sm_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem))) ||
-        (rc = B200_CUDA_CHECK(cudaDeviceSynchronize()))) { if (d) cudaFree(d); return rc; }
-    sm_probe_kernel<<<n_blocks, threads_per_block, smem>>>(d);
-    if ((rc = B200_CUDA_CHECK(cudaGetLastError())) || (rc = B200_CUDA_CHECK(cudaDeviceSynchronize())) ||
-        (rc = B200_CUDA_CHECK(cudaMemcpy(smids, d, n_blocks * sizeof(int), cudaMemcpyDeviceToHost)))) { cudaFree(d); return rc; }
-    cudaFree(d);
-    return 0;
-}
 
 int b200dsp_device_count(void)
 {

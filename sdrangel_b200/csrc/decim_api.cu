@@ -256,12 +256,13 @@ int make_plan(int in_fmt, int out_fmt, int bits, int log2, int mode, long long l
 }
 
 // best (warps per block, resident warps per SM) for a cascade kernel with L stages
-LaunchGeom pick_geom(cascade_fn fn, int L)
+// (the shared-memory opt-in and the occupancy belong to one device: the cache is keyed by it)
+LaunchGeom pick_geom(int device, cascade_fn fn, int L)
 {
     static std::mutex mu;
-    static std::map<std::pair<const void*, int>, LaunchGeom> cache;
+    static std::map<std::pair<std::pair<int, const void*>, int>, LaunchGeom> cache;
     std::lock_guard<std::mutex> g(mu);
-    auto key = std::make_pair((const void*) fn, L);
+    auto key = std::make_pair(std::make_pair(device, (const void*) fn), L);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
     LaunchGeom best = { 1, 1 };
@@ -281,7 +282,7 @@ LaunchGeom pick_geom(cascade_fn fn, int L)
 int launch_segment(b200dsp_decim* h, cascade_fn fn, const Plan& pl, int base, int L, const void* d_in, void* d_out, long long n0,
                    bool first, bool final, cudaStream_t st)
 {
-    const LaunchGeom g = pick_geom(fn, L);
+    const LaunchGeom g = pick_geom(h->device, fn, L);
     CascadeParams p;
     memset(&p, 0, sizeof(p));
     p.in = d_in; p.out = d_out;

@@ -316,11 +316,13 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel_t(const FrontendCh
 // Outputs listed by the schedule kernel before the closed form takes over (the stream's first output) and the carried
 // state (newest 128 channel samples + NCO phase) are block 0's.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int F54_NOUT = 9;
+constexpr int F54_NOUT = 7;                             // consecutive same-phase outputs per lane (35 inputs apart from the next lane's: odd)
 constexpr int F54_ROUNDS = 4;
-constexpr int F54_G = 32 * F54_ROUNDS;                  // lanes x rounds: groups of 36 outputs per block
-constexpr int F54_OPB = 4 * F54_NOUT * F54_G;           // 4608 outputs per block
-constexpr int F54_IPB = 5 * F54_NOUT * F54_G;           // 5760 inputs
+constexpr int F54_THREADS = 256;                        // warp w: phase residue w & 3, rounds 2 (w >> 2) and 2 (w >> 2) + 1
+constexpr int F54_G = 32 * F54_ROUNDS;                  // lanes x rounds: groups of 4 * F54_NOUT outputs per block
+constexpr int F54_RND = 32 * 4 * F54_NOUT;              // outputs per round
+constexpr int F54_OPB = F54_RND * F54_ROUNDS;           // 3584 outputs per block
+constexpr int F54_IPB = 5 * F54_NOUT * F54_G;           // 4480 inputs
 constexpr int F54_ZN = F54_IPB + 72 + 8;                // mixed samples a block may touch
 constexpr int F54_SROW = 4 * F54_NOUT + 1;              // staging row of one lane group, padded to an odd number of float2
 constexpr int F54_STAGE = 32 * F54_SROW;
@@ -334,14 +336,14 @@ __device__ __forceinline__ float2 fe_mix(uint32_t w, unsigned phase0, int i, int
     return make_float2(x * u - y * v, x * v + y * u);
 }
 
-__global__ void __launch_bounds__(128, 2) frontend54_kernel(const FrontendChan* __restrict__ chans, const float* __restrict__ nco_table, const PassInfo pi)
+__global__ void __launch_bounds__(F54_THREADS, 2) frontend54_kernel(const FrontendChan* __restrict__ chans, const float* __restrict__ nco_table, const PassInfo pi)
 {
     extern __shared__ float2 f54_smem[];
     float2* z = f54_smem;
     float2* stage = f54_smem + F54_ZN;
     float* nco = reinterpret_cast<float*>(f54_smem + F54_ZN + 2 * F54_STAGE);      // the NCO table: the mix gathers two entries per sample
     const FrontendChan c = chans[blockIdx.y];
-    const int tid = threadIdx.x, lane = tid & 31, cc = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, cc = (tid >> 5) & 3, quad = tid >> 7;
     const int m = pi.n_new[c.depth];
     const uint32_t* __restrict__ in = c.in + pi.out_count[c.depth];
     const uint32_t* __restrict__ hin = c.hist + pi.parity * c.hist_stride;
@@ -351,12 +353,12 @@ __global__ void __launch_bounds__(128, 2) frontend54_kernel(const FrontendChan* 
     const int out_base = c.state[3] - c.state[2];
     if (blockIdx.x == 0) {
         uint32_t* hout = c.hist + (pi.parity ^ 1) * c.hist_stride;
-        {
+        if (tid < FE_MAX_TAPS) {
             const int i = m - FE_MAX_TAPS + tid;
             hout[tid] = (i >= 0) ? in[i] : hin[FE_MAX_TAPS + i];
             if (tid == 0) hout[FE_MAX_TAPS] = (phase0 + (unsigned) m * (unsigned) c.inc) & 4095u;
         }
-        for (int o = tid; o < k0; o += 128) {                  // before the closed form: straight from global memory (a handful per stream)
+        for (int o = tid; o < k0; o += F54_THREADS) {          // before the closed form: straight from global memory (a handful per stream)
             const unsigned s = (unsigned) c.sched[o];
             const int idx = (int) (s >> 8);
             const float* row = c.taps + (s & 0xffu) * c.ntaps;
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(128, 2) frontend54_kernel(const FrontendChan* 
     const int kb = blockIdx.x * F54_OPB;
     if (kb >= ncf) return;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(nco)[tid + 128 * q] = __ldg(reinterpret_cast<const float4*>(nco_table) + tid + 128 * q);
+    for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(nco)[tid + F54_THREADS * q] = __ldg(reinterpret_cast<const float4*>(nco_table) + tid + F54_THREADS * q);
     const long long Eb = D0 + (long long) kb * c.A;
     const int zlo = (int) (i0 + (Eb >> 23) - 1) - 71;          // oldest sample any output of this block taps (>= -71: inside the history)
     // samples up to the newest one the block's last output taps (a channel's last block is usually partly empty)
@@ -391,22 +393,25 @@ __global__ void __launch_bounds__(128, 2) frontend54_kernel(const FrontendChan* 
         taprow = reinterpret_cast<const float4*>(c.taps + (int) ((Ec & 0x7fffffll) >> c.phshift) * 72);      // 72 floats per phase: 16-byte aligned rows
     }
     __syncthreads();
-    // mix: all loads of eight samples in flight, no branches (out-of-range indices are clamped, their result zeroed)
-    for (int kk = tid; kk < zn; kk += 128 * 8) {
+    // mix: all loads of eight samples in flight; the common case (every index inside this pass) has no selects
+    const bool inside = (zlo >= 0) && (zlo + zn + 8 * F54_THREADS <= m);
+    for (int kk = tid; kk < zn; kk += F54_THREADS * 8) {
         uint32_t w[8];
         float u[8], v[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            const int i = zlo + kk + 128 * q;
-            const int ii = (i < m) ? i : m - 1;
-            const uint32_t* src = (ii >= 0) ? in + ii : hin + FE_MAX_TAPS + ii;
-            w[q] = __ldg(src);
+            const int i = zlo + kk + F54_THREADS * q;
+            if (inside) w[q] = __ldg(in + i);
+            else {
+                const int ii = (i < m) ? i : m - 1;
+                w[q] = __ldg((ii >= 0) ? in + ii : hin + FE_MAX_TAPS + ii);
+            }
             const int p = (int) ((phase0 + (unsigned) (i + 1) * (unsigned) c.inc) & 4095u);
             u[q] = nco[p]; v[q] = -nco[(p + 1024) & 4095];
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            const int k = kk + 128 * q, i = zlo + k;
+            const int k = kk + F54_THREADS * q, i = zlo + k;
             const float x = (float) (short) (w[q] & 0xffffu), y = (float) ((int) w[q] >> 16);
             if (k < F54_ZN) z[k] = (i < m) ? make_float2(x * u[q] - y * v[q], x * v[q] + y * u[q]) : make_float2(0.0f, 0.0f);
         }
@@ -416,9 +421,9 @@ __global__ void __launch_bounds__(128, 2) frontend54_kernel(const FrontendChan* 
     for (int k = 0; k < 18; ++k) { const float4 f = __ldg(taprow + k); t[4 * k] = f.x; t[4 * k + 1] = f.y; t[4 * k + 2] = f.z; t[4 * k + 3] = f.w; }
     __syncthreads();
 #pragma unroll 1
-    for (int round = 0; round < F54_ROUNDS; ++round) {
-        const int kr = kb + 32 * 4 * F54_NOUT * round;
-        if (kr >= ncf) break;                                   // block-uniform
+    for (int step = 0; step < 2; ++step) {
+        if (kb + F54_RND * step >= ncf && kb + F54_RND * (2 + step) >= ncf) break;       // block-uniform: neither quad has outputs left
+        const int round = 2 * quad + step;
         const int g = lane + 32 * round;
         float ra[F54_NOUT], ia[F54_NOUT];
 #pragma unroll
@@ -435,15 +440,18 @@ __global__ void __launch_bounds__(128, 2) frontend54_kernel(const FrontendChan* 
                 }
             }
         }
-        float2* st = stage + (round & 1) * F54_STAGE + lane * F54_SROW + cc;
+        float2* st = stage + quad * F54_STAGE + lane * F54_SROW + cc;
 #pragma unroll
         for (int n = 0; n < F54_NOUT; ++n) st[4 * n] = make_float2(ra[n], ia[n]);
         __syncthreads();
-        const float2* sr = stage + (round & 1) * F54_STAGE;
-        for (int o = tid; o < 32 * 4 * F54_NOUT; o += 128) {
-            const int r = o / (4 * F54_NOUT);
-            if (kr + o < ncf) c.out[out_base + k0 + kr + o] = sr[r * F54_SROW + (o - r * 4 * F54_NOUT)];
+        // both quads' rounds go out as contiguous runs
+        for (int o = tid; o < 2 * F54_RND; o += F54_THREADS) {
+            const int qd = (o >= F54_RND) ? 1 : 0, oo = o - qd * F54_RND;
+            const int r = oo / (4 * F54_NOUT);
+            const int ko = kb + F54_RND * (2 * qd + step) + oo;
+            if (ko < ncf) c.out[out_base + k0 + ko] = stage[qd * F54_STAGE + r * F54_SROW + (oo - r * 4 * F54_NOUT)];
         }
+        __syncthreads();
     }
 }
 

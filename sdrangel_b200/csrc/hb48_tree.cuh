@@ -39,11 +39,6 @@ struct LevelParams {
     int flip;          // (C_before / 2) & 1 : parity of the absolute pair index of B[0]
     int slices, bps;   // slices per family, batches per slice
     int opq_zero, opq_one, opq_mone;
-    // work-queue mode (queue != null): resident warps pull (family, slice) items from *queue; blocks that land on an SM
-    // whose bit is set in rsv[] exit at once, leaving those SMs to a concurrent collective (NCCL's ring CTAs need a whole
-    // SM's registers and otherwise only get placed between kernels)
-    int* queue;
-    uint32_t rsv[5];
 };
 
 __device__ __forceinline__ constexpr int hb48_h(int i)
@@ -336,215 +331,4 @@ __global__ void __launch_bounds__(256, 2) hb48_level_kernel(const LevelParams p)
     hb48_level_warp(p, w, reinterpret_cast<int32_t*>(hb48_smem) + (size_t) wib * HB_STAGE_WORDS, lane);
 }
 
-// work-queue form: one resident wave; blocks on reserved SMs exit, the other warps pull items until none is left
-__global__ void __launch_bounds__(256, 2) hb48_level_queue_kernel(const LevelParams p)
-{
-    extern __shared__ __align__(16) unsigned char hb48_smem[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    int32_t* X = reinterpret_cast<int32_t*>(hb48_smem) + (size_t) wib * HB_STAGE_WORDS;
-    const int total = p.n_fam * p.slices;
-    unsigned smid;
-    asm("mov.u32 %0, %%smid;" : "=r"(smid));
-    if (smid < 160u && ((p.rsv[smid >> 5] >> (smid & 31)) & 1u)) return;
-    for (;;) {
-        int w = 0;
-        if (lane == 0) w = atomicAdd(p.queue, 1);
-        w = __shfl_sync(0xffffffffu, w, 0);
-        if (w >= total) break;
-        hb48_level_warp(p, w, X, lane);
-        __syncwarp();
-    }
-}
-
-
-// ---------------------------------------------------------------------------------------------------------
-// Two tree levels per launch ("pair kernel"): a warp owns (root = a node of level d-1 with children, time slice) and
-// produces the root's children (level d) into warp-private shared-memory buffers and, from those, the grandchildren
-// (level d+1) to HBM.  Level d never round-trips HBM (only children that are some channel's leaf are also written out),
-// and the grandchildren stage needs no global loader, no unpack and no -32768 scan of packed words.  Used when the call
-// is aligned at both levels (no pending sample, even output counts, whole batch pairs); anything else takes the
-// one-level kernel above, so arbitrary feed lengths stay exact.
-// Slices other than the first recompute one batch pair of warm-up for the children's history (FIR: exact).
-// ---------------------------------------------------------------------------------------------------------
-struct PairParams {
-    const uint32_t* in_base;  long long in_stride;     // level d-1 buffers (roots)
-    uint32_t*       mid_base; long long mid_stride;    // level d buffers (children): written only for leaf children
-    uint32_t*       out_base; long long out_stride;    // level d+1 buffers (grandchildren)
-    const uint32_t* root_tail_in;  uint32_t* root_tail_out;     // [roots][TAIL_WORDS]   (level d-1 tails)
-    const uint32_t* child_tail_in; uint32_t* child_tail_out;    // [children][TAIL_WORDS] (level d tails)
-    const int*      fam;                               // [n_fam][16]: root, child[3], child_is_leaf[3], grandchild[3][3]
-    int n_fam;
-    int n_in;          // root samples consumed this call: a multiple of 768
-    int slices, pps;   // slices per family, batch pairs per slice
-    int opq_zero, opq_one, opq_mone;
-};
-
-__device__ __forceinline__ void hb48_hist_fill(int32_t* X, const uint32_t* src, int lane, uint32_t& bad)
-{
-    const uint32_t s0 = src[2 * lane], s1 = src[2 * lane + 1];
-    bad = has_m32768(s0) | has_m32768(s1);
-    X[0 * HB_ARR + lane] = sext_lo16((int32_t) s0);
-    X[1 * HB_ARR + lane] = sext_lo16((int32_t) s1);
-    X[2 * HB_ARR + lane] = sext_hi16((int32_t) s0);
-    X[3 * HB_ARR + lane] = sext_hi16((int32_t) s1);
-}
-
-__global__ void __launch_bounds__(256, 2) hb48_pair_kernel(const PairParams p)
-{
-    extern __shared__ __align__(16) unsigned char hb48_smem2[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int w = blockIdx.x * (blockDim.x >> 5) + wib;
-    if (w >= p.n_fam * p.slices) return;
-    const int f = w / p.slices, slice = w - f * p.slices;
-    const int nwarps = blockDim.x >> 5;
-    int32_t* X0 = reinterpret_cast<int32_t*>(hb48_smem2) + (size_t) wib * 4 * HB_STAGE_WORDS;     // root samples
-    int32_t* XC = X0 + HB_STAGE_WORDS;                                                           // 3 child buffers
-    int* fam = reinterpret_cast<int*>(hb48_smem2 + (size_t) nwarps * 4 * HB_STAGE_BYTES) + 16 * wib;   // the family, in shared memory
-    if (lane < 16) fam[lane] = p.fam[16 * f + lane];
-    __syncwarp();
-    const int root = fam[0];
-    const int comp = lane >> 4, j = lane & 15;
-    const IntOpaque opq = { p.opq_zero, p.opq_one, p.opq_mone };
-    const uint32_t* B = p.in_base + (long long) root * p.in_stride;
-    const uint32_t* rtail = p.root_tail_in + (long long) root * TAIL_WORDS;
-    const int npairs = p.n_in / (2 * HB_IN);
-    const int p0 = slice * p.pps;
-    int p1 = p0 + p.pps;
-    if (p1 > npairs) p1 = npairs;
-    const bool last = (slice == p.slices - 1);
-    if (last) {      // root tail carry (aligned: no pending sample)
-        uint32_t* tout = p.root_tail_out + (long long) root * TAIL_WORDS;
-        for (int t = lane; t <= 64; t += 32) {
-            const int i = p.n_in - 64 + t;
-            tout[t] = (i < 0) ? rtail[i + 64] : ((t < 64) ? B[i] : 0u);
-        }
-    }
-    if (p0 >= p1) return;
-    const int pw = (slice == 0) ? p0 : p0 - 1;          // first processed pair (one warm-up pair for later slices)
-    const int n_child = p.n_in >> 1, n_grand = p.n_in >> 2;
-    const bool any_rot_child = (fam[2] >= 0) || (fam[3] >= 0);
-
-    // histories
-    uint32_t hb;
-    hb48_hist_fill(X0, (pw == 0) ? rtail : (B + (long long) pw * 2 * HB_IN - 64), lane, hb);
-    bool prev_bad = any_rot_child && __any_sync(0xffffffffu, hb != 0);
-    unsigned cprev_mask = 0;                            // bit c: child c's previous batch held a -32768
-#pragma unroll 1
-    for (int c = 0; c < 3; ++c) {
-        if (fam[1 + c] < 0) continue;
-        int32_t* Xc = XC + c * HB_STAGE_WORDS;
-        if (slice == 0) {
-            uint32_t cb;
-            hb48_hist_fill(Xc, p.child_tail_in + (long long) fam[1 + c] * TAIL_WORDS, lane, cb);
-            if (__any_sync(0xffffffffu, cb != 0)) cprev_mask |= 1u << c;
-        } else {
-#pragma unroll
-            for (int a = 0; a < 4; ++a) Xc[a * HB_ARR + lane] = 0;
-        }
-    }
-
-    int4 pre[3];
-    auto fetch = [&](int q) {
-        const uint32_t* src = B + (long long) q * HB_IN + 4 * lane;
-#pragma unroll
-        for (int t = 0; t < 3; ++t) pre[t] = ldg_nc_v4(src + 128 * t);
-    };
-    fetch(2 * pw);
-#pragma unroll 1
-    for (int pr = pw; pr < p1; ++pr) {
-        const bool emit = (pr >= p0);
-        unsigned cbad_mask = 0;
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-            const int q = 2 * pr + half;
-            uint32_t bad = 0;
-            if (any_rot_child) {
-#pragma unroll
-                for (int t = 0; t < 3; ++t)
-                    bad |= has_m32768((uint32_t) pre[t].x) | has_m32768((uint32_t) pre[t].y) | has_m32768((uint32_t) pre[t].z) | has_m32768((uint32_t) pre[t].w);
-            }
-            CascadeParams dummy;
-            LoaderI16<false>::store(dummy, X0, lane, pre);
-            if (q + 1 < 2 * p1) fetch(q + 1);
-            const bool bad_now = any_rot_child && __any_sync(0xffffffffu, bad != 0);
-            const bool slow = bad_now || prev_bad;
-            prev_bad = bad_now;
-            __syncwarp();
-            {
-                const int4 tl = hb64_tail_load<int32_t>(X0, lane);
-#pragma unroll 1
-                for (int c = 0; c < 3; ++c) {       // children: centre, lower half (+j), upper half (-j); the rotated two share code
-                    const int child = fam[1 + c];
-                    if (child < 0) continue;
-                    int32_t wv[36], cx[16], y[HB_R];
-                    hb48_load_windows2(X0, comp, j, c != 0, wv, cx);
-                    if (c == 0) {
-                        hb48_item<false, false>(wv, cx, 0, opq, y);
-                    } else {
-                        const int sigma = (c == 1) ? 1 : -1;
-                        if (!slow) hb48_item<true, false>(wv, cx, comp ? sigma : -sigma, opq, y);
-                        else       hb48_slow_child(X0, comp, j, sigma, 0, opq, y);
-                    }
-                    uint32_t yb = 0;
-#pragma unroll
-                    for (int r = 0; r < HB_R; ++r) { y[r] = wrap16(y[r]); yb |= (y[r] == -32768) ? 1u : 0u; }
-                    if (__any_sync(0xffffffffu, yb != 0)) cbad_mask |= 1u << c;
-                    hb64_store_next<int32_t>(XC + c * HB_STAGE_WORDS, comp, j, half * (HB_BATCH / 2), y);
-                    if (fam[4 + c] && emit)       // the child is some channel's leaf: it also goes to its level buffer
-                        hb48_store_child(p.mid_base + (long long) child * p.mid_stride, y, comp, j, q * HB_BATCH, 0, n_child);
-                }
-                __syncwarp();
-                hb64_tail_store<int32_t>(X0, lane, tl);
-            }
-            __syncwarp();
-        }
-        // grandchildren: each child buffer now holds a full batch (384 child samples)
-#pragma unroll 1
-        for (int c = 0; c < 3; ++c) {
-            if (fam[1 + c] < 0) continue;
-            const int* gk = fam + 7 + 3 * c;
-            int32_t* Xc = XC + c * HB_STAGE_WORDS;
-            const bool has_g = (gk[0] >= 0) || (gk[1] >= 0) || (gk[2] >= 0);
-            const bool slowc = ((cbad_mask | cprev_mask) >> c) & 1u;
-            if (!has_g) continue;
-            const int4 tl = hb64_tail_load<int32_t>(Xc, lane);
-#pragma unroll 1
-            for (int m = 0; m < 3; ++m) {
-                const int g = gk[m];
-                if (g < 0) continue;
-                int32_t wv[36], cx[16], y[HB_R];
-                hb48_load_windows2(Xc, comp, j, m != 0, wv, cx);
-                if (m == 0) {
-                    hb48_item<false, false>(wv, cx, 0, opq, y);
-                } else {
-                    const int sigma = (m == 1) ? 1 : -1;
-                    if (!slowc) hb48_item<true, false>(wv, cx, comp ? sigma : -sigma, opq, y);
-                    else        hb48_slow_child(Xc, comp, j, sigma, 0, opq, y);
-                }
-                if (emit) hb48_store_child(p.out_base + (long long) g * p.out_stride, y, comp, j, pr * HB_BATCH, 0, n_grand);
-            }
-            __syncwarp();
-            hb64_tail_store<int32_t>(Xc, lane, tl);
-            __syncwarp();
-        }
-        cprev_mask = cbad_mask;
-    }
-    if (last) {      // children's tails for the next call: the 64 newest child samples sit in the history regions
-#pragma unroll 1
-        for (int c = 0; c < 3; ++c) {
-            if (fam[1 + c] < 0) continue;
-            const int32_t* Xc = XC + c * HB_STAGE_WORDS;
-            uint32_t* tout = p.child_tail_out + (long long) fam[1 + c] * TAIL_WORDS;
-            const bool has_g = (fam[7 + 3 * c] >= 0) || (fam[8 + 3 * c] >= 0) || (fam[9 + 3 * c] >= 0);
-            // without grandchildren the buffer was never rotated into the history region: the newest samples are at [192,224)
-            const int off = has_g ? 0 : HB_BATCH;
-            const uint32_t e = ((uint32_t) Xc[0 * HB_ARR + off + lane] & 0xffffu) | ((uint32_t) Xc[2 * HB_ARR + off + lane] << 16);
-            const uint32_t o = ((uint32_t) Xc[1 * HB_ARR + off + lane] & 0xffffu) | ((uint32_t) Xc[3 * HB_ARR + off + lane] << 16);
-            tout[2 * lane] = e; tout[2 * lane + 1] = o;
-            if (lane == 0) tout[64] = 0u;
-        }
-    }
-}
-
 } // namespace b200dsp
-

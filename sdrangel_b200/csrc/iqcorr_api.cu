@@ -145,12 +145,9 @@ int launch_dc(b200dsp_iqcorr* h, const uint32_t* d_in, uint32_t* d_out, long lon
     p.in = d_in; p.out = d_out; p.hist_in = h->d_hist[h->cur]; p.hist_out = h->d_hist[h->cur ^ 1]; p.n = n;
     const long long blocks = (n + DC_TILE - 1) / DC_TILE;
     const size_t smem = 2 * DC_WORDS * sizeof(int);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute((const void*) dc_correct_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        cudaFuncSetAttribute((const void*) dc_correct_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        attr_done = true;
-    }
+    // per launch: the attribute belongs to the current device and the call is cheap
+    cudaFuncSetAttribute((const void*) dc_correct_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    cudaFuncSetAttribute((const void*) dc_correct_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (((uintptr_t) d_in & 15) == 0) dc_correct_kernel<true><<<(unsigned) blocks, DC_THREADS, smem, st>>>(p);
     else                              dc_correct_kernel<false><<<(unsigned) blocks, DC_THREADS, smem, st>>>(p);
     int rc = B200_CUDA_CHECK(cudaGetLastError());

@@ -37,7 +37,8 @@ struct SpecParams {
     const float2*   tw;        // [SPEC_MAX_N] exp(-2 pi i t / SPEC_MAX_N)
     float*          out;       // [frames_out][n]
     float*          power;     // moving mode: [hist + frames][n] raw |X|^2 of every frame (hist = avg_nb - 1 carried frames first)
-    double*         fix_sum;   // fixed mode: carried partial sums [n] (in/out)
+    const double*   fix_sum;   // fixed mode: carried partial sums [n] of the previous feed (read by CTA 0)
+    double*         fix_sum_out;   // ... of this feed (written by CTA save_sums): the other half of a ping-pong pair
     int n, log2n;
     int fill;                  // samples in `partial`
     int frames;                // input frames completed by this feed
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(SPEC_THREADS, 2) spectrum_kernel_4096(const Sp
     if (fixed && !emit) {
         if (g == p.save_sums) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) p.fix_sum[tid + 256 * k] = acc[fixed ? k : 0];
+            for (int k = 0; k < 16; ++k) p.fix_sum_out[tid + 256 * k] = acc[fixed ? k : 0];
         }
         return;
     }
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(SPEC_THREADS) spectrum_kernel(const SpecParams
     if (p.mode == AVG_FIXED && p.avg_nb > 1 && !emit) {
         if (g == p.save_sums) {
 #pragma unroll
-            for (int k = 0; k < BPT; ++k) { const int b = threadIdx.x + k * SPEC_THREADS; if (b < n) p.fix_sum[b] = acc[k]; }
+            for (int k = 0; k < BPT; ++k) { const int b = threadIdx.x + k * SPEC_THREADS; if (b < n) p.fix_sum_out[b] = acc[k]; }
         }
         return;
     }
@@ -359,8 +360,8 @@ __global__ void __launch_bounds__(SPEC_THREADS) spectrum_kernel(const SpecParams
 __global__ void spectrum_moving_kernel(const SpecParams p)
 {
     const int n = p.n, half = n >> 1;
-    const long long f = blockIdx.y;
-    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x) {
+    const long long f = blockIdx.x;                       // frames on grid.x: a feed may hold more than 65535 of them
+    for (int b = blockIdx.y * blockDim.x + threadIdx.x; b < n; b += gridDim.y * blockDim.x) {
         double s = 0.0;
         for (int k = 0; k < p.avg_nb; ++k) s += (double) p.power[(f + k) * n + b];
         const float res = spec_value(p, (float) (s / (double) p.avg_nb));
@@ -401,7 +402,7 @@ struct b200dsp_spectrum {
     bool configured;
     float* d_window; float2* d_tw;
     uint32_t* d_partial[2]; int pcur; int fill;         // carried partial frame (ping-pong)
-    double* d_fix_sum; int fix_idx;
+    double* d_fix_sum; int fix_idx; int fix_cur;     // d_fix_sum: two halves of SPEC_MAX_N doubles, fix_cur = the one last written
     float* d_power; long long power_cap;                // moving mode history + frames
     float* d_tmp; long long tmp_cap;
     uint32_t* d_in; long long in_cap; float* d_out; long long out_cap;   // host-path staging
@@ -430,7 +431,7 @@ int spectrum_feed_impl(b200dsp_spectrum* s, const uint32_t* d_in, long long n_sa
     SpecParams p;
     memset(&p, 0, sizeof(p));
     p.in = d_in; p.partial = s->d_partial[s->pcur]; p.window = s->d_window; p.tw = s->d_tw; p.out = d_out;
-    p.fix_sum = s->d_fix_sum; p.n = n; p.log2n = s->log2n; p.fill = s->fill; p.frames = (int) frames;
+    p.fix_sum = s->d_fix_sum + (size_t) s->fix_cur * SPEC_MAX_N; p.fix_sum_out = s->d_fix_sum + (size_t) (s->fix_cur ^ 1) * SPEC_MAX_N; p.n = n; p.log2n = s->log2n; p.fill = s->fill; p.frames = (int) frames;
     p.mode = s->mode; p.avg_nb = s->avg_nb; p.linear = s->linear; p.positive_only = positive_only; p.fix_idx = s->fix_idx;
     p.frames_out = (int) frames_out; p.save_sums = -1;
     p.scalef = s->scalef; p.ofs = 20.0f * log10f(1.0f / (float) n); p.div = (float) (n * n); p.mult = 10.0f / log2f(10.0f);
@@ -439,7 +440,7 @@ int spectrum_feed_impl(b200dsp_spectrum* s, const uint32_t* d_in, long long n_sa
         long long ctas = frames;
         if (fixed) {
             ctas = (s->fix_idx + frames + s->avg_nb - 1) / s->avg_nb;          // groups touched, the last may be incomplete
-            if ((s->fix_idx + frames) % s->avg_nb) p.save_sums = (int) (ctas - 1);
+            if ((s->fix_idx + frames) % s->avg_nb) { p.save_sums = (int) (ctas - 1); s->fix_cur ^= 1; }
         }
         if (moving) {
             const long long need = (frames + s->avg_nb - 1) * n;
@@ -468,7 +469,7 @@ int spectrum_feed_impl(b200dsp_spectrum* s, const uint32_t* d_in, long long n_sa
         else           spectrum_kernel<<<(unsigned) ctas, threads, (size_t) n * sizeof(float2), st>>>(p);
         if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
         if (moving) {
-            spectrum_moving_kernel<<<dim3((n + 255) / 256, (unsigned) frames), 256, 0, st>>>(p);
+            spectrum_moving_kernel<<<dim3((unsigned) frames, (n + 255) / 256), 256, 0, st>>>(p);
             if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
             // carry the last avg_nb-1 power frames to the front for the next feed (through a bounce buffer: the ranges may overlap)
             const size_t hb = (size_t) (s->avg_nb - 1) * n * 4;
@@ -520,7 +521,7 @@ int b200dsp_spectrum_create(b200dsp_spectrum_t** out, float scalef)
         (rc = B200_CUDA_CHECK(cudaMemcpy(s->d_tw, tw.data(), SPEC_MAX_N * sizeof(float2), cudaMemcpyHostToDevice))) ||
         (rc = B200_CUDA_CHECK(cudaMalloc(&s->d_window, SPEC_MAX_N * sizeof(float)))) ||
         (rc = B200_CUDA_CHECK(cudaMalloc(&s->d_partial[0], SPEC_MAX_N * 4))) || (rc = B200_CUDA_CHECK(cudaMalloc(&s->d_partial[1], SPEC_MAX_N * 4))) ||
-        (rc = B200_CUDA_CHECK(cudaMalloc(&s->d_fix_sum, SPEC_MAX_N * sizeof(double))))) { b200dsp_spectrum_destroy(s); return rc; }
+        (rc = B200_CUDA_CHECK(cudaMalloc(&s->d_fix_sum, 2 * SPEC_MAX_N * sizeof(double))))) { b200dsp_spectrum_destroy(s); return rc; }
     *out = s;
     // same defaults as the reference constructor (spectrumvis.cpp:20-34): 1024 points, Blackman-Harris, no averaging
     return b200dsp_spectrum_configure(s, 1024, 0, 0, AVG_NONE, 1, 0);
@@ -562,8 +563,8 @@ int b200dsp_spectrum_configure(b200dsp_spectrum_t* s, int fft_size, int overlap_
     make_window(window, fft_size, w);
     if ((rc = B200_CUDA_CHECK(cudaMemcpy(s->d_window, w.data(), (size_t) fft_size * 4, cudaMemcpyHostToDevice)))) return rc;
     // handleConfigure restarts the frame buffer and both averagers (spectrumvis.cpp:317-321)
-    s->fill = 0; s->fix_idx = 0; s->pcur = 0;
-    if ((rc = B200_CUDA_CHECK(cudaMemset(s->d_fix_sum, 0, SPEC_MAX_N * sizeof(double))))) return rc;
+    s->fill = 0; s->fix_idx = 0; s->fix_cur = 0; s->pcur = 0;
+    if ((rc = B200_CUDA_CHECK(cudaMemset(s->d_fix_sum, 0, 2 * SPEC_MAX_N * sizeof(double))))) return rc;
     if (s->d_power) { cudaFree(s->d_power); s->d_power = nullptr; s->power_cap = 0; }
     if ((rc = B200_CUDA_CHECK(cudaDeviceSynchronize()))) return rc;      // the copies above ran on the default stream
     s->configured = true;

@@ -216,11 +216,6 @@ class DownChannelizerBank:
         capi.check(capi.lib().b200dsp_bank_tree_time(self._h, C.byref(ms), C.byref(k)))
         return ms.value, k.value
 
-    def set_reserved_sms(self, smids):
-        """Keep the tree kernels off these SMs (left to a concurrent NCCL broadcast); [] turns it off."""
-        a = np.ascontiguousarray(smids, dtype=np.int32)
-        capi.check(capi.lib().b200dsp_bank_set_reserved_sms(self._h, a.ctypes.data if a.size else None, int(a.size)))
-
     def node_count(self):
         n = capi.lib().b200dsp_bank_node_count(self._h)
         if n < 0:

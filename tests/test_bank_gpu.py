@@ -397,39 +397,6 @@ def test_cooperative_bank_device_path_wrapped_halo(gpu_lib, port, golden_meta):
 
 
 @pytest.mark.gpu
-def test_bank_reserved_sms_work_queue_bit_exact(gpu_lib, port, golden_meta):
-    """K6 support: with SMs reserved for a concurrent collective the tree levels run as a work queue on the other SMs.
-    Same results bit for bit (ragged feeds, 32 channels), and the probe hands back distinct, valid SM ids."""
-    from sdrangel_b200 import DownChannelizerBank, capi
-    order = np.zeros(32, dtype=np.int32)
-    capi.check(capi.lib().b200dsp_probe_sm_order(32, 640, order.ctypes.data))
-    assert len(set(order.tolist())) == 32 and order.min() >= 0 and order.max() < capi.lib().b200dsp_sm_count()
-    plan = golden_meta["chan_plans"]["bank1024"]
-    rows = plan["channels"][7::32]
-    rs = np.random.RandomState(99)
-    x = rs.randint(-32768, 32768, size=(1_500_001, 2)).astype(np.int16)
-    a_bank, b_bank = DownChannelizerBank(plan["input_rate"]), DownChannelizerBank(plan["input_rate"])
-    ids = [(a_bank.add_channel(48000, r[0])[0], b_bank.add_channel(48000, r[0])[0]) for r in rows]
-    b_bank.set_reserved_sms(order[:24])
-    oracle = port.PortDownChannelizer()
-    oracle.configure(plan["input_rate"], 48000, rows[5][0])
-    for lo, hi in ((0, 700_001), (700_001, 700_004), (700_004, 1_500_001)):
-        a_bank.feed(x[lo:hi])
-        b_bank.feed(x[lo:hi])
-        want = oracle.feed(x[lo:hi])
-        for k, (ia, ib) in enumerate(ids):
-            ga, gb = a_bank.fetch(ia), b_bank.fetch(ib)
-            assert ga.shape == gb.shape and np.array_equal(ga, gb), (lo, k)
-            if k == 5:
-                assert np.array_equal(gb, want)
-    b_bank.set_reserved_sms([])
-    with pytest.raises(RuntimeError):
-        b_bank.set_reserved_sms(list(range(148)))            # cannot reserve every SM
-    a_bank.close()
-    b_bank.close()
-
-
-@pytest.mark.gpu
 @pytest.mark.parametrize("plan_name,chunk", [("bank64", 2304), ("bank1024", 768 * 5), ("bank64", 100_000)])
 def test_bank_frontends_many_internal_passes(gpu_lib, port, golden_meta, plan_name, chunk):
     """A feed larger than the bank's chunk runs as several internal passes: the front-end's per-feed output count, its
