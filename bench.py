@@ -513,107 +513,121 @@ def bench_iqcorr(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity
     return res
 
 
+def _bank_parity(c, bank, info, mine, fs, cutoff, d_ptr, m, sptr, stream):
+    """Oracle check (checker only) of THIS rank's bank on the first m samples of the device buffer at d_ptr -- at N > 1 the
+    block this rank actually received: tree outputs bit for bit, front-end within 1e-5 relative RMS, for the first, middle
+    and last of the rank's channels (downchannelizer.cpp:50-91, nfmdemod.cpp:150-155,315)."""
+    torch, capi = c.torch, c.capi
+    _oracle_mod()
+    from oracle import portbind
+    xs = _tensor_from_ptr(c, d_ptr, 2 * m).cpu().numpy().reshape(-1, 2)
+    bank.reset(sptr)
+    bank.feed_dev(d_ptr, m, sptr)
+    stream.synchronize()
+    ok = True
+    for k in sorted({0, len(info) // 2, len(info) - 1}):
+        cid, rate, ofs, path = info[k]
+        o = portbind.PortDownChannelizer()
+        o.configure(fs, 48000, mine[k])
+        ch = o.feed(xs)
+        ok = ok and np.array_equal(bank.fetch(cid), ch)
+        fe = portbind.PortFrontEnd(-ofs, rate, 48000, cutoff).feed(ch)
+        got = bank.fetch(cid, capi.STAGE_FRONTEND)
+        ok = ok and got.shape == fe.shape and float(np.sqrt(np.mean((got - fe) ** 2)) / np.sqrt(np.mean(fe ** 2))) <= 1e-5
+    return bool(ok)
+
+
+def _tensor_from_ptr(c, ptr, n_int16):
+    """A torch int16 view of n_int16 scalars of device memory owned by the library (no copy)."""
+    class _Arr:
+        pass
+    a = _Arr()
+    a.__cuda_array_interface__ = {"shape": (int(n_int16),), "typestr": "<i2", "data": (int(ptr), False), "version": 3}
+    return c.torch.as_tensor(a, device=c.dev)
+
+
 def bench_bank(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=True):
+    """The channel bank (configs 3 and 5).  N = 1: one bank, device-resident baseband.  N > 1: channels sharded by frequency
+    block (b200dsp_dist_shard); every step the library object b200dsp_dist NCCL-broadcasts the block from rank 0's device
+    buffer into a receive slot (the transfer of step k+1 under the kernels of step k) and feeds this rank's bank from it."""
     import sdrangel_b200 as S
     torch, capi, dist = c.torch, c.capi, c.dist
     fs, fcs = wl["plan"]()
     n = args.samples or wl["n"]
-    # shard: contiguous-in-frequency blocks of channels per rank
-    from sdrangel_b200.sharding import shard_channels
-    lo_ch, hi_ch = shard_channels(len(fcs), c.world, c.rank)
-    mine = fcs[lo_ch:hi_ch]
     cutoff = float(np.float32(np.float32(12500) / np.float32(2.2)))
-    bank = S.DownChannelizerBank(fs)
-    bank.set_chunk(n)                     # one pass over the tree per step: launch latencies amortised over the whole batch
-    info = []
-    for fc in mine:
-        cid, rate, ofs, path = bank.add_channel(48000, fc)
-        bank.set_frontend(cid, -ofs, cutoff, 48000)
-        info.append((cid, rate, ofs, path))
+    sb = None
+    if c.world > 1:
+        ids = [S.ShardedBank.unique_id() if c.rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        sb = S.ShardedBank(fs, fcs, 48000, c.rank, c.world, ids[0], frontend=(cutoff, 48000), chunk=n)
+        bank, info, lo_ch, hi_ch = sb.bank, sb.info, sb.lo, sb.hi
+        sb.reserve(n)
+        # transports: the copy-engine chain (IPC slots, no SMs) when the driver allows it, NCCL broadcast otherwise
+        p2p_ok = not os.environ.get("B200_BENCH_NO_P2P")
+        blob = None
+        if p2p_ok:
+            try:
+                blob = sb.p2p_export(n)
+            except Exception:
+                blob = None
+        blobs = [None] * c.world
+        dist.all_gather_object(blobs, blob)
+        p2p_ok = all(b is not None for b in blobs)
+        if p2p_ok:
+            sb.p2p_import(blobs)
+    else:
+        bank = S.DownChannelizerBank(fs)
+        bank.set_chunk(n)                     # one pass over the tree per step: launch latencies amortised over the whole batch
+        info = []
+        for fc in fcs:
+            cid, rate, ofs, path = bank.add_channel(48000, fc)
+            bank.set_frontend(cid, -ofs, cutoff, 48000)
+            info.append((cid, rate, ofs, path))
+        lo_ch, hi_ch = 0, len(fcs)
+    mine = fcs[lo_ch:hi_ch]
     nodes = bank.node_count()
     stage_inputs = sum(2.0 ** -(k - 1) for k in _node_depths([p for _, _, _, p in info]))
     g = torch.Generator(device=c.dev)
     g.manual_seed(1)
-    x = torch.randint(-2048, 2048, (2 * n,), dtype=torch.int16, device=c.dev, generator=g) if c.rank == 0 else \
-        torch.empty((2 * n,), dtype=torch.int16, device=c.dev)
-    # N > 1: double-buffered receive buffers; the NCCL broadcast of step k+1 (on NCCL's own stream) overlaps the kernels of
-    # step k.  NCCL has no int16 type: the broadcast moves raw bytes (one IQ sample per int32).
-    bufs = [x, (x.clone() if c.rank == 0 else torch.empty_like(x))] if c.world > 1 else [x]
-    bviews = [b.view(torch.int32) for b in bufs]
-    pending = {}
+    x = torch.randint(-2048, 2048, (2 * n,), dtype=torch.int16, device=c.dev, generator=g) if c.rank == 0 else None
     stream = torch.cuda.Stream(device=c.dev)
     sptr = stream.cuda_stream
-
-    parity = None
-    if c.rank == 0 and want_parity:       # oracle = checker only: 3 channels, first 2^19 samples
-        _, _ = _oracle_mod()
-        from oracle import portbind
-        m = 1 << 19
-        bank.feed_dev(x.data_ptr(), m, sptr)
-        stream.synchronize()
-        xs = x[: 2 * m].cpu().numpy().reshape(-1, 2)
-        ok = True
-        for k in (0, len(info) // 2, len(info) - 1):
-            cid, rate, ofs, path = info[k]
-            o = portbind.PortDownChannelizer()
-            o.configure(fs, 48000, mine[k])
-            ch = o.feed(xs)
-            ok = ok and np.array_equal(bank.fetch(cid), ch)
-            fe = portbind.PortFrontEnd(-ofs, rate, 48000, cutoff).feed(ch)
-            got = bank.fetch(cid, capi.STAGE_FRONTEND)
-            ok = ok and got.shape == fe.shape and float(np.sqrt(np.mean((got - fe) ** 2)) / np.sqrt(np.mean(fe ** 2))) <= 1e-5
-        parity = bool(ok)
+    torch.cuda.synchronize()
     barrier(c)
-
-    state = {"i": 0, "overlap": True, "group": None}
+    state = {"i": 0, "overlap": True, "begun": set(), "mode": "nccl", "pbegun": 0}
 
     def step():
         i = state["i"]
-        cur = i % len(bufs)
-        if c.world > 1 and not os.environ.get("B200_BENCH_NO_BCAST"):      # (developer switch: isolate the compute time)
+        if sb is None:
+            bank.feed_dev(x.data_ptr(), n, sptr)
+        elif state["mode"] == "p2p":
+            # blocks i+1 and i+2 are already on their way down the chain while block i is computed (three slots)
+            xp = x.data_ptr() if c.rank == 0 else 0
+            while state["pbegun"] <= i + 2:
+                sb.p2p_begin(state["pbegun"] % 3, xp, n, None)
+                state["pbegun"] += 1
+            sb.p2p_feed(i % 3, sptr)
+        else:
+            cur = i & 1
+            xp = x.data_ptr() if c.rank == 0 else 0
+            if cur not in state["begun"]:
+                sb.bcast_begin(cur, xp, n, 0, None)
+                state["begun"].add(cur)
             if state["overlap"]:
-                if cur not in pending:
-                    pending[cur] = dist.broadcast(bviews[cur], src=0, async_op=True, group=state["group"])
-                pending.pop(cur).wait()            # stream-level wait: the compute stream waits for this step's baseband
-                nxt = (i + 1) % len(bufs)
-                # the next step's baseband starts moving now; its buffer was last read by step i-1, already ordered on `stream`
-                pending[nxt] = dist.broadcast(bviews[nxt], src=0, async_op=True, group=state["group"])
-            else:
-                for w in list(pending.values()):
-                    w.wait()
-                pending.clear()
-                dist.broadcast(bviews[cur], src=0, group=state["group"])     # in stream order: broadcast, then the kernels
-        bank.feed_dev(bufs[cur].data_ptr(), n, sptr)
+                # the next step's block starts moving now (collective stream), under this step's kernels; its slot was last
+                # read by step i-1, which the begin waits for
+                sb.bcast_begin(cur ^ 1, xp, n, 0, None)
+                state["begun"].add(cur ^ 1)
+            sb.feed(cur, sptr)
+            state["begun"].discard(cur)
         state["i"] = i + 1
 
-    bcast_mode = None
-    reserved = 0
-    if c.world > 1 and not os.environ.get("B200_BENCH_NO_BCAST"):
-        # The NCCL broadcast of step k+1 can run under step k's kernels, but its ring CTAs need (nearly) a whole SM's registers
-        # each: while a tree kernel has blocks queued they are only placed in the gaps between kernels, and every late CTA
-        # stalls the ring on all ranks.  Reserving R SMs (the ones the block scheduler fills first: b200dsp_probe_sm_order) for
-        # the collective lets it start at once; the tree kernels then run as a work queue on the other SMs.  Which of
-        # {in stream order, overlapped, overlapped + R reserved} wins depends on the rank count: try each for a few steps
-        # and keep the fastest (all ranks agree through a MAX all-reduce of the trial times).
-        order = np.zeros(48, dtype=np.int32)
-        capi.check(capi.lib().b200dsp_probe_sm_order(48, 640, order.ctypes.data))
-        # NCCL communicators with fewer CTAs (ncclConfig maxCTAs): fewer SMs to give up, at some cost in ring bandwidth
-        groups = {0: None}
-        for ctas in (16,):
-            o = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
-            o.config.max_ctas = ctas
-            groups[ctas] = dist.new_group(ranks=list(range(c.world)), backend="nccl", pg_options=o)
-        cands = [(False, 0, 0), (True, 0, 0), (True, 0, 16), (True, 0, 32), (True, 16, 0), (True, 16, 16)]
-        if os.environ.get("B200_BENCH_BCAST_MODE"):            # developer switch: "overlap,ctas,reserved"
-            o_, g_, r_ = os.environ["B200_BENCH_BCAST_MODE"].split(",")
-            cands = [(o_ == "1", int(g_), int(r_))]
+    bcast_mode, bcast_trials = None, None
+    if sb is not None:
+        # overlapped or in stream order: whichever is faster at this N (all ranks agree through a MAX all-reduce)
         trial = {}
-        for mode, g, r in cands:
-            for w in list(pending.values()):
-                w.wait()
-            pending.clear()
-            state["overlap"], state["group"] = mode, groups[g]
-            bank.set_reserved_sms(order[:r])
+        for mode in (False, True):
+            state["overlap"] = mode
             with torch.cuda.stream(stream):
                 for _ in range(3):
                     step()
@@ -624,146 +638,194 @@ def bench_bank(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=T
                     step()
                 e1.record(stream)
                 barrier(c)
-                trial[(mode, g, r)] = max_over_ranks(c, e0.elapsed_time(e1) / 8)
-        best = min(trial, key=lambda k: trial[k])
-        for w in list(pending.values()):
-            w.wait()
-        pending.clear()
-        state["overlap"], reserved = best[0], best[2]
-        state["group"] = groups[best[1]]
-        bank.set_reserved_sms(order[:reserved])
-        bcast_mode = "in stream order before the step's kernels"
-        if state["overlap"]:
-            bcast_mode = "overlapped with the previous step's kernels" + (", NCCL limited to %d CTAs" % best[1] if best[1] else "") + \
-                         (", %d SMs reserved for the collective" % reserved if reserved else "")
-        bcast_trials = {("%s/ctas%s/rsv%d" % ("overlap" if m else "serial", g or "dflt", r)): round(t, 4) for (m, g, r), t in trial.items()}
-        if reserved:
-            # the work-queue form of the tree kernels must give the very same samples: same feed from a reset state, both ways
-            outs = []
-            for r in (0, reserved):
-                bank.set_reserved_sms(order[:r])
-                bank.reset(sptr)
-                bank.feed_dev(bufs[0].data_ptr(), min(n, 3 << 20), sptr)
-                stream.synchronize()
-                outs.append((bank.fetch(info[0][0]), bank.fetch(info[-1][0], capi.STAGE_FRONTEND)))
-            same = all(np.array_equal(a, b) for a, b in zip(outs[0], outs[1]))
-            if parity is not None or c.rank != 0:
-                parity = bool(same) if parity is None else bool(parity and same)
-            ok_all = max_over_ranks(c, 0.0 if same else 1.0)
-            if c.rank == 0:
-                parity = bool(parity and ok_all == 0.0)
+                trial[mode] = max_over_ranks(c, e0.elapsed_time(e1) / 8)
+        state["overlap"] = trial[True] <= trial[False]
+        bcast_mode = "NCCL broadcast per step, " + ("overlapped with the previous step's kernels" if state["overlap"] else "in stream order before the step's kernels")
+        bcast_trials = {"nccl_serial": round(trial[False], 4), "nccl_overlap": round(trial[True], 4)}
+        if p2p_ok:
+            state["mode"] = "p2p"
+            state["i"] = 0
+            with torch.cuda.stream(stream):
+                for _ in range(3):
+                    step()
+                barrier(c)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(8):
+                    step()
+                e1.record(stream)
+                barrier(c)
+                t_p2p = max_over_ranks(c, e0.elapsed_time(e1) / 8)
+            bcast_trials["p2p_chain"] = round(t_p2p, 4)
+            if t_p2p <= min(trial.values()):
+                bcast_mode = "copy-engine chain rank 0 -> ... -> N-1 (b200dsp_dist_p2p_*: IPC slots, stream-ordered counters), two blocks ahead of the kernels"
+            else:
+                state["mode"] = "nccl"
 
     total_ms, kern_ms, clocks = timed_steps(c, stream, step, steps, warmup)
     value = n * steps / (total_ms * 1e-3) / 1e6
-    step_ms = float(np.mean(kern_ms))
-    tree_ms, tree_launches = bank.tree_time()         # the level launches of the last timed step, between events on its stream
-    out_bytes = sum(48000.0 / fs * 8 for _ in mine)
-    instr_per_sample = _tree_instr_per_sample([p for _, _, _, p in info]) + len(mine) * 48000.0 / fs * 160
-    f_clk = (clocks.get("sm_mhz") or 1965) * 1e6
-    issue_roof = c.sm_count * 128 * f_clk / instr_per_sample / 1e6
-    passes = 1                            # bank.set_chunk(n): one pass per step
-    depth = max(len(p) for _, _, _, p in info)
-    # Dominant kernel = hb48_level_kernel, one launch per tree level.  Algorithmic bytes of a launch = the packed int16 IQ
-    # streams it must read (its distinct parents) and write (its nodes): 4 B x samples each, summed over the levels and divided
-    # by the number of launches; duration = the measured tree time / launches.
+    step_ms = total_ms / steps
+    tree_ms, tree_launches = bank.tree_time()         # the tree launches of the last timed step, between events on its stream
+
+    parity = None
+    if want_parity:
+        # every rank checks ITS channels on the block IT holds (N > 1: the slot the last broadcast landed in), and that this
+        # block is rank 0's, byte for byte (a checksum all-reduced as min and max)
+        m = min(n, 1 << 19)
+        if sb is None:
+            dptr = x.data_ptr()
+        else:
+            sb.sync()
+            stream.synchronize()
+            dptr = sb.p2p_slot((state["i"] - 1) % 3)[0] if state["mode"] == "p2p" else sb.slot((state["i"] - 1) & 1)[0]
+        ok = _bank_parity(c, bank, info, mine, fs, cutoff, dptr, m, sptr, stream)
+        if sb is not None:
+            cs = _tensor_from_ptr(c, dptr, 2 * n).to(torch.int64).sum().to(torch.float64)
+            lo_, hi_ = cs.clone(), cs.clone()
+            dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+            ok = ok and float(lo_.item()) == float(hi_.item())
+            ok = max_over_ranks(c, 0.0 if ok else 1.0) == 0.0
+        parity = bool(ok)
+
     paths = [p for _, _, _, p in info]
-    lvl_bytes = 0.0
-    for d in range(1, depth + 1):
-        nodes_d = {p[:d] for p in paths if len(p) >= d}
-        parents_d = {p[:d - 1] for p in nodes_d}
-        lvl_bytes += 4.0 * n * (len(parents_d) / 2.0 ** (d - 1) + len(nodes_d) / 2.0 ** d)
-    launch_ms = tree_ms / max(tree_launches, 1)
-    achieved = lvl_bytes / max(tree_launches, 1) / (launch_ms * 1e-3) / 1e9
-    step_alg_bytes = n * (4 + out_bytes)
+    out_bytes = sum(48000.0 / fs * 8 for _ in fcs)                  # whole job: every channel's 48 kS/s complex64 output
+    tree_instr = _tree_instr_per_sample(paths)
+    fe_instr = len(mine) * (48000.0 / fs * 144 + (fs / 2.0 ** len(paths[0]) if paths else 0) / fs * 12)
+    instr_per_sample = tree_instr + fe_instr
+    f_clk = (clocks.get("sm_mhz") or 1965) * 1e6
+    issue_peak = c.sm_count * 128 * f_clk                            # thread-instructions per second per GPU
+    issue_roof = issue_peak / instr_per_sample / 1e6                 # input MS/s per GPU for this rank's share of the work
+    rank_rate = n / (step_ms * 1e-3) / 1e6
+    alg_bytes = 4 + out_bytes                                        # 7.2 B per input sample at 1024 channels
     traffic = measured_traffic(wl_name, n) if c.world == 1 else None
-    res = {"value": value, "ms_per_step": total_ms / steps, "clocks": clocks, "parity": parity,
-           "launches": steps * passes * (depth + 3),
+    roofline = {
+        "bound": "issue", "kernel": "hb48_fused_kernel (%d launches per step) + frontend54_kernel" % tree_launches,
+        "achieved": rank_rate * instr_per_sample / 1e3, "peak": issue_peak / 1e9, "unit": "G thread-instr/s", "frac": rank_rate / issue_roof,
+        "instr_per_sample": instr_per_sample,
+        "note": "binding roof (SURVEY.md 8d): algorithmic instructions of this rank's step -- per parent sample 27 per child of the shared-prefix tree, "
+                "31 for a lower/upper pair (one shared tap sum); 144 FFMA per front-end output + 12 per mixed channel sample -- over 128 lanes x SMs x "
+                "sampled clock",
+        "tree_share_of_step": tree_ms / step_ms, "tree_ms": tree_ms,
+        "traffic": traffic,
+        "traffic_note": "dram__bytes_read+write of every kernel of one step (ncu, profiles/r02_traffic.json), scaled to this step's samples",
+        "hbm": {"algorithmic_bytes_per_sample": alg_bytes, "achieved": alg_bytes * n / (step_ms * 1e-3) / 1e9, "peak": c.hbm_peak, "unit": "GB/s",
+                "frac": alg_bytes * n / (step_ms * 1e-3) / 1e9 / c.hbm_peak, "peak_source": c.peak_src,
+                "traffic_over_algorithmic": (traffic / (alg_bytes * n)) if traffic else None},
+        "issue": {"instr_per_sample": instr_per_sample, "roof_MSps_at_sampled_clk": issue_roof, "frac": rank_rate / issue_roof},
+    }
+    if c.world > 1:
+        roofline["nvlink"] = {"bytes_per_sample_per_gpu": 4, "peak_GBps": 770.0, "roof_MSps": 770e9 / 4 / 1e6, "frac": value / (770e9 / 4 / 1e6),
+                              "note": "every GPU ingests the whole baseband: 4 B per input sample against the measured 770 GB/s peer bandwidth (B200_PROFILING.md)"}
+    res = {"value": value, "ms_per_step": step_ms, "clocks": clocks, "parity": parity,
+           "launches": steps * (tree_launches + 2),
            "config": {"workload": wl_name, "desc": wl["desc"], "samples_per_step": n, "input_rate": fs, "channels": len(fcs),
                       "channels_this_rank": len(mine), "tree_nodes_this_rank": nodes, "stage_inputs_per_sample_this_rank": stage_inputs,
-                      "l2": "input %.0f MiB per step > 126 MB L2, streamed from HBM every step; tree levels are HBM-resident int16 arrays" % (n * 4 / 2 ** 20),
-                      "parallelism": "channels sharded x%d (contiguous frequency blocks), baseband %s" % (c.world, ("NCCL broadcast per step, " + str(bcast_mode)) if c.world > 1 else "local"),
-                      "broadcast_trials_ms_per_step": bcast_trials if bcast_mode else None},
-           "roofline": {"bound": "hbm", "achieved": achieved, "peak": c.hbm_peak, "unit": "GB/s", "frac": achieved / c.hbm_peak,
-                        "traffic": traffic, "traffic_note": "ncu dram bytes of one hb48_level_kernel launch (profiles/r01_traffic.json), like `achieved` per launch",
-                        "peak_source": c.peak_src, "kernel": "hb48_level_kernel (one launch per tree level: %d per step)" % tree_launches,
-                        "kernel_ms": launch_ms, "launches_per_step": tree_launches, "algorithmic_bytes_per_launch": lvl_bytes / max(tree_launches, 1),
-                        "share_of_step": tree_ms / step_ms,
-                        "step": {"ms": step_ms, "algorithmic_bytes_per_sample": 4 + out_bytes, "achieved_GBps": step_alg_bytes / (step_ms * 1e-3) / 1e9,
-                                 "note": "whole step against its external bytes only (baseband in, 48 kS/s complex64 channels out): the tree's level arrays are "
-                                         "this design's own HBM traffic, not algorithmic minimum"},
-                        "issue": {"instr_per_sample": instr_per_sample, "roof_MSps_at_sampled_clk": issue_roof,
-                                  "frac": (n / (step_ms * 1e-3) / 1e6) / issue_roof,
-                                  "note": "binding roof: 27 instructions per child per parent sample over the shared-prefix tree (31 for a lower/upper pair, which shares its tap sum) + ~160 per front-end output"}},
-           "dtype": "s32", "scaling": "strong"}
+                      "l2": "input %.0f MiB per step > 126 MB L2, streamed from HBM every step" % (n * 4 / 2 ** 20),
+                      "parallelism": "channels sharded x%d (contiguous frequency blocks), baseband %s" % (
+                          c.world, ("b200dsp_dist (library object): " + str(bcast_mode)) if c.world > 1 else "local"),
+                      "broadcast_trials_ms_per_step": bcast_trials},
+           "roofline": roofline, "dtype": "s32", "scaling": "strong"}
     if want_e2e:
-        # end to end through the plugin-facing calls: the baseband starts in pinned host memory (on rank 0: the ingest GPU's
-        # host) and is processed in K blocks so that the H2D copy of block k+1, the kernels of block k (NCCL broadcast first
-        # when N > 1) and the pooled device-to-host copy of block k-1's channel outputs overlap (three streams)
-        K = 4
-        nb_ = n // K
-        hx = torch.empty((2 * n,), dtype=torch.int16, pin_memory=True) if c.rank == 0 else None
-        if c.rank == 0:
-            hx.copy_(x)
-        stride = int(nb_ * 48000.0 / fs) + 64
-        nch = max(len(info), 1)
-        pools = [torch.empty((nch, stride, 2), dtype=torch.float32, device=c.dev) for _ in range(2)]
-        dcnt = [torch.zeros((nch,), dtype=torch.int64, device=c.dev) for _ in range(2)]
-        hout = torch.empty((K, nch, stride, 2), dtype=torch.float32, pin_memory=True)
-        hcnt = torch.zeros((K, nch), dtype=torch.int64, pin_memory=True)
-        s_in, s_out = torch.cuda.Stream(device=c.dev), torch.cuda.Stream(device=c.dev)
-        for w in list(pending.values()):
-            w.wait()
-        pending.clear()
-        state["group"] = None
-        bank.set_reserved_sms([])
-        torch.cuda.synchronize()
-
-        def e2e_step():
-            ev_out = [None] * K
-            for k in range(K):
-                xs = x[2 * k * nb_: 2 * (k + 1) * nb_]
-                if c.rank == 0:
-                    with torch.cuda.stream(s_in):
-                        xs.copy_(hx[2 * k * nb_: 2 * (k + 1) * nb_], non_blocking=True)
-                        e_in = torch.cuda.Event()
-                        e_in.record(s_in)
-                    stream.wait_event(e_in)
-                if c.world > 1:
-                    dist.broadcast(xs.view(torch.int32), src=0)
-                bank.feed_dev(xs.data_ptr(), nb_, sptr)
-                if k >= 2:
-                    stream.wait_event(ev_out[k - 2])           # the pool being gathered into has left for the host
-                bank.gather_dev(capi.STAGE_FRONTEND, pools[k % 2].data_ptr(), stride, dcnt[k % 2].data_ptr(), sptr)
-                e_g = torch.cuda.Event()
-                e_g.record(stream)
-                with torch.cuda.stream(s_out):
-                    s_out.wait_event(e_g)
-                    hout[k].copy_(pools[k % 2], non_blocking=True)
-                    hcnt[k].copy_(dcnt[k % 2], non_blocking=True)
-                    ev_out[k] = torch.cuda.Event()
-                    ev_out[k].record(s_out)
-            s_out.synchronize()
-            stream.synchronize()
-
-        with torch.cuda.stream(stream):
-            e2e_step()
-            barrier(c)
-            t0 = time.perf_counter()
-            ksteps = 3
-            for _ in range(ksteps):
-                e2e_step()
-            torch.cuda.synchronize()
-            dt = max_over_ranks(c, time.perf_counter() - t0)
-            tot = torch.tensor([float(hcnt.sum()) * 8], device=c.dev, dtype=torch.float64)
-            if c.world > 1:
-                dist.all_reduce(tot)
-        res["e2e"] = {"value": n * ksteps / dt / 1e6, "unit": "input MS/s", "h2d_bytes_per_step": int(n * 4),
-                      "d2h_bytes_per_step": int(tot.item()), "steps": ksteps,
-                      "api": "pinned host baseband -> H2D%s -> b200dsp_bank_feed_dev -> b200dsp_bank_gather_dev + D2H of every channel's front-end output "
-                             "(pinned host), in %d blocks pipelined over three streams" % (" on rank 0 -> NCCL broadcast" if c.world > 1 else "", K),
-                      "samples_per_step": n}
-    bank.close()
+        res["e2e"] = _bank_e2e(c, args, fs, fcs, cutoff, n, x, sb)
+    if sb is not None:
+        sb.close()
+    else:
+        bank.close()
     return res
+
+
+def _bank_e2e(c, args, fs, fcs, cutoff, n, x, sb):
+    """End to end through the plugin-facing calls, host buffers both sides, 16 sub-blocks per step.
+    N = 1: b200dsp_bank_process (one call per step: pinned host baseband in, every channel's 48 kS/s complex64 output to pinned
+    host memory; H2D / kernels / D2H of finished columns overlapped inside the library).
+    N > 1: b200dsp_dist_ingest_begin per sub-block -- every rank copies ITS 1/N time slice over its own PCIe link, an in-place
+    NCCL all-gather completes the block on every GPU -- then b200dsp_dist_feed and the pooled D2H of this rank's channels."""
+    import sdrangel_b200 as S
+    torch, capi, dist = c.torch, c.capi, c.dist
+    K = 16
+    nb_ = n // K
+    ksteps = 3
+    if sb is None:
+        bank = S.DownChannelizerBank(fs)
+        bank.set_chunk(nb_)
+        for fc in fcs:
+            cid, rate, ofs, path = bank.add_channel(48000, fc)
+            bank.set_frontend(cid, -ofs, cutoff, 48000)
+        hx = torch.empty((2 * n,), dtype=torch.int16, pin_memory=True)
+        hx.copy_(x)
+        stride = int(n * 48000.0 / fs) + 64
+        hout = torch.empty((len(fcs), stride, 2), dtype=torch.float32, pin_memory=True)
+        torch.cuda.synchronize()
+        cnt = bank.process(hx.data_ptr(), n, capi.STAGE_FRONTEND, hout.data_ptr(), stride)       # warm-up (allocations)
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            cnt = bank.process(hx.data_ptr(), n, capi.STAGE_FRONTEND, hout.data_ptr(), stride)
+        dt = time.perf_counter() - t0
+        d2h = int(cnt.sum()) * 8
+        bank.close()
+        return {"value": n * ksteps / dt / 1e6, "unit": "input MS/s", "h2d_bytes_per_step": int(n * 4), "d2h_bytes_per_step": d2h, "steps": ksteps,
+                "api": "b200dsp_bank_process: pinned host baseband -> every channel's front-end output in pinned host memory, %d passes per call "
+                       "(H2D, kernels and the strided D2H of finished output columns overlapped on three streams inside the library)" % K,
+                "samples_per_step": n}
+    # N > 1
+    bank, info = sb.bank, sb.info
+    # the same synthetic block on every rank's host (set-up, untimed): rank 0's buffer through one broadcast
+    xd = x if c.rank == 0 else torch.empty((2 * n,), dtype=torch.int16, device=c.dev)
+    dist.broadcast(xd.view(torch.int32), src=0)
+    hx = torch.empty((2 * n,), dtype=torch.int16, pin_memory=True)
+    hx.copy_(xd)
+    del xd
+    cnt_slice = nb_ // c.world
+    nch = max(len(info), 1)
+    stride = int(nb_ * 48000.0 / fs) + 64
+    pools = [torch.empty((nch, stride, 2), dtype=torch.float32, device=c.dev) for _ in range(2)]
+    dcnt = [torch.zeros((nch,), dtype=torch.int64, device=c.dev) for _ in range(2)]
+    hout = torch.empty((K, nch, stride, 2), dtype=torch.float32, pin_memory=True)
+    hcnt = torch.zeros((K, nch), dtype=torch.int64, pin_memory=True)
+    s_out = torch.cuda.Stream(device=c.dev)
+    stream = torch.cuda.Stream(device=c.dev)
+    sptr = stream.cuda_stream
+    torch.cuda.synchronize()
+
+    def slice_ptr(k):
+        return hx.data_ptr() + 4 * (k * nb_ + c.rank * cnt_slice)
+
+    def e2e_step():
+        ev_out = [None] * K
+        sb.ingest_begin(0, slice_ptr(0), nb_)
+        for k in range(K):
+            if k + 1 < K:
+                sb.ingest_begin((k + 1) & 1, slice_ptr(k + 1), nb_)        # the next sub-block moves under this one's kernels
+            sb.feed(k & 1, sptr)
+            if k >= 2:
+                stream.wait_event(ev_out[k - 2])           # the pool being gathered into has left for the host
+            bank.gather_dev(capi.STAGE_FRONTEND, pools[k % 2].data_ptr(), stride, dcnt[k % 2].data_ptr(), sptr)
+            e_g = torch.cuda.Event()
+            e_g.record(stream)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(e_g)
+                hout[k].copy_(pools[k % 2], non_blocking=True)
+                hcnt[k].copy_(dcnt[k % 2], non_blocking=True)
+                ev_out[k] = torch.cuda.Event()
+                ev_out[k].record(s_out)
+        s_out.synchronize()
+        stream.synchronize()
+
+    with torch.cuda.stream(stream):
+        e2e_step()
+        barrier(c)
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = max_over_ranks(c, time.perf_counter() - t0)
+        tot = torch.tensor([float(hcnt.sum()) * 8], device=c.dev, dtype=torch.float64)
+        dist.all_reduce(tot)
+    return {"value": n * ksteps / dt / 1e6, "unit": "input MS/s", "h2d_bytes_per_step": int(n * 4), "d2h_bytes_per_step": int(tot.item()), "steps": ksteps,
+            "api": "b200dsp_dist_ingest_begin (every rank H2D-copies its 1/%d time slice from pinned host memory, in-place NCCL all-gather) -> "
+                   "b200dsp_dist_feed -> b200dsp_bank_gather_dev + D2H of this rank's channels (pinned host), %d sub-blocks per step" % (c.world, K),
+            "samples_per_step": n}
 
 
 def bench_spectrum(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=True):
@@ -1047,7 +1109,8 @@ def run_ours(args, wl_name, wl):
                 o = WORKLOADS[other]
                 full = o["type"] == "decim"                      # the 1-GPU decimation targets: complete figures
                 r = fns[o["type"]](c, args, other, o, 10 if full else 5, 3, want_e2e=full and not args.no_e2e)
-                also[other] = {"value": r["value"], "unit": "input MS/s", "ms_per_step": r["ms_per_step"], "hbm_frac": r["roofline"]["frac"],
+                also[other] = {"value": r["value"], "unit": "input MS/s", "ms_per_step": r["ms_per_step"],
+                               "hbm_frac": r["roofline"].get("hbm", {}).get("frac", r["roofline"]["frac"]),
                                "issue_frac": r["roofline"]["issue"]["frac"], "parity_checked_vs_oracle": r["parity"],
                                "samples_per_step": r["config"]["samples_per_step"]}
                 if full:

@@ -147,6 +147,14 @@ int b200dsp_bank_fetch_dev(b200dsp_bank_t* b, int chan_id, int stage, const void
  * bytes by stage), counts[c] = its sample count (0 for a channel without that stage); waits for the stream (NULL: the
  * bank's own) before returning.  Pinned `out` makes it one DMA. */
 int b200dsp_bank_fetch_all(b200dsp_bank_t* b, int stage, void* out, int64_t stride_samples, int64_t* counts, void* cuda_stream);
+/* == one engine work cycle for the whole bank, host buffers in and out (DSPDeviceSourceEngine::work's FIFO read + loop over
+ * the channel sinks, dspdevicesourceengine.cpp:325-408): the results of b200dsp_bank_feed(iq, n) followed by
+ * b200dsp_bank_fetch_all(stage, out, stride, counts), with the host-to-device copy of pass p+1, the kernels of pass p and
+ * the device-to-host copy of the output columns already complete overlapped on three streams.  Pin iq and out. */
+int b200dsp_bank_process(b200dsp_bank_t* b, const int16_t* iq, int64_t n_samples, int stage,
+                         void* out, int64_t stride_samples, int64_t* counts);
+/* the bank's own CUDA stream (cudaStream_t), the one the host-pointer calls and NULL-stream _dev calls use */
+void* b200dsp_bank_stream(b200dsp_bank_t* b);
 /* the device half of fetch_all: gathers into a caller-owned device array [channel][stride_samples] and device counts,
  * asynchronously on the stream (for callers that overlap the device-to-host copy with the next block's kernels) */
 int b200dsp_bank_gather_dev(b200dsp_bank_t* b, int stage, void* d_out, int64_t stride_samples, int64_t* d_counts, void* cuda_stream);
@@ -155,6 +163,46 @@ int b200dsp_bank_copy_out_dev(b200dsp_bank_t* b, int chan_id, int64_t skip, int6
 int b200dsp_bank_sync(b200dsp_bank_t* b);
 /* device time (ms) and count of the tree-level kernel launches of the last internal pass (instrumentation for bench.py) */
 int b200dsp_bank_tree_time(b200dsp_bank_t* b, float* ms, int* launches);
+
+/* ---- K6: one bank's channels sharded over the GPUs of one box --------------------------------------------------------
+ * No reference counterpart: the reference hands one SampleVector span to every channel sink of one process
+ * (dspdevicesourceengine.cpp:325-408).  Here the channels are split by frequency block over N GPUs, one process (or host
+ * thread) per GPU, each with an ordinary bank for its channels; every GPU needs the whole baseband:
+ *   device-resident source: b200dsp_dist_bcast_begin  -- NCCL broadcast over NVLink from the GPU that holds it;
+ *   host-fed source:        b200dsp_dist_ingest_begin -- every rank copies ITS 1/N time slice over its own PCIe link, an
+ *                                                        in-place NCCL all-gather completes the block on every GPU.
+ * Two receive slots: the transfer of block k+1 runs on the handle's collective stream under the kernels of block k.
+ * NCCL (libnccl.so.2) is loaded at run time by these calls only. */
+typedef struct b200dsp_dist b200dsp_dist_t;
+#define B200DSP_DIST_ID_BYTES 128
+/* channels [lo, hi) of n_channels served by `rank`: contiguous blocks in the order given (frequency order) */
+int b200dsp_dist_shard(int n_channels, int world, int rank, int* lo, int* hi);
+int b200dsp_dist_unique_id(void* id_out);                  /* one rank makes it, all ranks pass it to _create (ncclGetUniqueId) */
+int b200dsp_dist_create(b200dsp_dist_t** d, const void* id, int rank, int world);       /* collective; device = b200dsp_init's */
+int b200dsp_dist_destroy(b200dsp_dist_t* d);
+int b200dsp_dist_reserve(b200dsp_dist_t* d, int64_t n_samples);                          /* two slots of n_samples (grows on demand) */
+/* collective: block of n_samples int16 IQ from `root`'s device buffer d_iq (ignored elsewhere) into `slot` (0/1);
+ * after_stream (root, may be NULL): a stream whose work so far produced d_iq */
+int b200dsp_dist_bcast_begin(b200dsp_dist_t* d, int slot, const void* d_iq, int64_t n_samples, int root, void* after_stream);
+/* collective: host_slice = this rank's samples [rank * n/world, (rank+1) * n/world) of the block (n_samples_total a multiple of 4 * world) */
+int b200dsp_dist_ingest_begin(b200dsp_dist_t* d, int slot, const int16_t* host_slice, int64_t n_samples_total);
+/* feed `bank` from the slot once its transfer has landed (stream order; NULL = the bank's stream); the slot may be refilled
+ * by the next _begin, which waits for this feed */
+int b200dsp_dist_feed(b200dsp_dist_t* d, int slot, b200dsp_bank_t* bank, void* cuda_stream);
+int b200dsp_dist_slot(b200dsp_dist_t* d, int slot, const void** d_ptr, int64_t* n_samples);     /* the received block (for checks) */
+int b200dsp_dist_sync(b200dsp_dist_t* d);
+/* Copy-engine chain for the device-resident case (one process per GPU): the block travels rank 0 -> 1 -> ... -> N-1 in 16
+ * sub-blocks, each rank forwarding by DMA copies into the next rank's receive slot (CUDA IPC mapping), ordered by counters
+ * in device memory that the streams wait on / write (cuStreamWaitValue32 and 4-byte copies).  No SM is taken from the FIR
+ * kernels and every NVLink port carries the block once in, once out.  Set-up: every rank _export()s (allocates 3 slots of
+ * n_samples), the B200DSP_DIST_P2P_BLOB_BYTES blobs of all ranks are gathered by the caller's own means, in rank order, and
+ * every rank _import()s the array.  Then per block, on every rank, in the same order: _p2p_begin(slot) ... _p2p_feed(slot). */
+#define B200DSP_DIST_P2P_BLOB_BYTES 512
+int b200dsp_dist_p2p_export(b200dsp_dist_t* d, int64_t n_samples, void* blob_out);
+int b200dsp_dist_p2p_import(b200dsp_dist_t* d, const void* blobs_all);
+int b200dsp_dist_p2p_begin(b200dsp_dist_t* d, int slot, const void* d_iq_rank0, int64_t n_samples, void* after_stream);
+int b200dsp_dist_p2p_feed(b200dsp_dist_t* d, int slot, b200dsp_bank_t* bank, void* cuda_stream);
+int b200dsp_dist_p2p_slot(b200dsp_dist_t* d, int slot, const void** d_ptr, int64_t* n_samples);
 
 /* ---- engine-side sample corrections ----------------------------------------------------------------
  * == DSPDeviceSourceEngine::iqCorrections(begin, end, imbalanceCorrection)  sdrbase/dsp/dspdevicesourceengine.cpp:175-262,

@@ -57,6 +57,23 @@ SIGNATURES = {
     "b200dsp_bank_fetch_dev": (_i32, [_vp, _i32, _i32, _pvp, _pi64]),
     "b200dsp_bank_fetch_all": (_i32, [_vp, _i32, _vp, _i64, _vp, _vp]),
     "b200dsp_bank_gather_dev": (_i32, [_vp, _i32, _vp, _i64, _vp, _vp]),
+    "b200dsp_bank_process": (_i32, [_vp, _vp, _i64, _i32, _vp, _i64, _vp]),
+    "b200dsp_bank_stream": (_vp, [_vp]),
+    "b200dsp_dist_shard": (_i32, [_i32, _i32, _i32, _pi32, _pi32]),
+    "b200dsp_dist_unique_id": (_i32, [_vp]),
+    "b200dsp_dist_create": (_i32, [_pvp, _vp, _i32, _i32]),
+    "b200dsp_dist_destroy": (_i32, [_vp]),
+    "b200dsp_dist_reserve": (_i32, [_vp, _i64]),
+    "b200dsp_dist_bcast_begin": (_i32, [_vp, _i32, _vp, _i64, _i32, _vp]),
+    "b200dsp_dist_ingest_begin": (_i32, [_vp, _i32, _vp, _i64]),
+    "b200dsp_dist_feed": (_i32, [_vp, _i32, _vp, _vp]),
+    "b200dsp_dist_slot": (_i32, [_vp, _i32, _pvp, _pi64]),
+    "b200dsp_dist_sync": (_i32, [_vp]),
+    "b200dsp_dist_p2p_export": (_i32, [_vp, _i64, _vp]),
+    "b200dsp_dist_p2p_import": (_i32, [_vp, _vp]),
+    "b200dsp_dist_p2p_begin": (_i32, [_vp, _i32, _vp, _i64, _vp]),
+    "b200dsp_dist_p2p_feed": (_i32, [_vp, _i32, _vp, _vp]),
+    "b200dsp_dist_p2p_slot": (_i32, [_vp, _i32, _pvp, _pi64]),
     "b200dsp_bank_copy_out_dev": (_i32, [_vp, _i32, _i64, _i64, _vp, _vp]),
     "b200dsp_bank_sync": (_i32, [_vp]),
     "b200dsp_bank_tree_time": (_i32, [_vp, _vp, _vp]),

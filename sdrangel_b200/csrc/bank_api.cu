@@ -183,6 +183,11 @@ struct b200dsp_bank {
     struct FusedLaunch { int b, k, T; size_t smem; int n_groups, n_fams; FusedGroup* d_groups; FusedFam* d_fams; int lvl_off[FZ_MAXK]; };
     std::vector<FusedLaunch> flaunch;
     bool fused_on;                               // B200DSP_NO_FUSED_TREE unset: aligned passes take hb48_fused_kernel
+    // per-channel device buffers are rows of a few slabs (one allocation each, not seven per channel)
+    uint32_t* slab_out; long long out_pitch;     // [channel][out_pitch] packed int16 IQ: channelizer outputs of the current feed
+    float2* slab_fe; int* slab_sched; int* slab_tile; long long fe_pitch, tile_pitch;     // [channel][...] front-end outputs / schedule / tile table
+    float* slab_taps; long long taps_pitch; int* slab_state; long long* slab_plan; uint32_t* slab_hist;      // [front-end][...] static + carried state
+    cudaStream_t d2h; cudaEvent_t ev_pass;       // b200dsp_bank_process: device-to-host copies of finished output columns under the next pass
     std::vector<int> node_chan;                  // per node: the one channel ending there (-1 none, -2 several)
     std::vector<char> chan_direct;               // per channel: the fused kernel writes its output itself
     int n_indirect;                              // channels with stages that still need hb48_finalize_kernel after a fused pass
@@ -217,15 +222,12 @@ void free_device(b200dsp_bank* b)
     if (b->d_gsrc) cudaFree(b->d_gsrc);
     if (b->d_gcnt) cudaFree(b->d_gcnt);
     b->d_pool = nullptr; b->pool_bytes = 0; b->d_gsrc = nullptr; b->d_gcnt = nullptr; b->gcap = 0;
+    void* slabs[] = { b->slab_out, b->slab_fe, b->slab_sched, b->slab_tile, b->slab_taps, b->slab_state, b->slab_plan, b->slab_hist };
+    for (void* p : slabs) if (p) cudaFree(p);
+    b->slab_out = nullptr; b->slab_fe = nullptr; b->slab_sched = nullptr; b->slab_tile = nullptr;
+    b->slab_taps = nullptr; b->slab_state = nullptr; b->slab_plan = nullptr; b->slab_hist = nullptr;
+    b->out_pitch = b->fe_pitch = b->tile_pitch = b->taps_pitch = 0;
     for (auto& c : b->chans) {
-        if (c.d_out) cudaFree(c.d_out);
-        if (c.d_hist) cudaFree(c.d_hist);
-        if (c.d_taps) cudaFree(c.d_taps);
-        if (c.d_fe_out) cudaFree(c.d_fe_out);
-        if (c.d_sched) cudaFree(c.d_sched);
-        if (c.d_tile) cudaFree(c.d_tile);
-        if (c.d_state) cudaFree(c.d_state);
-        if (c.d_plan) cudaFree(c.d_plan);
         c.d_out = nullptr; c.d_hist = nullptr; c.d_taps = nullptr; c.d_fe_out = nullptr; c.d_sched = nullptr; c.d_tile = nullptr; c.d_state = nullptr; c.d_plan = nullptr;
         c.out_cap = c.fe_cap = 0;
     }
@@ -428,16 +430,28 @@ int build(b200dsp_bank* b)
     b->tables_dirty = true;
     b->out_count_depth.assign(32, 0);
     b->fe_index.clear();
+    size_t max_taps = 0;
     for (size_t i = 0; i < nc; ++i) {
         Channel& c = b->chans[i];
         c.out_count = 0;
         if (!c.fe) continue;
         b->fe_index.push_back((int) i);
-        const size_t tb = c.taps.size() * sizeof(float);
-        if ((rc = B200_CUDA_CHECK(cudaMalloc(&c.d_taps, tb))) || (rc = B200_CUDA_CHECK(cudaMemcpy(c.d_taps, c.taps.data(), tb, cudaMemcpyHostToDevice))) ||
-            (rc = B200_CUDA_CHECK(cudaMalloc(&c.d_state, 4 * sizeof(int)))) || (rc = B200_CUDA_CHECK(cudaMemset(c.d_state, 0, 4 * sizeof(int)))) ||
-            (rc = B200_CUDA_CHECK(cudaMalloc(&c.d_plan, 4 * sizeof(long long)))) || (rc = B200_CUDA_CHECK(cudaMemset(c.d_plan, 0, 4 * sizeof(long long)))) ||
-            (rc = B200_CUDA_CHECK(cudaMalloc(&c.d_hist, 2 * FE_HIST_WORDS * 4))) || (rc = B200_CUDA_CHECK(cudaMemset(c.d_hist, 0, 2 * FE_HIST_WORDS * 4)))) return rc;
+        if (c.taps.size() > max_taps) max_taps = c.taps.size();
+    }
+    if (const size_t nfe = b->fe_index.size()) {
+        b->taps_pitch = (long long) ((max_taps + 3) & ~(size_t) 3);
+        if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->slab_taps, nfe * b->taps_pitch * sizeof(float)))) ||
+            (rc = B200_CUDA_CHECK(cudaMalloc(&b->slab_state, nfe * 4 * sizeof(int)))) || (rc = B200_CUDA_CHECK(cudaMemset(b->slab_state, 0, nfe * 4 * sizeof(int)))) ||
+            (rc = B200_CUDA_CHECK(cudaMalloc(&b->slab_plan, nfe * 4 * sizeof(long long)))) || (rc = B200_CUDA_CHECK(cudaMemset(b->slab_plan, 0, nfe * 4 * sizeof(long long)))) ||
+            (rc = B200_CUDA_CHECK(cudaMalloc(&b->slab_hist, nfe * 2 * FE_HIST_WORDS * 4))) || (rc = B200_CUDA_CHECK(cudaMemset(b->slab_hist, 0, nfe * 2 * FE_HIST_WORDS * 4)))) return rc;
+        std::vector<float> all(nfe * (size_t) b->taps_pitch, 0.0f);
+        for (size_t k = 0; k < nfe; ++k) {
+            Channel& c = b->chans[b->fe_index[k]];
+            std::copy(c.taps.begin(), c.taps.end(), all.begin() + k * b->taps_pitch);
+            c.d_taps = b->slab_taps + k * b->taps_pitch;
+            c.d_state = b->slab_state + 4 * k; c.d_plan = b->slab_plan + 4 * k; c.d_hist = b->slab_hist + 2 * FE_HIST_WORDS * k;
+        }
+        if ((rc = B200_CUDA_CHECK(cudaMemcpy(b->slab_taps, all.data(), all.size() * sizeof(float), cudaMemcpyHostToDevice)))) return rc;
     }
     b->h_fe.resize(b->fe_index.size());
     if (!b->d_nco) {
@@ -452,30 +466,42 @@ int build(b200dsp_bank* b)
     return 0;
 }
 
-// make sure per-channel output buffers can take the outputs of a feed of n input samples
+// make sure the output slabs can take the outputs of a feed of n input samples (rows of one pitch: the longest channel's)
 int reserve_outputs(b200dsp_bank* b, long long n)
 {
     int rc;
-    for (auto& c : b->chans) {
-        const long long need = (n >> c.S) + 2;
-        if (c.out_cap < need) {
-            if (c.d_out) cudaFree(c.d_out);
-            c.d_out = nullptr; c.out_cap = 0;
-            if ((rc = B200_CUDA_CHECK(cudaMalloc(&c.d_out, (size_t) need * 4)))) return rc;
-            c.out_cap = need;
-            b->tables_dirty = true;
-        }
-        if (c.fe && c.fe_cap < need) {
-            if (c.d_fe_out) cudaFree(c.d_fe_out);
-            if (c.d_sched) cudaFree(c.d_sched);
-            if (c.d_tile) cudaFree(c.d_tile);
-            c.d_fe_out = nullptr; c.d_sched = nullptr; c.d_tile = nullptr; c.fe_cap = 0;
-            if ((rc = B200_CUDA_CHECK(cudaMalloc(&c.d_fe_out, (size_t) need * sizeof(float2)))) ||
-                (rc = B200_CUDA_CHECK(cudaMalloc(&c.d_sched, (size_t) need * sizeof(int)))) ||
-                (rc = B200_CUDA_CHECK(cudaMalloc(&c.d_tile, (size_t) (need / FE_TILE + 4) * sizeof(int))))) return rc;
+    const size_t nc = b->chans.size();
+    if (nc == 0) return 0;
+    long long need = 0;
+    for (auto& c : b->chans) if ((n >> c.S) + 2 > need) need = (n >> c.S) + 2;
+    need = (need + 3) & ~3ll;
+    if (b->out_pitch < need) {
+        if ((rc = B200_CUDA_CHECK(cudaStreamSynchronize(b->stream)))) return rc;
+        if (b->slab_out) cudaFree(b->slab_out);
+        b->slab_out = nullptr; b->out_pitch = 0;
+        if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->slab_out, nc * (size_t) need * 4)))) return rc;
+        b->out_pitch = need;
+        for (size_t i = 0; i < nc; ++i) { b->chans[i].d_out = b->slab_out + i * (size_t) need; b->chans[i].out_cap = need; }
+        b->tables_dirty = true;
+    }
+    if (!b->fe_index.empty() && b->fe_pitch < need) {
+        if ((rc = B200_CUDA_CHECK(cudaStreamSynchronize(b->stream)))) return rc;
+        if (b->slab_fe) cudaFree(b->slab_fe);
+        if (b->slab_sched) cudaFree(b->slab_sched);
+        if (b->slab_tile) cudaFree(b->slab_tile);
+        b->slab_fe = nullptr; b->slab_sched = nullptr; b->slab_tile = nullptr; b->fe_pitch = 0;
+        const long long tp = need / FE_TILE + 4;
+        if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->slab_fe, nc * (size_t) need * sizeof(float2)))) ||
+            (rc = B200_CUDA_CHECK(cudaMalloc(&b->slab_sched, nc * (size_t) need * sizeof(int)))) ||
+            (rc = B200_CUDA_CHECK(cudaMalloc(&b->slab_tile, nc * (size_t) tp * sizeof(int))))) return rc;
+        b->fe_pitch = need; b->tile_pitch = tp;
+        for (size_t i = 0; i < nc; ++i) {
+            Channel& c = b->chans[i];
+            if (!c.fe) continue;
+            c.d_fe_out = b->slab_fe + i * (size_t) need; c.d_sched = b->slab_sched + i * (size_t) need; c.d_tile = b->slab_tile + i * (size_t) tp;
             c.fe_cap = need;
-            b->tables_dirty = true;
         }
+        b->tables_dirty = true;
     }
     return 0;
 }
@@ -680,6 +706,29 @@ long long next_pass_len(const b200dsp_bank* b, long long remaining)
     return m - m % unit;
 }
 
+// the two staging buffers of the host-pointer feeds (a pass is at most `chunk` samples)
+int ensure_root_buffers(b200dsp_bank* b, long long n_samples)
+{
+    int rc;
+    const long long first_m = n_samples < b->chunk ? n_samples : b->chunk;
+    if (b->root_cap >= first_m + 8 && b->root_alt_cap >= first_m + 8) return 0;
+    if ((rc = B200_CUDA_CHECK(cudaStreamSynchronize(b->stream))) || (rc = B200_CUDA_CHECK(cudaStreamSynchronize(b->copy)))) return rc;
+    const long long cap = (b->chunk > first_m ? b->chunk : first_m) + 8;
+    if (b->root_cap < cap) {
+        if (b->d_root) cudaFree(b->d_root);
+        b->d_root = nullptr; b->root_cap = 0;
+        if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_root, (size_t) cap * 4)))) return rc;
+        b->root_cap = cap;
+    }
+    if (b->root_alt_cap < cap) {
+        if (b->d_root_alt) cudaFree(b->d_root_alt);
+        b->d_root_alt = nullptr; b->root_alt_cap = 0;
+        if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_root_alt, (size_t) cap * 4)))) return rc;
+        b->root_alt_cap = cap;
+    }
+    return 0;
+}
+
 // a feed of zero samples (DownChannelizer::feed with begin == end): nothing moves, every channel's outputs of "the last
 // feed" are empty -- the front-ends' per-feed counts live on the device and are zeroed by an empty schedule pass
 int empty_feed(b200dsp_bank* b, cudaStream_t st)
@@ -742,12 +791,17 @@ int b200dsp_bank_create(b200dsp_bank_t** out, int input_rate_hz)
     b->built = false; b->depth = 0; b->chunk = 3ll << 22; b->tables_dirty = true;
     b->fused_on = (getenv("B200DSP_NO_FUSED_TREE") == nullptr);
     b->d_root = nullptr; b->root_cap = 0;
+    b->slab_out = nullptr; b->slab_fe = nullptr; b->slab_sched = nullptr; b->slab_tile = nullptr;
+    b->slab_taps = nullptr; b->slab_state = nullptr; b->slab_plan = nullptr; b->slab_hist = nullptr;
+    b->out_pitch = b->fe_pitch = b->tile_pitch = b->taps_pitch = 0; b->d2h = nullptr; b->ev_pass = nullptr;
     b->d_leaf = nullptr; b->d_fe = nullptr; b->d_nco = nullptr; b->tcur = 0;
     if ((rc = B200_CUDA_CHECK(cudaSetDevice(b->device))) || (rc = B200_CUDA_CHECK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking))) ||
         (rc = B200_CUDA_CHECK(cudaStreamCreateWithPriority(&b->side, cudaStreamNonBlocking, -5))) ||
         (rc = B200_CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_begin, cudaEventDisableTiming))) ||
         (rc = B200_CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_sched, cudaEventDisableTiming))) ||
-        (rc = B200_CUDA_CHECK(cudaStreamCreateWithFlags(&b->copy, cudaStreamNonBlocking)))) { delete b; return rc; }
+        (rc = B200_CUDA_CHECK(cudaStreamCreateWithFlags(&b->copy, cudaStreamNonBlocking))) ||
+        (rc = B200_CUDA_CHECK(cudaStreamCreateWithFlags(&b->d2h, cudaStreamNonBlocking))) ||
+        (rc = B200_CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_pass, cudaEventDisableTiming)))) { delete b; return rc; }
     if ((rc = B200_CUDA_CHECK(cudaEventCreate(&b->ev_tree0))) || (rc = B200_CUDA_CHECK(cudaEventCreate(&b->ev_tree1)))) { delete b; return rc; }
     for (int i = 0; i < 2; ++i)
         if ((rc = B200_CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_h2d[i], cudaEventDisableTiming))) ||
@@ -768,6 +822,8 @@ int b200dsp_bank_destroy(b200dsp_bank_t* b)
     if (b->d_root_alt) cudaFree(b->d_root_alt);
     if (b->d_nco) cudaFree(b->d_nco);
     if (b->copy) cudaStreamDestroy(b->copy);
+    if (b->d2h) { cudaStreamSynchronize(b->d2h); cudaStreamDestroy(b->d2h); }
+    if (b->ev_pass) cudaEventDestroy(b->ev_pass);
     for (int i = 0; i < 2; ++i) { if (b->ev_h2d[i]) cudaEventDestroy(b->ev_h2d[i]); if (b->ev_done[i]) cudaEventDestroy(b->ev_done[i]); }
     cudaStreamDestroy(b->stream);
     cudaStreamDestroy(b->side);
@@ -845,12 +901,11 @@ int b200dsp_bank_reset(b200dsp_bank_t* b, void* cuda_stream)
     for (int d = 0; d < b->depth; ++d)
         for (int k = 0; k < 2; ++k)
             if ((rc = B200_CUDA_CHECK(cudaMemsetAsync(b->d_tail[k][d], 0, (size_t) b->levels[d].size() * TAIL_WORDS * 4, st)))) return rc;
-    for (auto& c : b->chans) {
-        c.out_count = 0;
-        if (!c.fe) continue;
-        if ((rc = B200_CUDA_CHECK(cudaMemsetAsync(c.d_state, 0, 4 * sizeof(int), st))) ||
-            (rc = B200_CUDA_CHECK(cudaMemsetAsync(c.d_hist, 0, 2 * FE_HIST_WORDS * 4, st))) ||
-            (rc = B200_CUDA_CHECK(cudaMemsetAsync(c.d_plan, 0, 4 * sizeof(long long), st)))) return rc;
+    for (auto& c : b->chans) c.out_count = 0;
+    if (const size_t nfe = b->fe_index.size()) {
+        if ((rc = B200_CUDA_CHECK(cudaMemsetAsync(b->slab_state, 0, nfe * 4 * sizeof(int), st))) ||
+            (rc = B200_CUDA_CHECK(cudaMemsetAsync(b->slab_hist, 0, nfe * 2 * FE_HIST_WORDS * 4, st))) ||
+            (rc = B200_CUDA_CHECK(cudaMemsetAsync(b->slab_plan, 0, nfe * 4 * sizeof(long long), st)))) return rc;
     }
     b->produced.assign(b->depth + 1, 0);
     b->out_count_depth.assign(32, 0);
@@ -945,23 +1000,7 @@ int b200dsp_bank_feed(b200dsp_bank_t* b, const int16_t* iq, int64_t n_samples)
     if (n_samples == 0) return empty_feed(b, b->stream);
     // Passes of `chunk` samples through two staging buffers: the H2D copy of pass p+1 (copy stream) runs under the kernels of
     // pass p (bank stream); a buffer is refilled only after the pass that read it has finished (ev_done).
-    const long long first_m = n_samples < b->chunk ? n_samples : b->chunk;
-    if (b->root_cap < first_m + 8 || b->root_alt_cap < first_m + 8) {
-        if ((rc = B200_CUDA_CHECK(cudaStreamSynchronize(b->stream))) || (rc = B200_CUDA_CHECK(cudaStreamSynchronize(b->copy)))) return rc;
-        const long long cap = (b->chunk > first_m ? b->chunk : first_m) + 8;
-        if (b->root_cap < cap) {
-            if (b->d_root) cudaFree(b->d_root);
-            b->d_root = nullptr; b->root_cap = 0;
-            if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_root, (size_t) cap * 4)))) return rc;
-            b->root_cap = cap;
-        }
-        if (b->root_alt_cap < cap) {
-            if (b->d_root_alt) cudaFree(b->d_root_alt);
-            b->d_root_alt = nullptr; b->root_alt_cap = 0;
-            if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_root_alt, (size_t) cap * 4)))) return rc;
-            b->root_alt_cap = cap;
-        }
-    }
+    if ((rc = ensure_root_buffers(b, n_samples))) return rc;
     long long done = 0;
     int pass = 0;
     while (done < n_samples) {
@@ -1064,8 +1103,42 @@ int b200dsp_bank_gather_dev(b200dsp_bank_t* b, int stage, void* d_out, int64_t s
     return B200_CUDA_CHECK(cudaGetLastError());
 }
 
-// Every channel's outputs of the last feed with one gather kernel and one device-to-host transfer (the per-channel
-// b200dsp_bank_fetch costs a synchronous small copy per channel: latency-bound for a 1024-channel bank).
+namespace {
+
+// per-channel output counts of the last feed for `stage` (front-end counts live on the device: one small copy)
+int stage_counts(b200dsp_bank* b, int stage, int64_t* counts, cudaStream_t st)
+{
+    const size_t nc = b->chans.size();
+    for (size_t i = 0; i < nc; ++i) counts[i] = 0;
+    if (!b->built) return 0;
+    if (stage == B200DSP_STAGE_CHANNELIZER) { for (size_t i = 0; i < nc; ++i) counts[i] = b->chans[i].out_count; return 0; }
+    const size_t nfe = b->fe_index.size();
+    if (!nfe || !b->slab_fe) return 0;
+    std::vector<int> stt(nfe * 4);
+    int rc;
+    if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(stt.data(), b->slab_state, nfe * 4 * sizeof(int), cudaMemcpyDeviceToHost, st))) ||
+        (rc = B200_CUDA_CHECK(cudaStreamSynchronize(st)))) return rc;
+    for (size_t k = 0; k < nfe; ++k) counts[b->fe_index[k]] = stt[4 * k + 3];
+    return 0;
+}
+
+// columns [c0, c1) of every channel's output row -> out (row pitch stride_samples), asynchronously
+int copy_columns(b200dsp_bank* b, int stage, void* out, int64_t stride_samples, long long c0, long long c1, cudaStream_t st)
+{
+    if (c1 <= c0) return 0;
+    const size_t elem = (stage == B200DSP_STAGE_FRONTEND) ? sizeof(float2) : sizeof(uint32_t);
+    const char* src = (stage == B200DSP_STAGE_FRONTEND) ? (const char*) b->slab_fe : (const char*) b->slab_out;
+    const long long pitch = (stage == B200DSP_STAGE_FRONTEND) ? b->fe_pitch : b->out_pitch;
+    if (!src) return 0;
+    return B200_CUDA_CHECK(cudaMemcpy2DAsync((char*) out + (size_t) c0 * elem, (size_t) stride_samples * elem, src + (size_t) c0 * elem, (size_t) pitch * elem,
+                                             (size_t) (c1 - c0) * elem, b->chans.size(), cudaMemcpyDeviceToHost, st));
+}
+
+} // namespace
+
+// Every channel's outputs of the last feed in one strided device-to-host transfer (the per-channel b200dsp_bank_fetch costs
+// a synchronous small copy per channel: latency-bound for a 1024-channel bank).  The channels' output buffers are rows of
+// one device slab, so this is a single 2-D copy of the occupied columns.
 int b200dsp_bank_fetch_all(b200dsp_bank_t* b, int stage, void* out, int64_t stride_samples, int64_t* counts, void* cuda_stream)
 {
     if (!b || !out || !counts || stride_samples <= 0) return b200_fail(B200DSP_EINVAL, "bank_fetch_all: bad argument");
@@ -1075,31 +1148,82 @@ int b200dsp_bank_fetch_all(b200dsp_bank_t* b, int stage, void* out, int64_t stri
     int rc = B200_CUDA_CHECK(cudaSetDevice(b->device));
     if (rc) return rc;
     cudaStream_t st = cuda_stream ? (cudaStream_t) cuda_stream : b->stream;
-    const size_t elem = (stage == B200DSP_STAGE_FRONTEND) ? sizeof(float2) : sizeof(uint32_t);
-    const size_t need = nc * (size_t) stride_samples * elem;
-    if (b->pool_bytes < need) {
-        if ((rc = B200_CUDA_CHECK(cudaStreamSynchronize(st)))) return rc;
-        if (b->d_pool) cudaFree(b->d_pool);
-        b->d_pool = nullptr; b->pool_bytes = 0;
-        if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_pool, need)))) return rc;
-        b->pool_bytes = need;
-    }
-    if (b->gcap < nc) {       // (gather_dev allocates d_gcnt; make sure it exists before it is used as the counts target)
-        if ((rc = B200_CUDA_CHECK(cudaStreamSynchronize(st)))) return rc;
-        if (b->d_gsrc) cudaFree(b->d_gsrc);
-        if (b->d_gcnt) cudaFree(b->d_gcnt);
-        b->d_gsrc = nullptr; b->d_gcnt = nullptr; b->gcap = 0;
-        if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_gsrc, 2 * nc * sizeof(GatherSrc)))) || (rc = B200_CUDA_CHECK(cudaMalloc(&b->d_gcnt, nc * sizeof(long long))))) return rc;
-        b->gcap = nc;
-    }
-    if ((rc = b200dsp_bank_gather_dev(b, stage, b->d_pool, stride_samples, (int64_t*) b->d_gcnt, (void*) st))) return rc;
-    if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(out, b->d_pool, need, cudaMemcpyDeviceToHost, st))) ||
-        (rc = B200_CUDA_CHECK(cudaMemcpyAsync(counts, b->d_gcnt, nc * sizeof(long long), cudaMemcpyDeviceToHost, st))) ||
-        (rc = B200_CUDA_CHECK(cudaStreamSynchronize(st)))) return rc;
-    for (size_t i = 0; i < nc; ++i)
+    if ((rc = stage_counts(b, stage, counts, st))) return rc;
+    long long mx = 0;
+    for (size_t i = 0; i < nc; ++i) {
         if (counts[i] > stride_samples) return b200_fail(B200DSP_EINVAL, "bank_fetch_all: stride too small (channel %d has %lld samples)", (int) i, (long long) counts[i]);
-    return 0;
+        if (counts[i] > mx) mx = counts[i];
+    }
+    if ((rc = copy_columns(b, stage, out, stride_samples, 0, mx, st))) return rc;
+    return B200_CUDA_CHECK(cudaStreamSynchronize(st));
 }
+
+// == one engine work cycle for the whole bank, host to host (what DSPDeviceSourceEngine::work does with one FIFO read:
+// dspdevicesourceengine.cpp:325-408): feed n samples from a host buffer and receive every channel's outputs of `stage` at
+// out + c * stride_samples, counts[c] samples each -- the same results as b200dsp_bank_feed followed by b200dsp_bank_fetch_all.
+// The block runs as passes of `chunk` samples over three streams: the host-to-device copy of pass p+1, the kernels of pass
+// p, and the device-to-host copy of the output columns every channel has completed so far (a strided 2-D copy straight
+// out of the channels' slab) overlap; the ragged last columns follow after the last pass.  Pin `iq` and `out`
+// (cudaHostRegister) for the copies to be asynchronous.
+int b200dsp_bank_process(b200dsp_bank_t* b, const int16_t* iq, int64_t n_samples, int stage, void* out, int64_t stride_samples, int64_t* counts)
+{
+    if (!b || !out || !counts || stride_samples <= 0) return b200_fail(B200DSP_EINVAL, "bank_process: bad argument");
+    if (stage != B200DSP_STAGE_CHANNELIZER && stage != B200DSP_STAGE_FRONTEND) return b200_fail(B200DSP_EINVAL, "bank_process: bad stage");
+    if (n_samples < 0 || (n_samples > 0 && !iq)) return b200_fail(B200DSP_EINVAL, "bank_process: bad buffer");
+    int rc = B200_CUDA_CHECK(cudaSetDevice(b->device));
+    if (rc) return rc;
+    if (!b->built && (rc = build(b))) return rc;
+    if ((rc = reserve_outputs(b, n_samples))) return rc;
+    const size_t nc = b->chans.size();
+    for (auto& c : b->chans) c.out_count = 0;
+    b->out_count_depth.assign(32, 0);
+    if (n_samples == 0) { for (size_t i = 0; i < nc; ++i) counts[i] = 0; return empty_feed(b, b->stream); }
+    if ((rc = ensure_root_buffers(b, n_samples))) return rc;
+    long long done = 0, copied = 0;
+    int pass = 0;
+    while (done < n_samples) {
+        const long long m = next_pass_len(b, n_samples - done);
+        const int pend = (b->depth >= 1) ? (int) (b->produced[0] - 2 * b->produced[1]) : 0;
+        const int slot = pass & 1;
+        if (pass >= 2 && (rc = B200_CUDA_CHECK(cudaStreamWaitEvent(b->copy, b->ev_done[slot], 0)))) return rc;
+        if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(b->d_root + pend, iq + 2 * done, (size_t) m * 4, cudaMemcpyHostToDevice, b->copy))) ||
+            (rc = B200_CUDA_CHECK(cudaEventRecord(b->ev_h2d[slot], b->copy))) ||
+            (rc = B200_CUDA_CHECK(cudaStreamWaitEvent(b->stream, b->ev_h2d[slot], 0)))) return rc;
+        if ((rc = feed_chunk(b, b->d_root + pend, m, b->stream, done == 0))) return rc;
+        if ((rc = B200_CUDA_CHECK(cudaEventRecord(b->ev_done[slot], b->stream)))) return rc;
+        std::swap(b->d_root, b->d_root_alt);
+        std::swap(b->root_cap, b->root_alt_cap);
+        done += m;
+        ++pass;
+        // columns every channel is certain to hold by now (front-end: a safe lower bound from its input count and ratio)
+        long long ready = -1;
+        for (size_t i = 0; i < nc; ++i) {
+            const Channel& c = b->chans[i];
+            long long r;
+            if (stage == B200DSP_STAGE_CHANNELIZER) r = b->out_count_depth[c.S];
+            else if (!c.fe) continue;
+            else r = (long long) ((double) b->out_count_depth[c.S] / (double) c.ratio) - 2;
+            if (ready < 0 || r < ready) ready = r;
+        }
+        if (ready > stride_samples) ready = stride_samples;
+        if (ready > copied && done < n_samples) {
+            if ((rc = B200_CUDA_CHECK(cudaEventRecord(b->ev_pass, b->stream))) || (rc = B200_CUDA_CHECK(cudaStreamWaitEvent(b->d2h, b->ev_pass, 0))) ||
+                (rc = copy_columns(b, stage, out, stride_samples, copied, ready, b->d2h))) return rc;
+            copied = ready;
+        }
+    }
+    if ((rc = B200_CUDA_CHECK(cudaStreamSynchronize(b->stream)))) return rc;
+    if ((rc = stage_counts(b, stage, counts, b->stream))) return rc;
+    long long mx = 0;
+    for (size_t i = 0; i < nc; ++i) {
+        if (counts[i] > stride_samples) { cudaStreamSynchronize(b->d2h); return b200_fail(B200DSP_EINVAL, "bank_process: stride too small (channel %d has %lld samples)", (int) i, (long long) counts[i]); }
+        if (counts[i] > mx) mx = counts[i];
+    }
+    if ((rc = copy_columns(b, stage, out, stride_samples, copied, mx, b->d2h))) return rc;
+    return B200_CUDA_CHECK(cudaStreamSynchronize(b->d2h));
+}
+
+void* b200dsp_bank_stream(b200dsp_bank_t* b) { return b ? (void*) b->stream : nullptr; }
 
 // device-to-device copy of part of a channel's output of the last feed (asynchronous on the stream): the building block of
 // the cooperative multi-GPU bank, where one bank's node outputs are exchanged and become another bank's input

@@ -250,6 +250,12 @@ class DownChannelizerBank:
         capi.check(capi.lib().b200dsp_bank_fetch(self._h, chan_id, stage, out.ctypes.data, out.shape[0], C.byref(n)))
         return out[:n.value]
 
+    def process(self, iq_ptr, n_samples, stage, out_ptr, stride):
+        """== b200dsp_bank_process: host buffer in (pointer), every channel's outputs to out_ptr [channel][stride]; returns counts."""
+        counts = np.zeros(max(self._n_channels, 1), dtype=np.int64)
+        capi.check(capi.lib().b200dsp_bank_process(self._h, C.c_void_p(iq_ptr), int(n_samples), stage, C.c_void_p(out_ptr), int(stride), counts.ctypes.data))
+        return counts[:self._n_channels]
+
     def fetch_all(self, stage=capi.STAGE_CHANNELIZER, stride=None, out_ptr=None, stream=None, n_channels=None):
         """Every channel's outputs of the last feed in one transfer.  Returns (array [n_channels, stride, 2], counts);
         with `out_ptr` (e.g. pinned memory of n_channels * stride samples) only the counts array is returned."""
@@ -266,6 +272,97 @@ class DownChannelizerBank:
         out = np.empty((nc, int(stride), 2), dtype=np.int16 if stage == capi.STAGE_CHANNELIZER else np.float32)
         capi.check(L.b200dsp_bank_fetch_all(self._h, stage, out.ctypes.data, int(stride), counts.ctypes.data, C.c_void_p(stream or 0)))
         return out, counts
+
+
+class ShardedBank:
+    """One rank's share of a DownChannelizer bank sharded by channel over the GPUs of one box (include/b200dsp.h, K6):
+    an ordinary bank for channels [lo, hi) of the plan plus the b200dsp_dist object that brings the whole baseband to this
+    GPU (NCCL broadcast from a device buffer, or sliced host-to-device copies + in-place all-gather).  The 128-byte NCCL id
+    made by one rank has to reach the others by the caller's own means (torch.distributed in bench.py)."""
+
+    def __init__(self, input_rate, offsets, requested_rate, rank, world, nccl_id, frontend=None, chunk=None):
+        L = capi.lib()
+        lo, hi = C.c_int32(), C.c_int32()
+        capi.check(L.b200dsp_dist_shard(len(offsets), world, rank, C.byref(lo), C.byref(hi)))
+        self.lo, self.hi, self.rank, self.world = lo.value, hi.value, rank, world
+        self.bank = DownChannelizerBank(input_rate)
+        if chunk:
+            self.bank.set_chunk(chunk)
+        self.info = []
+        for fc in offsets[self.lo:self.hi]:
+            cid, rate, ofs, path = self.bank.add_channel(requested_rate, fc)
+            if frontend is not None:
+                cutoff, out_rate = frontend
+                self.bank.set_frontend(cid, -ofs, cutoff, out_rate)
+            self.info.append((cid, rate, ofs, path))
+        h = C.c_void_p()
+        idb = (C.c_char * 128).from_buffer_copy(bytes(nccl_id))
+        capi.check(L.b200dsp_dist_create(C.byref(h), idb, rank, world))
+        self._h = h
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_char * 128)()
+        capi.check(capi.lib().b200dsp_dist_unique_id(buf))
+        return bytes(buf)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            capi.lib().b200dsp_dist_destroy(self._h)
+            self._h = None
+        if getattr(self, "bank", None):
+            self.bank.close()
+            self.bank = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reserve(self, n_samples):
+        capi.check(capi.lib().b200dsp_dist_reserve(self._h, int(n_samples)))
+
+    def bcast_begin(self, slot, d_iq, n_samples, root=0, after_stream=None):
+        capi.check(capi.lib().b200dsp_dist_bcast_begin(self._h, slot, C.c_void_p(d_iq or 0), int(n_samples), root, C.c_void_p(after_stream or 0)))
+
+    def ingest_begin(self, slot, host_slice_ptr, n_samples_total):
+        capi.check(capi.lib().b200dsp_dist_ingest_begin(self._h, slot, C.c_void_p(host_slice_ptr), int(n_samples_total)))
+
+    def feed(self, slot, stream=None):
+        capi.check(capi.lib().b200dsp_dist_feed(self._h, slot, self.bank._h, C.c_void_p(stream or 0)))
+
+    def slot(self, slot):
+        ptr, n = C.c_void_p(), C.c_int64(0)
+        capi.check(capi.lib().b200dsp_dist_slot(self._h, slot, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def sync(self):
+        capi.check(capi.lib().b200dsp_dist_sync(self._h))
+
+    # copy-engine chain (one process per GPU): export -> gather the blobs of all ranks in rank order -> import
+    P2P_SLOTS = 3
+
+    def p2p_export(self, n_samples):
+        blob = (C.c_char * 512)()
+        capi.check(capi.lib().b200dsp_dist_p2p_export(self._h, int(n_samples), blob))
+        return bytes(blob)
+
+    def p2p_import(self, blobs):
+        data = b"".join(bytes(b) for b in blobs)
+        buf = (C.c_char * len(data)).from_buffer_copy(data)
+        capi.check(capi.lib().b200dsp_dist_p2p_import(self._h, buf))
+
+    def p2p_begin(self, slot, d_iq, n_samples, after_stream=None):
+        capi.check(capi.lib().b200dsp_dist_p2p_begin(self._h, slot, C.c_void_p(d_iq or 0), int(n_samples), C.c_void_p(after_stream or 0)))
+
+    def p2p_feed(self, slot, stream=None):
+        capi.check(capi.lib().b200dsp_dist_p2p_feed(self._h, slot, self.bank._h, C.c_void_p(stream or 0)))
+
+    def p2p_slot(self, slot):
+        ptr, n = C.c_void_p(), C.c_int64(0)
+        capi.check(capi.lib().b200dsp_dist_p2p_slot(self._h, slot, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
 
 
 class SpectrumVis:

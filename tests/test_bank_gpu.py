@@ -1,6 +1,8 @@
 """GPU parity tests of K3 (shared-prefix HB48 tree) and K4 (NCO + polyphase Interpolator front-end) through the
 C ABI.  Channelizer outputs: bit-exact (int16).  Front-end: identical output count/schedule, values within
 1e-5 relative RMS (north_star tolerance)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -431,3 +433,202 @@ def test_bank_frontends_many_internal_passes(gpu_lib, port, golden_meta, plan_na
             if want.size:
                 assert rel_rms(got, want) <= 1e-5, (a, cid)
     b.close()
+
+
+def test_bank_process_equals_feed_then_fetch_all(gpu_lib, port, golden_meta):
+    """b200dsp_bank_process (host buffer in, every channel's outputs out, H2D / kernels / D2H of finished columns overlapped
+    over several internal passes) hands out exactly what b200dsp_bank_feed + b200dsp_bank_fetch_all do, for both stages, and
+    the tree outputs equal the oracle's -- ragged and aligned block sizes, mixed channel depths (bank64: S = 6 and 7)."""
+    import torch
+    from sdrangel_b200 import DownChannelizerBank, capi
+    plan = golden_meta["chan_plans"]["bank64"]
+    fs = plan["input_rate"]
+    rows = plan["channels"][1::6]
+    cutoff = float(np.float32(np.float32(12500) / np.float32(2.2)))
+    rs = np.random.RandomState(5)
+    sizes = [1 << 18, 100_003, 3 * (1 << 16)]
+    x = rs.randint(-32768, 32768, size=(sum(sizes), 2)).astype(np.int16)
+    a, b = DownChannelizerBank(fs), DownChannelizerBank(fs)
+    for bk in (a, b):
+        bk.set_chunk(768 * 32)
+        for fc, rate, ofs, path in rows:
+            cid = bk.add_channel(48000, fc)[0]
+            bk.set_frontend(cid, -ofs, cutoff, 48000)
+    oracles = []
+    for fc, rate, ofs, path in rows:
+        o = port.PortDownChannelizer()
+        o.configure(fs, 48000, fc)
+        oracles.append(o)
+    pos = 0
+    for sz in sizes:
+        blk = np.ascontiguousarray(x[pos:pos + sz])
+        pos += sz
+        hx = torch.from_numpy(blk.reshape(-1)).pin_memory()
+        a.feed(blk)
+        ch_all, ch_cnt = a.fetch_all(capi.STAGE_CHANNELIZER)
+        fe_all, fe_cnt = a.fetch_all(capi.STAGE_FRONTEND, stride=ch_all.shape[1])
+        stride = ch_all.shape[1] + 8
+        for stage, want, wcnt, dt in ((capi.STAGE_FRONTEND, fe_all, fe_cnt, torch.float32),):
+            out = torch.zeros((len(rows), stride, 2), dtype=dt).pin_memory()
+            cnt = b.process(hx.data_ptr(), sz, stage, out.data_ptr(), stride)
+            assert np.array_equal(cnt, wcnt), (sz, stage)
+            got = out.numpy()
+            for i in range(len(rows)):
+                assert np.array_equal(got[i, :cnt[i]], want[i, :wcnt[i]]), (sz, stage, i)
+        for i, o in enumerate(oracles):
+            w = o.feed(blk)
+            assert np.array_equal(b.fetch(i), w), (sz, i)
+    # the channelizer stage through process() on a fresh pair of banks
+    c2, d2 = DownChannelizerBank(fs), DownChannelizerBank(fs)
+    for bk in (c2, d2):
+        bk.set_chunk(768 * 16)
+        for fc, rate, ofs, path in rows:
+            bk.add_channel(48000, fc)
+    blk = np.ascontiguousarray(x[:200_001])
+    hx = torch.from_numpy(blk.reshape(-1)).pin_memory()
+    c2.feed(blk)
+    want, wcnt = c2.fetch_all(capi.STAGE_CHANNELIZER)
+    out = torch.zeros((len(rows), want.shape[1] + 4, 2), dtype=torch.int16).pin_memory()
+    cnt = d2.process(hx.data_ptr(), blk.shape[0], capi.STAGE_CHANNELIZER, out.data_ptr(), want.shape[1] + 4)
+    assert np.array_equal(cnt, wcnt)
+    for i in range(len(rows)):
+        assert np.array_equal(out.numpy()[i, :cnt[i]], want[i, :wcnt[i]]), i
+    for bk in (a, b, c2, d2):
+        bk.close()
+
+
+def test_one_gpu_equals_two_gpus(gpu_lib, golden_meta):
+    """SURVEY.md 8(d) gate '1-GPU == G-GPU': the same feed through one bank holding every channel on device 0 and through two
+    banks holding the two frequency blocks on devices 0 and 1 (b200dsp_dist_shard) gives byte-identical channel outputs and
+    identical front-end outputs.  Needs two devices (the driver's 1-GPU run skips it; run under `gpurun --gpus 2`)."""
+    import ctypes as C
+    from sdrangel_b200 import DownChannelizerBank, capi
+    if capi.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    plan = golden_meta["chan_plans"]["bank1024"]
+    fs = plan["input_rate"]
+    rows = plan["channels"][::16]
+    cutoff = float(np.float32(np.float32(12500) / np.float32(2.2)))
+    rs = np.random.RandomState(8)
+    x = rs.randint(-32768, 32768, size=((1 << 18) + 4096, 2)).astype(np.int16)
+    whole = DownChannelizerBank(fs, device=0)
+    for fc, rate, ofs, path in rows:
+        cid = whole.add_channel(48000, fc)[0]
+        whole.set_frontend(cid, -ofs, cutoff, 48000)
+    parts = []
+    for r in range(2):
+        lo, hi = C.c_int32(), C.c_int32()
+        capi.check(capi.lib().b200dsp_dist_shard(len(rows), 2, r, C.byref(lo), C.byref(hi)))
+        bk = DownChannelizerBank(fs, device=r)
+        for fc, rate, ofs, path in rows[lo.value:hi.value]:
+            cid = bk.add_channel(48000, fc)[0]
+            bk.set_frontend(cid, -ofs, cutoff, 48000)
+        parts.append((bk, lo.value, hi.value))
+    for a, e in ((0, 1 << 18), (1 << 18, x.shape[0])):
+        whole.feed(x[a:e])
+        for bk, lo, hi in parts:
+            bk.feed(x[a:e])
+            for i in range(lo, hi):
+                assert np.array_equal(bk.fetch(i - lo), whole.fetch(i)), (a, i)
+                assert np.array_equal(bk.fetch(i - lo, capi.STAGE_FRONTEND), whole.fetch(i, capi.STAGE_FRONTEND)), (a, i)
+    capi.init(0)
+    whole.close()
+    for bk, _, _ in parts:
+        bk.close()
+
+
+def _sharded_worker(rank, world, nccl_id, fs, rows, q, qs):
+    import torch
+    sys_path_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import sys
+    sys.path.insert(0, sys_path_root)
+    import subprocess
+    subprocess.check_call(["make", "-s", "-C", os.path.join(sys_path_root, "oracle"), "port"])
+    from oracle import portbind
+    from sdrangel_b200 import ShardedBank, capi
+    capi.init(rank)
+    torch.cuda.set_device(rank)
+    cutoff = float(np.float32(np.float32(12500) / np.float32(2.2)))
+    n = 1 << 18
+    rs = np.random.RandomState(3)
+    X = rs.randint(-32768, 32768, size=(4 * n, 2)).astype(np.int16)          # every rank can build the expected input itself
+    sb = ShardedBank(fs, [r[0] for r in rows], 48000, rank, world, nccl_id, frontend=(cutoff, 48000))
+    oracles = []
+    for fc, rate, ofs, path in rows[sb.lo:sb.hi]:
+        o = portbind.PortDownChannelizer()
+        o.configure(fs, 48000, fc)
+        oracles.append((o, portbind.PortFrontEnd(-ofs, rate, 48000, cutoff)))
+    ok = True
+    # block 0: NCCL broadcast of rank 0's device buffer; block 1: sliced host ingest + all-gather
+    xd = torch.from_numpy(X[:n].reshape(-1)).cuda() if rank == 0 else None
+    sb.bcast_begin(0, xd.data_ptr() if rank == 0 else 0, n, 0, None)
+    sb.feed(0)
+    sb.bank.sync()
+    for blk, lo_s in ((0, 0), (1, n)):
+        if blk == 1:
+            cnt = n // world
+            hs = torch.from_numpy(np.ascontiguousarray(X[n + rank * cnt: n + (rank + 1) * cnt]).reshape(-1)).pin_memory()
+            sb.ingest_begin(1, hs.data_ptr(), n)
+            sb.feed(1)
+            sb.bank.sync()
+        for k, (o, fe) in enumerate(oracles):
+            ch = o.feed(X[lo_s:lo_s + n])
+            ok = ok and np.array_equal(sb.bank.fetch(k), ch)
+            wf = fe.feed(ch)
+            gf = sb.bank.fetch(k, capi.STAGE_FRONTEND)
+            ok = ok and gf.shape == wf.shape and rel_rms(gf, wf) <= 1e-5
+    # blocks 2 and 3: the copy-engine chain (IPC slots, stream-ordered counters); the blobs travel through the parent's queues
+    blob = sb.p2p_export(n)
+    q.put(("blob", rank, blob))
+    blobs = qs[rank].get(timeout=120)
+    sb.p2p_import(blobs)
+    for blk in (2, 3):
+        xd = torch.from_numpy(X[blk * n:(blk + 1) * n].reshape(-1)).cuda() if rank == 0 else None
+        torch.cuda.synchronize()
+        sb.p2p_begin(blk % 3, xd.data_ptr() if rank == 0 else 0, n)
+        sb.p2p_feed(blk % 3)
+        sb.bank.sync()
+        sb.sync()
+        for k, (o, fe) in enumerate(oracles):
+            ch = o.feed(X[blk * n:(blk + 1) * n])
+            ok = ok and np.array_equal(sb.bank.fetch(k), ch)
+            wf = fe.feed(ch)
+            gf = sb.bank.fetch(k, capi.STAGE_FRONTEND)
+            ok = ok and gf.shape == wf.shape and rel_rms(gf, wf) <= 1e-5
+    q.put(("done", rank, bool(ok), sb.lo, sb.hi))
+    sb.close()
+
+
+def test_sharded_bank_two_ranks_nccl(gpu_lib, golden_meta):
+    """K6 through the library object: two processes, one GPU each, b200dsp_dist_* (NCCL broadcast of a device-resident block,
+    then a host-fed block by per-rank slices + all-gather), every rank's channels against oracle chains fed the same stream.
+    Needs two devices (run under `gpurun --gpus 2`)."""
+    import torch.multiprocessing as mp
+    from sdrangel_b200 import ShardedBank, capi
+    if capi.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    plan = golden_meta["chan_plans"]["bank1024"]
+    rows = plan["channels"][5::32]
+    nccl_id = ShardedBank.unique_id()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    qs = [ctx.Queue() for _ in range(2)]
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, nccl_id, plan["input_rate"], rows, q, qs)) for r in range(2)]
+    for p in procs:
+        p.start()
+    blobs, res = {}, []
+    while len(res) < 2:
+        msg = q.get(timeout=300)
+        if msg[0] == "blob":
+            blobs[msg[1]] = msg[2]
+            if len(blobs) == 2:
+                for r in range(2):
+                    qs[r].put([blobs[0], blobs[1]])
+        else:
+            res.append(msg[1:])
+    res.sort()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert [r[1] for r in res] == [True, True], res
+    assert res[0][2] == 0 and res[0][3] == res[1][2] and res[1][3] == len(rows)

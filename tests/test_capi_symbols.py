@@ -92,3 +92,23 @@ def test_out_count_8bit_formats_and_bad_arguments(port):
         assert L.b200dsp_decim_out_count(fmt, capi.FMT_F32, 4, 2, 1024) == -1        # 8-bit -> float does not exist in the reference
     assert L.b200dsp_decim_out_count(0, 0, 7, 2, 1024) == -1 and L.b200dsp_decim_out_count(0, 0, 4, 5, 1024) == -1
     assert L.b200dsp_decim_out_count(9, 0, 4, 2, 1024) == -1
+
+
+def test_dist_shard_is_a_partition_and_matches_the_python_helper():
+    """b200dsp_dist_shard (pure host arithmetic): contiguous, disjoint, complete, sizes within one of each other."""
+    import ctypes as C
+    from sdrangel_b200 import capi
+    from sdrangel_b200.sharding import shard_channels
+    L = capi.lib()
+    for n in (0, 1, 7, 64, 1024, 1031):
+        for world in (1, 2, 3, 4, 8):
+            prev = 0
+            for r in range(world):
+                lo, hi = C.c_int32(), C.c_int32()
+                assert L.b200dsp_dist_shard(n, world, r, C.byref(lo), C.byref(hi)) == 0
+                assert (lo.value, hi.value) == shard_channels(n, world, r)
+                assert lo.value == prev and hi.value - lo.value in (n // world, n // world + 1)
+                prev = hi.value
+            assert prev == n
+    lo, hi = C.c_int32(), C.c_int32()
+    assert L.b200dsp_dist_shard(8, 2, 2, C.byref(lo), C.byref(hi)) < 0
