@@ -228,6 +228,31 @@ int b200dsp_interp_destroy(b200dsp_interp_t* h);
 int b200dsp_interp_info(b200dsp_interp_t* h, int* taps_per_phase, float* taps, int taps_cap);
 int b200dsp_interp_decimate(b200dsp_interp_t* h, float* distance_remain, float distance, const float* in_c64, int64_t n_samples,
                             float* out_c64, int64_t cap_samples, int64_t* n_out);
+/* == Interpolator::interpolate (interpolator.h:39-52) in the loop every Tx plugin writes around it
+ *    (plugins/channeltx/modnfm/nfmmod.cpp:126-133, modam/ammod.cpp:120-127, modssb/ssbmod.cpp:146-153):
+ *      for each OUTPUT: if (interp.interpolate(&remain, x[i], &y)) ++i;  out[m++] = y;  remain += distance;
+ *    until the next call would need x[n_samples].  All n_samples inputs are consumed; about n_samples / distance outputs. */
+int b200dsp_interp_interpolate(b200dsp_interp_t* h, float* distance_remain, float distance, const float* in_c64, int64_t n_samples,
+                               float* out_c64, int64_t cap_samples, int64_t* n_out);
+/* == Interpolator::resample (interpolator.h:55-76), the arbitrary P/Q form, in its canonical loop:
+ *      for each input c: consumed = false; do { if (interp.resample(&remain, c, &consumed, &y)) { out[m++] = y; remain += distance; } } while (!consumed); */
+int b200dsp_interp_resample(b200dsp_interp_t* h, float* distance_remain, float distance, const float* in_c64, int64_t n_samples,
+                            float* out_c64, int64_t cap_samples, int64_t* n_out);
+
+/* ---- stand-alone NCO -------------------------------------------------------------------------------------------------
+ * == NCO (sdrbase/dsp/nco.h:40-53, nco.cpp:30-64): 4096-entry cosine table, integer phase advanced BEFORE each lookup,
+ *    nextIQ() = (T[p], -T[(p + 1024) mod 4096]).  One handle == one NCO object (its phase). */
+typedef struct b200dsp_nco b200dsp_nco_t;
+int b200dsp_nco_create(b200dsp_nco_t** h);
+int b200dsp_nco_destroy(b200dsp_nco_t* h);
+int b200dsp_nco_set_freq(b200dsp_nco_t* h, float freq, float sample_rate);       /* == NCO::setFreq: increment = (int) (freq * 4096 / rate) */
+int b200dsp_nco_set_phase(b200dsp_nco_t* h, int phase);                            /* == NCO::setPhase */
+int b200dsp_nco_get(b200dsp_nco_t* h, int* phase, int* phase_increment);
+/* n x nextIQ(): interleaved (re, im) floats; the phase advances by n increments */
+int b200dsp_nco_next_iq(b200dsp_nco_t* h, int64_t n, float* out_c64);
+int b200dsp_nco_next_iq_dev(b200dsp_nco_t* h, int64_t n, float* d_out_c64, void* cuda_stream);
+/* the mix a channel plugin does per sample, as a block: out[i] = Complex(in[i].re, in[i].im) * nco.nextIQ()  (nfmdemod.cpp:152-153) */
+int b200dsp_nco_mix_dev(b200dsp_nco_t* h, const void* d_in_i16, int64_t n, float* d_out_c64, void* cuda_stream);
 
 /* ---- K5: SpectrumVis -------------------------------------------------------------------------------------
  * One handle == one reference SpectrumVis sink (sdrgui/dsp/spectrumvis.cpp:77-254,283-327) with its FFTWindow

@@ -632,6 +632,96 @@ int orc_frontend_feed(void* h, const int16_t* iq, int n, float* out, int cap, in
     return m;
 }
 
+/* Interpolator::decimate / interpolate / resample on complex float input in their callers' loops (no NCO):
+ * mode 0 decimate   interpolator.h:23-36 + nfmdemod.cpp:150-155,315
+ * mode 1 interpolate interpolator.h:39-52 + plugins/channeltx/modnfm/nfmmod.cpp:126-133 (one call per output, fetch on consumed)
+ * mode 2 resample   interpolator.h:55-76, per input "do { if (resample) { emit; remain += distance } } while (!consumed)" */
+static void frontend_push(frontend_t* f, float re, float im)
+{
+    f->ptr--;
+    if (f->ptr < 0) f->ptr = f->ntaps - 1;
+    f->ring[2 * f->ptr] = re;
+    f->ring[2 * f->ptr + 1] = im;
+}
+static void frontend_dot(frontend_t* f, float* out)
+{
+    int ph = (int) floorf(f->remain * (float) f->phase_steps);
+    if (ph < 0) ph = 0;
+    const float* t = f->taps + (size_t) ph * f->ntaps;
+    float ra = 0, ia = 0;
+    int s = f->ptr;
+    for (int k = 0; k < f->ntaps; k++) {
+        ra += t[k] * f->ring[2 * s];
+        ia += t[k] * f->ring[2 * s + 1];
+        s = (s + 1) % f->ntaps;
+    }
+    out[0] = ra; out[1] = ia;
+}
+int orc_interp_run(void* h, int mode, const float* cin, int n, float* out, int cap)
+{
+    frontend_t* f = (frontend_t*) h;
+    int m = 0;
+    if (mode == 0) {
+        for (int i = 0; i < n; i++) {
+            frontend_push(f, cin[2 * i], cin[2 * i + 1]);
+            f->remain = (float) ((double) f->remain - 1.0);
+            if (f->remain >= 1.0f) continue;
+            if (m >= cap) return -1;
+            frontend_dot(f, out + 2 * m); m++;
+            f->remain += f->distance;
+        }
+    } else if (mode == 1) {
+        int i = 0;
+        for (;;) {
+            if (f->remain >= 1.0f) {
+                if (i >= n) break;
+                frontend_push(f, cin[2 * i], cin[2 * i + 1]);
+                f->remain = (float) ((double) f->remain - 1.0);
+                i++;
+            }
+            if (m >= cap) return -1;
+            frontend_dot(f, out + 2 * m); m++;
+            f->remain += f->distance;
+        }
+    } else {
+        for (int i = 0; i < n; i++) {
+            int consumed = 0;
+            do {
+                int ok = 1;
+                while (f->remain >= 1.0f) {
+                    if (!consumed) {
+                        frontend_push(f, cin[2 * i], cin[2 * i + 1]);
+                        f->remain = (float) ((double) f->remain - 1.0);
+                        consumed = 1;
+                    } else { ok = 0; break; }
+                }
+                if (ok) {
+                    if (m >= cap) return -1;
+                    frontend_dot(f, out + 2 * m); m++;
+                    f->remain += f->distance;
+                }
+            } while (!consumed);
+        }
+    }
+    return m;
+}
+float orc_frontend_remain(void* h) { return ((frontend_t*) h)->remain; }
+/* NCO::nextIQ n times (nco.h:40-53, nco.cpp:30-64) */
+void orc_nco_block(float freq, float rate, int n, float* out)
+{
+    static float table[4096];
+    static int init = 0;
+    if (!init) { orc_nco_table(table); init = 1; }
+    int inc = orc_nco_increment(freq, rate), phase = 0;
+    for (int i = 0; i < n; i++) {
+        phase += inc;
+        while (phase >= 4096) phase -= 4096;
+        while (phase < 0) phase += 4096;
+        out[2 * i] = table[phase];
+        out[2 * i + 1] = -table[(phase + 1024) % 4096];
+    }
+}
+
 /* ------------------------------------------------------------------------------------------------
  * FFT window (fftwindow.h:52-84, fftwindow.cpp:20-52): Real(n), Real(i) arguments, double evaluation, float result
  * ---------------------------------------------------------------------------------------------- */

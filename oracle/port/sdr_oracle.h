@@ -62,6 +62,10 @@ void* orc_frontend_create(float nco_freq, float nco_rate, int phase_steps, doubl
                           double taps_per_phase, float distance);
 void  orc_frontend_destroy(void* h);
 int   orc_frontend_feed(void* h, const int16_t* iq, int n, float* out, int cap, int32_t* idx, int32_t* phase);
+/* Interpolator::decimate (mode 0) / interpolate (1) / resample (2) on complex float input in their callers' loops */
+int   orc_interp_run(void* h, int mode, const float* cin, int n, float* out, int cap);
+float orc_frontend_remain(void* h);
+void  orc_nco_block(float freq, float rate, int n, float* out);
 
 /* FFTWindow / KissFFT / SpectrumVis: fftwindow.cpp:20-73, kissfft.h:44-80,127-238, sdrgui/dsp/spectrumvis.cpp:77-327 */
 void  orc_fft_window(int function, int n, float* w);

@@ -52,6 +52,8 @@ def load():
         "orc_interp_ntaps": (i32, [i32, f64]), "orc_interp_taps": (None, [i32, f64, f64, f64, pf32]),
         "orc_frontend_create": (vp, [f32, f32, i32, f64, f64, f64, f32]), "orc_frontend_destroy": (None, [vp]),
         "orc_frontend_feed": (i32, [vp, pi16, i32, pf32, i32, pi32, pi32]),
+        "orc_interp_run": (i32, [vp, i32, pf32, i32, pf32, i32]), "orc_frontend_remain": (f32, [vp]),
+        "orc_nco_block": (None, [f32, f32, i32, pf32]),
         "orc_fft_window": (None, [i32, i32, pf32]), "orc_kissfft_forward": (None, [i32, pf32, pf32]),
         "orc_spectrum_create": (vp, [f32]), "orc_spectrum_destroy": (None, [vp]),
         "orc_spectrum_configure": (None, [vp, i32, i32, C.c_uint, i32, i32, i32]),
@@ -172,11 +174,31 @@ class PortFrontEnd(_Handle):
             return out[:m].copy(), idx[:m].copy(), ph[:m].copy()
         return out[:m].copy()
 
+    def run_c64(self, mode, x, cap=None):
+        """Interpolator::decimate (mode 0) / interpolate (1) / resample (2) on complex64 input in the callers' loops."""
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        n = x.shape[0]
+        cap = int(cap or (n * 64 + 64))
+        out = np.empty((cap, 2), dtype=np.float32)
+        m = load().orc_interp_run(self.h, int(mode), _p(x.view(np.float32), C.c_float), n, _p(out, C.c_float), cap)
+        assert m >= 0
+        return out[:m].copy().view(np.complex64).reshape(-1)
+
+    def remain(self):
+        return float(load().orc_frontend_remain(self.h))
+
 
 def nco_table():
     t = np.empty(4096, dtype=np.float32)
     load().orc_nco_table(_p(t, C.c_float))
     return t
+
+
+def nco_block(freq, rate, n):
+    """NCO::setFreq(freq, rate) then n x nextIQ() as complex64."""
+    out = np.empty((n, 2), dtype=np.float32)
+    load().orc_nco_block(float(freq), float(rate), int(n), _p(out, C.c_float))
+    return out.view(np.complex64).reshape(-1)
 
 
 def fft_window(function, n):

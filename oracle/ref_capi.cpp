@@ -356,6 +356,57 @@ int ref_interp_decimate(void* p, const float* cin, int n, float* out, int cap)
     return m;
 }
 
+// Interpolator::interpolate in the loop every Tx plugin writes around it (plugins/channeltx/modnfm/nfmmod.cpp:126-133,
+// modam/ammod.cpp:120-127, modssb/ssbmod.cpp:146-153): one call per OUTPUT sample, a new input is fetched when the call
+// consumed the current one, then distanceRemain += distance.  Stops when the next call would need input n.
+int ref_interp_interpolate(void* p, const float* cin, int n, float* out, int cap)
+{
+    FrontEnd* f = (FrontEnd*) p;
+    int m = 0, i = 0;
+    Complex ci;
+    while (i < n || f->distanceRemain < 1.0f) {
+        if (f->distanceRemain >= 1.0f && i >= n) break;
+        Complex c = (i < n) ? Complex(cin[2 * i], cin[2 * i + 1]) : Complex(0, 0);     // (not consumed when i == n: distanceRemain < 1)
+        if (f->interp.interpolate(&f->distanceRemain, c, &ci)) i++;
+        if (m >= cap) return -1;
+        out[2 * m] = ci.real();
+        out[2 * m + 1] = ci.imag();
+        m++;
+        f->distanceRemain += f->distance;
+    }
+    return m;
+}
+// Interpolator::resample (the arbitrary P/Q form, interpolator.h:55-76) in its canonical loop: per input, call until consumed;
+// every call that returns true yields an output and distanceRemain += distance.
+int ref_interp_resample(void* p, const float* cin, int n, float* out, int cap)
+{
+    FrontEnd* f = (FrontEnd*) p;
+    int m = 0;
+    Complex ci;
+    for (int i = 0; i < n; i++) {
+        Complex c(cin[2 * i], cin[2 * i + 1]);
+        bool consumed = false;
+        do {
+            if (f->interp.resample(&f->distanceRemain, c, &consumed, &ci)) {
+                if (m >= cap) return -1;
+                out[2 * m] = ci.real();
+                out[2 * m + 1] = ci.imag();
+                m++;
+                f->distanceRemain += f->distance;
+            }
+        } while (!consumed);
+    }
+    return m;
+}
+float ref_frontend_remain(void* p) { return ((FrontEnd*) p)->distanceRemain; }
+// NCO::nextIQ n times (nco.h:40-53, nco.cpp:48-64): (re, im) pairs
+void ref_nco_block(float freq, float rate, int n, float* out)
+{
+    NCO nco;
+    nco.setFreq(freq, rate);
+    for (int i = 0; i < n; i++) { Complex c = nco.nextIQ(); out[2 * i] = c.real(); out[2 * i + 1] = c.imag(); }
+}
+
 // ---------------------------------------------------------------- SpectrumVis (glue restated, arithmetic is reference code)
 void ref_spectrum_configure(void* p, int fftSize, int overlapPercent, unsigned int averageNb, int averagingMode, int window, int linear);
 

@@ -55,6 +55,8 @@ def load(strict=False):
         "ref_frontend_taps": (None, [vp, pf32]), "ref_nco_table": (None, [pf32]),
         "ref_frontend_feed": (i32, [vp, pi16, i32, pf32, i32, pi32, pi32]),
         "ref_interp_decimate": (i32, [vp, pf32, i32, pf32, i32]),
+        "ref_interp_interpolate": (i32, [vp, pf32, i32, pf32, i32]), "ref_interp_resample": (i32, [vp, pf32, i32, pf32, i32]),
+        "ref_frontend_remain": (f32, [vp]), "ref_nco_block": (None, [f32, f32, i32, pf32]),
         "ref_spectrum_create": (vp, [f32]), "ref_spectrum_destroy": (None, [vp]),
         "ref_spectrum_configure": (None, [vp, i32, i32, C.c_uint, i32, i32, i32]),
         "ref_spectrum_window": (None, [vp, pf32]), "ref_spectrum_fft": (None, [vp, pf32, pf32]),
@@ -174,6 +176,26 @@ class RefFrontEnd(_Handle):
         if want_schedule:
             return out[:m].copy(), idx[:m].copy(), ph[:m].copy()
         return out[:m].copy()
+
+    def run_c64(self, mode, x, cap=None):
+        """Interpolator::decimate (mode 0) / interpolate (1) / resample (2) on complex64 input in the callers' loops."""
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        n = x.shape[0]
+        cap = int(cap or (n * 64 + 64))
+        out = np.empty((cap, 2), dtype=np.float32)
+        fn = (self.lib.ref_interp_decimate, self.lib.ref_interp_interpolate, self.lib.ref_interp_resample)[mode]
+        m = fn(self.h, _p(x.view(np.float32), C.c_float), n, _p(out, C.c_float), cap)
+        assert m >= 0
+        return out[:m].copy().view(np.complex64).reshape(-1)
+
+    def remain(self):
+        return float(self.lib.ref_frontend_remain(self.h))
+
+
+def nco_block(freq, rate, n, strict=False):
+    out = np.empty((n, 2), dtype=np.float32)
+    load(strict).ref_nco_block(float(freq), float(rate), int(n), _p(out, C.c_float))
+    return out.view(np.complex64).reshape(-1)
 
 
 def nco_table(strict=False):

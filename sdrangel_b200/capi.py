@@ -74,6 +74,16 @@ SIGNATURES = {
     "b200dsp_dist_p2p_begin": (_i32, [_vp, _i32, _vp, _i64, _vp]),
     "b200dsp_dist_p2p_feed": (_i32, [_vp, _i32, _vp, _vp]),
     "b200dsp_dist_p2p_slot": (_i32, [_vp, _i32, _pvp, _pi64]),
+    "b200dsp_interp_interpolate": (_i32, [_vp, C.POINTER(_f32), _f32, _vp, _i64, _vp, _i64, _pi64]),
+    "b200dsp_interp_resample": (_i32, [_vp, C.POINTER(_f32), _f32, _vp, _i64, _vp, _i64, _pi64]),
+    "b200dsp_nco_create": (_i32, [_pvp]),
+    "b200dsp_nco_destroy": (_i32, [_vp]),
+    "b200dsp_nco_set_freq": (_i32, [_vp, _f32, _f32]),
+    "b200dsp_nco_set_phase": (_i32, [_vp, _i32]),
+    "b200dsp_nco_get": (_i32, [_vp, _pi32, _pi32]),
+    "b200dsp_nco_next_iq": (_i32, [_vp, _i64, _vp]),
+    "b200dsp_nco_next_iq_dev": (_i32, [_vp, _i64, _vp, _vp]),
+    "b200dsp_nco_mix_dev": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "b200dsp_bank_copy_out_dev": (_i32, [_vp, _i32, _i64, _i64, _vp, _vp]),
     "b200dsp_bank_sync": (_i32, [_vp]),
     "b200dsp_bank_tree_time": (_i32, [_vp, _vp, _vp]),

@@ -156,7 +156,7 @@ struct b200dsp_interp {
     int phase_steps = 0, ntaps = 0, parity = 0;
     std::vector<float> taps;
     float* d_taps = nullptr; uint32_t* d_hist = nullptr; int* d_state = nullptr; long long* d_plan = nullptr; FrontendChan* d_chan = nullptr;
-    float2* d_in = nullptr; float2* d_out = nullptr; int* d_sched = nullptr; int* d_tile = nullptr; long long cap = 0;
+    float2* d_in = nullptr; float2* d_out = nullptr; int* d_sched = nullptr; int* d_tile = nullptr; long long cap = 0, cap_out = 0;
 };
 
 struct b200dsp_bank {
@@ -555,7 +555,7 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
             Channel& c = b->chans[b->fe_index[k]];
             FrontendChan& f = b->h_fe[k];
             f.in = c.d_out; f.hist = c.d_hist; f.taps = c.d_taps; f.out = c.d_fe_out; f.sched = c.d_sched; f.tile_start = c.d_tile; f.state = c.d_state; f.plan = c.d_plan; f.A = c.A; f.lattice = c.lattice; f.phshift = c.phshift; f.in_f32 = 0; f.hist_stride = FE_HIST_WORDS;
-            f.depth = c.S; f.inc = c.inc; f.ntaps = c.ntaps; f.phase_steps = c.phase_steps; f.ratio = c.ratio;
+            f.depth = c.S; f.inc = c.inc; f.ntaps = c.ntaps; f.phase_steps = c.phase_steps; f.ratio = c.ratio; f.mode = 0; f.sched_cap = (int) c.fe_cap;
         }
         if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(b->d_leaf, b->h_leaf.data(), nc * sizeof(LeafChan), cudaMemcpyHostToDevice, st)))) return rc;
         if (!b->h_fe.empty() && (rc = B200_CUDA_CHECK(cudaMemcpyAsync(b->d_fe, b->h_fe.data(), b->h_fe.size() * sizeof(FrontendChan), cudaMemcpyHostToDevice, st)))) return rc;
@@ -1295,29 +1295,41 @@ int b200dsp_interp_info(b200dsp_interp_t* h, int* taps_per_phase, float* taps, i
     return 0;
 }
 
-int b200dsp_interp_decimate(b200dsp_interp_t* h, float* distance_remain, float distance, const float* in_c64, int64_t n, float* out_c64, int64_t cap, int64_t* n_out)
+namespace {
+
+// the three caller loops around Interpolator (frontend.cuh: FrontendChan::mode) on one block of complex64 samples
+int interp_run(b200dsp_interp* h, int mode, float* distance_remain, float distance, const float* in_c64, int64_t n, float* out_c64, int64_t cap, int64_t* n_out)
 {
-    if (!h || !distance_remain) return b200_fail(B200DSP_EINVAL, "interp_decimate: null argument");
-    if (n < 0 || n >= (1 << 24) || (n > 0 && (!in_c64 || !out_c64))) return b200_fail(B200DSP_EINVAL, "interp_decimate: bad buffer (at most 2^24-1 samples per call)");
-    if (!(distance > 0.0f)) return b200_fail(B200DSP_EINVAL, "interp_decimate: distance must be positive");
+    if (!h || !distance_remain) return b200_fail(B200DSP_EINVAL, "interp: null argument");
+    if (n < 0 || n >= (1 << 24) - 1 || (n > 0 && !in_c64) || (cap > 0 && !out_c64) || cap < 0) return b200_fail(B200DSP_EINVAL, "interp: bad buffer (at most 2^24-2 samples per call)");
+    if (!(distance > 0.0f)) return b200_fail(B200DSP_EINVAL, "interp: distance must be positive");
     if (n_out) *n_out = 0;
-    if (n == 0) return 0;
+    if (n == 0 && mode != 1) return 0;                       // (the interpolate loop may still emit outputs while distance_remain < 1)
     int rc = B200_CUDA_CHECK(cudaSetDevice(h->device));
     if (rc) return rc;
-    if (h->cap < n) {
+    // outputs of one call: never more than the inputs when decimating; otherwise bounded by (n + 2) / distance + 2
+    long long cap_out = n + 2;
+    if (mode != 0) {
+        const double bound = ((double) n + 2.0) / (double) distance + 4.0;
+        if (bound >= (double) (1 << 28)) return b200_fail(B200DSP_EINVAL, "interp: distance too small for one call");
+        if ((long long) bound > cap_out) cap_out = (long long) bound;
+    }
+    if (h->cap < n || h->cap_out < cap_out) {
         void* old[] = { h->d_in, h->d_out, h->d_sched, h->d_tile };
         for (void* p : old) if (p) cudaFree(p);
-        h->d_in = nullptr; h->d_out = nullptr; h->d_sched = nullptr; h->d_tile = nullptr; h->cap = 0;
-        if ((rc = B200_CUDA_CHECK(cudaMalloc(&h->d_in, (size_t) n * 8))) || (rc = B200_CUDA_CHECK(cudaMalloc(&h->d_out, (size_t) (n + 2) * 8))) ||
-            (rc = B200_CUDA_CHECK(cudaMalloc(&h->d_sched, (size_t) (n + 2) * 4))) || (rc = B200_CUDA_CHECK(cudaMalloc(&h->d_tile, (size_t) (n / FE_TILE + 4) * 4)))) return rc;
-        h->cap = n;
+        h->d_in = nullptr; h->d_out = nullptr; h->d_sched = nullptr; h->d_tile = nullptr; h->cap = 0; h->cap_out = 0;
+        const long long ci = n > h->cap ? n : h->cap, co = cap_out > h->cap_out ? cap_out : h->cap_out;
+        if ((rc = B200_CUDA_CHECK(cudaMalloc(&h->d_in, (size_t) (ci + 1) * 8))) || (rc = B200_CUDA_CHECK(cudaMalloc(&h->d_out, (size_t) (co + 2) * 8))) ||
+            (rc = B200_CUDA_CHECK(cudaMalloc(&h->d_sched, (size_t) (co + 2) * 4))) || (rc = B200_CUDA_CHECK(cudaMalloc(&h->d_tile, (size_t) (ci / FE_TILE + 4) * 4)))) return rc;
+        h->cap = ci; h->cap_out = co;
     }
     FrontendChan f;
     memset(&f, 0, sizeof(f));
     f.in = (const uint32_t*) h->d_in; f.hist = h->d_hist; f.taps = h->d_taps; f.out = h->d_out; f.sched = h->d_sched; f.tile_start = h->d_tile;
     f.state = h->d_state; f.plan = h->d_plan; f.in_f32 = 1; f.hist_stride = 2 * FE_MAX_TAPS + 4;
     f.depth = 0; f.inc = 0; f.ntaps = h->ntaps; f.phase_steps = h->phase_steps; f.ratio = distance;
-    f.lattice = lattice_params(distance, h->phase_steps, &f.A, &f.phshift) ? 1 : 0;
+    f.mode = mode; f.sched_cap = (int) h->cap_out;
+    f.lattice = (mode == 0 && lattice_params(distance, h->phase_steps, &f.A, &f.phshift)) ? 1 : 0;
     // the caller owns the distance (Real* distance in the reference): it travels in, and back out
     int st[4] = { 0, 0, 0, 0 };
     memcpy(&st[1], distance_remain, 4);
@@ -1328,21 +1340,41 @@ int b200dsp_interp_decimate(b200dsp_interp_t* h, float* distance_remain, float d
     memset(&pi, 0, sizeof(pi));
     pi.n_new[0] = (int) n; pi.first_pass = 1; pi.parity = h->parity;
     const size_t smem = ((((size_t) ((h->ntaps + 2 * FE_PAD) | 1) * h->phase_steps + 3) & ~(size_t) 3)) * 4 + (size_t) (FE_MAX_TAPS + FE_TILE + FE_Z_EXTRA) * sizeof(float2);
-    if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(h->d_in, in_c64, (size_t) n * 8, cudaMemcpyHostToDevice, h->stream))) ||
+    if ((n > 0 && (rc = B200_CUDA_CHECK(cudaMemcpyAsync(h->d_in, in_c64, (size_t) n * 8, cudaMemcpyHostToDevice, h->stream)))) ||
         (rc = B200_CUDA_CHECK(cudaMemcpyAsync(h->d_state, st, 16, cudaMemcpyHostToDevice, h->stream))) ||
         (rc = B200_CUDA_CHECK(cudaMemcpyAsync(h->d_chan, &f, sizeof(f), cudaMemcpyHostToDevice, h->stream)))) return rc;
+    if (smem > 48 * 1024 && (rc = B200_CUDA_CHECK(cudaFuncSetAttribute((const void*) frontend_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)))) return rc;
     frontend_schedule_kernel<<<1, 32, 0, h->stream>>>(h->d_chan, 1, pi);
-    frontend_kernel_t<false><<<dim3((unsigned) ((n + FE_TILE - 1) / FE_TILE), 1), FE_THREADS, smem, h->stream>>>(h->d_chan, nullptr, pi);
+    const unsigned tiles = (unsigned) ((n + FE_TILE - 1) / FE_TILE);
+    frontend_kernel_t<false><<<dim3(tiles ? tiles : 1, 1), FE_THREADS, smem, h->stream>>>(h->d_chan, nullptr, pi);
     if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
     if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(st, h->d_state, 16, cudaMemcpyDeviceToHost, h->stream))) ||
         (rc = B200_CUDA_CHECK(cudaStreamSynchronize(h->stream)))) return rc;
     h->parity ^= 1;
+    if (st[0]) return b200_fail(B200DSP_ESTATE, "interp: more outputs than the schedule buffer holds (internal bound exceeded)");
     memcpy(distance_remain, &st[1], 4);
     const long long m = st[2];
     if (n_out) *n_out = m;
-    if (m > cap) return b200_fail(B200DSP_EINVAL, "interp_decimate: output buffer too small (%lld needed)", m);
+    if (m > cap) return b200_fail(B200DSP_EINVAL, "interp: output buffer too small (%lld needed)", m);
     if (m > 0) return B200_CUDA_CHECK(cudaMemcpy(out_c64, h->d_out, (size_t) m * 8, cudaMemcpyDeviceToHost));
     return 0;
+}
+
+} // namespace
+
+int b200dsp_interp_decimate(b200dsp_interp_t* h, float* distance_remain, float distance, const float* in_c64, int64_t n, float* out_c64, int64_t cap, int64_t* n_out)
+{
+    return interp_run(h, 0, distance_remain, distance, in_c64, n, out_c64, cap, n_out);
+}
+
+int b200dsp_interp_interpolate(b200dsp_interp_t* h, float* distance_remain, float distance, const float* in_c64, int64_t n, float* out_c64, int64_t cap, int64_t* n_out)
+{
+    return interp_run(h, 1, distance_remain, distance, in_c64, n, out_c64, cap, n_out);
+}
+
+int b200dsp_interp_resample(b200dsp_interp_t* h, float* distance_remain, float distance, const float* in_c64, int64_t n, float* out_c64, int64_t cap, int64_t* n_out)
+{
+    return interp_run(h, 2, distance_remain, distance, in_c64, n, out_c64, cap, n_out);
 }
 
 } // extern "C"

@@ -42,6 +42,9 @@ struct FrontendChan {            // one per channel with a front-end, device arr
     int             inc;         // NCO phase increment
     int             ntaps, phase_steps;
     float           ratio;       // m_interpolatorDistance
+    int             mode;        // caller loop the schedule replays: 0 Interpolator::decimate (Rx plugins), 1 ::interpolate (Tx pull loop),
+                                 // 2 ::resample (do-while per input); modes 1-2 store idx + 1 (an output may precede the pass's first input)
+    int             sched_cap;   // entries of `sched` (modes 1-2: outputs are not bounded by the input count)
 };
 
 // per-pass scalars, identical for all nodes/channels of one depth (every stream of a depth has the same length)
@@ -92,6 +95,49 @@ __global__ void frontend_schedule_kernel(const FrontendChan* __restrict__ chans,
             sched[n++] = (int) (((unsigned) i << 8) | (unsigned) ph);   /* i < 2^24, ph < 256 */ \
             d = __fadd_rn(r, ratio);                                                           \
         }
+        if (c.mode != 0) {
+            // Interpolator::interpolate / resample in their callers' loops (interpolator.h:39-76; nfmmod.cpp:126-133): per OUTPUT
+            // one iteration; `-= 1.0` is exact for d in [1, 2^24), `+= ratio` and the phase product are float32 operations
+            int over = 0;
+            if (c.mode == 1) {
+                for (;;) {
+                    if (d >= 1.0f) {
+                        if (i + 1 >= m) break;
+                        ++i;
+                        d = __fsub_rn(d, 1.0f);
+                    }
+                    if (n >= c.sched_cap) { over = 1; break; }
+                    int ph = (int) floorf(__fmul_rn(d, steps));
+                    ph = ph < 0 ? 0 : ph;
+                    sched[n++] = (int) (((unsigned) (i + 1) << 8) | (unsigned) ph);
+                    d = __fadd_rn(d, ratio);
+                }
+            } else {
+                for (int ii = 0; ii < m && !over; ++ii) {
+                    bool consumed = false;
+                    do {
+                        bool ok = true;
+                        while (d >= 1.0f) {
+                            if (!consumed) { i = ii; d = __fsub_rn(d, 1.0f); consumed = true; }
+                            else { ok = false; break; }
+                        }
+                        if (ok) {
+                            if (n >= c.sched_cap) { over = 1; break; }
+                            int ph = (int) floorf(__fmul_rn(d, steps));
+                            ph = ph < 0 ? 0 : ph;
+                            sched[n++] = (int) (((unsigned) ((consumed ? ii : ii - 1) + 1) << 8) | (unsigned) ph);
+                            d = __fadd_rn(d, ratio);
+                        }
+                    } while (!consumed);
+                }
+            }
+            c.plan[0] = n; c.plan[1] = 0; c.plan[2] = 0; c.plan[3] = 0;
+            const int base = pi.first_pass ? 0 : c.state[3];
+            c.state[0] = over;
+            c.state[1] = __float_as_int(d);
+            c.state[2] = n;
+            c.state[3] = base + n;
+        } else {
         if (!c.lattice) {
             // an emission consumes at most max(1, floor(d)) <= max(d0, ratio + 1) inputs: 8 at a time while that is safe
             const int per8 = 8 * ((int) fmaxf(ratio + 1.0f, d) + 1);
@@ -131,6 +177,7 @@ __global__ void frontend_schedule_kernel(const FrontendChan* __restrict__ chans,
         c.state[1] = __float_as_int(d);
         c.state[2] = total;
         c.state[3] = base + total;
+        }
     }
     __syncwarp();
     n = __shfl_sync(0xffffffffu, n, 0);
@@ -141,8 +188,9 @@ __global__ void frontend_schedule_kernel(const FrontendChan* __restrict__ chans,
     for (int t = lane; t <= ntiles; t += 32) {
         const int T = t * FE_TILE;
         int lo = 0, hi = n;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int) ((unsigned) sched[mid] >> 8) < T) lo = mid + 1; else hi = mid; }
-        int o = lo;
+        const int bias = c.mode ? 1 : 0;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int) ((unsigned) sched[mid] >> 8) - bias < T) lo = mid + 1; else hi = mid; }
+        int o = (t == 0) ? 0 : lo;                 // (an output that precedes the pass's first input belongs to the first tile)
         if (lo == n && ncf > 0) {
             const long long need = (((long long) T - i0 + 1) << 23) - D;
             long long k = need <= 0 ? 0 : (need + c.A - 1) / c.A;
@@ -217,7 +265,7 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel_t(const FrontendCh
                 ph = (int) ((E & 0x7fffffll) >> c.phshift);
             } else {
                 const unsigned s = (unsigned) c.sched[o];
-                idx[q] = (int) (s >> 8); ph = (int) (s & 0xffu);
+                idx[q] = (int) (s >> 8) - (c.mode ? 1 : 0); ph = (int) (s & 0xffu);
             }
             trow[q] = taps + ph * nts + FE_PAD;
         }

@@ -453,6 +453,60 @@ class Interpolator:
         capi.check(capi.lib().b200dsp_interp_decimate(self._h, C.byref(rem), float(distance), x.ctypes.data, x.size, out.ctypes.data, out.size, C.byref(n)))
         return out[:n.value], rem.value
 
+    def _up(self, fn, distance_remain, distance, samples):
+        x = np.ascontiguousarray(samples, dtype=np.complex64)
+        out = np.empty(int((x.size + 2) / float(distance)) + x.size + 8, dtype=np.complex64)
+        rem = C.c_float(float(distance_remain))
+        n = C.c_int64(0)
+        capi.check(fn(self._h, C.byref(rem), float(distance), x.ctypes.data if x.size else None, x.size, out.ctypes.data, out.size, C.byref(n)))
+        return out[:n.value], rem.value
+
+    def interpolate(self, distance_remain, distance, samples):
+        """== the Tx plugins' loop around Interpolator::interpolate (nfmmod.cpp:126-133): (outputs, new distance_remain)."""
+        return self._up(capi.lib().b200dsp_interp_interpolate, distance_remain, distance, samples)
+
+    def resample(self, distance_remain, distance, samples):
+        """== the canonical loop around Interpolator::resample (interpolator.h:55-76): (outputs, new distance_remain)."""
+        return self._up(capi.lib().b200dsp_interp_resample, distance_remain, distance, samples)
+
+
+class NCO:
+    """NCO (sdrbase/dsp/nco.h:40-53, nco.cpp:30-64): setFreq, setPhase, block form of nextIQ()."""
+
+    def __init__(self, device=None):
+        if device is not None:
+            capi.init(device)
+        h = C.c_void_p()
+        capi.check(capi.lib().b200dsp_nco_create(C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            capi.lib().b200dsp_nco_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def setFreq(self, freq, sample_rate):
+        capi.check(capi.lib().b200dsp_nco_set_freq(self._h, float(freq), float(sample_rate)))
+
+    def setPhase(self, phase):
+        capi.check(capi.lib().b200dsp_nco_set_phase(self._h, int(phase)))
+
+    def state(self):
+        p, i = C.c_int32(), C.c_int32()
+        capi.check(capi.lib().b200dsp_nco_get(self._h, C.byref(p), C.byref(i)))
+        return p.value, i.value
+
+    def nextIQ(self, n):
+        out = np.empty(int(n), dtype=np.complex64)
+        capi.check(capi.lib().b200dsp_nco_next_iq(self._h, int(n), out.ctypes.data))
+        return out
+
 
 class IQCorrections:
     """DSPDeviceSourceEngine::iqCorrections (sdrbase/dsp/dspdevicesourceengine.cpp:175-262): the engine's DC (and I/Q

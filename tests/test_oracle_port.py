@@ -3,7 +3,10 @@ from the UNMODIFIED reference compiled in place (oracle/gen_golden.py).  This is
 import numpy as np
 import pytest
 
-from conftest import MODES, fnv1a64_u16, rel_rms, stream_input
+import json
+import os
+
+from conftest import GOLDEN_DIR, MODES, fnv1a64_u16, rel_rms, stream_input
 
 
 def test_sdrbench_generator_matches_reference(port, golden_meta):
@@ -185,3 +188,45 @@ def test_spectrum_window_fft_and_feed(port, golden, golden_meta):
             ok = np.isfinite(ref) & np.isfinite(keep)
             assert ok.mean() > 0.99
             assert np.max(np.abs(keep[ok] - ref[ok])) <= 2e-3
+
+
+@pytest.fixture(scope="module")
+def golden_interp():
+    z = np.load(os.path.join(GOLDEN_DIR, "golden_interp.npz"))
+    with open(os.path.join(GOLDEN_DIR, "golden_interp.json")) as f:
+        return {k: z[k] for k in z.files}, json.load(f)
+
+
+def interp_input(meta):
+    rs = np.random.RandomState(meta["seed"])
+    n = meta["n"]
+    return (rs.randint(-20000, 20000, size=n) + 1j * rs.randint(-20000, 20000, size=n)).astype(np.complex64)
+
+
+def test_interpolate_resample_and_nco_vs_reference(port, golden_interp):
+    """Interpolator::interpolate / resample in their callers' loops (interpolator.h:39-76; nfmmod.cpp:126-133) and the
+    stand-alone NCO: the C restatement against vectors from the reference built in place (oracle/gen_golden_interp.py) --
+    identical output counts per call and carried distance, values within float32 rounding of both reference builds."""
+    g, meta = golden_interp
+    x = interp_input(meta)
+    cuts = meta["cuts"]
+    for rin, rout in meta["cases"]:
+        cutoff = float(np.float32(min(rin, rout) / 2.2))
+        dist = float(np.float32(np.float32(rin) / np.float32(rout)))
+        for name, mode in meta["modes"].items():
+            key = "%s/strict/%d_%d" % (name, rin, rout)
+            if key + "/out" not in g:
+                continue
+            fe = port.PortFrontEnd(0, max(rin, rout), max(rin, rout), cutoff)
+            port.load().orc_frontend_destroy(fe.h)
+            fe.h = port.load().orc_frontend_create(0.0, float(max(rin, rout)), 16, float(max(rin, rout)), cutoff, 4.5, dist)
+            outs = [fe.run_c64(mode, x[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+            assert [o.shape[0] for o in outs] == g[key + "/counts"].tolist(), key
+            assert np.float32(fe.remain()) == g[key + "/remain"][0], key
+            out = np.concatenate(outs)
+            assert rel_rms(out.view(np.float32), g[key + "/out"].view(np.float32)) <= 1e-6, key
+            fast = "%s/fast/%d_%d" % (name, rin, rout)
+            assert g[fast + "/counts"].tolist() == g[key + "/counts"].tolist()
+            assert rel_rms(out.view(np.float32), g[fast + "/out"].view(np.float32)) <= 1e-5, key
+    for freq, rate in meta["nco_cases"]:
+        assert np.array_equal(port.nco_block(freq, rate, 5000), g["nco/%g_%g" % (freq, rate)]), (freq, rate)
