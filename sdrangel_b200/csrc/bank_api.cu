@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "hb48_tree.cuh"
 #include "hb48_fused.cuh"
+#include "hb48_chain.cuh"
 #include "frontend.cuh"
 #include <math.h>
 #include <stdlib.h>
@@ -182,6 +183,7 @@ struct b200dsp_bank {
     // fused multi-level launches (hb48_fused.cuh): the tree cut into depth ranges [b, b+k]
     struct FusedLaunch { int b, k, T; size_t smem; int n_groups, n_fams; FusedGroup* d_groups; FusedFam* d_fams; int lvl_off[FZ_MAXK]; };
     std::vector<FusedLaunch> flaunch;
+    int chain_L; int chain_rot[CH_MAXL + 1]; int chain_index[CH_MAXL + 1];     // leading run of single-child levels (hb48_chain.cuh): depth, stage modes, node index per level
     bool fused_on;                               // B200DSP_NO_FUSED_TREE unset: aligned passes take hb48_fused_kernel
     // per-channel device buffers are rows of a few slabs (one allocation each, not seven per channel)
     uint32_t* slab_out; long long out_pitch;     // [channel][out_pitch] packed int16 IQ: channelizer outputs of the current feed
@@ -327,7 +329,20 @@ int build_fused_plan(b200dsp_bank* b, const std::vector<char>& is_leaf)
         nc = (nc == -1) ? (int) i : -2;
     }
     b->chan_direct.assign(b->chans.size(), 0);
-    int b0 = 0;
+    // leading chain: while the node has exactly one child, and that child is not itself a channel's last stage
+    b->chain_L = 0;
+    b->chain_index[0] = 0;
+    for (int cur = 0; b->chain_L < CH_MAXL && b->chain_L < D - 1;) {
+        const Node& nd = b->nodes[cur];
+        int kids = 0, m1 = -1;
+        for (int m = 0; m < 3; ++m) if (nd.child[m] >= 0) { ++kids; m1 = m; }
+        if (kids != 1 || is_leaf[nd.child[m1]]) break;
+        cur = nd.child[m1];
+        ++b->chain_L;
+        b->chain_rot[b->chain_L] = (m1 == 0) ? 0 : (m1 == 1 ? 1 : -1);
+        b->chain_index[b->chain_L] = b->nodes[cur].index;
+    }
+    int b0 = b->chain_L;
     while (b0 < D) {
         const int left = D - b0;
         const int parts = (left + FZ_MAXK - 1) / FZ_MAXK;
@@ -576,6 +591,34 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
     // fused path: the pass starts aligned at every level (no pending sample, even pair index) and is a multiple of 2^depth long
     bool fused = b->fused_on && !b->flaunch.empty() && D >= 1 && n > 0 && (n % (1ll << D)) == 0 && n < (1ll << 31);
     for (int d = 1; d <= D && fused; ++d) fused = (Pb[d - 1] == 2 * Pb[d]) && !(Pb[d] & 1);
+    if (fused && b->chain_L > 0) {
+        // the leading single-child levels as one warp-private cascade (hb48_chain.cuh); the pyramid launches start below it
+        const int L = b->chain_L;
+        ChainParams q;
+        memset(&q, 0, sizeof(q));
+        q.in = rootB; q.out = b->d_level[L] + (long long) b->chain_index[L] * b->stride[L];
+        for (int s2 = 0; s2 < L; ++s2) {
+            q.tail_in[s2] = b->d_tail[tc][s2] + (long long) b->chain_index[s2] * TAIL_WORDS;
+            q.tail_out[s2] = b->d_tail[tn][s2] + (long long) b->chain_index[s2] * TAIL_WORDS;
+        }
+        for (int s2 = 1; s2 <= L; ++s2) q.rot[s2] = (signed char) b->chain_rot[s2];
+        q.n0 = n; q.L = L; q.opq_zero = 0; q.opq_one = 1; q.opq_mone = -1;
+        const long long U = (long long) HB_IN << (L - 1);
+        const long long sp_total = (n + U - 1) / U;
+        const int wpb = (L <= 4) ? 8 : 4;
+        const size_t smem = (size_t) wpb * L * HB_STAGE_BYTES;
+        if ((rc = B200_CUDA_CHECK(cudaFuncSetAttribute((const void*) hb48_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)))) return rc;
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*) hb48_chain_kernel, wpb * 32, smem) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 1; }
+        const long long max_warps = (long long) b->sm_count * nb * wpb;
+        long long slice_sp = (sp_total + max_warps - 1) / max_warps;
+        if (slice_sp < 4) slice_sp = (sp_total < 4) ? sp_total : 4;          // a slice pays one superphase of warm-up
+        if (slice_sp < 1) slice_sp = 1;
+        q.slice_sp = (int) slice_sp; q.n_slices = (int) ((sp_total + slice_sp - 1) / slice_sp);
+        hb48_chain_kernel<<<(unsigned) ((q.n_slices + wpb - 1) / wpb), wpb * 32, smem, st>>>(q);
+        if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
+        ++b->tree_launches;
+    }
     if (fused) {
         for (const auto& fl : b->flaunch) {
             if (fl.n_groups == 0) continue;

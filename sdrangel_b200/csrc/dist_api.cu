@@ -104,7 +104,8 @@ struct b200dsp_dist {
     uint32_t* nflags = nullptr;           // the next rank's flags (IPC): I write its arrived[]
     uint32_t* pflags = nullptr;           // the previous rank's flags (IPC): I write its "next freed"[]
     uint32_t* seqtab = nullptr;           // device table of the values 0..P2P_SEQ-1 (source of the 4-byte flag copies)
-    cudaStream_t fwd = nullptr, sig = nullptr;
+    cudaStream_t fwd = nullptr, fwd2 = nullptr, sig = nullptr;      // fwd2: second half of every sub-block on another copy engine
+    cudaEvent_t ev_half = nullptr, ev_go = nullptr;
     cudaEvent_t ev_fwd[P2P_SLOTS] = { nullptr, nullptr, nullptr }, ev_cons[P2P_SLOTS] = { nullptr, nullptr, nullptr };
     unsigned uses[P2P_SLOTS] = { 0, 0, 0 };
     long long pn[P2P_SLOTS] = { 0, 0, 0 };
@@ -174,6 +175,9 @@ int b200dsp_dist_destroy(b200dsp_dist_t* d)
         if (d->ev_free[i]) cudaEventDestroy(d->ev_free[i]);
     }
     if (d->fwd) cudaStreamSynchronize(d->fwd);
+    if (d->fwd2) { cudaStreamSynchronize(d->fwd2); cudaStreamDestroy(d->fwd2); }
+    if (d->ev_half) cudaEventDestroy(d->ev_half);
+    if (d->ev_go) cudaEventDestroy(d->ev_go);
     if (d->sig) cudaStreamSynchronize(d->sig);
     for (int i = 0; i < P2P_SLOTS; ++i) {
         if (d->nslot[i]) cudaIpcCloseMemHandle(d->nslot[i]);
@@ -282,7 +286,10 @@ int b200dsp_dist_p2p_export(b200dsp_dist_t* d, int64_t n_samples, void* blob_out
         (rc = B200_CUDA_CHECK(cudaIpcGetMemHandle(&blob.flags, d->flags))) ||
         (rc = B200_CUDA_CHECK(cudaMalloc(&d->seqtab, nseq * 4))) || (rc = B200_CUDA_CHECK(cudaMemcpy(d->seqtab, seq.data(), nseq * 4, cudaMemcpyHostToDevice))) ||
         (rc = B200_CUDA_CHECK(cudaStreamCreateWithPriority(&d->fwd, cudaStreamNonBlocking, -5))) ||
-        (rc = B200_CUDA_CHECK(cudaStreamCreateWithPriority(&d->sig, cudaStreamNonBlocking, -5)))) return rc;
+        (rc = B200_CUDA_CHECK(cudaStreamCreateWithPriority(&d->sig, cudaStreamNonBlocking, -5))) ||
+        (rc = B200_CUDA_CHECK(cudaStreamCreateWithPriority(&d->fwd2, cudaStreamNonBlocking, -5))) ||
+        (rc = B200_CUDA_CHECK(cudaEventCreateWithFlags(&d->ev_half, cudaEventDisableTiming))) ||
+        (rc = B200_CUDA_CHECK(cudaEventCreateWithFlags(&d->ev_go, cudaEventDisableTiming)))) return rc;
     for (int i = 0; i < P2P_SLOTS; ++i)
         if ((rc = B200_CUDA_CHECK(cudaEventCreateWithFlags(&d->ev_fwd[i], cudaEventDisableTiming))) ||
             (rc = B200_CUDA_CHECK(cudaEventCreateWithFlags(&d->ev_cons[i], cudaEventDisableTiming)))) return rc;
@@ -344,9 +351,14 @@ int b200dsp_dist_p2p_begin(b200dsp_dist_t* d, int slot, const void* d_iq, int64_
     if (d->rank + 1 < d->world) {
         // the next rank's slot must have finished its previous use (its consumer and its own forwards): it says so in my flags
         if (use > 0 && (rc = drv_check(drv().wait32((CUstream) d->fwd, (CUdeviceptr) (d->flags + 4 + slot), use, CU_STREAM_WAIT_VALUE_GEQ), "cuStreamWaitValue32"))) return rc;
+        const long long h1 = (sub / 2) & ~3ll;                 // a sub-block goes out as two halves on two streams (two copy engines)
         for (int j = 0; j < P2P_SUB; ++j) {
             if (d->rank > 0 && (rc = drv_check(drv().wait32((CUstream) d->fwd, (CUdeviceptr) (d->flags + slot), base + j + 1, CU_STREAM_WAIT_VALUE_GEQ), "cuStreamWaitValue32"))) return rc;
-            if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(d->nslot[slot] + j * sub, mine + j * sub, (size_t) sub * 4, cudaMemcpyDeviceToDevice, d->fwd))) ||
+            if ((rc = B200_CUDA_CHECK(cudaEventRecord(d->ev_go, d->fwd))) || (rc = B200_CUDA_CHECK(cudaStreamWaitEvent(d->fwd2, d->ev_go, 0))) ||
+                (rc = B200_CUDA_CHECK(cudaMemcpyAsync(d->nslot[slot] + j * sub + h1, mine + j * sub + h1, (size_t) (sub - h1) * 4, cudaMemcpyDeviceToDevice, d->fwd2))) ||
+                (rc = B200_CUDA_CHECK(cudaEventRecord(d->ev_half, d->fwd2))) ||
+                (rc = B200_CUDA_CHECK(cudaMemcpyAsync(d->nslot[slot] + j * sub, mine + j * sub, (size_t) h1 * 4, cudaMemcpyDeviceToDevice, d->fwd))) ||
+                (rc = B200_CUDA_CHECK(cudaStreamWaitEvent(d->fwd, d->ev_half, 0))) ||
                 (rc = B200_CUDA_CHECK(cudaMemcpyAsync(d->nflags + slot, d->seqtab + base + j + 1, 4, cudaMemcpyDeviceToDevice, d->fwd)))) return rc;
         }
     }

@@ -632,3 +632,47 @@ def test_sharded_bank_two_ranks_nccl(gpu_lib, golden_meta):
         assert p.exitcode == 0
     assert [r[1] for r in res] == [True, True], res
     assert res[0][2] == 0 and res[0][3] == res[1][2] and res[1][3] == len(rows)
+
+
+@pytest.mark.parametrize("lo,hi", [(0, 128), (512, 1024), (960, 992)])
+def test_bank_shard_chain_cascade_vs_oracle(gpu_lib, port, golden_meta, lo, hi):
+    """A rank's frequency block of the sharded 1024-channel bank: the top levels of its tree are single-child (3, 1 and 5
+    of them here) and run as one warp-private cascade (hb48_chain_kernel) ahead of the fused pyramid launches.  Aligned feeds
+    with runs of -32768 (also across a feed boundary, so the carried tails hold them) and a ragged one in between, every
+    16th channel of the block against its oracle chain and against a bank that only uses the one-level kernel."""
+    from sdrangel_b200 import DownChannelizerBank
+    plan = golden_meta["chan_plans"]["bank1024"]
+    fs = plan["input_rate"]
+    rows = plan["channels"][lo:hi]
+    rs = np.random.RandomState(lo + 1)
+    unit = 3 << 17
+    sizes = [unit, unit + 4096, 1234, unit, 4096]
+    n = sum(sizes)
+    x = rs.randint(-32768, 32768, size=(n, 2)).astype(np.int16)
+    x[7000:7100] = -32768
+    x[unit - 30:unit + 30, 0] = -32768
+    x[2 * unit + 5000:2 * unit + 9000] = -32768
+    fused, plain = DownChannelizerBank(fs), _plain_bank(fs)
+    for fc, rate, ofs, path in rows:
+        fused.add_channel(48000, fc)
+        plain.add_channel(48000, fc)
+    picks = list(range(0, len(rows), 16)) + [len(rows) - 1]
+    oracles = {}
+    for i in picks:
+        o = port.PortDownChannelizer()
+        o.configure(fs, 48000, rows[i][0])
+        oracles[i] = o
+    pos = 0
+    for sz in sizes:
+        blk = x[pos:pos + sz]
+        pos += sz
+        fused.feed(blk)
+        plain.feed(blk)
+        for i, o in oracles.items():
+            want = o.feed(blk)
+            got = fused.fetch(i)
+            assert got.shape == want.shape, (sz, i)
+            assert np.array_equal(got, want), (sz, i, int(np.argmax(np.any(got != want, axis=1))))
+            assert np.array_equal(plain.fetch(i), want), (sz, i)
+    fused.close()
+    plain.close()
