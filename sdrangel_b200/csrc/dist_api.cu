@@ -13,6 +13,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <cuda.h>
+#include <stdlib.h>
 #include <vector>
 
 using namespace b200dsp;
@@ -351,15 +352,20 @@ int b200dsp_dist_p2p_begin(b200dsp_dist_t* d, int slot, const void* d_iq, int64_
     if (d->rank + 1 < d->world) {
         // the next rank's slot must have finished its previous use (its consumer and its own forwards): it says so in my flags
         if (use > 0 && (rc = drv_check(drv().wait32((CUstream) d->fwd, (CUdeviceptr) (d->flags + 4 + slot), use, CU_STREAM_WAIT_VALUE_GEQ), "cuStreamWaitValue32"))) return rc;
-        const long long h1 = (sub / 2) & ~3ll;                 // a sub-block goes out as two halves on two streams (two copy engines)
+        // B200DSP_P2P_STRIPE=1: a sub-block goes out as two halves on two streams (two copy engines); measured slower on the
+        // 8-GPU box (r02: 0.67 vs 0.56 ms per 201 MB block), so one copy per sub-block by default
+        static const bool stripe = (getenv("B200DSP_P2P_STRIPE") && getenv("B200DSP_P2P_STRIPE")[0] == '1');
+        const long long h1 = stripe ? ((sub / 2) & ~3ll) : sub;
         for (int j = 0; j < P2P_SUB; ++j) {
             if (d->rank > 0 && (rc = drv_check(drv().wait32((CUstream) d->fwd, (CUdeviceptr) (d->flags + slot), base + j + 1, CU_STREAM_WAIT_VALUE_GEQ), "cuStreamWaitValue32"))) return rc;
-            if ((rc = B200_CUDA_CHECK(cudaEventRecord(d->ev_go, d->fwd))) || (rc = B200_CUDA_CHECK(cudaStreamWaitEvent(d->fwd2, d->ev_go, 0))) ||
-                (rc = B200_CUDA_CHECK(cudaMemcpyAsync(d->nslot[slot] + j * sub + h1, mine + j * sub + h1, (size_t) (sub - h1) * 4, cudaMemcpyDeviceToDevice, d->fwd2))) ||
-                (rc = B200_CUDA_CHECK(cudaEventRecord(d->ev_half, d->fwd2))) ||
-                (rc = B200_CUDA_CHECK(cudaMemcpyAsync(d->nslot[slot] + j * sub, mine + j * sub, (size_t) h1 * 4, cudaMemcpyDeviceToDevice, d->fwd))) ||
-                (rc = B200_CUDA_CHECK(cudaStreamWaitEvent(d->fwd, d->ev_half, 0))) ||
-                (rc = B200_CUDA_CHECK(cudaMemcpyAsync(d->nflags + slot, d->seqtab + base + j + 1, 4, cudaMemcpyDeviceToDevice, d->fwd)))) return rc;
+            if (h1 < sub) {
+                if ((rc = B200_CUDA_CHECK(cudaEventRecord(d->ev_go, d->fwd))) || (rc = B200_CUDA_CHECK(cudaStreamWaitEvent(d->fwd2, d->ev_go, 0))) ||
+                    (rc = B200_CUDA_CHECK(cudaMemcpyAsync(d->nslot[slot] + j * sub + h1, mine + j * sub + h1, (size_t) (sub - h1) * 4, cudaMemcpyDeviceToDevice, d->fwd2))) ||
+                    (rc = B200_CUDA_CHECK(cudaEventRecord(d->ev_half, d->fwd2)))) return rc;
+            }
+            if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(d->nslot[slot] + j * sub, mine + j * sub, (size_t) h1 * 4, cudaMemcpyDeviceToDevice, d->fwd)))) return rc;
+            if (h1 < sub && (rc = B200_CUDA_CHECK(cudaStreamWaitEvent(d->fwd, d->ev_half, 0)))) return rc;
+            if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(d->nflags + slot, d->seqtab + base + j + 1, 4, cudaMemcpyDeviceToDevice, d->fwd)))) return rc;
         }
     }
     return B200_CUDA_CHECK(cudaEventRecord(d->ev_fwd[slot], d->fwd));
@@ -367,13 +373,14 @@ int b200dsp_dist_p2p_begin(b200dsp_dist_t* d, int slot, const void* d_iq, int64_
 
 int b200dsp_dist_p2p_feed(b200dsp_dist_t* d, int slot, b200dsp_bank_t* bank, void* stream)
 {
-    if (!d || !d->p2p || !bank || slot < 0 || slot >= P2P_SLOTS || d->pn[slot] <= 0 || d->uses[slot] == 0) return b200_fail(B200DSP_EINVAL, "dist_p2p_feed: bad argument or empty slot");
+    // (bank == NULL with a stream: only wait for the block and release the slot -- transfer-rate measurements)
+    if (!d || !d->p2p || (!bank && !stream) || slot < 0 || slot >= P2P_SLOTS || d->pn[slot] <= 0 || d->uses[slot] == 0) return b200_fail(B200DSP_EINVAL, "dist_p2p_feed: bad argument or empty slot");
     int rc = B200_CUDA_CHECK(cudaSetDevice(d->device));
     if (rc) return rc;
     cudaStream_t st = stream ? (cudaStream_t) stream : (cudaStream_t) b200dsp_bank_stream(bank);
     const unsigned use = d->uses[slot] - 1;
     if (d->rank > 0 && (rc = drv_check(drv().wait32((CUstream) st, (CUdeviceptr) (d->flags + slot), use * P2P_SUB + P2P_SUB, CU_STREAM_WAIT_VALUE_GEQ), "cuStreamWaitValue32"))) return rc;
-    if ((rc = b200dsp_bank_feed_dev(bank, d->psrc[slot], d->pn[slot], (void*) st))) return rc;
+    if (bank && (rc = b200dsp_bank_feed_dev(bank, d->psrc[slot], d->pn[slot], (void*) st))) return rc;
     if ((rc = B200_CUDA_CHECK(cudaEventRecord(d->ev_cons[slot], st)))) return rc;
     if (d->rank > 0) {
         // this slot is free for its next use once the feed and the forwards have run: tell the previous rank

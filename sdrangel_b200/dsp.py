@@ -356,8 +356,8 @@ class ShardedBank:
     def p2p_begin(self, slot, d_iq, n_samples, after_stream=None):
         capi.check(capi.lib().b200dsp_dist_p2p_begin(self._h, slot, C.c_void_p(d_iq or 0), int(n_samples), C.c_void_p(after_stream or 0)))
 
-    def p2p_feed(self, slot, stream=None):
-        capi.check(capi.lib().b200dsp_dist_p2p_feed(self._h, slot, self.bank._h, C.c_void_p(stream or 0)))
+    def p2p_feed(self, slot, stream=None, consume_only=False):
+        capi.check(capi.lib().b200dsp_dist_p2p_feed(self._h, slot, None if consume_only else self.bank._h, C.c_void_p(stream or 0)))
 
     def p2p_slot(self, slot):
         ptr, n = C.c_void_p(), C.c_int64(0)

@@ -10,6 +10,8 @@ from bench import plan1024
 S.capi.init(0)
 fs, fcs = plan1024()
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 3 << 24
+lo, hi = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (0, len(fcs))
+fcs = fcs[lo:hi]
 x = torch.randint(-2048, 2048, (2 * n,), dtype=torch.int16, device="cuda")
 cutoff = float(np.float32(np.float32(12500) / np.float32(2.2)))
 for fe in (False, True):
