@@ -39,6 +39,7 @@ extern "C" {
 #define B200DSP_MODE_INF  0
 #define B200DSP_MODE_SUP  1
 #define B200DSP_MODE_CEN  2
+#define B200DSP_MODE_U    3   /* Decimators<>::decimate2_u (decimators.h:374-393): unfiltered /2 of offset-255 data; log2_decim 1, signed integer inputs */
 
 /* ---- library ------------------------------------------------------------------------------------------- */
 int         b200dsp_init(int device_ordinal);      /* selects the device for handles created afterwards */
@@ -78,6 +79,10 @@ int b200dsp_decim_run(b200dsp_decim_t* h, int log2_decim, int mode,
                       const void* in, int32_t len_scalars, void* out, int32_t* n_out);
 int b200dsp_decim_run_dev(b200dsp_decim_t* h, int log2_decim, int mode,
                           const void* d_in, int64_t len_scalars, void* d_out, int64_t* n_out, void* cuda_stream);
+/* == the overloads on separate I and Q arrays, decimate1 / decimate2_u / decimateN_cen(it, bufI, bufQ, len)
+ *    (decimators.h:359-371,395-417,2638-2700,...): len_per_array samples in each array; mode B200DSP_MODE_CEN or B200DSP_MODE_U */
+int b200dsp_decim_run_split(b200dsp_decim_t* h, int log2_decim, int mode,
+                            const void* in_i, const void* in_q, int32_t len_per_array, void* out, int32_t* n_out);
 /* number of output IQ samples decimate*_ would write for `len_scalars` (pure host arithmetic, no device) */
 int64_t b200dsp_decim_out_count(int in_fmt, int out_fmt, int log2_decim, int mode, int64_t len_scalars);
 

@@ -42,6 +42,21 @@ def main():
                 arrays[key + "/out"] = np.concatenate(outs)
                 arrays[key + "/counts"] = np.array([o.shape[0] for o in outs], dtype=np.int64)
                 arrays[key + "/remain"] = np.array([fe.remain()], dtype=np.float32)
+    # Decimators<qint32,qint16,16,12>: the split-I/Q overloads and decimate2_u (decimators.h:359-461,2638-3888), state carried over 3 calls
+    rs2 = np.random.RandomState(SEED + 1)
+    sx = rs2.randint(-2048, 2048, size=2 * 6000).astype(np.int16)
+    meta["split"] = {"seed": SEED + 1, "n_scalars": 2 * 6000, "cuts_samples": [0, 1000, 1003, 6000]}
+    for log2 in range(7):
+        d = refbind.RefDecimators("ii", 12)
+        outs = []
+        for a, b in ((0, 1000), (1000, 1003), (1003, 6000)):
+            outs.append(d.run_split(log2, sx[2 * a:2 * b:2], sx[2 * a + 1:2 * b:2]))
+        arrays["split/cen/%d" % log2] = np.concatenate(outs)
+        arrays["split/cen/%d/counts" % log2] = np.array([o.shape[0] for o in outs], dtype=np.int64)
+    d = refbind.RefDecimators("ii", 12)
+    arrays["split/2u"] = d.run_split(1, sx[0::2], sx[1::2], u=True)
+    for bits in (8, 12, 16):
+        arrays["dec2u/%d" % bits] = refbind.RefDecimators("ii", bits).run_2u(sx)
     for freq, rate in ((15433.0, 156250.0), (-4321.0, 60000.0), (0.0, 48000.0), (1e6, 10e6)):
         arrays["nco/%g_%g" % (freq, rate)] = refbind.nco_block(freq, rate, 5000)
     meta["nco_cases"] = [[15433.0, 156250.0], [-4321.0, 60000.0], [0.0, 48000.0], [1e6, 10e6]]

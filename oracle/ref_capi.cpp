@@ -168,6 +168,44 @@ int ref_decim_ii_run(void* p, int log2, int mode, const int16_t* buf, int len, i
     return n;
 }
 
+// the split-I/Q overloads (decimators.h:359-371,395-417,2638-2700,...,3888-...) and decimate2_u (:374-393): int16 in, 12-bit
+// log2 = 0 decimate1, 1..6 decimateN_cen on separate I and Q arrays of `len` samples each; mode_u = 1: decimate2_u (log2 must be 1)
+int ref_decim_ii_run_split(void* p, int log2, int mode_u, const int16_t* bufI, const int16_t* bufQ, int len, int16_t* out)
+{
+    DecimII* h = (DecimII*) p;
+    std::size_t need = (std::size_t) len + 8;
+    if (h->out.size() < need) h->out.resize(need);
+    SampleVector::iterator it = h->out.begin();
+    if (h->bits != 12) return -1;
+    if (mode_u) { if (log2 != 1) return -1; h->d12.decimate2_u(&it, bufI, bufQ, len); }
+    else switch (log2) {
+        case 0: h->d12.decimate1(&it, bufI, bufQ, len); break;
+        case 1: h->d12.decimate2_cen(&it, bufI, bufQ, len); break;
+        case 2: h->d12.decimate4_cen(&it, bufI, bufQ, len); break;
+        case 3: h->d12.decimate8_cen(&it, bufI, bufQ, len); break;
+        case 4: h->d12.decimate16_cen(&it, bufI, bufQ, len); break;
+        case 5: h->d12.decimate32_cen(&it, bufI, bufQ, len); break;
+        case 6: h->d12.decimate64_cen(&it, bufI, bufQ, len); break;
+        default: return -1;
+    }
+    int n = (int) (it - h->out.begin());
+    if (n > 0) memcpy(out, &h->out[0], (std::size_t) n * sizeof(Sample));
+    return n;
+}
+int ref_decim_ii_run_2u(void* p, const int16_t* buf, int len, int16_t* out)
+{
+    DecimII* h = (DecimII*) p;
+    std::size_t need = (std::size_t) (len / 2) + 8;
+    if (h->out.size() < need) h->out.resize(need);
+    SampleVector::iterator it = h->out.begin();
+    if (h->bits == 8) h->d8.decimate2_u(&it, buf, len);
+    else if (h->bits == 12) h->d12.decimate2_u(&it, buf, len);
+    else h->d16.decimate2_u(&it, buf, len);
+    int n = (int) (it - h->out.begin());
+    if (n > 0) memcpy(out, &h->out[0], (std::size_t) n * sizeof(Sample));
+    return n;
+}
+
 // ---------------------------------------------------------------- 8-bit inputs (int8 / uint8-127 -> int16)
 void* ref_decim_i8_create() { return new DecimI8; }
 void ref_decim_i8_destroy(void* p) { delete (DecimI8*) p; }

@@ -54,6 +54,7 @@ def load(strict=False):
         "ref_frontend_nco_increment": (i32, [vp]), "ref_frontend_ntaps": (i32, [vp]),
         "ref_frontend_taps": (None, [vp, pf32]), "ref_nco_table": (None, [pf32]),
         "ref_frontend_feed": (i32, [vp, pi16, i32, pf32, i32, pi32, pi32]),
+        "ref_decim_ii_run_split": (i32, [vp, i32, i32, pi16, pi16, i32, pi16]), "ref_decim_ii_run_2u": (i32, [vp, pi16, i32, pi16]),
         "ref_interp_decimate": (i32, [vp, pf32, i32, pf32, i32]),
         "ref_interp_interpolate": (i32, [vp, pf32, i32, pf32, i32]), "ref_interp_resample": (i32, [vp, pf32, i32, pf32, i32]),
         "ref_frontend_remain": (f32, [vp]), "ref_nco_block": (None, [f32, f32, i32, pf32]),
@@ -108,6 +109,21 @@ class RefDecimators(_Handle):
         n = self._run(self.h, log2, mode, _p(buf, ct_in), buf.size, _p(out, ct_out))
         if n < 0:
             raise ValueError("bad log2/mode")
+        return out[:n].copy()
+
+    def run_split(self, log2, buf_i, buf_q, u=False):
+        """The split-I/Q overloads: decimate1 / decimateN_cen(it, bufI, bufQ, len), or decimate2_u with u=True ('ii', 12 bits)."""
+        bi, bq = np.ascontiguousarray(buf_i, dtype=np.int16), np.ascontiguousarray(buf_q, dtype=np.int16)
+        out = np.empty((bi.size + 8, 2), dtype=np.int16)
+        n = self.lib.ref_decim_ii_run_split(self.h, log2, int(u), _p(bi, C.c_int16), _p(bq, C.c_int16), bi.size, _p(out, C.c_int16))
+        if n < 0:
+            raise ValueError("bad log2")
+        return out[:n].copy()
+
+    def run_2u(self, buf):
+        buf = np.ascontiguousarray(buf, dtype=np.int16)
+        out = np.empty((buf.size // 2 + 8, 2), dtype=np.int16)
+        n = self.lib.ref_decim_ii_run_2u(self.h, _p(buf, C.c_int16), buf.size, _p(out, C.c_int16))
         return out[:n].copy()
 
 

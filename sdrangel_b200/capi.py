@@ -6,7 +6,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200DSP_LIB") or os.path.join(_HERE, "lib", "libb200dsp.so")   # env override: kernel tuning experiments only
 
 FMT_I16, FMT_F32, FMT_I8, FMT_U8 = 0, 1, 2, 3
-MODE_INF, MODE_SUP, MODE_CEN = 0, 1, 2
+MODE_INF, MODE_SUP, MODE_CEN, MODE_U = 0, 1, 2, 3
 DECIM_STATE_ELEMS = 6 * 2 * 64
 ENODEV = -2
 
@@ -34,6 +34,7 @@ SIGNATURES = {
     "b200dsp_decim_set_shift": (_i32, [_vp, _i32]),
     "b200dsp_decim_set_exact_float": (_i32, [_vp, _i32]),
     "b200dsp_decim_run": (_i32, [_vp, _i32, _i32, _vp, _i32, _vp, _pi32]),
+    "b200dsp_decim_run_split": (_i32, [_vp, _i32, _i32, _vp, _vp, _i32, _vp, _pi32]),
     "b200dsp_decim_run_dev": (_i32, [_vp, _i32, _i32, _vp, _i64, _vp, _pi64, _vp]),
     "b200dsp_decim_out_count": (_i64, [_i32, _i32, _i32, _i32, _i64]),
     "b200dsp_decim_get_state": (_i32, [_vp, _vp]),

@@ -15,7 +15,7 @@ namespace {
 //   EW_HALF : float decimate2_inf/_sup     (decimatorsfi.cpp:55-93)   8 scalars -> 2 outputs, unfiltered
 //   EW_DIV4 : float decimate4_inf/_sup     (decimatorsfi.cpp:95-131)  8 scalars -> 1 output, unfiltered
 // ---------------------------------------------------------------------------------------------------------
-enum { EW_COPY = 0, EW_HALF = 1, EW_DIV4 = 2 };
+enum { EW_COPY = 0, EW_HALF = 1, EW_DIV4 = 2, EW_HALF_U = 3 };
 
 struct EwParams {
     const void* in; void* out;
@@ -95,6 +95,32 @@ __global__ void ew_int8_copy_kernel(const EwParams p)
         const uint32_t re = (uint32_t) (x - p.shift) << p.pre, im = (uint32_t) (y - p.shift) << p.pre;
         out[u] = (re & 0xffffu) | (im << 16);
     }
+}
+
+// Decimators<>::decimate2_u (decimators.h:374-393): per 8 scalars two samples,
+//   ((b0 - b3) << pre2) >> post2, ((b1 + b2 - 255) << pre2) >> post2;  ((b7 - b4) << pre2) >> post2, ((255 - b5 - b6) << pre2) >> post2
+template<typename TIN>
+__global__ void ew_int_half_u_kernel(const EwParams p)
+{
+    const TIN* in = reinterpret_cast<const TIN*>(p.in);
+    uint32_t* out = reinterpret_cast<uint32_t*>(p.out);
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (long long u = (long long) blockIdx.x * blockDim.x + threadIdx.x; u < p.n_units; u += stride) {
+        int32_t b[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b[i] = (int32_t) in[8 * u + i];
+        const int32_t x0 = (int32_t) ((uint32_t) (b[0] - b[3]) << p.pre) >> p.shift, y0 = (int32_t) ((uint32_t) (b[1] + b[2] - 255) << p.pre) >> p.shift;
+        const int32_t x1 = (int32_t) ((uint32_t) (b[7] - b[4]) << p.pre) >> p.shift, y1 = (int32_t) ((uint32_t) (255 - b[5] - b[6]) << p.pre) >> p.shift;
+        out[2 * u] = ((uint32_t) x0 & 0xffffu) | ((uint32_t) y0 << 16);
+        out[2 * u + 1] = ((uint32_t) x1 & 0xffffu) | ((uint32_t) y1 << 16);
+    }
+}
+
+// split I / Q arrays -> interleaved (the Decimators<> overloads taking bufI, bufQ: decimators.h:359-371,395-417,2638-...)
+template<typename T>
+__global__ void interleave_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long long n)
+{
+    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) { out[2 * i] = a[i]; out[2 * i + 1] = b[i]; }
 }
 
 // decimation_shifts<16, InputBits> (decimators.h:79-95 / 115-131 / 151-167), index = log2
@@ -184,9 +210,21 @@ struct Plan {
 
 int make_plan(int in_fmt, int out_fmt, int bits, int log2, int mode, long long len, Plan* pl)
 {
-    if (log2 < 0 || log2 > 6 || mode < 0 || mode > 2 || len < 0) return B200DSP_EINVAL;
+    if (log2 < 0 || log2 > 6 || mode < 0 || mode > 3 || len < 0) return B200DSP_EINVAL;
     memset(pl, 0, sizeof(*pl));
     const bool is_int = ((in_fmt == B200DSP_FMT_I16 || is_int8(in_fmt)) && out_fmt == B200DSP_FMT_I16);
+    if (mode == B200DSP_MODE_U) {
+        // Decimators<>::decimate2_u (decimators.h:374-393): unfiltered /2 of offset-255 data, signed integer inputs only
+        if (log2 != 1 || !is_int || in_fmt == B200DSP_FMT_U8) return B200DSP_EINVAL;
+        const int* PRE = bits == 8 ? PRE8 : bits == 12 ? PRE12 : PRE16;
+        const int* POST = bits == 8 ? POST8 : bits == 12 ? POST12 : POST16;
+        pl->pre = PRE[1]; pl->post = POST[1];
+        pl->elementwise = true; pl->ew_kind = EW_HALF_U;
+        pl->consumed_scalars = (len / 8) * 8;
+        pl->n_out = pl->consumed_scalars / 4;
+        pl->out_scale = 1.0f;
+        return 0;
+    }
     const int N = 1 << log2;
     pl->out_scale = 1.0f;
     if (in_fmt == B200DSP_FMT_I16 && out_fmt == B200DSP_FMT_F32)     // decimation_scale<InputBits>::scaleIn
@@ -326,7 +364,12 @@ int launch_plan(b200dsp_decim* h, const Plan& pl, const void* d_in, void* d_out,
         long long blocks = (ep.n_units + threads - 1) / threads;
         if (blocks > (long long) h->sm_count * 16) blocks = (long long) h->sm_count * 16;
         if (blocks < 1) blocks = 1;
-        if (h->in_fmt == B200DSP_FMT_I8) ew_int8_copy_kernel<false><<<(unsigned) blocks, threads, 0, st>>>(ep);
+        if (pl.ew_kind == EW_HALF_U) {
+            ep.shift = pl.post;               // (the 8-bit Shift does not enter decimate2_u: the 255 offset is in the formula)
+            if (h->in_fmt == B200DSP_FMT_I8) ew_int_half_u_kernel<signed char><<<(unsigned) blocks, threads, 0, st>>>(ep);
+            else ew_int_half_u_kernel<int16_t><<<(unsigned) blocks, threads, 0, st>>>(ep);
+        }
+        else if (h->in_fmt == B200DSP_FMT_I8) ew_int8_copy_kernel<false><<<(unsigned) blocks, threads, 0, st>>>(ep);
         else if (h->in_fmt == B200DSP_FMT_U8) ew_int8_copy_kernel<true><<<(unsigned) blocks, threads, 0, st>>>(ep);
         else if (h->in_fmt == B200DSP_FMT_I16 && h->out_fmt == B200DSP_FMT_I16) ew_int_copy_kernel<<<(unsigned) blocks, threads, 0, st>>>(ep);
         else if (h->in_fmt == B200DSP_FMT_F32 && h->out_fmt == B200DSP_FMT_I16) ew_float_kernel<float, OUT_I16_SCALE><<<(unsigned) blocks, threads, 0, st>>>(ep);
@@ -515,6 +558,46 @@ int b200dsp_decim_run(b200dsp_decim_t* h, int log2_decim, int mode, const void* 
         done += n; out_done += pl.n_out; slot ^= 1; ++nchunks;
     }
     return B200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+}
+
+// == the Decimators<> overloads on separate I and Q arrays (decimators.h:359-371 decimate1, :395-417 decimate2_u, :2638-2700 ...
+//    :3888-... decimateN_cen): `len_per_array` samples in each of in_i, in_q.  The arrays are interleaved on the device
+//    and take the same kernels as the interleaved entry points (the reference's two forms compute the same thing).
+int b200dsp_decim_run_split(b200dsp_decim_t* h, int log2_decim, int mode, const void* in_i, const void* in_q, int32_t len_per_array, void* out, int32_t* n_out)
+{
+    if (!h) return b200_fail(B200DSP_EINVAL, "null handle");
+    if (len_per_array < 0 || len_per_array > (1 << 29)) return b200_fail(B200DSP_EINVAL, "decim_run_split: bad length");
+    if (mode != B200DSP_MODE_CEN && mode != B200DSP_MODE_U) return b200_fail(B200DSP_EINVAL, "decim_run_split: the reference defines the split overloads for decimate1, decimate2_u and decimateN_cen only");
+    Plan whole;
+    if (make_plan(h->in_fmt, h->out_fmt, h->bits, log2_decim, mode, 2ll * len_per_array, &whole)) return b200_fail(B200DSP_EINVAL, "decim_run_split: bad log2/mode/len");
+    if (n_out) *n_out = (int32_t) whole.n_out;
+    if (whole.n_out == 0) return 0;
+    if (!in_i || !in_q || !out) return b200_fail(B200DSP_EINVAL, "decim_run_split: null buffer");
+    int rc = B200_CUDA_CHECK(cudaSetDevice(h->device));
+    if (rc) return rc;
+    const size_t ib = in_elem_bytes(h->in_fmt), ob = in_elem_bytes(h->out_fmt) * 2;
+    const long long n = whole.consumed_scalars / 2;                 // samples per array that take part
+    void *d_i = nullptr, *d_q = nullptr, *d_x = nullptr, *d_o = nullptr;
+    if ((rc = B200_CUDA_CHECK(cudaMalloc(&d_i, (size_t) n * ib))) || (rc = B200_CUDA_CHECK(cudaMalloc(&d_q, (size_t) n * ib))) ||
+        (rc = B200_CUDA_CHECK(cudaMalloc(&d_x, (size_t) n * ib * 2 + 64))) || (rc = B200_CUDA_CHECK(cudaMalloc(&d_o, (size_t) whole.n_out * ob + 64)))) goto done;
+    if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(d_i, in_i, (size_t) n * ib, cudaMemcpyHostToDevice, h->stream))) ||
+        (rc = B200_CUDA_CHECK(cudaMemcpyAsync(d_q, in_q, (size_t) n * ib, cudaMemcpyHostToDevice, h->stream)))) goto done;
+    {
+        const unsigned blocks = (unsigned) ((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+        if (ib == 1) interleave_kernel<unsigned char><<<blocks, 256, 0, h->stream>>>((const unsigned char*) d_i, (const unsigned char*) d_q, (unsigned char*) d_x, n);
+        else if (ib == 2) interleave_kernel<uint16_t><<<blocks, 256, 0, h->stream>>>((const uint16_t*) d_i, (const uint16_t*) d_q, (uint16_t*) d_x, n);
+        else interleave_kernel<uint32_t><<<blocks, 256, 0, h->stream>>>((const uint32_t*) d_i, (const uint32_t*) d_q, (uint32_t*) d_x, n);
+        if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) goto done;
+    }
+    if ((rc = launch_plan(h, whole, d_x, d_o, h->stream))) goto done;
+    if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(out, d_o, (size_t) whole.n_out * ob, cudaMemcpyDeviceToHost, h->stream)))) goto done;
+    rc = B200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+done:
+    if (d_i) cudaFree(d_i);
+    if (d_q) cudaFree(d_q);
+    if (d_x) cudaFree(d_x);
+    if (d_o) cudaFree(d_o);
+    return rc;
 }
 
 int b200dsp_decim_get_state(b200dsp_decim_t* h, void* state_host)

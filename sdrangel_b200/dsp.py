@@ -57,6 +57,20 @@ class _DecimatorsBase:
         assert n_out.value == n
         return out[:n]
 
+    def run_split(self, log2, mode, buf_i, buf_q):
+        """== decimate1 / decimate2_u / decimateN_cen(&it, bufI, bufQ, len): the overloads on separate I and Q arrays."""
+        bi = np.ascontiguousarray(buf_i, dtype=self.in_dtype).reshape(-1)
+        bq = np.ascontiguousarray(buf_q, dtype=self.in_dtype).reshape(-1)
+        assert bi.size == bq.size
+        out = np.empty((max(bi.size, 1), 2), dtype=self.out_dtype)
+        n_out = C.c_int32(0)
+        capi.check(capi.lib().b200dsp_decim_run_split(self._h, log2, mode, bi.ctypes.data, bq.ctypes.data, bi.size, out.ctypes.data, C.byref(n_out)))
+        return out[:n_out.value]
+
+    def decimate2_u(self, buf):
+        """== Decimators::decimate2_u(&it, buf, len) (decimators.h:374-393)."""
+        return self.run(1, capi.MODE_U, buf)
+
     def run_dev(self, log2, mode, d_in, len_scalars, d_out, stream=None):
         """Device-resident call (metric path): d_in / d_out are device pointers (ints); asynchronous."""
         n_out = C.c_int64(0)

@@ -209,3 +209,35 @@ def test_decimatefi_config2(gpu_lib, port, golden_meta):
     assert np.max(np.abs(fast.astype(np.int32) - ref.astype(np.int32))) <= 1
     assert rel_rms(fast, ref) <= 1e-5
     assert fast[100:103].tolist() == g["out100_102"] or np.max(np.abs(fast[100:103] - np.array(g["out100_102"]))) <= 1
+
+
+def test_split_iq_overloads_and_decimate2_u_golden(gpu_lib):
+    """The Decimators<> overloads on separate I and Q arrays (decimate1, decimateN_cen, decimate2_u; decimators.h:359-371,395-417,
+    2638-3888) and decimate2_u on interleaved input (:374-393), against the reference built in place
+    (tests/golden/golden_interp.npz, oracle/gen_golden_interp.py): bit-exact, state carried across three ragged calls."""
+    import json
+    import os
+    from conftest import GOLDEN_DIR
+    from sdrangel_b200 import Decimators, capi
+    z = np.load(os.path.join(GOLDEN_DIR, "golden_interp.npz"))
+    with open(os.path.join(GOLDEN_DIR, "golden_interp.json")) as f:
+        meta = json.load(f)["split"]
+    rs = np.random.RandomState(meta["seed"])
+    sx = rs.randint(-2048, 2048, size=meta["n_scalars"]).astype(np.int16)
+    cuts = meta["cuts_samples"]
+    for log2 in range(7):
+        d = Decimators(12)
+        outs = [d.run_split(log2, capi.MODE_CEN, sx[2 * a:2 * b:2], sx[2 * a + 1:2 * b:2]).copy() for a, b in zip(cuts[:-1], cuts[1:])]
+        assert [o.shape[0] for o in outs] == z["split/cen/%d/counts" % log2].tolist(), log2
+        assert np.array_equal(np.concatenate(outs), z["split/cen/%d" % log2]), log2
+        d.close()
+    d = Decimators(12)
+    assert np.array_equal(d.run_split(1, capi.MODE_U, sx[0::2], sx[1::2]), z["split/2u"])
+    d.close()
+    for bits in (8, 12, 16):
+        d = Decimators(bits)
+        assert np.array_equal(d.decimate2_u(sx), z["dec2u/%d" % bits]), bits
+        assert d.out_count(1, capi.MODE_U, sx.size) == z["dec2u/%d" % bits].shape[0]
+        d.close()
+    with pytest.raises(RuntimeError):
+        Decimators(12).run(2, capi.MODE_U, sx)            # decimate2_u exists for the factor 2 only
