@@ -244,6 +244,24 @@ int b200dsp_interp_interpolate(b200dsp_interp_t* h, float* distance_remain, floa
 int b200dsp_interp_resample(b200dsp_interp_t* h, float* distance_remain, float distance, const float* in_c64, int64_t n_samples,
                             float* out_c64, int64_t cap_samples, int64_t* n_out);
 
+/* one reference call (op 0 decimate, 1 interpolate, 2 resample) with the reference's exact effect on *distance; one launch
+ * per sample -- for plugin code not yet restructured into blocks.  *produced: a result was written; *consumed: `next` was taken */
+int b200dsp_interp_step(b200dsp_interp_t* h, int op, float* distance, const float* next_c64, float* result_c64, int* consumed, int* produced);
+
+/* ---- device-resident SampleSinkFifo -------------------------------------------------------------------------------------
+ * == SampleSinkFifo (sdrbase/dsp/samplesinkfifo.h:27-65, samplesinkfifo.cpp:113-231): the ring between a device plugin's
+ *    decimators and the engine's work loop, same semantics (overflow drops, two-span readBegin + readCommit), ring in device
+ *    memory: decimator output in with a device-to-device copy, b200dsp_bank_feed_dev straight from the spans. */
+typedef struct b200dsp_fifo b200dsp_fifo_t;
+int      b200dsp_fifo_create(b200dsp_fifo_t** f, uint32_t size_samples);
+int      b200dsp_fifo_destroy(b200dsp_fifo_t* f);
+uint32_t b200dsp_fifo_size(b200dsp_fifo_t* f);
+uint32_t b200dsp_fifo_fill(b200dsp_fifo_t* f);
+int      b200dsp_fifo_write(b200dsp_fifo_t* f, const void* samples, uint32_t count, int src_is_device, void* cuda_stream, uint32_t* written);
+int      b200dsp_fifo_read_begin(b200dsp_fifo_t* f, uint32_t count, const void** d_part1, uint32_t* n1, const void** d_part2, uint32_t* n2, uint32_t* total);
+int      b200dsp_fifo_read_commit(b200dsp_fifo_t* f, uint32_t count, uint32_t* committed);
+int      b200dsp_fifo_read(b200dsp_fifo_t* f, void* out_host, uint32_t count, void* cuda_stream, uint32_t* read);
+
 /* ---- stand-alone NCO -------------------------------------------------------------------------------------------------
  * == NCO (sdrbase/dsp/nco.h:40-53, nco.cpp:30-64): 4096-entry cosine table, integer phase advanced BEFORE each lookup,
  *    nextIQ() = (T[p], -T[(p + 1024) mod 4096]).  One handle == one NCO object (its phase). */

@@ -24,6 +24,13 @@ protected:
         check(b200dsp_decim_run(m_h, log2, mode, buf, len, len > 1 ? (void*) &(**it) : nullptr, &n));
         *it += n;
     }
+    /** the overloads on separate I and Q arrays (decimators.h:359-371,395-417,2638-...): len samples in each */
+    void runSplit(int log2, int mode, typename OutVec::iterator* it, const TIn* bufI, const TIn* bufQ, qint32 len)
+    {
+        int32_t n = 0;
+        check(b200dsp_decim_run_split(m_h, log2, mode, bufI, bufQ, len, len > 0 ? (void*) &(**it) : nullptr, &n));
+        *it += n;
+    }
     b200dsp_decim_t* m_h;
 };
 } // namespace b200dsp_cxx
@@ -59,5 +66,16 @@ class Decimators : public b200dsp_cxx::DecimatorsImpl<(sizeof(T) == 1 ? B200DSP_
 public:
     Decimators() : b200dsp_cxx::DecimatorsImpl<(sizeof(T) == 1 ? B200DSP_FMT_I8 : B200DSP_FMT_I16), B200DSP_FMT_I16, T, SampleVector>(InputBits) {}
     B200DSP_DECIM_ENTRY_POINTS(SampleVector, T)
+    /** decimators.h:374-393: unfiltered /2 of offset-255 data */
+    void decimate2_u(SampleVector::iterator* it, const T* buf, qint32 len) { this->run(1, B200DSP_MODE_U, it, buf, len); }
+    // the overloads on separate I and Q arrays that the reference defines (decimators.h:359-371,395-417,2638-3888)
+    void decimate1(SampleVector::iterator* it, const T* bufI, const T* bufQ, qint32 len) { this->runSplit(0, B200DSP_MODE_CEN, it, bufI, bufQ, len); }
+    void decimate2_u(SampleVector::iterator* it, const T* bufI, const T* bufQ, qint32 len) { this->runSplit(1, B200DSP_MODE_U, it, bufI, bufQ, len); }
+    void decimate2_cen(SampleVector::iterator* it, const T* bufI, const T* bufQ, qint32 len) { this->runSplit(1, B200DSP_MODE_CEN, it, bufI, bufQ, len); }
+    void decimate4_cen(SampleVector::iterator* it, const T* bufI, const T* bufQ, qint32 len) { this->runSplit(2, B200DSP_MODE_CEN, it, bufI, bufQ, len); }
+    void decimate8_cen(SampleVector::iterator* it, const T* bufI, const T* bufQ, qint32 len) { this->runSplit(3, B200DSP_MODE_CEN, it, bufI, bufQ, len); }
+    void decimate16_cen(SampleVector::iterator* it, const T* bufI, const T* bufQ, qint32 len) { this->runSplit(4, B200DSP_MODE_CEN, it, bufI, bufQ, len); }
+    void decimate32_cen(SampleVector::iterator* it, const T* bufI, const T* bufQ, qint32 len) { this->runSplit(5, B200DSP_MODE_CEN, it, bufI, bufQ, len); }
+    void decimate64_cen(SampleVector::iterator* it, const T* bufI, const T* bufQ, qint32 len) { this->runSplit(6, B200DSP_MODE_CEN, it, bufI, bufQ, len); }
 };
 #endif

@@ -77,6 +77,15 @@ SIGNATURES = {
     "b200dsp_dist_p2p_slot": (_i32, [_vp, _i32, _pvp, _pi64]),
     "b200dsp_interp_interpolate": (_i32, [_vp, C.POINTER(_f32), _f32, _vp, _i64, _vp, _i64, _pi64]),
     "b200dsp_interp_resample": (_i32, [_vp, C.POINTER(_f32), _f32, _vp, _i64, _vp, _i64, _pi64]),
+    "b200dsp_interp_step": (_i32, [_vp, _i32, C.POINTER(_f32), _vp, _vp, _pi32, _pi32]),
+    "b200dsp_fifo_create": (_i32, [_pvp, C.c_uint32]),
+    "b200dsp_fifo_destroy": (_i32, [_vp]),
+    "b200dsp_fifo_size": (C.c_uint32, [_vp]),
+    "b200dsp_fifo_fill": (C.c_uint32, [_vp]),
+    "b200dsp_fifo_write": (_i32, [_vp, _vp, C.c_uint32, _i32, _vp, C.POINTER(C.c_uint32)]),
+    "b200dsp_fifo_read_begin": (_i32, [_vp, C.c_uint32, _pvp, C.POINTER(C.c_uint32), _pvp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "b200dsp_fifo_read_commit": (_i32, [_vp, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "b200dsp_fifo_read": (_i32, [_vp, _vp, C.c_uint32, _vp, C.POINTER(C.c_uint32)]),
     "b200dsp_nco_create": (_i32, [_pvp]),
     "b200dsp_nco_destroy": (_i32, [_vp]),
     "b200dsp_nco_set_freq": (_i32, [_vp, _f32, _f32]),

@@ -1341,18 +1341,19 @@ int b200dsp_interp_info(b200dsp_interp_t* h, int* taps_per_phase, float* taps, i
 namespace {
 
 // the three caller loops around Interpolator (frontend.cuh: FrontendChan::mode) on one block of complex64 samples
-int interp_run(b200dsp_interp* h, int mode, float* distance_remain, float distance, const float* in_c64, int64_t n, float* out_c64, int64_t cap, int64_t* n_out)
+int interp_run(b200dsp_interp* h, int mode, float* distance_remain, float distance, const float* in_c64, int64_t n, float* out_c64, int64_t cap, int64_t* n_out,
+               bool single = false)
 {
     if (!h || !distance_remain) return b200_fail(B200DSP_EINVAL, "interp: null argument");
     if (n < 0 || n >= (1 << 24) - 1 || (n > 0 && !in_c64) || (cap > 0 && !out_c64) || cap < 0) return b200_fail(B200DSP_EINVAL, "interp: bad buffer (at most 2^24-2 samples per call)");
-    if (!(distance > 0.0f)) return b200_fail(B200DSP_EINVAL, "interp: distance must be positive");
+    if (!(distance > 0.0f) && !single) return b200_fail(B200DSP_EINVAL, "interp: distance must be positive");
     if (n_out) *n_out = 0;
     if (n == 0 && mode != 1) return 0;                       // (the interpolate loop may still emit outputs while distance_remain < 1)
     int rc = B200_CUDA_CHECK(cudaSetDevice(h->device));
     if (rc) return rc;
     // outputs of one call: never more than the inputs when decimating; otherwise bounded by (n + 2) / distance + 2
     long long cap_out = n + 2;
-    if (mode != 0) {
+    if (mode != 0 && !single) {
         const double bound = ((double) n + 2.0) / (double) distance + 4.0;
         if (bound >= (double) (1 << 28)) return b200_fail(B200DSP_EINVAL, "interp: distance too small for one call");
         if ((long long) bound > cap_out) cap_out = (long long) bound;
@@ -1371,7 +1372,7 @@ int interp_run(b200dsp_interp* h, int mode, float* distance_remain, float distan
     f.in = (const uint32_t*) h->d_in; f.hist = h->d_hist; f.taps = h->d_taps; f.out = h->d_out; f.sched = h->d_sched; f.tile_start = h->d_tile;
     f.state = h->d_state; f.plan = h->d_plan; f.in_f32 = 1; f.hist_stride = 2 * FE_MAX_TAPS + 4;
     f.depth = 0; f.inc = 0; f.ntaps = h->ntaps; f.phase_steps = h->phase_steps; f.ratio = distance;
-    f.mode = mode; f.sched_cap = (int) h->cap_out;
+    f.mode = mode; f.sched_cap = single ? 1 : (int) h->cap_out;
     f.lattice = (mode == 0 && lattice_params(distance, h->phase_steps, &f.A, &f.phshift)) ? 1 : 0;
     // the caller owns the distance (Real* distance in the reference): it travels in, and back out
     int st[4] = { 0, 0, 0, 0 };
@@ -1394,7 +1395,7 @@ int interp_run(b200dsp_interp* h, int mode, float* distance_remain, float distan
     if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(st, h->d_state, 16, cudaMemcpyDeviceToHost, h->stream))) ||
         (rc = B200_CUDA_CHECK(cudaStreamSynchronize(h->stream)))) return rc;
     h->parity ^= 1;
-    if (st[0]) return b200_fail(B200DSP_ESTATE, "interp: more outputs than the schedule buffer holds (internal bound exceeded)");
+    if (st[0] && !single) return b200_fail(B200DSP_ESTATE, "interp: more outputs than the schedule buffer holds (internal bound exceeded)");
     memcpy(distance_remain, &st[1], 4);
     const long long m = st[2];
     if (n_out) *n_out = m;
@@ -1418,6 +1419,44 @@ int b200dsp_interp_interpolate(b200dsp_interp_t* h, float* distance_remain, floa
 int b200dsp_interp_resample(b200dsp_interp_t* h, float* distance_remain, float distance, const float* in_c64, int64_t n, float* out_c64, int64_t cap, int64_t* n_out)
 {
     return interp_run(h, 2, distance_remain, distance, in_c64, n, out_c64, cap, n_out);
+}
+
+// One reference call, for plugin code that has not been restructured into blocks (one launch per sample: drop-in, not fast):
+//   op 0: Interpolator::decimate(distance, next, result)            -> *produced = its return value (a result was written)
+//   op 1: Interpolator::interpolate(distance, next, result)         -> *produced = 1, *consumed = its return value
+//   op 2: Interpolator::resample(distance, next, consumed, result)  -> *produced = its return value, *consumed in/out
+// `distance` is updated exactly as the reference method does (the caller adds its step afterwards, as in the reference).
+int b200dsp_interp_step(b200dsp_interp_t* h, int op, float* distance, const float* next_c64, float* result_c64, int* consumed, int* produced)
+{
+    if (!h || !distance || !next_c64 || !result_c64 || !produced || op < 0 || op > 2 || (op != 0 && !consumed)) return b200_fail(B200DSP_EINVAL, "interp_step: bad argument");
+    int64_t m = 0;
+    int rc;
+    *produced = 0;
+    if (op == 0) {
+        // push, distance -= 1, a result iff distance < 1 (interpolator.h:23-36): the block form with one input and step 0
+        if ((rc = interp_run(h, 0, distance, 0.0f, next_c64, 1, result_c64, 1, &m, true))) return rc;
+        *produced = (int) m;
+        return 0;
+    }
+    if (op == 1) {
+        // consume iff distance >= 1, then always a result (interpolator.h:39-52)
+        const int take = (*distance >= 1.0f) ? 1 : 0;
+        if ((rc = interp_run(h, 1, distance, 0.0f, next_c64, take, result_c64, 1, &m, true))) return rc;
+        *consumed = take; *produced = 1;
+        return 0;
+    }
+    // resample (interpolator.h:55-76)
+    if (*distance >= 1.0f) {
+        if (*consumed) return 0;                                   // "return false": nothing happens
+        *consumed = 1;
+        if (*distance >= 2.0f) return interp_run(h, 0, distance, 0.0f, next_c64, 1, result_c64, 1, &m, true);      // pushed, still >= 1: no result
+        if ((rc = interp_run(h, 1, distance, 0.0f, next_c64, 1, result_c64, 1, &m, true))) return rc;
+        *produced = 1;
+        return 0;
+    }
+    if ((rc = interp_run(h, 1, distance, 0.0f, next_c64, 0, result_c64, 1, &m, true))) return rc;
+    *produced = 1;
+    return 0;
 }
 
 } // extern "C"

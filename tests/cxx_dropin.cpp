@@ -13,6 +13,9 @@
 #include "sdrangel_b200/dsp/spectrumvis.h"
 #include "sdrangel_b200/dsp/interpolator.h"
 #include "sdrangel_b200/dsp/iqcorrections.h"
+#include "sdrangel_b200/dsp/nco.h"
+#include "sdrangel_b200/dsp/samplesinkfifo.h"
+#include "sdrangel_b200/dsp/devicesamplesource.h"
 
 static uint64_t fnv(const void* p, size_t n_u16)
 {
@@ -101,6 +104,138 @@ int main()
         Real distance = 0, step = (Real) 156250 / (Real) 48000;
         size_t m = interp.decimate(&distance, step, &cin[0], cin.size(), &cout[0], cout.size());
         printf("interpolator n_out=%zu\n", m);
+        // the reference's per-sample signatures (interpolator.h:23-52) give what the block forms give, sample for sample
+        {
+            Interpolator a, b;
+            a.create(16, 156250, 12500 / 2.2f);
+            b.create(16, 156250, 12500 / 2.2f);
+            Real da = 0, db = 0;
+            std::vector<Complex> blk(400), one;
+            const size_t mb = a.decimate(&da, step, &cin[0], 1200, &blk[0], blk.size());
+            for (size_t i = 0; i < 1200; i++) {
+                Complex ci;
+                if (b.decimate(&db, cin[i], &ci)) { one.push_back(ci); db += step; }
+            }
+            bool same = (one.size() == mb) && (da == db);
+            for (size_t i = 0; same && i < mb; i++) same = (one[i] == blk[i]);
+            printf("interpolator_per_sample_decimate %s n=%zu\n", same ? "same" : "DIFFERENT", one.size());
+            // Tx pull loop (nfmmod.cpp:126-133), 48 kS/s -> 156.25 kS/s
+            Interpolator c, d;
+            c.create(16, 156250, 48000 / 2.2f);
+            d.create(16, 156250, 48000 / 2.2f);
+            Real dc = 0, dd = 0;
+            const Real up = (Real) 48000 / (Real) 156250;
+            std::vector<Complex> ublk(2000), uone;
+            const size_t mu = c.interpolate(&dc, up, &cin[0], 300, &ublk[0], ublk.size());
+            size_t i = 0;
+            for (;;) {
+                if (dd >= 1.0f && i >= 300) break;
+                Complex ci;
+                if (d.interpolate(&dd, i < 300 ? cin[i] : Complex(0, 0), &ci)) i++;
+                uone.push_back(ci);
+                dd += up;
+            }
+            same = (uone.size() == mu) && (dc == dd);
+            for (size_t k = 0; same && k < mu; k++) same = (uone[k] == ublk[k]);
+            printf("interpolator_per_sample_interpolate %s n=%zu\n", same ? "same" : "DIFFERENT", uone.size());
+        }
+        // NCO: per-sample nextIQ() == the block form
+        {
+            NCO n1, n2;
+            n1.setFreq(15433, 156250);
+            n2.setFreq(15433, 156250);
+            std::vector<Complex> nb(500);
+            n1.nextIQ(&nb[0], nb.size());
+            bool same = (n1.phaseIncrement() == 404);
+            for (size_t k = 0; same && k < 40; k++) same = (n2.nextIQ() == nb[k]);
+            printf("nco inc=%d %s\n", n1.phaseIncrement(), same ? "same" : "DIFFERENT");
+        }
+        // SampleSinkFifo semantics (samplesinkfifo.cpp:113-231): overflow drops, two-span readBegin, readCommit; the device ring behaves alike
+        {
+            SampleSinkFifo fifo(1000);
+            SampleVector v(700);
+            for (size_t k = 0; k < v.size(); k++) { v[k].setReal((qint16) k); v[k].setImag((qint16) -(int) k); }
+            uint w1 = fifo.write(v.begin(), v.end());
+            SampleVector r(500);
+            uint r1 = fifo.read(r.begin(), r.end());
+            uint w2 = fifo.write(v.begin(), v.end());           // wraps: 300 at the end + 400 at the start
+            uint w3 = fifo.write(v.begin(), v.end());           // only 100 fit: overflow drops 600
+            SampleVector::iterator p1b, p1e, p2b, p2e;
+            uint t = fifo.readBegin(900, &p1b, &p1e, &p2b, &p2e);
+            printf("samplesinkfifo w=%u,%u,%u r=%u begin=%u spans=%zu+%zu first=%d second=%d fill=%u\n", w1, w2, w3, r1, t, (size_t) (p1e - p1b), (size_t) (p2e - p2b),
+                   (int) p1b->real(), (int) p2b->real(), fifo.fill());
+            fifo.readCommit(t);
+            DeviceSampleSinkFifo dfifo(1000);
+            uint dw1 = dfifo.write(v.begin(), v.end());
+            uint dr1 = dfifo.read(r.begin(), r.end());
+            uint dw2 = dfifo.write(v.begin(), v.end());
+            uint dw3 = dfifo.write(v.begin(), v.end());
+            const void *q1, *q2; uint n1 = 0, n2 = 0;
+            uint dt = dfifo.readBegin(900, &q1, &n1, &q2, &n2);
+            printf("devicesamplesinkfifo w=%u,%u,%u r=%u begin=%u spans=%u+%u fill=%u r0=%d\n", dw1, dw2, dw3, dr1, dt, n1, n2, dfifo.fill(), (int) r[499].real());
+            printf("frequencyshift %d %d %d\n", DeviceSampleSource::calculateFrequencyShift(2, DeviceSampleSource::FC_POS_INFRA, 10000000),
+                   DeviceSampleSource::calculateFrequencyShift(4, DeviceSampleSource::FC_POS_SUPRA, 10000000),
+                   (int) DeviceSampleSource::calculateDeviceCenterFrequency(435000000ull, 0, 4, DeviceSampleSource::FC_POS_SUPRA, 10000000));
+        }
+        // decimators -> device FIFO -> bank, never through the host: Decimators output written on the device, the bank fed from the FIFO's spans
+        {
+            b200dsp_decim_t* dh = nullptr;
+            b200dsp_cxx::check(b200dsp_decim_create(&dh, B200DSP_FMT_I16, B200DSP_FMT_I16, 12));
+            ChannelBank bankA(10000000 / 4), bankB(10000000 / 4);
+            CaptureSink sa, sb2;
+            bankA.addChannel(&sa, 48000, 300000);
+            bankB.addChannel(&sb2, 48000, 300000);
+            // host route: decimate4_cen through the wrappers, then ChannelBank::feed
+            SampleVector dec(nbSamples / 4);
+            it = dec.begin();
+            Decimators<qint32, qint16, SDR_RX_SAMP_SZ, 12> d4;
+            d4.decimate4_cen(&it, buf, nbSamples * 2);
+            bankA.feed(dec.begin(), it, false);
+            // device route (C ABI): the same, the samples staying in device memory
+            SampleVector viaDevice;
+            {
+                // a device buffer pair through the FIFO object itself: raw input in, decimated block out
+                DeviceSampleSinkFifo rawIn((uint) nbSamples), ring(300000);
+                SampleVector raw(nbSamples);
+                for (int k = 0; k < nbSamples; k++) { raw[k].setReal(buf[2 * k]); raw[k].setImag(buf[2 * k + 1]); }
+                rawIn.write(raw.begin(), raw.end());
+                const void *a1, *a2; uint m1 = 0, m2 = 0;
+                rawIn.readBegin((uint) nbSamples, &a1, &m1, &a2, &m2);
+                DeviceSampleSinkFifo stage((uint) nbSamples / 4);
+                const void *o1, *o2; uint k1 = 0, k2 = 0;
+                SampleVector zeros(nbSamples / 4);
+                stage.write(zeros.begin(), zeros.end());                 // reserve the ring's storage as the decimator's output buffer
+                stage.readBegin((uint) nbSamples / 4, &o1, &k1, &o2, &k2);
+                int64_t nd = 0;
+                b200dsp_cxx::check(b200dsp_decim_run_dev(dh, 2, B200DSP_MODE_CEN, a1, 2ll * m1, (void*) o1, &nd, nullptr));
+                b200dsp_cxx::check(b200dsp_decim_sync(dh));
+                ring.writeDevice(o1, (uint) nd);                          // decimators -> FIFO (device to device)
+                const void *p1, *p2; uint c1 = 0, c2 = 0;
+                uint tot = ring.readBegin(300000, &p1, &c1, &p2, &c2);   // engine side: spans -> the bank, still on the device
+                if (c1) b200dsp_cxx::check(b200dsp_bank_feed_dev(bankB.handle(), p1, c1, nullptr));
+                b200dsp_cxx::check(b200dsp_bank_sync(bankB.handle()));
+                ring.readCommit(tot);
+                int64_t mch = 0;
+                b200dsp_cxx::check(b200dsp_bank_fetch(bankB.handle(), 0, B200DSP_STAGE_CHANNELIZER, nullptr, (int64_t) 1 << 62, &mch));
+                viaDevice.resize((size_t) mch);
+                if (mch) b200dsp_cxx::check(b200dsp_bank_fetch(bankB.handle(), 0, B200DSP_STAGE_CHANNELIZER, &viaDevice[0], mch, &mch));
+            }
+            bool same = (viaDevice.size() == sa.captured.size()) && !viaDevice.empty();
+            for (size_t k = 0; same && k < viaDevice.size(); k++) same = (viaDevice[k].real() == sa.captured[k].real() && viaDevice[k].imag() == sa.captured[k].imag());
+            printf("device_fifo_route %s n=%zu\n", same ? "same" : "DIFFERENT", viaDevice.size());
+            b200dsp_decim_destroy(dh);
+            // split-I/Q overload == interleaved entry point (decimators.h:2858 vs :2966)
+            std::vector<qint16> bi(4096), bq(4096);
+            for (int k = 0; k < 4096; k++) { bi[k] = buf[2 * k]; bq[k] = buf[2 * k + 1]; }
+            Decimators<qint32, qint16, SDR_RX_SAMP_SZ, 12> ds, dn;
+            SampleVector os(4096), on(4096);
+            SampleVector::iterator is = os.begin(), in2 = on.begin();
+            ds.decimate16_cen(&is, &bi[0], &bq[0], 4096);
+            dn.decimate16_cen(&in2, buf, 8192);
+            same = (is - os.begin() == in2 - on.begin());
+            for (size_t k = 0; same && k < (size_t) (is - os.begin()); k++) same = (os[k].real() == on[k].real() && os[k].imag() == on[k].imag());
+            printf("split_iq_overload %s n=%zu\n", same ? "same" : "DIFFERENT", (size_t) (is - os.begin()));
+        }
         delete[] buf;
     } catch (const std::exception& e) {
         fprintf(stderr, "exception: %s\n", e.what());

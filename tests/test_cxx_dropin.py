@@ -51,3 +51,13 @@ def test_sdrbench_decimateii_through_cxx_wrappers(gpu_lib, port, golden_meta, go
     assert lines["downchannelizer"].startswith("rate=156250 ofs=-15433 n_out=937")
     assert lines["spectrumvis"] == "frames=2"
     assert lines["interpolator"] == "n_out=6145"          # 20 000 inputs at 156 250 -> 48 000
+    # the reference's per-sample method signatures equal the block forms; NCO increment of SURVEY.md Appendix D
+    assert lines["interpolator_per_sample_decimate"].startswith("same n=36")
+    assert lines["interpolator_per_sample_interpolate"].startswith("same")
+    assert lines["nco"] == "inc=404 same"
+    # SampleSinkFifo (samplesinkfifo.cpp:113-231): 700 in, 500 out, 700 in (wraps), then only 100 fit; read of 900 = two spans
+    assert lines["samplesinkfifo"] == "w=700,700,100 r=500 begin=900 spans=500+400 first=500 second=300 fill=1000"
+    assert lines["devicesamplesinkfifo"] == "w=700,700,100 r=500 begin=900 spans=500+400 fill=1000 r0=499"
+    assert lines["frequencyshift"] == "-1250000 625000 434375000"
+    assert lines["device_fifo_route"].startswith("same n=")
+    assert lines["split_iq_overload"] == "same n=256"
