@@ -305,9 +305,13 @@ def setup():
 
 def measured_traffic(name, samples_per_step, per_launch_scale=1.0):
     """roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture
-    (profiles/r01_traffic.json), scaled from the captured launch's sample count to this run's."""
+    (profiles/r02_traffic.json for the bank: every kernel of one step; profiles/r01_traffic.json for the kernels unchanged since
+    round 1), scaled from the captured sample count to this run's."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[name]
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))[name]
+        except Exception:
+            t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[name]
         return (t["dram_read"] + t["dram_write"]) * (samples_per_step / t["samples"]) * per_launch_scale
     except Exception:
         return None

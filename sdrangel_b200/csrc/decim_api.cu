@@ -208,7 +208,7 @@ struct Plan {
     long long n_out;
 };
 
-int make_plan(int in_fmt, int out_fmt, int bits, int log2, int mode, long long len, Plan* pl)
+int make_plan(int in_fmt, int out_fmt, int bits, int log2, int mode, long long len, Plan* pl, bool split = false)
 {
     if (log2 < 0 || log2 > 6 || mode < 0 || mode > 3 || len < 0) return B200DSP_EINVAL;
     memset(pl, 0, sizeof(*pl));
@@ -239,7 +239,8 @@ int make_plan(int in_fmt, int out_fmt, int bits, int log2, int mode, long long l
             return 0;
         }
         // scalars per loop iteration: _cen 2N (N>=8), 16 (N=4), 8 (N=2); _inf/_sup 4N
-        const long long blk = (mode == B200DSP_MODE_CEN) ? (N >= 8 ? 2 * N : (N == 4 ? 16 : 8)) : 4 * N;
+        // (the split-I/Q _cen overloads take N samples per array per output for every N: decimators.h:2641,2707)
+        const long long blk = (mode == B200DSP_MODE_CEN) ? ((N >= 8 || split) ? 2 * N : (N == 4 ? 16 : 8)) : 4 * N;
         const long long nblk = len / blk;
         pl->consumed_scalars = nblk * blk;
         pl->n0 = pl->consumed_scalars / 2;
@@ -569,7 +570,7 @@ int b200dsp_decim_run_split(b200dsp_decim_t* h, int log2_decim, int mode, const 
     if (len_per_array < 0 || len_per_array > (1 << 29)) return b200_fail(B200DSP_EINVAL, "decim_run_split: bad length");
     if (mode != B200DSP_MODE_CEN && mode != B200DSP_MODE_U) return b200_fail(B200DSP_EINVAL, "decim_run_split: the reference defines the split overloads for decimate1, decimate2_u and decimateN_cen only");
     Plan whole;
-    if (make_plan(h->in_fmt, h->out_fmt, h->bits, log2_decim, mode, 2ll * len_per_array, &whole)) return b200_fail(B200DSP_EINVAL, "decim_run_split: bad log2/mode/len");
+    if (make_plan(h->in_fmt, h->out_fmt, h->bits, log2_decim, mode, 2ll * len_per_array, &whole, true)) return b200_fail(B200DSP_EINVAL, "decim_run_split: bad log2/mode/len");
     if (n_out) *n_out = (int32_t) whole.n_out;
     if (whole.n_out == 0) return 0;
     if (!in_i || !in_q || !out) return b200_fail(B200DSP_EINVAL, "decim_run_split: null buffer");
