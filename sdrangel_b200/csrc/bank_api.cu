@@ -103,6 +103,7 @@ struct Channel {
     uint32_t* d_out; long long out_cap; long long out_count;       // channelizer outputs since the last feed start
     uint32_t* d_hist; float* d_taps; float2* d_fe_out; int* d_sched; int* d_tile; int* d_state; long long* d_plan; long long fe_cap;
     long long A; int lattice, phshift;
+    int scan_kb; long long scan_A;       // non-lattice ratio: parameters of the parallel exact replay
 };
 
 const double PI_D = 3.14159265358979323846;
@@ -131,6 +132,22 @@ void interp_taps(int phase_steps, double rate, double cutoff, double taps_per_ph
         for (int i = 0; i < np; i++) out[p * np + i] /= sum;
     }
     *per_phase = np;
+}
+
+// non-lattice ratios in [1, 64): units and ratio for the warp-parallel exact replay (frontend.cuh: fe_scan_chunk)
+bool scan_params(float ratio, int* kb_out, long long* A_out)
+{
+    *kb_out = 0; *A_out = 0;
+    if (!(ratio > 1.0f && ratio < 64.0f)) return false;
+    int e = 0;
+    while ((float) (2 << e) <= ratio) ++e;               // 2^e <= ratio < 2^(e+1)
+    const float P = (float) (2 << e);
+    if (!(ratio + 1.0f > P)) return false;                // no power of two inside [ratio, ratio + 1): the lattice case
+    const int kb = 23 - e;
+    const double a = (double) ratio * (double) (1ll << kb);
+    if (a != floor(a)) return false;
+    *kb_out = kb; *A_out = (long long) a;
+    return true;
 }
 
 // closed-form schedule when no sum r + ratio (< ratio + 1) can ever be rounded: ratio * 2^23 on the coarsest ulp lattice
@@ -569,7 +586,7 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
         for (size_t k = 0; k < b->fe_index.size(); ++k) {
             Channel& c = b->chans[b->fe_index[k]];
             FrontendChan& f = b->h_fe[k];
-            f.in = c.d_out; f.hist = c.d_hist; f.taps = c.d_taps; f.out = c.d_fe_out; f.sched = c.d_sched; f.tile_start = c.d_tile; f.state = c.d_state; f.plan = c.d_plan; f.A = c.A; f.lattice = c.lattice; f.phshift = c.phshift; f.in_f32 = 0; f.hist_stride = FE_HIST_WORDS;
+            f.in = c.d_out; f.hist = c.d_hist; f.taps = c.d_taps; f.out = c.d_fe_out; f.sched = c.d_sched; f.tile_start = c.d_tile; f.state = c.d_state; f.plan = c.d_plan; f.A = c.scan_kb ? c.scan_A : c.A; f.scan_kb = c.scan_kb; f.lattice = c.lattice; f.phshift = c.phshift; f.in_f32 = 0; f.hist_stride = FE_HIST_WORDS;
             f.depth = c.S; f.inc = c.inc; f.ntaps = c.ntaps; f.phase_steps = c.phase_steps; f.ratio = c.ratio; f.mode = 0; f.sched_cap = (int) c.fe_cap;
         }
         if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(b->d_leaf, b->h_leaf.data(), nc * sizeof(LeafChan), cudaMemcpyHostToDevice, st)))) return rc;
@@ -1007,6 +1024,8 @@ int b200dsp_bank_set_frontend(b200dsp_bank_t* b, int chan_id, float nco_freq_hz,
     c.ntaps = np;
     c.inc = (int) ((nco_freq_hz * 4096) / (float) c.out_rate);                 // NCO::setFreq: float arithmetic, truncation (nco.cpp:50)
     c.ratio = ratio; c.lattice = lattice; c.A = A; c.phshift = phshift;
+    c.scan_kb = 0; c.scan_A = 0;
+    if (!lattice && !getenv("B200DSP_SERIAL_SCHEDULE")) scan_params(ratio, &c.scan_kb, &c.scan_A);
     if (b->built) { cudaSetDevice(b->device); cudaStreamSynchronize(b->stream); free_device(b); }
     return 0;
 }
@@ -1374,6 +1393,7 @@ int interp_run(b200dsp_interp* h, int mode, float* distance_remain, float distan
     f.depth = 0; f.inc = 0; f.ntaps = h->ntaps; f.phase_steps = h->phase_steps; f.ratio = distance;
     f.mode = mode; f.sched_cap = single ? 1 : (int) h->cap_out;
     f.lattice = (mode == 0 && lattice_params(distance, h->phase_steps, &f.A, &f.phshift)) ? 1 : 0;
+    if (mode == 0 && !f.lattice && !single && !getenv("B200DSP_SERIAL_SCHEDULE")) { long long a = 0; int kb = 0; if (scan_params(distance, &kb, &a)) { f.scan_kb = kb; f.A = a; } }
     // the caller owns the distance (Real* distance in the reference): it travels in, and back out
     int st[4] = { 0, 0, 0, 0 };
     memcpy(&st[1], distance_remain, 4);

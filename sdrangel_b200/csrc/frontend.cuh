@@ -45,6 +45,8 @@ struct FrontendChan {            // one per channel with a front-end, device arr
     int             mode;        // caller loop the schedule replays: 0 Interpolator::decimate (Rx plugins), 1 ::interpolate (Tx pull loop),
                                  // 2 ::resample (do-while per input); modes 1-2 store idx + 1 (an output may precede the pass's first input)
     int             sched_cap;   // entries of `sched` (modes 1-2: outputs are not bounded by the input count)
+    int             scan_kb;     // > 0: mode 0, non-lattice ratio: the replay runs as a warp-parallel scan; the distance is an integer
+                                 // in units of 2^-scan_kb (the fine ulp of the binade below the power of two the sums r + ratio cross)
 };
 
 // per-pass scalars, identical for all nodes/channels of one depth (every stream of a depth has the same length)
@@ -68,6 +70,134 @@ struct PassInfo {
 //     (1.25 = 60 kS/s -> 48 kS/s, the 1024-channel plan, is such a ratio).
 // Depends only on counts, not on samples: runs on a high-priority side stream concurrently with the tree kernels.
 // One WARP per channel: lane 0 runs the serial recurrence (the other lanes idle), then all lanes fill the tile table.
+// ---- exact parallel replay of the float32 distance recurrence for non-lattice ratios ------------------------------------
+// In units u = 2^-kb the distance before an emission is an integer D in [A, A + q), q = 2^kb = 1.0, A = ratio / u.  An
+// emission takes j = D >> kb inputs, leaves R = D mod q, and the next distance is fl(R u + ratio): R + A exactly when that is
+// below the power of two P the interval [ratio, ratio + 1) straddles (P / u = 2^24), else R + A rounded to a multiple of 2
+// units, ties to even: an odd sum becomes the neighbouring multiple of 4.  So
+//   * without the +-1 corrections R_k = (R_0 + k A) mod q in closed form, and "the sum crosses P" (R_k + A >= 2^24) too;
+//   * whether a crossing step corrects, and by which sign, depends only on D mod 4, which follows a 4-state automaton
+//     driven by the crossing flags: s' = (s + A) mod 4, and 0 after a correction -- a scan over function composition;
+//   * the corrections accumulate in a small offset e_k (a prefix sum), R_k = closed form + e_k.
+// The closed-form crossing flags are then checked against the corrected R_k; the rare chunk where an offset moves a value
+// across a boundary is redone serially from its (exact) starting state.
+__device__ __forceinline__ unsigned fe_fcomp(unsigned g, unsigned f)       // first g, then f; functions on {0..3}, 2 bits per entry
+{
+    unsigned h = 0;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) h |= ((f >> (2 * ((g >> (2 * s)) & 3u))) & 3u) << (2 * s);
+    return h;
+}
+
+// one chunk of 128 candidate emissions by a whole warp, from the exact state (Db, ib = last consumed input, nb = emissions so far).
+// Returns false when the chunk must be replayed serially.  *nvalid = emissions whose input exists (a prefix of the chunk).
+__device__ __forceinline__ bool fe_scan_chunk(const FrontendChan& c, int lane, int m, long long Db, int ib, int nb, int* sched,
+                                              int* nvalid, long long* Dnext, int* inext)
+{
+    const int kb = c.scan_kb;
+    const long long q = 1ll << kb, qm = q - 1, P = 1ll << 24, A = c.A;
+    const long long Am = A & qm, R0 = Db & qm;
+    const unsigned a4 = (unsigned) (A & 3);
+    unsigned FL = 0, FH = 0;                   // the automaton's two step functions
+#pragma unroll
+    for (unsigned s2 = 0; s2 < 4; ++s2) {
+        const unsigned t = (s2 + a4) & 3u;
+        FL |= t << (2 * s2);
+        FH |= ((t & 1u) ? 0u : t) << (2 * s2);
+    }
+    long long Rz[4];                           // closed-form R of this lane's four emissions k = 4 lane + t
+    bool hi[4];
+    unsigned fn = 0xE4u;                       // identity
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const long long k = 4 * lane + t;
+        Rz[t] = (R0 + k * Am) & qm;
+        hi[t] = (Rz[t] + A >= P);
+        fn = fe_fcomp(fn, hi[t] ? FH : FL);
+    }
+    // exclusive scan of the step functions over the lanes
+    unsigned inc = fn;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned o = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc = fe_fcomp(o, inc);
+    }
+    unsigned exc = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) exc = 0xE4u;
+    unsigned st = (exc >> (2 * (unsigned) (Db & 3))) & 3u;          // D mod 4 before this lane's first emission
+    int cc[4], csum = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const unsigned tt = (st + a4) & 3u;
+        cc[t] = (hi[t] && (tt & 1u)) ? ((tt == 1u) ? -1 : 1) : 0;
+        st = (hi[t] && (tt & 1u)) ? 0u : tt;
+        csum += cc[t];
+    }
+    int einc = csum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, einc, off);
+        if (lane >= off) einc += o;
+    }
+    int e = einc - csum;                       // corrections before this lane's first emission
+    // distances D_k, inputs taken j_k, true R_k; consistency of the closed-form flags
+    bool ok = true;
+    long long Dk[4], Rk[4];
+    int jsum = 0, jj[4];
+    long long prevR0 = __shfl_up_sync(0xffffffffu, Rz[3], 1);        // closed-form R of emission 4 lane - 1
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const long long before = (t == 0) ? prevR0 : Rz[t - 1];
+        Dk[t] = (lane == 0 && t == 0) ? Db : before + A + e;         // (R0_{k-1} + A) + e_k
+        Rk[t] = Rz[t] + e;
+        ok = ok && Rk[t] >= 0 && Rk[t] < q && ((Rk[t] + A >= P) == hi[t]) && ((Dk[t] & qm) == Rk[t]);
+        jj[t] = (int) (Dk[t] >> kb);
+        jsum += jj[t];
+        e += cc[t];
+    }
+    if (!__all_sync(0xffffffffu, ok)) return false;
+    int jinc = jsum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, jinc, off);
+        if (lane >= off) jinc += o;
+    }
+    int idx = ib + (jinc - jsum);
+    const float steps = (float) c.phase_steps, uf = 1.0f / (float) q;
+    int cnt = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        idx += jj[t];
+        if (idx < m) {
+            int ph = (int) floorf(__fmul_rn(__fmul_rn((float) Rk[t], uf), steps));      // (float) R u is exact
+            ph = ph < 0 ? 0 : ph;
+            sched[nb + 4 * lane + t] = (int) (((unsigned) idx << 8) | (unsigned) ph);
+            ++cnt;
+        }
+    }
+    // the valid emissions are a prefix of the chunk; state after the last of them
+    int tot = cnt;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
+    *nvalid = tot;
+    // D after emission kl = tot - 1 is (closed-form R_kl + A) + e_{kl+1}; the lane that owns kl publishes it
+    long long Dn = 0;
+    int in_ = 0;
+    {
+        int ee = einc - csum, ii = ib + (jinc - jsum);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            ii += jj[t];
+            ee += cc[t];
+            if (4 * lane + t == tot - 1) { Dn = Rz[t] + A + ee; in_ = ii; }
+        }
+    }
+    const int owner = (tot > 0) ? (tot - 1) >> 2 : 0;
+    *Dnext = __shfl_sync(0xffffffffu, Dn, owner);
+    *inext = __shfl_sync(0xffffffffu, in_, owner);
+    return true;
+}
+
 __global__ void frontend_schedule_kernel(const FrontendChan* __restrict__ chans, int n_chans, const PassInfo pi)
 {
     const int ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -80,6 +210,47 @@ __global__ void frontend_schedule_kernel(const FrontendChan* __restrict__ chans,
     const int ntiles = (m + FE_TILE - 1) / FE_TILE;
     int n = 0;
     long long ncf = 0, i0 = 0, D = 0;
+    if (c.scan_kb > 0 && c.mode == 0) {
+        // non-lattice ratio: serial until the distance has been through one fl(r + ratio) (a few emissions at a stream's
+        // start), then 128 emissions per warp step
+        float d = __int_as_float(c.state[1]);
+        const float steps = (float) c.phase_steps, ratio = c.ratio;
+        int i = -1;
+        bool done = false;
+        auto serial_emit = [&]() -> bool {              // every lane computes, lane 0 writes: returns false when the input runs out
+            const float fj = fmaxf(floorf(d), 1.0f);
+            if (i + (int) fj >= m) return false;
+            i += (int) fj;
+            const float r = __fsub_rn(d, fj);
+            int ph = (int) floorf(__fmul_rn(r, steps));
+            ph = ph < 0 ? 0 : ph;
+            if (lane == 0) sched[n] = (int) (((unsigned) i << 8) | (unsigned) ph);
+            ++n;
+            d = __fadd_rn(r, ratio);
+            return true;
+        };
+        for (int k = 0; k < 2 && !done; ++k) done = !serial_emit();
+        while (!done && !(d >= ratio && d < ratio + 1.0f)) done = !serial_emit();
+        const float qf = (float) (1ll << c.scan_kb);
+        while (!done) {
+            long long Db = (long long) (d * qf), Dn;          // exact: d is a multiple of 2^-kb below 2^25
+            int nv, in_;
+            if (fe_scan_chunk(c, lane, m, Db, i, n, sched, &nv, &Dn, &in_)) {
+                if (nv > 0) { n += nv; i = in_; d = (float) Dn / qf; }
+                if (nv < 128) done = true;
+            } else {
+                for (int k = 0; k < 128 && !done; ++k) done = !serial_emit();     // rare: an offset moved a value across a boundary
+            }
+        }
+        d = __fadd_rn(d, -(float) (m - 1 - i));        // the remaining inputs of this pass each subtract 1.0f (exact)
+        if (lane == 0) {
+            c.plan[0] = n; c.plan[1] = 0; c.plan[2] = 0; c.plan[3] = 0;
+            const int base = pi.first_pass ? 0 : c.state[3];
+            c.state[1] = __float_as_int(d);
+            c.state[2] = n;
+            c.state[3] = base + n;
+        }
+    } else
     if (lane == 0) {
         float d = __int_as_float(c.state[1]);      // distance remain before the next input
         const float steps = (float) c.phase_steps, ratio = c.ratio;

@@ -83,3 +83,32 @@ def test_nco_block_golden(gpu_lib, golden_interp):
         p, inc = nco.state()
         assert p == (5000 * inc) % 4096
         nco.close()
+
+
+@pytest.mark.parametrize("ratio", [156250.0 / 48000.0, 78125.0 / 48000.0, 1.0000001, 1.9999, 3.0000002, 7.3, 15.99, 31.9, 63.5])
+def test_parallel_schedule_equals_serial_replay(gpu_lib, ratio):
+    """K4's exact schedule for non-lattice ratios runs as a warp-parallel scan (closed-form residues + a 4-state automaton for
+    the float32 tie-rounding corrections); B200DSP_SERIAL_SCHEDULE=1 forces the one-lane serial replay of the same recurrence.
+    Both must give the same outputs bit for bit (same schedule, same arithmetic), call after call, with the carried distance
+    identical -- 2^21 inputs per ratio, ragged calls, a caller-set off-lattice starting distance."""
+    from sdrangel_b200 import Interpolator
+    rs = np.random.RandomState(int(ratio * 1000))
+    n = 1 << 21
+    x = (rs.randint(-20000, 20000, size=n) + 1j * rs.randint(-20000, 20000, size=n)).astype(np.complex64)
+    a, b = Interpolator(16, 48000.0 * ratio, 12500 / 2.2), Interpolator(16, 48000.0 * ratio, 12500 / 2.2)
+    step = float(np.float32(ratio))
+    ra = rb = 0.1
+    cuts = [0, 5, 1000, 1001, 700_000, 700_129, n]
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        os.environ.pop("B200DSP_SERIAL_SCHEDULE", None)
+        ya, ra = a.decimate(ra, step, x[lo:hi])
+        os.environ["B200DSP_SERIAL_SCHEDULE"] = "1"
+        try:
+            yb, rb = b.decimate(rb, step, x[lo:hi])
+        finally:
+            os.environ.pop("B200DSP_SERIAL_SCHEDULE", None)
+        assert ya.shape == yb.shape, (ratio, lo, hi, ya.shape, yb.shape)
+        assert np.float32(ra) == np.float32(rb), (ratio, lo, hi)
+        assert np.array_equal(ya, yb), (ratio, lo, hi)
+    a.close()
+    b.close()
