@@ -23,7 +23,9 @@ for i, h in enumerate(hdr):
         print("%-70s %s" % (h, r[i]))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hdr, data = rows[1], rows[2:]
+ks = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]      # several captured launches: the first
+rows = rows[ks[0]:ks[1]]
+hdr, data = rows[1], [r for r in rows[2:] if len(r) > 10]
 iS, iI, iN = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
 tot = sum(int(x[iI]) for x in data)
 print("total warp instr", tot)
@@ -45,4 +47,4 @@ for a, b, c in regions:
             ops[op] = ops.get(op, 0) + 1
         top = sorted(ops.items(), key=lambda z: -z[1])[:9]
         smp = sum(int(x[iN]) for x in data[a:b + 1])
-        print("lines %d-%d n=%d exec=%d share=%.3f samples=%d %s" % (a, b, n, c, n * c / tot, smp, top))
+        print("lines %d-%d n=%d exec=%d share=%.3f samples=%.3f %s" % (a, b, n, c, n * c / tot, smp / max(sum(int(x[iN]) for x in data), 1), top))
