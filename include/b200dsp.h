@@ -213,7 +213,9 @@ int b200dsp_dist_p2p_slot(b200dsp_dist_t* d, int slot, const void** d_ptr, int64
  * == DSPDeviceSourceEngine::iqCorrections(begin, end, imbalanceCorrection)  sdrbase/dsp/dspdevicesourceengine.cpp:175-262,
  *    the step DSPDeviceSourceEngine::work applies between the device Decimators<> and the channel sinks (:343-347).
  * One handle == one engine's m_iBeta / m_qBeta state (MovingAverageUtil<int32_t,int64_t,1024>, dspdevicesourceengine.h:106-107).
- * imbalance must be 0 (DC correction, :254-259); the I/Q imbalance branch returns B200DSP_ESTATE. */
+ * imbalance 0: DC correction (:254-259), bit-exact.  imbalance 1: the I/Q imbalance branch (:219-252, the floating-point flavour
+ * the reference compiles): segments of 2048 samples replayed in the reference's operation order after a 2048-sample
+ * warm-up -- within 1 LSB of the reference (its running totals carry rounding drift from before the warm-up). */
 typedef struct b200dsp_iqcorr b200dsp_iqcorr_t;
 int b200dsp_iqcorr_create(b200dsp_iqcorr_t** h);
 int b200dsp_iqcorr_destroy(b200dsp_iqcorr_t* h);

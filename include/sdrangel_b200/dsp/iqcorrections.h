@@ -14,7 +14,7 @@ public:
     IQCorrections& operator=(const IQCorrections&) = delete;
 
     /** == DSPDeviceSourceEngine::iqCorrections(begin, end, imbalanceCorrection): corrects [begin, end) in place.
-     *  imbalanceCorrection == true throws (that branch is not implemented; no silent DC-only result). */
+     *  imbalanceCorrection selects the I/Q imbalance branch (:219-252) instead of DC correction only (:254-259). */
     void iqCorrections(SampleVector::iterator begin, SampleVector::iterator end, bool imbalanceCorrection)
     {
         if (begin == end) return;

@@ -114,13 +114,106 @@ __global__ void __launch_bounds__(DC_THREADS) dc_correct_kernel(const DcParams p
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// I/Q imbalance branch (dspdevicesourceengine.cpp:219-252, the floating-point flavour: IMBALANCE_INT is not defined).
+// Per sample: DC-corrected (xi, xq) / 32768; <I,I>, <I,Q> over 128 samples -> phase estimate phi = <I,Q>/<I,I>, itself averaged
+// over 128 pushes (pushed only while <I,I> != 0); yq = xq - phi xi; <I,I>, <Q,Q> of (xi, yq) -> amplitude estimate
+// sqrt(<I,I>/<Q,Q>), averaged over 128 pushes; zq = amp yq; output (xi, zq) * 32768 truncated to int16.  Every average
+// is a MovingAverageUtil (util/movingaverage.h) whose running total adds `sample - oldest` -- a float subtraction for the
+// power averages -- so the loop is sequential as written.  All estimators have finite memory (1024 + 4 x 128 samples):
+// the stream is cut into segments, ONE THREAD replays the reference loop over a segment in the reference's own
+// operation order (separately rounded float/double operations, IEEE division and square root), after a warm-up over the
+// 2048 samples before it (from zero state; its outputs are dropped).  What a segment cannot see is the rounding drift
+// the reference's running totals accumulated before the warm-up (relative 1e-7 after a million samples: an output LSB
+// in ~1e-4 of the samples) and estimator pushes skipped during digital silence older than the warm-up.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int IMB_WARM = 2048;
+constexpr int IMB_SEG = 2048;
+
+struct ImbParams {
+    const uint32_t* in; uint32_t* out;
+    const uint32_t* hist_in;      // the IMB_WARM raw samples before this call (oldest first)
+    uint32_t* hist_out;
+    uint32_t* dc_hist_out;        // the DC branch's carried history (last DC_N raw samples): both branches share m_iBeta / m_qBeta
+    long long n;
+};
+
+struct ImbAvgF { float s[128]; unsigned idx; double total; };
+struct ImbAvgD { double s[128]; unsigned idx; double total; };
+__device__ __forceinline__ void imb_push(ImbAvgF& m, float v)        // the ring starts full of zeros == the fill-up phase (the divisor is always N)
+{
+    const float d = __fsub_rn(v, m.s[m.idx]);
+    m.total = __dadd_rn(m.total, (double) d);
+    m.s[m.idx] = v;
+    m.idx = (m.idx + 1) & 127u;
+}
+__device__ __forceinline__ void imb_push(ImbAvgD& m, double v)
+{
+    m.total = __dadd_rn(m.total, __dsub_rn(v, m.s[m.idx]));
+    m.s[m.idx] = v;
+    m.idx = (m.idx + 1) & 127u;
+}
+
+__global__ void __launch_bounds__(32) iq_imbalance_kernel(const ImbParams p)
+{
+    const long long seg = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long start = seg * IMB_SEG;
+    if (start < p.n) {
+        const long long end = (start + IMB_SEG < p.n) ? start + IMB_SEG : p.n;
+        int dr[DC_N], di[DC_N];
+        unsigned didx = 0;
+        long long tr = 0, ti = 0;
+        ImbAvgF aII, aIQ, aII2, aQQ2;
+        ImbAvgD aPhi, aAmp;
+        for (int k = 0; k < DC_N; ++k) { dr[k] = 0; di[k] = 0; }
+        for (int k = 0; k < 128; ++k) { aII.s[k] = 0; aIQ.s[k] = 0; aII2.s[k] = 0; aQQ2.s[k] = 0; aPhi.s[k] = 0; aAmp.s[k] = 0; }
+        aII.idx = aIQ.idx = aII2.idx = aQQ2.idx = aPhi.idx = aAmp.idx = 0;
+        aII.total = aIQ.total = aII2.total = aQQ2.total = aPhi.total = aAmp.total = 0.0;
+        for (long long i = start - IMB_WARM; i < end; ++i) {
+            const uint32_t w = (i < 0) ? p.hist_in[IMB_WARM + i] : p.in[i];
+            const int re = (int) (short) (w & 0xffffu), im = (int) w >> 16;
+            tr += re - dr[didx]; dr[didx] = re;
+            ti += im - di[didx]; di[didx] = im;
+            didx = (didx + 1) & (DC_N - 1);
+            const int bi = (int) (tr / DC_N), bq = (int) (ti / DC_N);                 // operator T(): total / N, toward zero
+            const float xi = __fdiv_rn((float) (re - bi), 32768.0f), xq = __fdiv_rn((float) (im - bq), 32768.0f);
+            imb_push(aII, __fmul_rn(xi, xi));
+            imb_push(aIQ, __fmul_rn(xi, xq));
+            const double mII = aII.total / 128.0;
+            if (mII != 0.0) imb_push(aPhi, __ddiv_rn(aIQ.total / 128.0, mII));
+            const float yq = (float) __dsub_rn((double) xq, __dmul_rn(aPhi.total / 128.0, (double) xi));
+            imb_push(aII2, __fmul_rn(xi, xi));
+            imb_push(aQQ2, __fmul_rn(yq, yq));
+            const double mQQ = aQQ2.total / 128.0;
+            if (mQQ != 0.0) imb_push(aAmp, sqrt(__ddiv_rn(aII2.total / 128.0, mQQ)));
+            const float zq = (float) __dmul_rn(aAmp.total / 128.0, (double) yq);
+            if (i >= start) {
+                const int ore = (int) __fmul_rn(xi, 32768.0f), oim = (int) __fmul_rn(zq, 32768.0f);      // C conversion: toward zero
+                p.out[i] = ((uint32_t) ore & 0xffffu) | ((uint32_t) oim << 16);
+            }
+        }
+    }
+    // carried raw history for the next call: thread 0 of block 0
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int t = 0; t < IMB_WARM; ++t) {
+            const long long i = p.n - IMB_WARM + t;
+            p.hist_out[t] = (i < 0) ? p.hist_in[IMB_WARM + i] : p.in[i];
+        }
+        for (int t = 0; t < DC_N; ++t) {
+            const long long i = p.n - DC_N + t;
+            p.dc_hist_out[t] = (i < 0) ? p.hist_in[IMB_WARM + i] : p.in[i];
+        }
+    }
+}
+
 } // namespace
 
 struct b200dsp_iqcorr {
     int device;
     cudaStream_t stream;
     uint32_t* d_hist[2];
-    int cur;
+    uint32_t* d_ihist[2];                                     // imbalance branch: the last IMB_WARM raw samples it has seen
+    int cur, icur;
     uint32_t* d_in;  uint32_t* d_out; long long cap;       // staging for the host-pointer / in-place forms
 };
 
@@ -172,7 +265,8 @@ int b200dsp_iqcorr_create(b200dsp_iqcorr_t** out)
     if ((rc = B200_CUDA_CHECK(cudaSetDevice(h->device))) ||
         (rc = B200_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)))) { delete h; return rc; }
     for (int i = 0; i < 2; ++i)
-        if ((rc = B200_CUDA_CHECK(cudaMalloc(&h->d_hist[i], DC_N * 4))) || (rc = B200_CUDA_CHECK(cudaMemset(h->d_hist[i], 0, DC_N * 4)))) { b200dsp_iqcorr_destroy(h); return rc; }
+        if ((rc = B200_CUDA_CHECK(cudaMalloc(&h->d_hist[i], DC_N * 4))) || (rc = B200_CUDA_CHECK(cudaMemset(h->d_hist[i], 0, DC_N * 4))) ||
+            (rc = B200_CUDA_CHECK(cudaMalloc(&h->d_ihist[i], IMB_WARM * 4))) || (rc = B200_CUDA_CHECK(cudaMemset(h->d_ihist[i], 0, IMB_WARM * 4)))) { b200dsp_iqcorr_destroy(h); return rc; }
     if ((rc = B200_CUDA_CHECK(cudaDeviceSynchronize()))) { b200dsp_iqcorr_destroy(h); return rc; }
     *out = h;
     return 0;
@@ -183,7 +277,7 @@ int b200dsp_iqcorr_destroy(b200dsp_iqcorr_t* h)
     if (!h) return 0;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (int i = 0; i < 2; ++i) if (h->d_hist[i]) cudaFree(h->d_hist[i]);
+    for (int i = 0; i < 2; ++i) { if (h->d_hist[i]) cudaFree(h->d_hist[i]); if (h->d_ihist[i]) cudaFree(h->d_ihist[i]); }
     if (h->d_in) cudaFree(h->d_in);
     if (h->d_out) cudaFree(h->d_out);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -196,14 +290,24 @@ int b200dsp_iqcorr_reset(b200dsp_iqcorr_t* h)
     if (!h) return b200_fail(B200DSP_EINVAL, "null handle");
     int rc = B200_CUDA_CHECK(cudaSetDevice(h->device));
     if (rc) return rc;
-    for (int i = 0; i < 2; ++i) if ((rc = B200_CUDA_CHECK(cudaMemsetAsync(h->d_hist[i], 0, DC_N * 4, h->stream)))) return rc;
+    for (int i = 0; i < 2; ++i)
+        if ((rc = B200_CUDA_CHECK(cudaMemsetAsync(h->d_hist[i], 0, DC_N * 4, h->stream))) || (rc = B200_CUDA_CHECK(cudaMemsetAsync(h->d_ihist[i], 0, IMB_WARM * 4, h->stream)))) return rc;
     return B200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
 }
 
-static int check_mode(int imbalance)
+static int check_mode(int imbalance) { (void) imbalance; return 0; }
+
+static int launch_imbalance(b200dsp_iqcorr* h, const uint32_t* d_in, uint32_t* d_out, long long n, cudaStream_t st)
 {
-    if (imbalance) return b200_fail(B200DSP_ESTATE, "iqcorr: the I/Q imbalance branch (dspdevicesourceengine.cpp:184-252) is not implemented; only DC correction");
-    return 0;
+    ImbParams p;
+    p.in = d_in; p.out = d_out; p.hist_in = h->d_ihist[h->icur]; p.hist_out = h->d_ihist[h->icur ^ 1];
+    p.dc_hist_out = h->d_hist[h->cur ^ 1]; p.n = n;
+    const long long segs = (n + IMB_SEG - 1) / IMB_SEG;
+    // one thread per segment, 32 per block: the rings (12 KB per thread) live in local memory
+    iq_imbalance_kernel<<<(unsigned) ((segs + 31) / 32), 32, 0, st>>>(p);
+    int rc = B200_CUDA_CHECK(cudaGetLastError());
+    if (rc == 0) { h->icur ^= 1; h->cur ^= 1; }
+    return rc;
 }
 
 int b200dsp_iqcorr_run_dev(b200dsp_iqcorr_t* h, const void* d_in, void* d_out, int64_t n_samples, int imbalance, void* cuda_stream)
@@ -221,6 +325,7 @@ int b200dsp_iqcorr_run_dev(b200dsp_iqcorr_t* h, const void* d_in, void* d_out, i
         if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(h->d_in, d_in, (size_t) n_samples * 4, cudaMemcpyDeviceToDevice, st)))) return rc;
         src = h->d_in;
     }
+    if (imbalance) return launch_imbalance(h, src, (uint32_t*) d_out, n_samples, st);
     return launch_dc(h, src, (uint32_t*) d_out, n_samples, st);
 }
 
@@ -234,7 +339,7 @@ int b200dsp_iqcorr_run(b200dsp_iqcorr_t* h, int16_t* iq, int64_t n_samples, int 
     if ((rc = B200_CUDA_CHECK(cudaSetDevice(h->device)))) return rc;
     if ((rc = ensure_staging(h, n_samples, h->stream))) return rc;
     if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(h->d_in, iq, (size_t) n_samples * 4, cudaMemcpyHostToDevice, h->stream))) ||
-        (rc = launch_dc(h, h->d_in, h->d_out, n_samples, h->stream)) ||
+        (rc = imbalance ? launch_imbalance(h, h->d_in, h->d_out, n_samples, h->stream) : launch_dc(h, h->d_in, h->d_out, n_samples, h->stream)) ||
         (rc = B200_CUDA_CHECK(cudaMemcpyAsync(iq, h->d_out, (size_t) n_samples * 4, cudaMemcpyDeviceToHost, h->stream)))) return rc;
     return B200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
 }
