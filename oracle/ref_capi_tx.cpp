@@ -1,0 +1,165 @@
+// ORACLE (test infrastructure, never shipped, never on the product path).
+//
+// C-ABI driver around the UNMODIFIED reference Tx-side classes, compiled in place from /root/reference by
+// oracle/Makefile into oracle/_ref/libsdrref*.so next to ref_capi.cpp:
+//   Interpolators<T,SdrBits,OutputBits>::interpolate{1,2,...,64}_cen     sdrbase/dsp/interpolators.h:104-617
+//   IntHalfbandFilterEO1<order>::myInterpolate / workInterpolate*         sdrbase/dsp/inthalfbandfiltereo1.h:98-127,291-355,490-554,601-622
+//   UpChannelizer::pull / applyConfiguration / createFilterChain          sdrbase/dsp/upchannelizer.cpp:51-104,175-209,252-327
+// Nothing of the reference is copied: this file #includes the reference headers and calls them.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "dsp/dsptypes.h"
+#include "dsp/interpolators.h"
+#include "dsp/dspcommands.h"
+#include "util/messagequeue.h"
+
+#define private public
+#define protected public
+#include "dsp/upchannelizer.h"
+#undef private
+#undef protected
+
+// "fake moc" for the Qt signals these classes declare (no event loop here)
+void UpChannelizer::outputSampleRateChanged() {}
+void SampleSourceFifo::dataWrite(int) {}
+void SampleSourceFifo::dataRead(int) {}
+
+namespace {
+
+struct Interps {
+    int bits;
+    Interpolators<qint16, 16, 16> d16;
+    Interpolators<qint16, 16, 12> d12;
+    Interpolators<qint8, 16, 8> d8;
+    SampleVector in;
+};
+
+template<typename D, typename T>
+bool interp_dispatch(D& d, int log2, SampleVector::iterator* it, T* buf, int len)
+{
+    switch (log2) {
+    case 0: d.interpolate1(it, buf, len); return true;
+    case 1: d.interpolate2_cen(it, buf, len); return true;
+    case 2: d.interpolate4_cen(it, buf, len); return true;
+    case 3: d.interpolate8_cen(it, buf, len); return true;
+    case 4: d.interpolate16_cen(it, buf, len); return true;
+    case 5: d.interpolate32_cen(it, buf, len); return true;
+    case 6: d.interpolate64_cen(it, buf, len); return true;
+    }
+    return false;
+}
+
+// the modulator behind an UpChannelizer: hands out the samples of one block in order, zeros when it runs dry
+class VectorSource : public BasebandSampleSource {
+public:
+    std::vector<Sample> data;
+    std::size_t pos = 0;
+    virtual void start() {}
+    virtual void stop() {}
+    virtual void pull(Sample& s) { if (pos < data.size()) s = data[pos]; else s = Sample(); ++pos; }
+    virtual bool handleMessage(const Message&) { return false; }
+};
+
+struct UpChan {
+    VectorSource src;
+    UpChannelizer* chan;
+    UpChan() { chan = new UpChannelizer(&src); }
+    ~UpChan() { delete chan; }
+};
+
+} // namespace
+
+extern "C" {
+
+void* ref_interps_create(int output_bits)
+{
+    if (output_bits != 8 && output_bits != 12 && output_bits != 16) return 0;
+    Interps* h = new Interps;
+    h->bits = output_bits;
+    return h;
+}
+void ref_interps_destroy(void* p) { delete (Interps*) p; }
+
+// == interpolateN_cen(&it, buf, len): `len` counts output scalars; consumes len / (2 << log2) samples from `iq`
+// (n_samples must cover that).  buf is int16 (bits 12/16) or int8 (bits 8).  Returns samples consumed.
+int ref_interps_run(void* p, int log2, const int16_t* iq, int n_samples, void* buf, int len)
+{
+    Interps* h = (Interps*) p;
+    h->in.resize((std::size_t) n_samples + 1);
+    if (n_samples > 0) memcpy(&h->in[0], iq, (std::size_t) n_samples * sizeof(Sample));
+    SampleVector::iterator it = h->in.begin();
+    bool ok;
+    if (h->bits == 16) ok = interp_dispatch(h->d16, log2, &it, (qint16*) buf, len);
+    else if (h->bits == 12) ok = interp_dispatch(h->d12, log2, &it, (qint16*) buf, len);
+    else ok = interp_dispatch(h->d8, log2, &it, (qint8*) buf, len);
+    if (!ok) return -1;
+    return (int) (it - h->in.begin());
+}
+
+// integer coefficients of the interpolating half-bands (hbfiltertraits.cpp); returns order / 4 and the shift
+int ref_hb_coeffs(int order, int32_t* out, int* shift)
+{
+    switch (order) {
+    case 16: for (int i = 0; i < 4; i++) out[i] = HBFIRFilterTraits<16>::hbCoeffs[i]; *shift = HBFIRFilterTraits<16>::hbShift; return 4;
+    case 32: for (int i = 0; i < 8; i++) out[i] = HBFIRFilterTraits<32>::hbCoeffs[i]; *shift = HBFIRFilterTraits<32>::hbShift; return 8;
+    case 64: for (int i = 0; i < 16; i++) out[i] = HBFIRFilterTraits<64>::hbCoeffs[i]; *shift = HBFIRFilterTraits<64>::hbShift; return 16;
+    case 96: for (int i = 0; i < 24; i++) out[i] = HBFIRFilterTraits<96>::hbCoeffs[i]; *shift = HBFIRFilterTraits<96>::hbShift; return 24;
+    }
+    return -1;
+}
+
+void* ref_upchan_create() { return new UpChan; }
+void ref_upchan_destroy(void* p) { delete (UpChan*) p; }
+
+// the two messages the sink engine and the modulator plugin send (DSPSignalNotification with the device rate,
+// DSPConfigureChannelizer with the modulator's rate and offset); modes[i]: 0 centre, 1 lower half, 2 upper half,
+// in the reference's stage order (stage 0 runs at the output rate).  Returns the number of stages.
+int ref_upchan_configure(void* p, int output_rate, int requested_rate, int center_offset,
+                         int* in_rate, int* residual_offset, int* modes, int modes_cap)
+{
+    UpChan* h = (UpChan*) p;
+    DSPSignalNotification sig(output_rate, 0);
+    h->chan->handleMessage(sig);
+    DSPConfigureChannelizer cfg(requested_rate, center_offset);
+    h->chan->handleMessage(cfg);
+    Message* m;
+    int rate = 0, ofs = 0;
+    while ((m = h->src.getInputMessageQueue()->pop()) != 0) {
+        if (UpChannelizer::MsgChannelizerNotification::match(*m)) {
+            UpChannelizer::MsgChannelizerNotification* n = (UpChannelizer::MsgChannelizerNotification*) m;
+            rate = n->getSampleRate();
+            ofs = (int) n->getFrequencyOffset();
+        }
+        delete m;
+    }
+    if (in_rate) *in_rate = rate;
+    if (residual_offset) *residual_offset = ofs;
+    typedef IntHalfbandFilterEO1<UPCHANNELIZER_HB_FILTER_ORDER> F;
+    int i = 0;
+    for (UpChannelizer::FilterStages::iterator it = h->chan->m_filterStages.begin(); it != h->chan->m_filterStages.end(); ++it, ++i) {
+        if (modes && i < modes_cap)
+            modes[i] = (*it)->m_workFunction == &F::workInterpolateCenter ? 0 : (*it)->m_workFunction == &F::workInterpolateLowerHalf ? 1 : 2;
+    }
+    return i;
+}
+
+// n_out calls of UpChannelizer::pull; the modulator hands out `iq` (n_in samples, then zeros).  Returns how many
+// modulator samples were pulled.
+int ref_upchan_pull(void* p, const int16_t* iq, int n_in, int16_t* out, int n_out)
+{
+    UpChan* h = (UpChan*) p;
+    h->src.data.resize((std::size_t) n_in);
+    if (n_in > 0) memcpy(&h->src.data[0], iq, (std::size_t) n_in * sizeof(Sample));
+    h->src.pos = 0;
+    Sample s;
+    for (int i = 0; i < n_out; i++) {
+        h->chan->pull(s);
+        out[2 * i] = s.real();
+        out[2 * i + 1] = s.imag();
+    }
+    return (int) h->src.pos;
+}
+
+} // extern "C"

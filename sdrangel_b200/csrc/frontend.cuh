@@ -356,7 +356,8 @@ __global__ void frontend_schedule_kernel(const FrontendChan* __restrict__ chans,
     i0 = __shfl_sync(0xffffffffu, i0, 0);
     D = __shfl_sync(0xffffffffu, D, 0);
     // tile table, one tile per lane at a time: listed outputs by binary search, closed-form outputs by division
-    for (int t = lane; t <= ntiles; t += 32) {
+    // (entry 1 is written even for a pass without new samples: block 0 of the front-end kernel always reads entries 0 and 1)
+    for (int t = lane; t <= (ntiles > 1 ? ntiles : 1); t += 32) {
         const int T = t * FE_TILE;
         int lo = 0, hi = n;
         const int bias = c.mode ? 1 : 0;
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel_t(const FrontendCh
     __syncthreads();
     // outputs of this pass whose input index falls in [t0, t1)
     const int out_base = c.state[3] - c.state[2];
-    const int o0 = c.tile_start[blockIdx.x], o1 = c.tile_start[blockIdx.x + 1];
+    const int o0 = c.tile_start[blockIdx.x], o1 = (t0 < m || c.mode != 0) ? c.tile_start[blockIdx.x + 1] : o0;    // Interpolator::decimate: no new samples, no outputs
     const int k0 = (int) c.plan[0];
     const long long pi0 = c.plan[1], D0 = c.plan[2];
     // LAT54: the generic loop only takes the outputs listed by the schedule kernel (stream start, before the closed form)
@@ -430,7 +431,7 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel_t(const FrontendCh
         for (int q = 0; q < FE_NOUT; ++q) {
             const int o = (ob + q < o1g) ? ob + q : o1g - 1;        // clamp: duplicates are computed but not stored
             int ph;
-            if (o >= k0) {                                 // closed-form region (lattice ratios)
+            if (c.lattice && o >= k0) {                    // closed-form region (lattice ratios)
                 const long long E = D0 + (long long) (o - k0) * c.A;
                 idx[q] = (int) (pi0 + (E >> 23) - 1);
                 ph = (int) ((E & 0x7fffffll) >> c.phshift);

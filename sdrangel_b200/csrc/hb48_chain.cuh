@@ -114,7 +114,13 @@ __global__ void __launch_bounds__(256, 2) hb48_chain_kernel(const ChainParams p)
             }
             if (sigma == 0)   hb48_item<false, false>(wv, cv, 0, opq, y);
             else if (!slow)   hb48_item<true, false>(wv, cv, comp ? sigma : -sigma, opq, y);
-            else              hb48_slow_child(Xin, comp, j, sigma, 0, opq, y);
+            else {
+                // (a temporary: handing y itself to the non-inlined function would pin it to local memory on the hot path too)
+                int32_t ys[HB_R];
+                hb48_slow_child(Xin, comp, j, sigma, 0, opq, ys);
+#pragma unroll
+                for (int r = 0; r < HB_R; ++r) y[r] = ys[r];
+            }
             __syncwarp();
             hb64_tail_store<int32_t>(Xin, lane, tl);
             if (s < L) {
