@@ -279,6 +279,48 @@ int b200dsp_nco_next_iq_dev(b200dsp_nco_t* h, int64_t n, float* d_out_c64, void*
 /* the mix a channel plugin does per sample, as a block: out[i] = Complex(in[i].re, in[i].im) * nco.nextIQ()  (nfmdemod.cpp:152-153) */
 int b200dsp_nco_mix_dev(b200dsp_nco_t* h, const void* d_in_i16, int64_t n, float* d_out_c64, void* cuda_stream);
 
+/* ---- Tx mirror: device-side interpolators and the UpChannelizer -------------------------------------------
+ * K8 == Interpolators<T, SDR_TX_SAMP_SZ 16, OutputBits> (sdrbase/dsp/interpolators.h:104-617): the step a sample-sink plugin
+ *    runs between the engine's SampleVector and the device buffer,
+ *      out I16, output_bits 16 : Interpolators<qint16,16,16>   plugins/samplesink/filesink/filesinkthread.h:73, plutosdroutputthread.h:57
+ *      out I16, output_bits 12 : Interpolators<qint16,16,12>   plugins/samplesink/bladerfoutput/bladerfoutputthread.h:53, limesdroutputthread.h:57
+ *      out I8,  output_bits 8  : Interpolators<qint8,16,8>     plugins/samplesink/hackrfoutput/hackrfoutputthread.h:52
+ *    One handle == one Interpolators object: six interpolating half-bands (orders 64, 32, 16, 16, 16, 16;
+ *    IntHalfbandFilterEO1<>::myInterpolate, inthalfbandfiltereo1.h:601-622) whose rings persist across calls and factors. */
+typedef struct b200dsp_interps b200dsp_interps_t;
+int b200dsp_interps_create(b200dsp_interps_t** h, int out_fmt, int output_bits);
+int b200dsp_interps_destroy(b200dsp_interps_t* h);
+int b200dsp_interps_reset(b200dsp_interps_t* h);
+/* Samples interpolate*_ consumes for `len_scalars` output scalars: len / (2 << log2) (pure host arithmetic) */
+int64_t b200dsp_interps_in_count(int log2_interp, int64_t len_scalars);
+/* == interpolate{1,2,4,...,64}_cen(SampleVector::iterator* it, T* buf, qint32 len): `len` counts OUTPUT scalars; reads
+ *    *n_consumed = len / (2 << log2) Samples (the iterator's advance), writes n_consumed * (2 << log2) scalars of `buf`;
+ *    a trailing partial block is left alone like the reference's loops do.  interpolate64_cen writes only scalars 0..109 of
+ *    every block of 128 (its store list stops there, interpolators.h): those 18 scalars of `buf` stay untouched here too. */
+int b200dsp_interps_run(b200dsp_interps_t* h, int log2_interp, const int16_t* samples_iq, void* buf, int32_t len_scalars, int32_t* n_consumed);
+int b200dsp_interps_run_dev(b200dsp_interps_t* h, int log2_interp, const void* d_samples_iq, void* d_buf, int64_t len_scalars,
+                            int64_t* n_consumed, void* cuda_stream);
+
+/* K9 == UpChannelizer (sdrbase/dsp/upchannelizer.cpp:51-104,175-209,252-327) with its IntHalfbandFilterEO1<96> stages
+ *    (workInterpolateCenter / LowerHalf / UpperHalf, inthalfbandfiltereo1.h:98-127,291-355,490-554): the modulator's samples
+ *    at rate out / 2^S interpolated to the device sink's rate and shifted to the channel's offset.  One handle == one object. */
+typedef struct b200dsp_upchan b200dsp_upchan_t;
+int b200dsp_upchan_create(b200dsp_upchan_t** h);
+int b200dsp_upchan_destroy(b200dsp_upchan_t* h);
+/* == DSPSignalNotification(output rate) + DSPConfigureChannelizer(requested rate, offset) -> applyConfiguration: the filter
+ *    chain is rebuilt (fresh filters); reports what MsgChannelizerNotification carries: modulator rate and residual offset */
+int b200dsp_upchan_configure(b200dsp_upchan_t* h, int output_rate_hz, int requested_rate_hz, int center_offset_hz,
+                             int* in_rate_hz, int* residual_offset_hz);
+/* the stage list given directly: 0 centre, 1 lower half, 2 upper half; stage 0 runs at the output rate (upchannelizer.h:83-104) */
+int b200dsp_upchan_set_path(b200dsp_upchan_t* h, const int* modes, int n_modes);
+int b200dsp_upchan_path(b200dsp_upchan_t* h, int* modes, int cap);            /* returns S */
+/* modulator samples the next n_out calls of pull() take from m_sampleSource->pull (depends on the stages' phases; host arithmetic) */
+int64_t b200dsp_upchan_source_count(b200dsp_upchan_t* h, int64_t n_out);
+/* == n_out x UpChannelizer::pull(sample): source = the samples m_sampleSource->pull hands out during those calls, in order
+ *    (at least b200dsp_upchan_source_count(n_out) of them; exactly that many are consumed) */
+int b200dsp_upchan_pull(b200dsp_upchan_t* h, const int16_t* source_iq, int64_t n_source, int16_t* out_iq, int64_t n_out);
+int b200dsp_upchan_pull_dev(b200dsp_upchan_t* h, const void* d_source_iq, int64_t n_source, void* d_out_iq, int64_t n_out, void* cuda_stream);
+
 /* ---- K5: SpectrumVis -------------------------------------------------------------------------------------
  * One handle == one reference SpectrumVis sink (sdrgui/dsp/spectrumvis.cpp:77-254,283-327) with its FFTWindow
  * (sdrbase/dsp/fftwindow.cpp:20-73), FFT engine (sdrbase/dsp/kissengine.cpp, kissfft.h) and per-bin averagers

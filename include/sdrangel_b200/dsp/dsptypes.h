@@ -18,6 +18,7 @@ typedef unsigned int uint;
 
 #define SDR_RX_SAMP_SZ 16
 #define SDR_RX_SCALEF 32768.0f
+#define SDR_TX_SAMP_SZ 16       // sdrbase/dsp/dsptypes.h:37
 #define SDR_RX_SCALED 32768.0
 typedef qint16 FixReal;
 typedef float Real;

@@ -969,3 +969,183 @@ int orc_spectrum_feed(void* h, const int16_t* iq, int cnt, int positive_only, fl
     }
     return nframes;
 }
+
+/* ======================================================================================================
+ * Tx mirror: interpolating half-bands, Interpolators<>, UpChannelizer
+ * ====================================================================================================== */
+/* hbfiltertraits.cpp: (int32_t) (c * (1 << hbShift)); hbShift 12 for orders 16/32/64, 16 for order 96 */
+static const int32_t HI16[4] = { -21, 95, -311, 1260 };
+static const int32_t HI32[8] = { -7, 15, -33, 65, -117, 207, -401, 1294 };
+static const int32_t HI96[24] = { -1, 3, -6, 11, -19, 31, -47, 70, -99, 139, -189, 254, -335, 436, -563, 722, -923, 1181, -1525, 2004,
+                                  -2730, 3990, -6842, 20823 };
+
+/* IntHalfbandFilterEO1<order> as the interpolating entry points use it: m_samples ring of order/2 complex int32, m_ptr,
+ * m_state (inthalfbandfiltereo1.h:625-631,823-838) */
+typedef struct { int32_t ring[48][2]; int ptr, state, K, shift; const int32_t* h; } hbup;
+
+static void hbup_init(hbup* f, int order)
+{
+    memset(f, 0, sizeof(*f));
+    f->K = order / 2;
+    f->h = order == 16 ? HI16 : order == 32 ? HI32 : order == 64 ? H64 : HI96;
+    f->shift = order == 96 ? 16 : 12;
+}
+
+static void hbup_insert(hbup* f, int32_t re, int32_t im)      /* "insert sample into ring double buffer" + "advance pointer" */
+{
+    f->ring[f->ptr][0] = re; f->ring[f->ptr][1] = im;
+    f->ptr = (f->ptr < f->K - 1) ? f->ptr + 1 : 0;
+}
+
+static void hbup_mid(const hbup* f, int32_t* re, int32_t* im)  /* m_samples[m_ptr + hbOrder/4 - 1] */
+{
+    const int q = (f->ptr + f->K / 2 - 1) % f->K;
+    *re = f->ring[q][0]; *im = f->ring[q][1];
+}
+
+static void hbup_fir(const hbup* f, int32_t* re, int32_t* im)  /* doInterpolateFIR, inthalfbandfiltereo1.h:777-815 */
+{
+    uint32_t ia = 0, qa = 0;
+    int a = f->ptr, b = f->ptr + f->K - 1;
+    for (int i = 0; i < f->K / 2; i++) {
+        ia += (uint32_t) (f->ring[a % f->K][0] + f->ring[b % f->K][0]) * (uint32_t) f->h[i];
+        qa += (uint32_t) (f->ring[a % f->K][1] + f->ring[b % f->K][1]) * (uint32_t) f->h[i];
+        a++; b--;
+    }
+    *re = (int32_t) ia >> (f->shift - 1);
+    *im = (int32_t) qa >> (f->shift - 1);
+}
+
+/* ---- Interpolators<T, 16, OutputBits> (interpolators.h:104-617) ---- */
+typedef struct { hbup st[6]; int bits; } interps_t;
+
+void* orc_interps_create(int output_bits)
+{
+    static const int order[6] = { 64, 32, 16, 16, 16, 16 };       /* INTERPOLATORS_HB_FILTER_ORDER_FIRST / SECOND / NEXT */
+    if (output_bits != 8 && output_bits != 12 && output_bits != 16) return 0;
+    interps_t* d = (interps_t*) calloc(1, sizeof(interps_t));
+    for (int s = 0; s < 6; s++) hbup_init(&d->st[s], order[s]);
+    d->bits = output_bits;
+    return d;
+}
+void orc_interps_destroy(void* h) { free(h); }
+
+/* one stage input through myInterpolate (inthalfbandfiltereo1.h:601-622) and on through the later stages; every stage sees its
+ * inputs in time order, which is all its ring depends on */
+static void interps_push(interps_t* d, int L, int s, int32_t re, int32_t im, int32_t* blk, int* k)
+{
+    if (s == L) { blk[2 * *k] = re; blk[2 * *k + 1] = im; ++*k; return; }
+    hbup* f = &d->st[s];
+    int32_t r1, i1, r2, i2;
+    hbup_insert(f, re, im);
+    hbup_mid(f, &r1, &i1);
+    hbup_fir(f, &r2, &i2);
+    interps_push(d, L, s + 1, r1, i1, blk, k);
+    interps_push(d, L, s + 1, r2, i2, blk, k);
+}
+
+/* buf: int16 (12/16 output bits) or int8 (8); len counts output scalars.  Returns the samples consumed. */
+int orc_interps_run(void* h, int log2, const int16_t* iq, void* buf, int len)
+{
+    interps_t* d = (interps_t*) h;
+    if (log2 < 0 || log2 > 6) return -1;
+    const int pre = log2 < 3 ? log2 : 3;                        /* interpolation_shifts<16,*>: pre2 1, pre4 2, pre8.. 3 */
+    const int post = pre + (16 - d->bits);                      /* post = pre + (SdrBits - OutputBits) */
+    const int blk = 2 << log2;
+    int32_t tmp[128];
+    int n = 0;
+    for (int pos = 0; pos + blk <= len; pos += blk, n++) {
+        int k = 0;
+        if (log2 == 0) { tmp[0] = iq[2 * n]; tmp[1] = iq[2 * n + 1]; }
+        else interps_push(d, log2, 0, (int32_t) iq[2 * n] << pre, (int32_t) iq[2 * n + 1] << pre, tmp, &k);
+        /* interpolate64_cen stores only buf[pos+0 .. pos+109] (the store list of its loop body ends there) */
+        const int stores = (log2 == 6) ? 110 : blk;
+        for (int j = 0; j < stores; j++) {
+            if (d->bits == 8) ((int8_t*) buf)[pos + j] = (int8_t) (tmp[j] >> post);
+            else ((int16_t*) buf)[pos + j] = (int16_t) (tmp[j] >> post);
+        }
+    }
+    return n;
+}
+
+/* ---- UpChannelizer (upchannelizer.cpp:51-104,175-209,252-327) ---- */
+typedef struct { hbup st[32]; int mode[32]; int16_t stage_sample[32][2]; int16_t sample_in[2]; int nstages; } upchan_t;
+
+void* orc_upchan_create(void) { return calloc(1, sizeof(upchan_t)); }
+void orc_upchan_destroy(void* h) { free(h); }
+
+int orc_upchan_configure(void* h, int output_rate, int requested_rate, int center_offset, int* in_rate, int* residual_offset, int* modes, int modes_cap)
+{
+    upchan_t* u = (upchan_t*) h;
+    /* applyConfiguration: freeFilterChain + createFilterChain: the same selection as DownChannelizer's, run on a scratch chan_t */
+    chan_t c;
+    memset(&c, 0, sizeof(c));
+    if (output_rate == 0) return 0;
+    float ofs = create_chain(&c, (float) (output_rate / -2), (float) (output_rate / 2),
+                             (float) (center_offset - requested_rate / 2), (float) (center_offset + requested_rate / 2));
+    int16_t keep_in[2] = { u->sample_in[0], u->sample_in[1] };  /* m_sampleIn is not reset by applyConfiguration */
+    memset(u, 0, sizeof(*u));
+    u->sample_in[0] = keep_in[0]; u->sample_in[1] = keep_in[1];
+    u->nstages = c.nstages;
+    for (int i = 0; i < c.nstages; i++) { u->mode[i] = c.st[i].mode; hbup_init(&u->st[i], 96); }
+    if (in_rate) *in_rate = output_rate / (1 << c.nstages);
+    if (residual_offset) *residual_offset = (int) ofs;
+    for (int i = 0; i < c.nstages && i < modes_cap; i++) if (modes) modes[i] = c.st[i].mode;
+    return c.nstages;
+}
+
+/* workInterpolateCenter / LowerHalf / UpperHalf (inthalfbandfiltereo1.h:98-127,291-355,490-554): returns 1 when `in` was consumed */
+static int hbup_work(hbup* f, int mode, const int16_t* in, int16_t* out)
+{
+    int32_t re, im;
+    const int st = f->state;
+    if ((st & 1) == 0) {
+        hbup_mid(f, &re, &im);
+        if (mode == 0) { out[0] = (int16_t) re; out[1] = (int16_t) im; f->state = 1; return 0; }
+        /* lower half: state 0 (imag, -real), state 2 (-imag, real); upper half the opposite */
+        const int flip = (mode == 1) ? (st == 2) : (st == 0);
+        if (!flip) { out[0] = (int16_t) im; out[1] = (int16_t) -re; }
+        else       { out[0] = (int16_t) -im; out[1] = (int16_t) re; }
+        f->state = st + 1;
+        return 0;
+    }
+    hbup_fir(f, &re, &im);
+    int16_t sr = (int16_t) re, si = (int16_t) im;               /* doInterpolateFIR(Sample*): setReal / setImag narrow to int16 */
+    if (mode != 0 && st == 1) { sr = (int16_t) -sr; si = (int16_t) -si; }
+    out[0] = sr; out[1] = si;
+    hbup_insert(f, in[0], in[1]);
+    f->state = (mode == 0) ? 0 : ((st + 1) & 3);
+    return 1;
+}
+
+/* n_out calls of UpChannelizer::pull (upchannelizer.cpp:51-104); the modulator hands out iq[0..n_in) then zeros.
+ * Returns how many modulator samples were pulled. */
+int orc_upchan_pull(void* h, const int16_t* iq, int n_in, int16_t* out, int n_out)
+{
+    upchan_t* u = (upchan_t*) h;
+    int pos = 0;
+    for (int k = 0; k < n_out; k++) {
+        if (u->nstages == 0) {
+            if (pos < n_in) { out[2 * k] = iq[2 * pos]; out[2 * k + 1] = iq[2 * pos + 1]; } else { out[2 * k] = 0; out[2 * k + 1] = 0; }
+            pos++;
+            continue;
+        }
+        for (int s = 0; s < u->nstages; s++) {
+            if (s == u->nstages - 1) {
+                if (hbup_work(&u->st[s], u->mode[s], u->sample_in, u->stage_sample[s])) {
+                    if (pos < n_in) { u->sample_in[0] = iq[2 * pos]; u->sample_in[1] = iq[2 * pos + 1]; } else { u->sample_in[0] = 0; u->sample_in[1] = 0; }
+                    pos++;
+                }
+            } else if (!hbup_work(&u->st[s], u->mode[s], u->stage_sample[s + 1], u->stage_sample[s])) break;
+        }
+        out[2 * k] = u->stage_sample[0][0];
+        out[2 * k + 1] = u->stage_sample[0][1];
+    }
+    return pos;
+}
+
+void orc_hb_interp_coeffs(int order, int32_t* out)
+{
+    const int32_t* h = order == 16 ? HI16 : order == 32 ? HI32 : order == 64 ? H64 : HI96;
+    for (int i = 0; i < order / 4; i++) out[i] = h[i];
+}

@@ -75,6 +75,19 @@ void  orc_spectrum_destroy(void* h);
 void  orc_spectrum_configure(void* h, int fft_size, int overlap_pct, unsigned avg_nb, int avg_mode, int window, int linear);
 int   orc_spectrum_feed(void* h, const int16_t* iq, int n, int positive_only, float* frames, int cap_frames);
 
+/* Tx mirror.  Interpolators<T,16,OutputBits>: sdrbase/dsp/interpolators.h:104-617 over
+ * IntHalfbandFilterEO1<>::myInterpolate (inthalfbandfiltereo1.h:601-622); buf int16 (12/16 bits) or int8 (8 bits) */
+void* orc_interps_create(int output_bits);
+void  orc_interps_destroy(void* h);
+int   orc_interps_run(void* h, int log2, const int16_t* iq, void* buf, int len);
+/* UpChannelizer: sdrbase/dsp/upchannelizer.cpp:51-104,175-209,252-327, IntHalfbandFilterEO1<96>::workInterpolate* */
+void* orc_upchan_create(void);
+void  orc_upchan_destroy(void* h);
+int   orc_upchan_configure(void* h, int output_rate, int requested_rate, int center_offset, int* in_rate, int* residual_offset,
+                           int* modes, int modes_cap);
+int   orc_upchan_pull(void* h, const int16_t* iq, int n_in, int16_t* out, int n_out);
+void  orc_hb_interp_coeffs(int order, int32_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,10 @@ def load():
         "orc_spectrum_create": (vp, [f32]), "orc_spectrum_destroy": (None, [vp]),
         "orc_spectrum_configure": (None, [vp, i32, i32, C.c_uint, i32, i32, i32]),
         "orc_spectrum_feed": (i32, [vp, pi16, i32, i32, pf32, i32]),
+        "orc_interps_create": (vp, [i32]), "orc_interps_destroy": (None, [vp]), "orc_interps_run": (i32, [vp, i32, pi16, vp, i32]),
+        "orc_upchan_create": (vp, []), "orc_upchan_destroy": (None, [vp]),
+        "orc_upchan_configure": (i32, [vp, i32, i32, i32, pi32, pi32, pi32, i32]),
+        "orc_upchan_pull": (i32, [vp, pi16, i32, pi16, i32]), "orc_hb_interp_coeffs": (None, [i32, pi32]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -247,3 +251,45 @@ def sdrbench_f32(n_samples):
     buf = np.empty(2 * n_samples, dtype=np.float32)
     load().orc_sdrbench_gen_f32(_p(buf, C.c_float), buf.size)
     return buf
+
+
+class PortInterpolators(_Handle):
+    """Interpolators<T,16,output_bits> restated (oracle/port/sdr_oracle.c: orc_interps_*)."""
+
+    def __init__(self, output_bits=16):
+        L = load()
+        super().__init__(L.orc_interps_create(output_bits), L.orc_interps_destroy)
+        self.dtype = np.int8 if output_bits == 8 else np.int16
+
+    def run(self, log2, samples, length=None, fill=0):
+        x = np.ascontiguousarray(samples, dtype=np.int16).reshape(-1, 2)
+        if length is None:
+            length = x.shape[0] * (2 << log2)
+        assert length // (2 << log2) <= x.shape[0]
+        buf = np.full(int(length), fill, dtype=self.dtype)
+        n = load().orc_interps_run(self.h, log2, _p(x, C.c_int16), buf.ctypes.data, int(length))
+        return buf, n
+
+
+class PortUpChannelizer(_Handle):
+    def __init__(self):
+        L = load()
+        super().__init__(L.orc_upchan_create(), L.orc_upchan_destroy)
+
+    def configure(self, output_rate, requested_rate, center_offset):
+        rate, ofs = C.c_int32(0), C.c_int32(0)
+        modes = np.zeros(32, dtype=np.int32)
+        n = load().orc_upchan_configure(self.h, output_rate, requested_rate, center_offset, C.byref(rate), C.byref(ofs), _p(modes, C.c_int32), 32)
+        return rate.value, ofs.value, [int(m) for m in modes[:n]]
+
+    def pull(self, source, n_out):
+        x = np.ascontiguousarray(source, dtype=np.int16).reshape(-1, 2)
+        out = np.empty((n_out, 2), dtype=np.int16)
+        used = load().orc_upchan_pull(self.h, _p(x, C.c_int16), x.shape[0], _p(out, C.c_int16), n_out)
+        return out, used
+
+
+def hb_interp_coeffs(order):
+    a = np.zeros(order // 4, dtype=np.int32)
+    load().orc_hb_interp_coeffs(order, _p(a, C.c_int32))
+    return a

@@ -64,6 +64,11 @@ def load(strict=False):
         "ref_spectrum_feed": (i32, [vp, pi16, i32, i32, pf32, i32]),
         "ref_sdrbench_gen_s16": (None, [pi16, i32]), "ref_sdrbench_gen_f32": (None, [pf32, i32]),
         "ref_build_info": (C.c_char_p, []),
+        "ref_interps_create": (vp, [i32]), "ref_interps_destroy": (None, [vp]), "ref_interps_run": (i32, [vp, i32, pi16, i32, vp, i32]),
+        "ref_hb_coeffs": (i32, [i32, pi32, pi32]),
+        "ref_upchan_create": (vp, []), "ref_upchan_destroy": (None, [vp]),
+        "ref_upchan_configure": (i32, [vp, i32, i32, i32, pi32, pi32, pi32, i32]),
+        "ref_upchan_pull": (i32, [vp, pi16, i32, pi16, i32]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -277,3 +282,46 @@ def fnv1a64_u16(a):
     for v in a.tolist():
         h = ((h ^ v) * prime) & mask
     return "%016x" % h
+
+
+class RefInterpolators(_Handle):
+    """The reference's Interpolators<qint16,16,16> / <qint16,16,12> / <qint8,16,8> (oracle/ref_capi_tx.cpp)."""
+
+    def __init__(self, output_bits=16, strict=False):
+        L = load(strict)
+        super().__init__(L, L.ref_interps_create(output_bits), L.ref_interps_destroy)
+        self.dtype = np.int8 if output_bits == 8 else np.int16
+
+    def run(self, log2, samples, length=None, fill=0):
+        x = np.ascontiguousarray(samples, dtype=np.int16).reshape(-1, 2)
+        if length is None:
+            length = x.shape[0] * (2 << log2)
+        assert length // (2 << log2) <= x.shape[0]
+        buf = np.full(int(length), fill, dtype=self.dtype)
+        n = self.lib.ref_interps_run(self.h, log2, _p(x, C.c_int16), x.shape[0], buf.ctypes.data, int(length))
+        return buf, n
+
+
+class RefUpChannelizer(_Handle):
+    def __init__(self, strict=False):
+        L = load(strict)
+        super().__init__(L, L.ref_upchan_create(), L.ref_upchan_destroy)
+
+    def configure(self, output_rate, requested_rate, center_offset):
+        rate, ofs = C.c_int32(0), C.c_int32(0)
+        modes = np.zeros(32, dtype=np.int32)
+        n = self.lib.ref_upchan_configure(self.h, output_rate, requested_rate, center_offset, C.byref(rate), C.byref(ofs), _p(modes, C.c_int32), 32)
+        return rate.value, ofs.value, [int(m) for m in modes[:n]]
+
+    def pull(self, source, n_out):
+        x = np.ascontiguousarray(source, dtype=np.int16).reshape(-1, 2)
+        out = np.empty((n_out, 2), dtype=np.int16)
+        used = self.lib.ref_upchan_pull(self.h, _p(x, C.c_int16), x.shape[0], _p(out, C.c_int16), n_out)
+        return out, used
+
+
+def hb_coeffs(order, strict=False):
+    a = np.zeros(24, dtype=np.int32)
+    sh = C.c_int32(0)
+    n = load(strict).ref_hb_coeffs(order, _p(a, C.c_int32), C.byref(sh))
+    return a[:n].copy(), sh.value

@@ -106,6 +106,20 @@ SIGNATURES = {
     "b200dsp_interp_destroy": (_i32, [_vp]),
     "b200dsp_interp_info": (_i32, [_vp, _pi32, _vp, _i32]),
     "b200dsp_interp_decimate": (_i32, [_vp, C.POINTER(C.c_float), _f32, _vp, _i64, _vp, _i64, _pi64]),
+    "b200dsp_interps_create": (_i32, [_pvp, _i32, _i32]),
+    "b200dsp_interps_destroy": (_i32, [_vp]),
+    "b200dsp_interps_reset": (_i32, [_vp]),
+    "b200dsp_interps_in_count": (_i64, [_i32, _i64]),
+    "b200dsp_interps_run": (_i32, [_vp, _i32, _vp, _vp, _i32, _pi32]),
+    "b200dsp_interps_run_dev": (_i32, [_vp, _i32, _vp, _vp, _i64, _pi64, _vp]),
+    "b200dsp_upchan_create": (_i32, [_pvp]),
+    "b200dsp_upchan_destroy": (_i32, [_vp]),
+    "b200dsp_upchan_configure": (_i32, [_vp, _i32, _i32, _i32, _pi32, _pi32]),
+    "b200dsp_upchan_set_path": (_i32, [_vp, _pi32, _i32]),
+    "b200dsp_upchan_path": (_i32, [_vp, _pi32, _i32]),
+    "b200dsp_upchan_source_count": (_i64, [_vp, _i64]),
+    "b200dsp_upchan_pull": (_i32, [_vp, _vp, _i64, _vp, _i64]),
+    "b200dsp_upchan_pull_dev": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp]),
     "b200dsp_spectrum_create": (_i32, [_pvp, _f32]),
     "b200dsp_spectrum_destroy": (_i32, [_vp]),
     "b200dsp_spectrum_configure": (_i32, [_vp, _i32, _i32, C.c_uint, _i32, _i32, _i32]),

@@ -557,3 +557,109 @@ class IQCorrections:
 
     def run_dev(self, d_in, d_out, n_samples, stream=None):
         capi.check(capi.lib().b200dsp_iqcorr_run_dev(self._h, C.c_void_p(d_in), C.c_void_p(d_out), int(n_samples), 0, C.c_void_p(stream or 0)))
+
+
+class Interpolators:
+    """Interpolators<T, 16, OutputBits> (sdrbase/dsp/interpolators.h:104-617): the device-side Tx interpolators.
+    output_bits 16 / 12 -> int16 device buffers, 8 -> int8 (HackRF).  interpolateN_cen(samples, len) returns the device buffer
+    (len output scalars, the trailing partial block untouched = the fill value) and the number of Samples consumed."""
+
+    def __init__(self, output_bits=16, device=None):
+        if device is not None:
+            capi.init(device)
+        self.output_bits = int(output_bits)
+        self.fmt = capi.FMT_I8 if self.output_bits == 8 else capi.FMT_I16
+        self.dtype = np.int8 if self.output_bits == 8 else np.int16
+        h = C.c_void_p()
+        capi.check(capi.lib().b200dsp_interps_create(C.byref(h), self.fmt, self.output_bits))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            capi.lib().b200dsp_interps_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        capi.check(capi.lib().b200dsp_interps_reset(self._h))
+
+    def run(self, log2, samples, length=None, fill=0):
+        """== interpolate{2^log2}_cen(&it, buf, len): samples int16 [n, 2]; len defaults to everything the samples give."""
+        x = np.ascontiguousarray(samples, dtype=np.int16).reshape(-1, 2)
+        if length is None:
+            length = x.shape[0] * (2 << log2)
+        need = capi.lib().b200dsp_interps_in_count(log2, length)
+        if need < 0 or need > x.shape[0]:
+            raise ValueError("interpolate: %d output scalars need %d samples, %d given" % (length, need, x.shape[0]))
+        buf = np.full(int(length), fill, dtype=self.dtype)
+        n = C.c_int32(0)
+        capi.check(capi.lib().b200dsp_interps_run(self._h, log2, x.ctypes.data if x.size else None, buf.ctypes.data if buf.size else None, int(length), C.byref(n)))
+        return buf, n.value
+
+    def run_dev(self, log2, d_samples, d_buf, len_scalars, stream=None):
+        n = C.c_int64(0)
+        capi.check(capi.lib().b200dsp_interps_run_dev(self._h, log2, d_samples, d_buf, len_scalars, C.byref(n), stream))
+        return n.value
+
+    def interpolate1(self, samples, length=None):
+        return self.run(0, samples, length)
+
+
+for _l in range(1, 7):
+    setattr(Interpolators, "interpolate%d_cen" % (1 << _l), (lambda l: lambda self, samples, length=None, fill=0: self.run(l, samples, length, fill))(_l))
+
+
+class UpChannelizer:
+    """UpChannelizer (sdrbase/dsp/upchannelizer.cpp:51-104,175-209,252-327): block form of pull()."""
+
+    def __init__(self, device=None):
+        if device is not None:
+            capi.init(device)
+        h = C.c_void_p()
+        capi.check(capi.lib().b200dsp_upchan_create(C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            capi.lib().b200dsp_upchan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def configure(self, output_rate, requested_rate, center_offset):
+        """Returns (modulator rate, residual offset, path) -- what MsgChannelizerNotification reports + the stage modes."""
+        r, o = C.c_int32(), C.c_int32()
+        capi.check(capi.lib().b200dsp_upchan_configure(self._h, output_rate, requested_rate, center_offset, C.byref(r), C.byref(o)))
+        return r.value, o.value, self.path()
+
+    def set_path(self, modes):
+        m = (C.c_int32 * max(1, len(modes)))(*modes)
+        capi.check(capi.lib().b200dsp_upchan_set_path(self._h, m, len(modes)))
+
+    def path(self):
+        m = (C.c_int32 * 32)()
+        n = capi.lib().b200dsp_upchan_path(self._h, m, 32)
+        return [int(m[i]) for i in range(n)]
+
+    def source_count(self, n_out):
+        return int(capi.lib().b200dsp_upchan_source_count(self._h, n_out))
+
+    def pull(self, source, n_out):
+        """n_out calls of pull(); source int16 [>= source_count(n_out), 2].  Returns (out int16 [n_out, 2], samples consumed)."""
+        need = self.source_count(n_out)
+        x = np.ascontiguousarray(source, dtype=np.int16).reshape(-1, 2)
+        out = np.empty((n_out, 2), dtype=np.int16)
+        capi.check(capi.lib().b200dsp_upchan_pull(self._h, x.ctypes.data if x.size else None, x.shape[0], out.ctypes.data if n_out else None, n_out))
+        return out, need
+
+    def pull_dev(self, d_source, n_source, d_out, n_out, stream=None):
+        capi.check(capi.lib().b200dsp_upchan_pull_dev(self._h, d_source, n_source, d_out, n_out, stream))

@@ -16,6 +16,8 @@
 #include "sdrangel_b200/dsp/nco.h"
 #include "sdrangel_b200/dsp/samplesinkfifo.h"
 #include "sdrangel_b200/dsp/devicesamplesource.h"
+#include "sdrangel_b200/dsp/upchannelizer.h"
+#include "sdrangel_b200/dsp/interpolators.h"
 
 static uint64_t fnv(const void* p, size_t n_u16)
 {
@@ -29,6 +31,12 @@ struct CaptureSink : BasebandSampleSink {
     SampleVector captured;
     void start() {} void stop() {}
     void feed(const SampleVector::const_iterator& b, const SampleVector::const_iterator& e, bool) { captured.insert(captured.end(), b, e); }
+};
+// a modulator: hands out a deterministic sequence, one Sample per pull (what a channel Tx plugin's pull() does)
+struct RampSource : BasebandSampleSource {
+    int k = 0;
+    void start() {} void stop() {}
+    void pull(Sample& s) { s.setReal((qint16) (k * 37 - 20000)); s.setImag((qint16) (15000 - k * 91)); ++k; }
 };
 struct CountDisplay : SpectrumDisplay { int frames = 0; double last0 = 0; void newSpectrum(const std::vector<Real>& s, int) { frames++; last0 = s[0]; } };
 
@@ -235,6 +243,27 @@ int main()
             same = (is - os.begin() == in2 - on.begin());
             for (size_t k = 0; same && k < (size_t) (is - os.begin()); k++) same = (os[k].real() == on[k].real() && os[k].imag() == on[k].imag());
             printf("split_iq_overload %s n=%zu\n", same ? "same" : "DIFFERENT", (size_t) (is - os.begin()));
+        }
+        {
+            // Tx mirror: modulator -> UpChannelizer::pull (per sample, as the reference is driven) == pullBlock; then the device
+            // plugin's Interpolators<qint16, SDR_TX_SAMP_SZ, 12>::interpolate8_cen into the device buffer (bladerfoutputthread.cpp)
+            RampSource m1, m2;
+            UpChannelizer u1(&m1, 1000), u2(&m2);
+            u1.setOutputSampleRate(4000000); u1.configure(100000, 1200000);
+            u2.setOutputSampleRate(4000000); u2.configure(100000, 1200000);
+            SampleVector a(10000), b(10000);
+            for (size_t k = 0; k < a.size(); k++) u1.pull(a[k]);
+            u2.pullBlock(&b[0], (int) b.size());
+            bool same = true;
+            for (size_t k = 0; same && k < a.size(); k++) same = (a[k].real() == b[k].real() && a[k].imag() == b[k].imag());
+            printf("upchannelizer %s rate=%d ofs=%d pulled=%d out=%016llx\n", same ? "same" : "DIFFERENT", u2.getCurrentInputSampleRate(),
+                   u2.getCurrentCenterFrequency(), m2.k, (unsigned long long) fnv(&b[0], 2 * b.size()));
+            Interpolators<qint16, SDR_TX_SAMP_SZ, 12> interp;
+            std::vector<qint16> dev(10000 * 16 + 5, 77);
+            SampleVector::iterator it = b.begin();
+            interp.interpolate8_cen(&it, &dev[0], (qint32) dev.size());
+            printf("interpolators8_cen consumed=%zu tail=%d out=%016llx\n", (size_t) (it - b.begin()), (int) dev[dev.size() - 1],
+                   (unsigned long long) fnv(&dev[0], dev.size()));
         }
         delete[] buf;
     } catch (const std::exception& e) {

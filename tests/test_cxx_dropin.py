@@ -61,3 +61,12 @@ def test_sdrbench_decimateii_through_cxx_wrappers(gpu_lib, port, golden_meta, go
     assert lines["frequencyshift"] == "-1250000 625000 434375000"
     assert lines["device_fifo_route"].startswith("same n=")
     assert lines["split_iq_overload"] == "same n=256"
+    # Tx mirror: per-sample pull == block pull == the oracle; Interpolators<qint16,16,12>::interpolate8_cen of that stream
+    k = np.arange(700, dtype=np.int64)
+    src = np.stack([((k * 37 - 20000 + 32768) % 65536 - 32768), ((15000 - k * 91 + 32768) % 65536 - 32768)], axis=1).astype(np.int16)
+    u = port.PortUpChannelizer()
+    rate, ofs, _ = u.configure(4000000, 100000, 1200000)
+    out, used = u.pull(src, 10000)
+    assert lines["upchannelizer"] == "same rate=%d ofs=%d pulled=%d out=%s" % (rate, ofs, used, fnv1a64_u16(out))
+    dev, n = port.PortInterpolators(12).run(3, out, 10000 * 16 + 5, fill=77)
+    assert lines["interpolators8_cen"] == "consumed=%d tail=77 out=%s" % (n, fnv1a64_u16(dev))
