@@ -53,6 +53,12 @@ WORKLOADS = {
                      desc="SpectrumVis: 4096-pt Blackman-Harris windowed FFT, log power, fixed averaging over 10 frames, synthetic int16 IQ (61.44 MS/s LimeSDR-rate stream)"),
     "iqcorr": dict(type="iqcorr", n=1 << 27,
                    desc="DSPDeviceSourceEngine::iqCorrections, DC branch (1024-sample moving average removed per component), synthetic int16 IQ"),
+    "interps": dict(type="tx", kind="interps", bits=12, log2=5, n=1 << 22,
+                    desc="Tx: Interpolators<qint16,16,12>::interpolate32_cen, SampleVector -> device buffer (LimeSDR / BladeRF sink), synthetic int16 IQ"),
+    "upchan": dict(type="tx", kind="upchan", plan=(3_072_000, 48_000, 300_000), n=1 << 27,
+                   desc="Tx: UpChannelizer::pull, 48 kS/s modulator -> 3.072 MS/s (6 interpolating half-bands of order 96), n = output samples"),
+    "demod": dict(type="tx", kind="demod", channels=1024, n=1 << 26,
+                  desc="NFM back-end: PhaseDiscriminators::phaseDiscriminatorDelta on the pooled front-end outputs of 1024 channels, n = channel samples"),
     "bank1024": dict(type="bank", plan=plan1024, n=3 << 24,
                      desc="1024 channels over a synthetic 122.88 MS/s int16 stream: DownChannelizer tree + NCO + Interpolator to 48 kS/s, channels sharded"),
 }
@@ -237,7 +243,45 @@ def cpu_reference_iqcorr(wl, seconds, threads=None):
             "sample": "%d x 2^20-sample buffer per thread, state carried, %.1f s wall" % (max(counts), wall)}
 
 
+def cpu_reference_tx(wl, seconds, threads=None):
+    """The reference's Tx-side / demodulator classes (oracle/_ref), one object per host thread, 2^16-sample blocks."""
+    kind, mod = _oracle_mod()
+    threads = threads or (os.cpu_count() or 1)
+    ref = (kind == "reference")
+    rs = np.random.RandomState(4)
+    if wl["kind"] == "interps":
+        n = 1 << 14
+        x = rs.randint(-32768, 32768, size=(n, 2)).astype(np.int16)
+        objs = [(mod.RefInterpolators(wl["bits"]) if ref else mod.PortInterpolators(wl["bits"])) for _ in range(threads)]
+        run = lambda o: o.run(wl["log2"], x)                                  # noqa: E731
+    elif wl["kind"] == "upchan":
+        n = 1 << 18
+        objs = [(mod.RefUpChannelizer() if ref else mod.PortUpChannelizer()) for _ in range(threads)]
+        for o in objs:
+            o.configure(*wl["plan"])
+        x = rs.randint(-32768, 32768, size=(n // 32, 2)).astype(np.int16)
+        run = lambda o: o.pull(x, n)                                          # noqa: E731
+    else:
+        n = 1 << 18
+        x = ((rs.randn(n) + 1j * rs.randn(n)) * 8000).astype(np.complex64)
+        objs = [(mod.RefDemod(1, 0.25) if ref else mod.PortDemod(1, 0.25)) for _ in range(threads)]
+        run = lambda o: o.run(x)                                              # noqa: E731
+    counts = [0] * threads
+    t_end = time.perf_counter() + seconds
+
+    def work(i):
+        while time.perf_counter() < t_end:
+            run(objs[i])
+            counts[i] += 1
+
+    wall = _run_threads(work, threads)
+    return {"value": sum(counts) * n / wall / 1e6, "unit": "input MS/s", "cores": threads, "kind": kind,
+            "sample": "%d blocks of %d samples per thread, state carried, %.1f s wall" % (max(counts), n, wall)}
+
+
 def cpu_reference(wl, seconds):
+    if wl["type"] == "tx":
+        return cpu_reference_tx(wl, seconds)
     if wl["type"] == "iqcorr":
         return cpu_reference_iqcorr(wl, seconds)
     if wl["type"] == "decim":
@@ -514,6 +558,96 @@ def bench_iqcorr(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity
                       "steps": 3, "api": "b200dsp_iqcorr_run (pinned host buffer, corrected in place)", "samples_per_step": n}
         q2.close()
     q.close()
+    return res
+
+
+def bench_tx(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=True):
+    """SURVEY.md 8f-3 / 8f-4 kernels on device-resident data (replicas at N > 1): the fused Interpolators<> cascade (value = samples
+    consumed per second), UpChannelizer::pull (value = output samples per second), the pooled discriminator (channel samples)."""
+    import sdrangel_b200 as S
+    torch = c.torch
+    n = args.samples or wl["n"]
+    stream = torch.cuda.Stream(device=c.dev)
+    sptr = stream.cuda_stream
+    g = torch.Generator(device=c.dev)
+    g.manual_seed(5)
+    parity = None
+    _oracle_mod()
+    from oracle import portbind
+    if wl["kind"] == "interps":
+        L2 = wl["log2"]
+        x = torch.randint(-32768, 32768, (n, 2), dtype=torch.int16, device=c.dev, generator=g)
+        y = torch.empty((n << L2, 2), dtype=torch.int16, device=c.dev)
+        obj = S.Interpolators(wl["bits"])
+        if c.rank == 0 and want_parity:
+            m = 1 << 15
+            chk = S.Interpolators(wl["bits"])
+            chk.run_dev(L2, x.data_ptr(), y.data_ptr(), m * (2 << L2), sptr)
+            stream.synchronize()
+            want, _ = portbind.PortInterpolators(wl["bits"]).run(L2, x[:m].cpu().numpy())
+            parity = bool(np.array_equal(y[:m << L2].cpu().numpy().ravel(), want))
+            chk.close()
+
+        def step():
+            obj.run_dev(L2, x.data_ptr(), y.data_ptr(), n * (2 << L2), sptr)
+        bytes_per, kernel = 4.0 + 4.0 * (1 << L2), "interps_cascade_kernel"
+        # per consumed sample: stage s produces 2^(s-1) FIR outputs of order/4 taps x (add + mad) x 2 components (+ shift, centre copy, pack)
+        instr = sum((1 << s) * t * 4 for s, t in zip(range(L2), (16, 8, 4, 4, 4, 4))) + 6.0 * (1 << L2)
+    elif wl["kind"] == "upchan":
+        obj = S.UpChannelizer()
+        obj.configure(*wl["plan"])
+        need = obj.source_count(n) + 64
+        x = torch.randint(-32768, 32768, (need, 2), dtype=torch.int16, device=c.dev, generator=g)
+        y = torch.empty((n, 2), dtype=torch.int16, device=c.dev)
+        if c.rank == 0 and want_parity:
+            m = 1 << 18
+            chk = S.UpChannelizer(); chk.configure(*wl["plan"])
+            o = portbind.PortUpChannelizer(); o.configure(*wl["plan"])
+            chk.pull_dev(x.data_ptr(), chk.source_count(m), y.data_ptr(), m, sptr)
+            stream.synchronize()
+            parity = bool(np.array_equal(y[:m].cpu().numpy(), o.pull(x[:m].cpu().numpy(), m)[0]))
+            chk.close()
+
+        def step():
+            obj.pull_dev(x.data_ptr(), obj.source_count(n), y.data_ptr(), n, sptr)
+        S_ = len(obj.path())
+        bytes_per, kernel = 4.0 + 4.0 / (1 << S_), "upchan_stage_kernel x%d" % S_
+        instr = sum(0.5 ** s for s in range(S_)) * (24 * 2 * 2 / 2.0 + 6.0)      # per output sample: half the calls run the 24-tap FIR on 2 components
+    else:
+        nc = wl["channels"]
+        per = n // nc
+        x = torch.randn((nc, per, 2), dtype=torch.float32, device=c.dev, generator=g) * 8000
+        cnt = torch.full((nc,), per, dtype=torch.int64, device=c.dev)
+        y = torch.empty((3, nc, per), dtype=torch.float32, device=c.dev)
+        obj = S.Demod(S.Demod.FM_DELTA, 0.25, n_channels=nc)
+        if c.rank == 0 and want_parity:
+            chk = S.Demod(S.Demod.FM_DELTA, 0.25, n_channels=nc)
+            chk.run_pool_dev(x.data_ptr(), per, cnt.data_ptr(), y[0].data_ptr(), per, y[1].data_ptr(), y[2].data_ptr(), sptr)
+            stream.synchronize()
+            ch = nc // 3
+            want = portbind.PortDemod(1, 0.25).run(x[ch].cpu().numpy().view(np.complex64).ravel())
+            parity = all(bool(np.array_equal(y[j, ch].cpu().numpy(), want[j])) for j in range(3))
+            chk.close()
+
+        def step():
+            obj.run_pool_dev(x.data_ptr(), per, cnt.data_ptr(), y[0].data_ptr(), per, y[1].data_ptr(), y[2].data_ptr(), sptr)
+        bytes_per, kernel, instr = 8.0 + 12.0, "demod_kernel", None
+    total_ms, kern_ms, clocks = timed_steps(c, stream, step, steps, warmup)
+    k_ms = float(np.mean(kern_ms))
+    achieved = n * bytes_per / (k_ms * 1e-3) / 1e9
+    clk = (clocks or {}).get("sm_mhz") or 1965.0
+    issue = None
+    if instr:
+        roof = c.sm_count * 128 * clk * 1e6 / instr / 1e6
+        issue = {"instr_per_sample": instr, "roof_MSps_at_sampled_clk": roof, "frac": (n / (k_ms * 1e-3) / 1e6) / roof}
+    else:
+        issue = {"instr_per_sample": None, "roof_MSps_at_sampled_clk": None, "frac": None, "note": "HBM-bound: 8 B in + 12 B out per sample"}
+    res = {"value": c.world * n * steps / (total_ms * 1e-3) / 1e6, "ms_per_step": total_ms / steps, "clocks": clocks, "parity": parity, "launches": steps,
+           "config": {"workload": wl_name, "desc": wl["desc"], "samples_per_step": n, "l2": "outputs > 126 MB L2 per step", "parallelism": "replicas x%d" % c.world},
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": c.hbm_peak, "unit": "GB/s", "frac": achieved / c.hbm_peak, "traffic": None,
+                        "peak_source": c.peak_src, "kernel": kernel, "kernel_ms": k_ms, "algorithmic_bytes_per_sample": bytes_per, "issue": issue},
+           "dtype": "f32" if wl["kind"] == "demod" else "s32", "scaling": "weak"}
+    obj.close()
     return res
 
 
@@ -1099,7 +1233,7 @@ def _node_depths(paths):
 
 def run_ours(args, wl_name, wl):
     c = setup()
-    fns = {"decim": bench_decim, "bank": bench_bank, "spectrum": bench_spectrum, "iqcorr": bench_iqcorr}
+    fns = {"decim": bench_decim, "bank": bench_bank, "spectrum": bench_spectrum, "iqcorr": bench_iqcorr, "tx": bench_tx}
     main_fn = fns[wl["type"]]
     if wl["type"] == "bank" and c.world > 1 and os.environ.get("B200_BENCH_COOP"):
         main_fn = bench_bank_coop          # developer switch: time-sliced top levels + all-to-all; measured slower

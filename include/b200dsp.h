@@ -321,6 +321,44 @@ int64_t b200dsp_upchan_source_count(b200dsp_upchan_t* h, int64_t n_out);
 int b200dsp_upchan_pull(b200dsp_upchan_t* h, const int16_t* source_iq, int64_t n_source, int16_t* out_iq, int64_t n_out);
 int b200dsp_upchan_pull_dev(b200dsp_upchan_t* h, const void* d_source_iq, int64_t n_source, void* d_out_iq, int64_t n_out, void* cuda_stream);
 
+/* ---- demodulator back-ends after Interpolator::decimate ------------------------------------------------
+ * == PhaseDiscriminators (sdrbase/dsp/phasediscri.h:26-198) and the magnitude lines of AMDemod::processOneSample
+ *    (plugins/channelrx/demodam/amdemod.cpp:154-156,241), as block calls over the complex64 outputs of the front-end.
+ * One handle == n_channels discriminator objects of one kind (their m_m1Sample / m_m2Sample / m_prevArg carried between calls).
+ * Kinds 1-3 are bit-identical to the reference compiled without -ffast-math; kind 0 differs by the device's atan2f (<= 2 ulp).
+ * Squelch, audio filters, AGC and the audio FIFO behind them are audio back-end, out of scope. */
+typedef struct b200dsp_demod b200dsp_demod_t;
+#define B200DSP_DEMOD_FM_ATAN2    0   /* phaseDiscriminator(sample)                       phasediscri.h:48-53  */
+#define B200DSP_DEMOD_FM_DELTA    1   /* phaseDiscriminatorDelta(sample, magsq, fmDev)    phasediscri.h:59-77 (NFMDemod, nfmdemod.cpp:165): aux0 = magsq, aux1 = fmDev */
+#define B200DSP_DEMOD_FM_DISCRI2  2   /* phaseDiscriminator2(sample)                      phasediscri.h:84-96  */
+#define B200DSP_DEMOD_AM_MAG      3   /* re, im / SDR_RX_SCALEF; magsq; sqrt(magsq)       amdemod.cpp:154-156,241: aux0 = magsq */
+int b200dsp_demod_create(b200dsp_demod_t** h, int kind, float fm_scaling, int n_channels);
+int b200dsp_demod_destroy(b200dsp_demod_t* h);
+int b200dsp_demod_reset(b200dsp_demod_t* h);                                   /* == PhaseDiscriminators::reset (+ m_prevArg = 0) */
+int b200dsp_demod_set_fm_scaling(b200dsp_demod_t* h, float fm_scaling);        /* == setFMScaling */
+/* one stream, host buffers (1-channel handles); aux0 / aux1 may be NULL */
+int b200dsp_demod_run(b200dsp_demod_t* h, const float* in_c64, int64_t n_samples, float* out, float* aux0, float* aux1);
+/* every channel of a pooled block: channel c's samples at d_pool + c * stride (complex64), d_counts[c] of them (device array) --
+ * the layout b200dsp_bank_gather_dev(STAGE_FRONTEND) writes; outputs at d_out + c * out_stride */
+int b200dsp_demod_run_pool_dev(b200dsp_demod_t* h, const void* d_pool_c64, int64_t stride_samples, const int64_t* d_counts, int n_channels,
+                               float* d_out, int64_t out_stride, float* d_aux0, float* d_aux1, void* cuda_stream);
+
+/* ---- .sdriq record files: FileRecord / the file-source plugin's on-disk format -----------------------
+ * == FileRecord::writeHeader / readHeader / feed (sdrbase/dsp/filerecord.cpp:72-148): 24-byte header (qint32 sample rate,
+ *    quint64 centre frequency, 8-byte time_t start, quint32 sample size), then raw Samples.  Pure host code, no device. */
+typedef struct b200dsp_sdriq b200dsp_sdriq_t;
+#define B200DSP_SDRIQ_HEADER_BYTES 24
+int b200dsp_sdriq_header_encode(int32_t sample_rate, uint64_t center_frequency, int64_t start_timestamp, uint32_t sample_size, void* out24);
+int b200dsp_sdriq_header_decode(const void* in24, int32_t* sample_rate, uint64_t* center_frequency, int64_t* start_timestamp, uint32_t* sample_size);
+/* reader (what FileSourceThread streams from): header fields + number of Samples in the file */
+int b200dsp_sdriq_open(b200dsp_sdriq_t** r, const char* path, int32_t* sample_rate, uint64_t* center_frequency, int64_t* start_timestamp,
+                       uint32_t* sample_size, int64_t* n_samples);
+int b200dsp_sdriq_read(b200dsp_sdriq_t* r, int16_t* iq, int64_t cap_samples, int64_t* got);
+/* writer == FileRecord::startRecording ... feed ... stopRecording: the header goes out with the first non-empty feed */
+int b200dsp_sdriq_create(b200dsp_sdriq_t** w, const char* path, int32_t sample_rate, uint64_t center_frequency, int64_t start_timestamp);
+int b200dsp_sdriq_write(b200dsp_sdriq_t* w, const int16_t* iq, int64_t n_samples);
+int b200dsp_sdriq_close(b200dsp_sdriq_t* r);
+
 /* ---- K5: SpectrumVis -------------------------------------------------------------------------------------
  * One handle == one reference SpectrumVis sink (sdrgui/dsp/spectrumvis.cpp:77-254,283-327) with its FFTWindow
  * (sdrbase/dsp/fftwindow.cpp:20-73), FFT engine (sdrbase/dsp/kissengine.cpp, kissfft.h) and per-bin averagers

@@ -1149,3 +1149,86 @@ void orc_hb_interp_coeffs(int order, int32_t* out)
     const int32_t* h = order == 16 ? HI16 : order == 32 ? HI32 : order == 64 ? H64 : HI96;
     for (int i = 0; i < order / 4; i++) out[i] = h[i];
 }
+
+/* ======================================================================================================
+ * demodulator back-ends after Interpolator::decimate, and the .sdriq header
+ * ====================================================================================================== */
+/* PhaseDiscriminators (sdrbase/dsp/phasediscri.h:26-198) */
+typedef struct { float m1[2], m2[2], scaling, prev_arg; } discri_t;
+
+void* orc_discri_create(float fm_scaling)
+{
+    discri_t* d = (discri_t*) calloc(1, sizeof(discri_t));
+    d->scaling = fm_scaling;
+    return d;
+}
+void orc_discri_destroy(void* h) { free(h); }
+
+/* phasediscri.h:162-194: |error| < 0.005 */
+static float atan2_approximation2(float y, float x)
+{
+    const float PI_FLOAT = 3.14159265f, PIBY2_FLOAT = 1.5707963f;
+    if (x == 0.0f) {
+        if (y > 0.0f) return PIBY2_FLOAT;
+        if (y == 0.0f) return 0.0f;
+        return -PIBY2_FLOAT;
+    }
+    float atan;
+    float z = y / x;
+    if (fabsf(z) < 1.0f) {
+        atan = z / (1.0f + 0.28f * z * z);
+        if (x < 0.0f) {
+            if (y < 0.0f) return atan - PI_FLOAT;
+            return atan + PI_FLOAT;
+        }
+    } else {
+        atan = PIBY2_FLOAT - z / (z * z + 0.28f);
+        if (y < 0.0f) return atan - PI_FLOAT;
+    }
+    return atan;
+}
+
+/* kind 0: phaseDiscriminator (:48-53), 1: phaseDiscriminatorDelta (:59-77; aux0 = magsq, aux1 = fmDev), 2: phaseDiscriminator2
+ * (:84-96), 3: AMDemod::processOneSample's magnitude (plugins/channelrx/demodam/amdemod.cpp:154-156,241; aux0 = magsq) */
+void orc_discri_run(void* h, int kind, const float* in, int n, float* out, float* aux0, float* aux1)
+{
+    discri_t* d = (discri_t*) h;
+    const double PI = 3.14159265358979323846;
+    for (int i = 0; i < n; i++) {
+        const float re = in[2 * i], im = in[2 * i + 1];
+        if (kind == 0) {
+            /* d = conj(m1) * sample */
+            const float dr = d->m1[0] * re + d->m1[1] * im;
+            const float di = d->m1[0] * im - d->m1[1] * re;
+            d->m1[0] = re; d->m1[1] = im;
+            out[i] = (float) (((double) atan2f(di, dr) / PI) * (double) d->scaling);
+        } else if (kind == 1) {
+            const float magsq = re * re + im * im;
+            const float cur = atan2_approximation2(im, re);
+            float dev = (float) ((double) (cur - d->prev_arg) / PI);
+            d->prev_arg = cur;
+            if (dev < -1.0f) dev += 2.0f; else if (dev > 1.0f) dev -= 2.0f;
+            if (aux0) aux0[i] = magsq;
+            if (aux1) aux1[i] = dev;
+            out[i] = dev * d->scaling;
+        } else if (kind == 2) {
+            const float ip = re - d->m2[0], qp = im - d->m2[1];
+            const float h1 = d->m1[0] * qp, h2 = d->m1[1] * ip;
+            d->m2[0] = d->m1[0]; d->m2[1] = d->m1[1];
+            d->m1[0] = re; d->m1[1] = im;
+            out[i] = (h1 - h2) * d->scaling;
+        } else {
+            const float r = re / 32768.0f, q = im / 32768.0f;
+            const float magsq = r * r + q * q;
+            if (aux0) aux0[i] = magsq;
+            out[i] = sqrtf(magsq);
+        }
+    }
+}
+
+/* FileRecord::writeHeader / readHeader (sdrbase/dsp/filerecord.cpp:129-148): qint32 rate, quint64 centre frequency,
+ * time_t (8 bytes) start, quint32 sample size; 24 bytes, native little-endian, no padding */
+void orc_sdriq_header(int32_t rate, uint64_t center, int64_t ts, uint32_t sample_size, uint8_t* out24)
+{
+    memcpy(out24, &rate, 4); memcpy(out24 + 4, &center, 8); memcpy(out24 + 12, &ts, 8); memcpy(out24 + 20, &sample_size, 4);
+}

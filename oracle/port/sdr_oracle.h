@@ -88,6 +88,14 @@ int   orc_upchan_configure(void* h, int output_rate, int requested_rate, int cen
 int   orc_upchan_pull(void* h, const int16_t* iq, int n_in, int16_t* out, int n_out);
 void  orc_hb_interp_coeffs(int order, int32_t* out);
 
+/* SURVEY.md 8f-4.  PhaseDiscriminators: sdrbase/dsp/phasediscri.h:26-198; AM magnitude: plugins/channelrx/demodam/amdemod.cpp:154-156,241.
+ * kind 0 phaseDiscriminator, 1 phaseDiscriminatorDelta (aux0 magsq, aux1 fmDev), 2 phaseDiscriminator2, 3 AM magnitude (aux0 magsq) */
+void* orc_discri_create(float fm_scaling);
+void  orc_discri_destroy(void* h);
+void  orc_discri_run(void* h, int kind, const float* in_c64, int n, float* out, float* aux0, float* aux1);
+/* .sdriq header: FileRecord::writeHeader, sdrbase/dsp/filerecord.cpp:129-137 */
+void  orc_sdriq_header(int32_t rate, uint64_t center, int64_t ts, uint32_t sample_size, uint8_t* out24);
+
 #ifdef __cplusplus
 }
 #endif

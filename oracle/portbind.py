@@ -62,6 +62,8 @@ def load():
         "orc_upchan_create": (vp, []), "orc_upchan_destroy": (None, [vp]),
         "orc_upchan_configure": (i32, [vp, i32, i32, i32, pi32, pi32, pi32, i32]),
         "orc_upchan_pull": (i32, [vp, pi16, i32, pi16, i32]), "orc_hb_interp_coeffs": (None, [i32, pi32]),
+        "orc_discri_create": (vp, [f32]), "orc_discri_destroy": (None, [vp]), "orc_discri_run": (None, [vp, i32, pf32, i32, pf32, pf32, pf32]),
+        "orc_sdriq_header": (None, [C.c_int32, C.c_uint64, C.c_int64, C.c_uint32, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -293,3 +295,24 @@ def hb_interp_coeffs(order):
     a = np.zeros(order // 4, dtype=np.int32)
     load().orc_hb_interp_coeffs(order, _p(a, C.c_int32))
     return a
+
+
+class PortDemod(_Handle):
+    """PhaseDiscriminators / AM magnitude restated (orc_discri_*): kind 0 atan2, 1 delta, 2 discri2, 3 AM magnitude."""
+
+    def __init__(self, kind, fm_scaling=1.0):
+        L = load()
+        super().__init__(L.orc_discri_create(fm_scaling), L.orc_discri_destroy)
+        self.kind = kind
+
+    def run(self, x):
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        out, a0, a1 = (np.zeros(x.size, dtype=np.float32) for _ in range(3))
+        load().orc_discri_run(self.h, self.kind, _p(x.view(np.float32), C.c_float), x.size, _p(out, C.c_float), _p(a0, C.c_float), _p(a1, C.c_float))
+        return out, a0, a1
+
+
+def sdriq_header(rate, center, ts, sample_size=16):
+    b = np.zeros(24, dtype=np.uint8)
+    load().orc_sdriq_header(rate, center, ts, sample_size, b.ctypes.data)
+    return b.tobytes()

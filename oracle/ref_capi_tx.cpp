@@ -163,3 +163,82 @@ int ref_upchan_pull(void* p, const int16_t* iq, int n_in, int16_t* out, int n_ou
 }
 
 } // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// demodulator back-ends after Interpolator::decimate, and the .sdriq record format
+//   PhaseDiscriminators (sdrbase/dsp/phasediscri.h:26-198): reference code, header-only, called as-is
+//   AMDemod::processOneSample's magnitude (plugins/channelrx/demodam/amdemod.cpp:154-156,241): three lines restated here
+//     (amdemod.cpp pulls in Qt audio and cannot be compiled without Qt)
+//   FileRecord (sdrbase/dsp/filerecord.cpp:72-148): reference code compiled in place
+// ---------------------------------------------------------------------------------------------------------
+#include <complex>
+#include "dsp/phasediscri.h"
+#include "dsp/filerecord.h"
+
+extern "C" {
+
+void* ref_discri_create(float fm_scaling)
+{
+    PhaseDiscriminators* d = new PhaseDiscriminators;
+    d->reset();
+    d->setFMScaling(fm_scaling);
+    // m_prevArg and the phaseDiscriminator3 members are left uninitialised by the reference (phasediscri.h:31-35,133-140); a
+    // freshly constructed demodulator object is zero-filled memory in practice: start from zero
+    double ms; Real dev;
+    Complex z(1.0f, 0.0f);
+    d->phaseDiscriminatorDelta(z, ms, dev);       // atan2(0, 1) = 0 -> m_prevArg = 0
+    d->reset();
+    return d;
+}
+void ref_discri_destroy(void* p) { delete (PhaseDiscriminators*) p; }
+
+// kind 0: phaseDiscriminator, 1: phaseDiscriminatorDelta (aux0 = magsq as float, aux1 = fmDev), 2: phaseDiscriminator2,
+// 3: AM magnitude (out = sqrt(magsq), aux0 = magsq)
+void ref_discri_run(void* p, int kind, const float* in_c64, int n, float* out, float* aux0, float* aux1)
+{
+    PhaseDiscriminators* d = (PhaseDiscriminators*) p;
+    for (int i = 0; i < n; i++) {
+        Complex ci(in_c64[2 * i], in_c64[2 * i + 1]);
+        if (kind == 0) out[i] = d->phaseDiscriminator(ci);
+        else if (kind == 1) {
+            double magsq; Real dev;
+            out[i] = d->phaseDiscriminatorDelta(ci, magsq, dev);
+            if (aux0) aux0[i] = (float) magsq;
+            if (aux1) aux1[i] = dev;
+        } else if (kind == 2) out[i] = d->phaseDiscriminator2(ci);
+        else {
+            Real re = ci.real() / SDR_RX_SCALEF;          // amdemod.cpp:154-156
+            Real im = ci.imag() / SDR_RX_SCALEF;
+            Real magsq = re*re + im*im;
+            if (aux0) aux0[i] = magsq;
+            out[i] = sqrt(magsq);                         // amdemod.cpp:241 (the delay line between them only delays)
+        }
+    }
+}
+
+// FileRecord driven the way the engine drives it: DSPSignalNotification, startRecording, feed ..., stopRecording
+int ref_filerecord_write(const char* path, int sample_rate, long long center_frequency, const int16_t* iq, int n1, int n2)
+{
+    FileRecord rec((QString(path)));
+    DSPSignalNotification sig(sample_rate, center_frequency);
+    rec.handleMessage(sig);
+    rec.startRecording();
+    SampleVector v((std::size_t) (n1 + n2));
+    if (n1 + n2 > 0) memcpy(&v[0], iq, (std::size_t) (n1 + n2) * sizeof(Sample));
+    rec.feed(v.begin(), v.begin() + n1, false);
+    rec.feed(v.begin() + n1, v.end(), false);
+    rec.stopRecording();
+    return (int) rec.getByteCount();
+}
+
+int ref_filerecord_read_header(const char* path, int* sample_rate, unsigned long long* center_frequency, long long* ts, unsigned* sample_size)
+{
+    std::ifstream f(path, std::ios::binary);
+    if (!f.is_open()) return -1;
+    FileRecord::Header h;
+    FileRecord::readHeader(f, h);
+    *sample_rate = h.sampleRate; *center_frequency = h.centerFrequency; *ts = (long long) h.startTimeStamp; *sample_size = h.sampleSize;
+    return (int) f.tellg();
+}
+
+} // extern "C"

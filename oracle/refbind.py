@@ -69,6 +69,9 @@ def load(strict=False):
         "ref_upchan_create": (vp, []), "ref_upchan_destroy": (None, [vp]),
         "ref_upchan_configure": (i32, [vp, i32, i32, i32, pi32, pi32, pi32, i32]),
         "ref_upchan_pull": (i32, [vp, pi16, i32, pi16, i32]),
+        "ref_discri_create": (vp, [f32]), "ref_discri_destroy": (None, [vp]), "ref_discri_run": (None, [vp, i32, pf32, i32, pf32, pf32, pf32]),
+        "ref_filerecord_write": (i32, [C.c_char_p, i32, C.c_longlong, pi16, i32, i32]),
+        "ref_filerecord_read_header": (i32, [C.c_char_p, pi32, C.POINTER(C.c_ulonglong), C.POINTER(C.c_longlong), C.POINTER(C.c_uint)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -325,3 +328,30 @@ def hb_coeffs(order, strict=False):
     sh = C.c_int32(0)
     n = load(strict).ref_hb_coeffs(order, _p(a, C.c_int32), C.byref(sh))
     return a[:n].copy(), sh.value
+
+
+class RefDemod(_Handle):
+    """The reference's PhaseDiscriminators (kinds 0-2) and the AM magnitude lines of AMDemod::processOneSample (kind 3)."""
+
+    def __init__(self, kind, fm_scaling=1.0, strict=False):
+        L = load(strict)
+        super().__init__(L, L.ref_discri_create(fm_scaling), L.ref_discri_destroy)
+        self.kind = kind
+
+    def run(self, x):
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        out, a0, a1 = (np.zeros(x.size, dtype=np.float32) for _ in range(3))
+        self.lib.ref_discri_run(self.h, self.kind, _p(x.view(np.float32), C.c_float), x.size, _p(out, C.c_float), _p(a0, C.c_float), _p(a1, C.c_float))
+        return out, a0, a1
+
+
+def filerecord_write(path, sample_rate, center_frequency, iq, n1):
+    """FileRecord: DSPSignalNotification, startRecording, feed(first n1), feed(rest), stopRecording.  Returns getByteCount()."""
+    iq = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1, 2)
+    return load().ref_filerecord_write(path.encode(), sample_rate, center_frequency, _p(iq, C.c_int16), n1, iq.shape[0] - n1)
+
+
+def filerecord_read_header(path):
+    r, c, t, s = C.c_int32(), C.c_ulonglong(), C.c_longlong(), C.c_uint()
+    pos = load().ref_filerecord_read_header(path.encode(), C.byref(r), C.byref(c), C.byref(t), C.byref(s))
+    return {"sample_rate": r.value, "center_frequency": c.value, "timestamp": t.value, "sample_size": s.value, "data_offset": pos}

@@ -663,3 +663,79 @@ class UpChannelizer:
 
     def pull_dev(self, d_source, n_source, d_out, n_out, stream=None):
         capi.check(capi.lib().b200dsp_upchan_pull_dev(self._h, d_source, n_source, d_out, n_out, stream))
+
+
+class Demod:
+    """Demodulator back-ends after Interpolator::decimate (SURVEY.md 8f-4): PhaseDiscriminators (phasediscri.h:26-198; kinds
+    0 atan2, 1 delta, 2 discri2) and the AM magnitude of AMDemod::processOneSample (amdemod.cpp:154-156,241; kind 3)."""
+    FM_ATAN2, FM_DELTA, FM_DISCRI2, AM_MAG = 0, 1, 2, 3
+
+    def __init__(self, kind, fm_scaling=1.0, n_channels=1, device=None):
+        if device is not None:
+            capi.init(device)
+        h = C.c_void_p()
+        capi.check(capi.lib().b200dsp_demod_create(C.byref(h), kind, float(fm_scaling), n_channels))
+        self._h, self.kind, self.n_channels = h, kind, n_channels
+
+    def close(self):
+        if getattr(self, "_h", None):
+            capi.lib().b200dsp_demod_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        capi.check(capi.lib().b200dsp_demod_reset(self._h))
+
+    def setFMScaling(self, fm_scaling):
+        capi.check(capi.lib().b200dsp_demod_set_fm_scaling(self._h, float(fm_scaling)))
+
+    def run(self, x):
+        """One stream: (out, aux0, aux1) float32 arrays (aux0 = magsq for kinds 1 and 3, aux1 = fmDev for kind 1)."""
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        out, a0, a1 = (np.zeros(x.size, dtype=np.float32) for _ in range(3))
+        capi.check(capi.lib().b200dsp_demod_run(self._h, x.ctypes.data if x.size else None, x.size, out.ctypes.data, a0.ctypes.data, a1.ctypes.data))
+        return out, a0, a1
+
+    def run_pool_dev(self, d_pool, stride, d_counts, d_out, out_stride, d_aux0=None, d_aux1=None, stream=None):
+        capi.check(capi.lib().b200dsp_demod_run_pool_dev(self._h, d_pool, stride, d_counts, self.n_channels, d_out, out_stride, d_aux0, d_aux1, stream))
+
+
+class SdriqFile:
+    """.sdriq record files (FileRecord, sdrbase/dsp/filerecord.cpp:72-148): host-side reader / writer."""
+
+    def __init__(self, path, mode="r", sample_rate=0, center_frequency=0, timestamp=0):
+        h = C.c_void_p()
+        self.mode = mode
+        if mode == "r":
+            r, c, t, s, n = C.c_int32(), C.c_uint64(), C.c_int64(), C.c_uint32(), C.c_int64()
+            capi.check(capi.lib().b200dsp_sdriq_open(C.byref(h), path.encode(), C.byref(r), C.byref(c), C.byref(t), C.byref(s), C.byref(n)))
+            self.sample_rate, self.center_frequency, self.timestamp, self.sample_size, self.n_samples = r.value, c.value, t.value, s.value, n.value
+        else:
+            capi.check(capi.lib().b200dsp_sdriq_create(C.byref(h), path.encode(), sample_rate, center_frequency, timestamp))
+        self._h = h
+
+    def read(self, n):
+        out = np.empty((n, 2), dtype=np.int16)
+        got = C.c_int64(0)
+        capi.check(capi.lib().b200dsp_sdriq_read(self._h, out.ctypes.data, n, C.byref(got)))
+        return out[:got.value]
+
+    def write(self, iq):
+        iq = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1, 2)
+        capi.check(capi.lib().b200dsp_sdriq_write(self._h, iq.ctypes.data if iq.size else None, iq.shape[0]))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            capi.lib().b200dsp_sdriq_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

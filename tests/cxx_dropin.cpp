@@ -18,6 +18,8 @@
 #include "sdrangel_b200/dsp/devicesamplesource.h"
 #include "sdrangel_b200/dsp/upchannelizer.h"
 #include "sdrangel_b200/dsp/interpolators.h"
+#include "sdrangel_b200/dsp/phasediscri.h"
+#include "sdrangel_b200/dsp/filerecord.h"
 
 static uint64_t fnv(const void* p, size_t n_u16)
 {
@@ -264,6 +266,36 @@ int main()
             interp.interpolate8_cen(&it, &dev[0], (qint32) dev.size());
             printf("interpolators8_cen consumed=%zu tail=%d out=%016llx\n", (size_t) (it - b.begin()), (int) dev[dev.size() - 1],
                    (unsigned long long) fnv(&dev[0], dev.size()));
+        }
+        {
+            // demodulator back-end: per-sample phaseDiscriminatorDelta (the reference's call) == the block form
+            PhaseDiscriminators pd1, pd2;
+            pd1.setFMScaling(0.25f); pd2.setFMScaling(0.25f);
+            std::vector<Complex> z(64);
+            for (int k = 0; k < 64; k++) z[k] = Complex(1000.0f * std::cos(0.3f * k * k * 0.01f), 1000.0f * std::sin(0.3f * k * k * 0.01f));
+            std::vector<Real> o1(64), o2(64), mg(64), dv(64);
+            for (int k = 0; k < 64; k++) { double ms; Real dev; o1[k] = pd1.phaseDiscriminatorDelta(z[k], ms, dev); }
+            pd2.phaseDiscriminatorDelta(&z[0], 64, &o2[0], &mg[0], &dv[0]);
+            bool same = true;
+            for (int k = 0; k < 64; k++) same = same && (o1[k] == o2[k]);
+            printf("phasediscri %s\n", same ? "same" : "DIFFERENT");
+            // FileRecord: record, read the header back the way the file-source plugin does
+            const char* path = "/tmp/b200dsp_cxx_dropin.sdriq";
+            FileRecord rec(path);
+            rec.setSampleRateAndFrequency(2400000, 434000000ull);
+            SampleVector v(1000);
+            for (int k = 0; k < 1000; k++) { v[k].setReal((qint16) (k - 500)); v[k].setImag((qint16) (3 * k)); }
+            rec.feed(v.begin(), v.end(), false);            // not recording yet: dropped
+            rec.startRecording();
+            rec.feed(v.begin(), v.begin() + 300, false);
+            rec.feed(v.begin() + 300, v.end(), false);
+            rec.stopRecording();
+            std::ifstream f(path, std::ios::binary);
+            FileRecord::Header hd;
+            FileRecord::readHeader(f, hd);
+            f.seekg(0, std::ios::end);
+            printf("filerecord rate=%d fc=%llu size=%u count=%llu bytes=%lld\n", hd.sampleRate, (unsigned long long) hd.centerFrequency, hd.sampleSize,
+                   (unsigned long long) rec.getByteCount(), (long long) f.tellg());
         }
         delete[] buf;
     } catch (const std::exception& e) {

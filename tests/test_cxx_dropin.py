@@ -70,3 +70,5 @@ def test_sdrbench_decimateii_through_cxx_wrappers(gpu_lib, port, golden_meta, go
     assert lines["upchannelizer"] == "same rate=%d ofs=%d pulled=%d out=%s" % (rate, ofs, used, fnv1a64_u16(out))
     dev, n = port.PortInterpolators(12).run(3, out, 10000 * 16 + 5, fill=77)
     assert lines["interpolators8_cen"] == "consumed=%d tail=77 out=%s" % (n, fnv1a64_u16(dev))
+    assert lines["phasediscri"] == "same"
+    assert lines["filerecord"] == "rate=2400000 fc=434000000 size=16 count=1000 bytes=4024"
