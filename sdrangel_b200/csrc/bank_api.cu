@@ -599,7 +599,7 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
     if (run_sched) {
         if ((rc = B200_CUDA_CHECK(cudaEventRecord(b->ev_begin, st))) || (rc = B200_CUDA_CHECK(cudaStreamWaitEvent(b->side, b->ev_begin, 0)))) return rc;
         const int nfe = (int) b->h_fe.size();
-        frontend_schedule_kernel<<<(nfe + 3) / 4, 128, 0, b->side>>>(b->d_fe, nfe, pi);      // one warp per channel
+        frontend_schedule_kernel<<<nfe, 32 * FE_SW, 0, b->side>>>(b->d_fe, nfe, pi);      // one CTA per channel
         if ((rc = B200_CUDA_CHECK(cudaGetLastError())) || (rc = B200_CUDA_CHECK(cudaEventRecord(b->ev_sched, b->side)))) return rc;
     }
     const int tc = b->tcur, tn = tc ^ 1;
@@ -637,6 +637,13 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
         ++b->tree_launches;
     }
     if (fused) {
+        // A heavy schedule kernel (channels on the scan path: one 256-thread, 128-register CTA each) running beside the first
+        // pyramid launch takes half an SM's registers wherever one of its CTAs lands, i.e. one of that SM's two pyramid CTA
+        // slots; the pyramid's ranges are a static partition, so a CTA without a slot would run after the others and nearly
+        // double the launch.  That launch therefore gets as many CTAs fewer as the schedule kernel has (all resident at once).
+        int displaced = 0;
+        if (run_sched) for (int ci : b->fe_index) if (b->chans[ci].scan_kb > 0) ++displaced;
+        if (displaced > b->sm_count) displaced = b->sm_count;
         for (const auto& fl : b->flaunch) {
             if (fl.n_groups == 0) continue;
             FusedParams q;
@@ -659,6 +666,8 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
             const long long tot = (long long) q.n_groups * q.tpr;
             // persistent CTAs over contiguous (group, tile) ranges; a range that starts inside a stream pays one warm-up tile
             long long ctas = (long long) b->sm_count * ((fl.smem <= FZ_SMEM_LIMIT) ? FZ_CTAS_PER_SM : 1);
+            if (ctas > displaced + b->sm_count / 2) ctas -= displaced;
+            displaced = 0;                                        // later launches start after the schedule kernel has drained
             if (ctas > (tot + 3) / 4) ctas = (tot + 3) / 4;
             if (ctas < 1) ctas = 1;
             if ((rc = B200_CUDA_CHECK(cudaFuncSetAttribute((const void*) hb48_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fl.smem)))) return rc;
@@ -799,7 +808,7 @@ int empty_feed(b200dsp_bank* b, cudaStream_t st)
     pi.first_pass = 1;
     const int nfe = (int) b->h_fe.size();
     if (b->tables_dirty) return 0;            // never fed: the device tables do not exist yet and every count is still zero
-    frontend_schedule_kernel<<<(nfe + 3) / 4, 128, 0, st>>>(b->d_fe, nfe, pi);
+    frontend_schedule_kernel<<<nfe, 32 * FE_SW, 0, st>>>(b->d_fe, nfe, pi);
     return B200_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -1408,7 +1417,7 @@ int interp_run(b200dsp_interp* h, int mode, float* distance_remain, float distan
         (rc = B200_CUDA_CHECK(cudaMemcpyAsync(h->d_state, st, 16, cudaMemcpyHostToDevice, h->stream))) ||
         (rc = B200_CUDA_CHECK(cudaMemcpyAsync(h->d_chan, &f, sizeof(f), cudaMemcpyHostToDevice, h->stream)))) return rc;
     if (smem > 48 * 1024 && (rc = B200_CUDA_CHECK(cudaFuncSetAttribute((const void*) frontend_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)))) return rc;
-    frontend_schedule_kernel<<<1, 32, 0, h->stream>>>(h->d_chan, 1, pi);
+    frontend_schedule_kernel<<<1, 32 * FE_SW, 0, h->stream>>>(h->d_chan, 1, pi);
     const unsigned tiles = (unsigned) ((n + FE_TILE - 1) / FE_TILE);
     frontend_kernel_t<false><<<dim3(tiles ? tiles : 1, 1), FE_THREADS, smem, h->stream>>>(h->d_chan, nullptr, pi);
     if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;

@@ -89,10 +89,26 @@ __device__ __forceinline__ unsigned fe_fcomp(unsigned g, unsigned f)       // fi
     return h;
 }
 
-// one chunk of 128 candidate emissions by a whole warp, from the exact state (Db, ib = last consumed input, nb = emissions so far).
-// Returns false when the chunk must be replayed serially.  *nvalid = emissions whose input exists (a prefix of the chunk).
-__device__ __forceinline__ bool fe_scan_chunk(const FrontendChan& c, int lane, int m, long long Db, int ib, int nb, int* sched,
-                                              int* nvalid, long long* Dnext, int* inext)
+// One super-step: FE_SW warps of a CTA take FE_SW consecutive chunks of 32 * FE_EPL candidate emissions (FE_EPL consecutive
+// emissions per lane) from the exact state (Db, ib = last consumed input, nb = emissions so far).  Everything a chunk needs
+// from the chunks before it is a composition / sum of per-chunk totals exchanged through shared memory: the automaton's
+// composed step function (-> D mod 4 at the chunk's start), the corrections' sum (-> the offset e), the inputs taken (-> the
+// input index).  A single warp's chunk is latency-bound (dependent integer chains, ~12 cycles per emission), so the warps of a
+// CTA multiply the rate; closed-form residues are recomputed where needed instead of being kept in registers.
+// On return sh.nv[w] = valid emissions of chunk w (a prefix of the super-step; 0 from the first inconsistent chunk sh.wf on),
+// sh.D[w] / sh.i[w] = the exact state after chunk w's last valid emission.
+constexpr int FE_EPL = 16;
+constexpr int FE_CHUNK = 32 * FE_EPL;
+constexpr int FE_SW = 8;                       // warps per channel
+
+struct FeScanShared {
+    unsigned fn[FE_SW];
+    int csum[FE_SW], jsum[FE_SW], ok[FE_SW], nv[FE_SW], i[FE_SW];
+    long long D[FE_SW];
+    int wf;
+};
+
+__device__ __forceinline__ void fe_scan_super(const FrontendChan& c, int lane, int warp, int m, long long Db, int ib, int nb, int* sched, FeScanShared& sh)
 {
     const int kb = c.scan_kb;
     const long long q = 1ll << kb, qm = q - 1, P = 1ll << 24, A = c.A;
@@ -105,18 +121,17 @@ __device__ __forceinline__ bool fe_scan_chunk(const FrontendChan& c, int lane, i
         FL |= t << (2 * s2);
         FH |= ((t & 1u) ? 0u : t) << (2 * s2);
     }
-    long long Rz[4];                           // closed-form R of this lane's four emissions k = 4 lane + t
-    bool hi[4];
-    unsigned fn = 0xE4u;                       // identity
+    const long long kbase = (long long) FE_CHUNK * warp + (long long) FE_EPL * lane;
+    auto Rz = [&](long long k) -> long long { return (R0 + k * Am) & qm; };      // closed-form R of emission k of the super-step
+    // pass 1: crossing flags and the composed step function of this lane's emissions
+    unsigned himask = 0, fn = 0xE4u;           // identity
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const long long k = 4 * lane + t;
-        Rz[t] = (R0 + k * Am) & qm;
-        hi[t] = (Rz[t] + A >= P);
-        fn = fe_fcomp(fn, hi[t] ? FH : FL);
+    for (int t = 0; t < FE_EPL; ++t) {
+        const bool hi = (Rz(kbase + t) + A >= P);
+        himask |= (hi ? 1u : 0u) << t;
+        fn = fe_fcomp(fn, hi ? FH : FL);
     }
-    // exclusive scan of the step functions over the lanes
-    unsigned inc = fn;
+    unsigned inc = fn;                         // inclusive scan of the step functions over the lanes
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
         const unsigned o = __shfl_up_sync(0xffffffffu, inc, off);
@@ -124,14 +139,21 @@ __device__ __forceinline__ bool fe_scan_chunk(const FrontendChan& c, int lane, i
     }
     unsigned exc = __shfl_up_sync(0xffffffffu, inc, 1);
     if (lane == 0) exc = 0xE4u;
-    unsigned st = (exc >> (2 * (unsigned) (Db & 3))) & 3u;          // D mod 4 before this lane's first emission
-    int cc[4], csum = 0;
+    if (lane == 31) sh.fn[warp] = inc;
+    __syncthreads();
+    unsigned g = 0xE4u;                        // the chunks before this one
+    for (int w = 0; w < warp; ++w) g = fe_fcomp(g, sh.fn[w]);
+    const unsigned s_chunk = (g >> (2 * (unsigned) (Db & 3))) & 3u;
+    unsigned st = (exc >> (2 * s_chunk)) & 3u;                      // D mod 4 before this lane's first emission
+    // pass 2: the corrections (+1 / -1 as two bit masks) and their sum
+    unsigned cpos = 0, cneg = 0;
+    int csum = 0;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
+    for (int t = 0; t < FE_EPL; ++t) {
         const unsigned tt = (st + a4) & 3u;
-        cc[t] = (hi[t] && (tt & 1u)) ? ((tt == 1u) ? -1 : 1) : 0;
-        st = (hi[t] && (tt & 1u)) ? 0u : tt;
-        csum += cc[t];
+        const bool corr = ((himask >> t) & 1u) && (tt & 1u);
+        if (corr) { if (tt == 1u) { cneg |= 1u << t; --csum; } else { cpos |= 1u << t; ++csum; } }
+        st = corr ? 0u : tt;
     }
     int einc = csum;
 #pragma unroll
@@ -139,69 +161,82 @@ __device__ __forceinline__ bool fe_scan_chunk(const FrontendChan& c, int lane, i
         const int o = __shfl_up_sync(0xffffffffu, einc, off);
         if (lane >= off) einc += o;
     }
-    int e = einc - csum;                       // corrections before this lane's first emission
-    // distances D_k, inputs taken j_k, true R_k; consistency of the closed-form flags
+    if (lane == 31) sh.csum[warp] = einc;
+    __syncthreads();
+    int e0 = einc - csum;                      // corrections before this lane's first emission
+    for (int w = 0; w < warp; ++w) e0 += sh.csum[w];
+    // pass 3: distances D_k, inputs taken j_k, true R_k; consistency of the closed-form flags
     bool ok = true;
-    long long Dk[4], Rk[4];
-    int jsum = 0, jj[4];
-    long long prevR0 = __shfl_up_sync(0xffffffffu, Rz[3], 1);        // closed-form R of emission 4 lane - 1
+    int jsum = 0, jj[FE_EPL];
+    {
+        int e = e0;
+        long long before = (kbase > 0) ? Rz(kbase - 1) : 0;          // closed-form R of the emission before this lane's first
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const long long before = (t == 0) ? prevR0 : Rz[t - 1];
-        Dk[t] = (lane == 0 && t == 0) ? Db : before + A + e;         // (R0_{k-1} + A) + e_k
-        Rk[t] = Rz[t] + e;
-        ok = ok && Rk[t] >= 0 && Rk[t] < q && ((Rk[t] + A >= P) == hi[t]) && ((Dk[t] & qm) == Rk[t]);
-        jj[t] = (int) (Dk[t] >> kb);
-        jsum += jj[t];
-        e += cc[t];
+        for (int t = 0; t < FE_EPL; ++t) {
+            const long long rz = Rz(kbase + t);
+            const long long Dk = (kbase == 0 && t == 0) ? Db : before + A + e;    // (R0_{k-1} + A) + e_k
+            const long long Rk = rz + e;
+            ok = ok && Rk >= 0 && Rk < q && ((Rk + A >= P) == (((himask >> t) & 1u) != 0)) && ((Dk & qm) == Rk);
+            jj[t] = (int) (Dk >> kb);
+            jsum += jj[t];
+            e += (int) ((cpos >> t) & 1u) - (int) ((cneg >> t) & 1u);
+            before = rz;
+        }
     }
-    if (!__all_sync(0xffffffffu, ok)) return false;
+    const bool ok_warp = __all_sync(0xffffffffu, ok);
     int jinc = jsum;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
         const int o = __shfl_up_sync(0xffffffffu, jinc, off);
         if (lane >= off) jinc += o;
     }
+    if (lane == 31) sh.jsum[warp] = jinc;
+    if (lane == 0) sh.ok[warp] = ok_warp ? 1 : 0;
+    __syncthreads();
+    int wf = FE_SW;
+    for (int w = FE_SW - 1; w >= 0; --w) if (!sh.ok[w]) wf = w;
+    // pass 4: the schedule entries; the valid emissions are a prefix, the lane that owns the last one publishes the state
+    // after it: D = (closed-form R + A) + e_{k+1}
     int idx = ib + (jinc - jsum);
+    for (int w = 0; w < warp; ++w) idx += sh.jsum[w];
     const float steps = (float) c.phase_steps, uf = 1.0f / (float) q;
-    int cnt = 0;
+    int cnt = 0, in_ = 0;
+    long long Dn = 0;
+    if (warp < wf) {
+        int e = e0;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        idx += jj[t];
-        if (idx < m) {
-            int ph = (int) floorf(__fmul_rn(__fmul_rn((float) Rk[t], uf), steps));      // (float) R u is exact
-            ph = ph < 0 ? 0 : ph;
-            sched[nb + 4 * lane + t] = (int) (((unsigned) idx << 8) | (unsigned) ph);
-            ++cnt;
+        for (int t = 0; t < FE_EPL; ++t) {
+            idx += jj[t];
+            const long long rz = Rz(kbase + t);
+            const long long Rk = rz + e;
+            e += (int) ((cpos >> t) & 1u) - (int) ((cneg >> t) & 1u);
+            if (idx < m) {
+                int ph = (int) floorf(__fmul_rn(__fmul_rn((float) Rk, uf), steps));      // (float) R u is exact
+                ph = ph < 0 ? 0 : ph;
+                sched[nb + (int) kbase + t] = (int) (((unsigned) idx << 8) | (unsigned) ph);
+                ++cnt;
+                Dn = rz + A + e; in_ = idx;
+            }
         }
     }
-    // the valid emissions are a prefix of the chunk; state after the last of them
     int tot = cnt;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
-    *nvalid = tot;
-    // D after emission kl = tot - 1 is (closed-form R_kl + A) + e_{kl+1}; the lane that owns kl publishes it
-    long long Dn = 0;
-    int in_ = 0;
-    {
-        int ee = einc - csum, ii = ib + (jinc - jsum);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            ii += jj[t];
-            ee += cc[t];
-            if (4 * lane + t == tot - 1) { Dn = Rz[t] + A + ee; in_ = ii; }
-        }
-    }
-    const int owner = (tot > 0) ? (tot - 1) >> 2 : 0;
-    *Dnext = __shfl_sync(0xffffffffu, Dn, owner);
-    *inext = __shfl_sync(0xffffffffu, in_, owner);
-    return true;
+    const int owner = (tot > 0) ? (tot - 1) / FE_EPL : 0;
+    Dn = __shfl_sync(0xffffffffu, Dn, owner);
+    in_ = __shfl_sync(0xffffffffu, in_, owner);
+    if (lane == 0) { sh.nv[warp] = tot; sh.D[warp] = Dn; sh.i[warp] = in_; }
+    if (threadIdx.x == 0) sh.wf = wf;
+    __syncthreads();
 }
 
-__global__ void frontend_schedule_kernel(const FrontendChan* __restrict__ chans, int n_chans, const PassInfo pi)
+// One CTA (FE_SW warps) per channel.
+__global__ void __launch_bounds__(32 * FE_SW) frontend_schedule_kernel(const FrontendChan* __restrict__ chans, int n_chans, const PassInfo pi)
 {
-    const int ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+    __shared__ FeScanShared sh;
+    __shared__ long long sh_res[4];
+    const int ch = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (ch >= n_chans) return;
     const FrontendChan c = chans[ch];
     const int m = pi.n_new[c.depth];
@@ -212,19 +247,19 @@ __global__ void frontend_schedule_kernel(const FrontendChan* __restrict__ chans,
     long long ncf = 0, i0 = 0, D = 0;
     if (c.scan_kb > 0 && c.mode == 0) {
         // non-lattice ratio: serial until the distance has been through one fl(r + ratio) (a few emissions at a stream's
-        // start), then 128 emissions per warp step
+        // start), then FE_SW * 32 * FE_EPL emissions per super-step.  Every thread carries the same (d, i, n).
         float d = __int_as_float(c.state[1]);
         const float steps = (float) c.phase_steps, ratio = c.ratio;
         int i = -1;
         bool done = false;
-        auto serial_emit = [&]() -> bool {              // every lane computes, lane 0 writes: returns false when the input runs out
+        auto serial_emit = [&]() -> bool {              // every thread computes, thread 0 writes: returns false when the input runs out
             const float fj = fmaxf(floorf(d), 1.0f);
             if (i + (int) fj >= m) return false;
             i += (int) fj;
             const float r = __fsub_rn(d, fj);
             int ph = (int) floorf(__fmul_rn(r, steps));
             ph = ph < 0 ? 0 : ph;
-            if (lane == 0) sched[n] = (int) (((unsigned) i << 8) | (unsigned) ph);
+            if (tid == 0) sched[n] = (int) (((unsigned) i << 8) | (unsigned) ph);
             ++n;
             d = __fadd_rn(r, ratio);
             return true;
@@ -233,17 +268,25 @@ __global__ void frontend_schedule_kernel(const FrontendChan* __restrict__ chans,
         while (!done && !(d >= ratio && d < ratio + 1.0f)) done = !serial_emit();
         const float qf = (float) (1ll << c.scan_kb);
         while (!done) {
-            long long Db = (long long) (d * qf), Dn;          // exact: d is a multiple of 2^-kb below 2^25
-            int nv, in_;
-            if (fe_scan_chunk(c, lane, m, Db, i, n, sched, &nv, &Dn, &in_)) {
-                if (nv > 0) { n += nv; i = in_; d = (float) Dn / qf; }
-                if (nv < 128) done = true;
-            } else {
-                for (int k = 0; k < 128 && !done; ++k) done = !serial_emit();     // rare: an offset moved a value across a boundary
+            const long long Db = (long long) (d * qf);          // exact: d is a multiple of 2^-kb below 2^25
+            fe_scan_super(c, lane, warp, m, Db, i, n, sched, sh);
+            const int wf = sh.wf;
+            int total = 0, wl = -1;
+            bool short_ = false;
+            for (int w = 0; w < wf; ++w) {
+                total += sh.nv[w];
+                if (sh.nv[w] > 0) wl = w;
+                if (sh.nv[w] < FE_CHUNK) short_ = true;
+            }
+            if (wl >= 0) { n += total; i = sh.i[wl]; d = (float) sh.D[wl] / qf; }
+            __syncthreads();                                    // the exchange arrays are free for the next super-step
+            if (short_) done = true;
+            else if (wf < FE_SW) {
+                for (int k = 0; k < FE_CHUNK && !done; ++k) done = !serial_emit();     // rare: an offset moved a value across a boundary
             }
         }
         d = __fadd_rn(d, -(float) (m - 1 - i));        // the remaining inputs of this pass each subtract 1.0f (exact)
-        if (lane == 0) {
+        if (tid == 0) {
             c.plan[0] = n; c.plan[1] = 0; c.plan[2] = 0; c.plan[3] = 0;
             const int base = pi.first_pass ? 0 : c.state[3];
             c.state[1] = __float_as_int(d);
@@ -251,7 +294,7 @@ __global__ void frontend_schedule_kernel(const FrontendChan* __restrict__ chans,
             c.state[3] = base + n;
         }
     } else
-    if (lane == 0) {
+    if (tid == 0) {
         float d = __int_as_float(c.state[1]);      // distance remain before the next input
         const float steps = (float) c.phase_steps, ratio = c.ratio;
         int i = -1;                                // index of the last consumed input
@@ -350,14 +393,17 @@ __global__ void frontend_schedule_kernel(const FrontendChan* __restrict__ chans,
         c.state[3] = base + total;
         }
     }
-    __syncwarp();
-    n = __shfl_sync(0xffffffffu, n, 0);
-    ncf = __shfl_sync(0xffffffffu, ncf, 0);
-    i0 = __shfl_sync(0xffffffffu, i0, 0);
-    D = __shfl_sync(0xffffffffu, D, 0);
-    // tile table, one tile per lane at a time: listed outputs by binary search, closed-form outputs by division
+    // (the serial forms ran on thread 0 only: hand its results to the CTA; the scan form left them in every thread)
+    if (!(c.scan_kb > 0 && c.mode == 0)) {
+        if (tid == 0) { sh_res[0] = n; sh_res[1] = ncf; sh_res[2] = i0; sh_res[3] = D; }
+        __syncthreads();
+        n = (int) sh_res[0]; ncf = sh_res[1]; i0 = sh_res[2]; D = sh_res[3];
+    } else {
+        __syncthreads();                       // thread 0's schedule entries (serial prologue / replay) are visible to the binary searches below
+    }
+    // tile table, one tile per thread at a time: listed outputs by binary search, closed-form outputs by division
     // (entry 1 is written even for a pass without new samples: block 0 of the front-end kernel always reads entries 0 and 1)
-    for (int t = lane; t <= (ntiles > 1 ? ntiles : 1); t += 32) {
+    for (int t = tid; t <= (ntiles > 1 ? ntiles : 1); t += blockDim.x) {
         const int T = t * FE_TILE;
         int lo = 0, hi = n;
         const int bias = c.mode ? 1 : 0;

@@ -74,6 +74,14 @@ struct InterpParams {
 };
 
 __device__ __forceinline__ int ip_hist(int l) { return l == 0 ? 32 : (l == 1 ? 16 : 8); }
+// level l: [2][len_l] ints, len_l = hist_l + (TN << l) + 4 (window overrun of the last group), a multiple of 4; levels are laid
+// out back to back, so the offsets are closed forms (no per-thread table in local memory)
+__device__ __forceinline__ int ip_len(int l, int TN) { return ip_hist(l) + (TN << l) + 4; }
+__device__ __forceinline__ int ip_off(int l, int TN)
+{
+    const int hs = l == 0 ? 0 : (l == 1 ? 32 : 32 + 8 * l);        // hist_0 + ... + hist_{l-1}
+    return 2 * (hs + 4 * l + TN * ((1 << l) - 1));
+}
 
 template<int H, bool LAST>
 __device__ __forceinline__ void ip_stage(const InterpParams& p, int* cur, int cur_len, int* nxt, int nxt_len, int nxt_hist,
@@ -157,13 +165,6 @@ __global__ void __launch_bounds__(IP_THREADS) interps_cascade_kernel(const Inter
     extern __shared__ __align__(16) int ip_smem[];
     const int tid = threadIdx.x;
     const int L = p.L, TN = 4096 >> L;
-    // level l: [2][len_l], len_l = hist_l + (TN << l) + 4 (window overrun of the last group), a multiple of 4
-    int off[IP_LEVELS], len[IP_LEVELS];
-    {
-        int o = 0;
-#pragma unroll
-        for (int l = 0; l < IP_LEVELS; ++l) { len[l] = ip_hist(l) + (TN << l) + 4; off[l] = o; if (l < L) o += 2 * len[l]; }
-    }
     const int t_begin = blockIdx.x * p.tiles_per_cta;
     int t_end = t_begin + p.tiles_per_cta;
     if (t_end > p.tiles) t_end = p.tiles;
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(IP_THREADS) interps_cascade_kernel(const Inter
     // histories: the handle's state for the stream's first tile, zeros (+ one warm-up tile) elsewhere
     for (int e = tid; e < IP_LEVELS * 2 * 32; e += IP_THREADS) {
         const int l = e >> 6, c = (e >> 5) & 1, q = e & 31;
-        if (l < L && q < ip_hist(l)) ip_smem[off[l] + c * len[l] + q] = (t_begin == 0) ? p.st_in[e] : 0;
+        if (l < L && q < ip_hist(l)) ip_smem[ip_off(l, TN) + c * ip_len(l, TN) + q] = (t_begin == 0) ? p.st_in[e] : 0;
     }
     __syncthreads();
     for (int t = (t_begin == 0 ? 0 : t_begin - 1); t < t_end; ++t) {
@@ -182,34 +183,35 @@ __global__ void __launch_bounds__(IP_THREADS) interps_cascade_kernel(const Inter
         // level 0: sample << pre
         for (int i = tid; i < TN; i += IP_THREADS) {
             const uint32_t wd = (i < nv) ? __ldg(p.in + i0 + i) : 0u;
-            ip_smem[off[0] + 32 + i] = (int) (short) (wd & 0xffffu) << p.pre;
-            ip_smem[off[0] + len[0] + 32 + i] = ((int) wd >> 16) << p.pre;
+            ip_smem[32 + i] = (int) (short) (wd & 0xffffu) << p.pre;
+            ip_smem[ip_len(0, TN) + 32 + i] = ((int) wd >> 16) << p.pre;
         }
         __syncthreads();
         for (int l = 0; l < L; ++l) {
-            int* cur = ip_smem + off[l];
+            int* cur = ip_smem + ip_off(l, TN);
+            const int cl = ip_len(l, TN);
             const int n_new = nv << l;
             const bool last = (l == L - 1);
-            int* nxt = last ? nullptr : ip_smem + off[l + 1];
-            const int nl = last ? 0 : len[l + 1], nh = last ? 0 : ip_hist(l + 1);
+            int* nxt = last ? nullptr : ip_smem + ip_off(l + 1, TN);
+            const int nl = last ? 0 : ip_len(l + 1, TN), nh = last ? 0 : ip_hist(l + 1);
             const long long os0 = i0 << L;                          // first output sample of the tile
-            if (l == 0) { if (last) ip_stage<32, true>(p, cur, len[l], nxt, nl, nh, n_new, os0, store); else ip_stage<32, false>(p, cur, len[l], nxt, nl, nh, n_new, os0, store); }
-            else if (l == 1) { if (last) ip_stage<16, true>(p, cur, len[l], nxt, nl, nh, n_new, os0, store); else ip_stage<16, false>(p, cur, len[l], nxt, nl, nh, n_new, os0, store); }
-            else { if (last) ip_stage<8, true>(p, cur, len[l], nxt, nl, nh, n_new, os0, store); else ip_stage<8, false>(p, cur, len[l], nxt, nl, nh, n_new, os0, store); }
+            if (l == 0) { if (last) ip_stage<32, true>(p, cur, cl, nxt, nl, nh, n_new, os0, store); else ip_stage<32, false>(p, cur, cl, nxt, nl, nh, n_new, os0, store); }
+            else if (l == 1) { if (last) ip_stage<16, true>(p, cur, cl, nxt, nl, nh, n_new, os0, store); else ip_stage<16, false>(p, cur, cl, nxt, nl, nh, n_new, os0, store); }
+            else { if (last) ip_stage<8, true>(p, cur, cl, nxt, nl, nh, n_new, os0, store); else ip_stage<8, false>(p, cur, cl, nxt, nl, nh, n_new, os0, store); }
             __syncthreads();
         }
         // slide: the newest hist_l samples of every level become the next tile's history (read, barrier, write: they may overlap)
         int keep = 0, kdst = -1;
         if (tid < IP_LEVELS * 2 * 32) {
             const int l = tid >> 6, c = (tid >> 5) & 1, q = tid & 31;
-            if (l < L && q < ip_hist(l)) { kdst = off[l] + c * len[l] + q; keep = ip_smem[kdst + (nv << l)]; }
+            if (l < L && q < ip_hist(l)) { kdst = ip_off(l, TN) + c * ip_len(l, TN) + q; keep = ip_smem[kdst + (nv << l)]; }
         }
         int keep2 = 0, kdst2 = -1;                                  // 384 entries, 256 threads: a second round
         {
             const int e = tid + IP_THREADS;
             if (e < IP_LEVELS * 2 * 32) {
                 const int l = e >> 6, c = (e >> 5) & 1, q = e & 31;
-                if (l < L && q < ip_hist(l)) { kdst2 = off[l] + c * len[l] + q; keep2 = ip_smem[kdst2 + (nv << l)]; }
+                if (l < L && q < ip_hist(l)) { kdst2 = ip_off(l, TN) + c * ip_len(l, TN) + q; keep2 = ip_smem[kdst2 + (nv << l)]; }
             }
         }
         __syncthreads();
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(IP_THREADS) interps_cascade_kernel(const Inter
         // the stream's last tile: the histories are the state the next call starts from; stages this call did not run keep theirs
         for (int e = tid; e < IP_LEVELS * 2 * 32; e += IP_THREADS) {
             const int l = e >> 6, c = (e >> 5) & 1, q = e & 31;
-            p.st_out[e] = (l < L && q < ip_hist(l)) ? ip_smem[off[l] + c * len[l] + q] : p.st_in[e];
+            p.st_out[e] = (l < L && q < ip_hist(l)) ? ip_smem[ip_off(l, TN) + c * ip_len(l, TN) + q] : p.st_in[e];
         }
     }
 }
