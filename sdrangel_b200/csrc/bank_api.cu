@@ -637,13 +637,6 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
         ++b->tree_launches;
     }
     if (fused) {
-        // A heavy schedule kernel (channels on the scan path: one 256-thread, 128-register CTA each) running beside the first
-        // pyramid launch takes half an SM's registers wherever one of its CTAs lands, i.e. one of that SM's two pyramid CTA
-        // slots; the pyramid's ranges are a static partition, so a CTA without a slot would run after the others and nearly
-        // double the launch.  That launch therefore gets as many CTAs fewer as the schedule kernel has (all resident at once).
-        int displaced = 0;
-        if (run_sched) for (int ci : b->fe_index) if (b->chans[ci].scan_kb > 0) ++displaced;
-        if (displaced > b->sm_count) displaced = b->sm_count;
         for (const auto& fl : b->flaunch) {
             if (fl.n_groups == 0) continue;
             FusedParams q;
@@ -666,8 +659,6 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
             const long long tot = (long long) q.n_groups * q.tpr;
             // persistent CTAs over contiguous (group, tile) ranges; a range that starts inside a stream pays one warm-up tile
             long long ctas = (long long) b->sm_count * ((fl.smem <= FZ_SMEM_LIMIT) ? FZ_CTAS_PER_SM : 1);
-            if (ctas > displaced + b->sm_count / 2) ctas -= displaced;
-            displaced = 0;                                        // later launches start after the schedule kernel has drained
             if (ctas > (tot + 3) / 4) ctas = (tot + 3) / 4;
             if (ctas < 1) ctas = 1;
             if ((rc = B200_CUDA_CHECK(cudaFuncSetAttribute((const void*) hb48_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fl.smem)))) return rc;

@@ -29,6 +29,7 @@ struct DemodParams {
     const float* st_in; float* st_out;
     float scaling;
     int kind;
+    int vec;                   // strides and base pointers allow 128-bit accesses
 };
 
 // phasediscri.h:162-194
@@ -55,6 +56,86 @@ __device__ __forceinline__ float dm_atan2_approx2(float y, float x)
     return at;
 }
 
+// A thread owns 4 consecutive samples: the look-back values (previous sample's argument for kind 1) are computed once per
+// thread instead of once per sample, loads and stores are 128-bit when the strides allow.
+template<int KIND>
+__device__ __forceinline__ void demod_run4(const DemodParams& p, const float2* __restrict__ x, long long n, const float* si, float* so, int c)
+{
+    const double PI = 3.14159265358979323846;
+    const float2 m1s = make_float2(si[0], si[1]), m2s = make_float2(si[2], si[3]);
+    const float prev_s = si[4];
+    const bool vec = p.vec != 0;
+    for (long long i0 = 4 * ((long long) blockIdx.x * blockDim.x + threadIdx.x); i0 < n; i0 += 4ll * gridDim.x * blockDim.x) {
+        float2 s[6];                               // s[k] = x[i0 - 2 + k]
+        s[0] = (i0 >= 2) ? x[i0 - 2] : m2s;        // (i0 is a multiple of 4: i0 - 2 < 0 only for i0 == 0)
+        s[1] = (i0 >= 1) ? x[i0 - 1] : m1s;
+        if (i0 == 0) s[0] = m2s;
+        if (vec && i0 + 4 <= n) {
+            const float4 a = *reinterpret_cast<const float4*>(x + i0), b = *reinterpret_cast<const float4*>(x + i0 + 2);
+            s[2] = make_float2(a.x, a.y); s[3] = make_float2(a.z, a.w); s[4] = make_float2(b.x, b.y); s[5] = make_float2(b.z, b.w);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) s[2 + r] = (i0 + r < n) ? x[i0 + r] : make_float2(0.0f, 0.0f);
+        }
+        float o[4], a0[4], a1[4];
+        float prev = 0.0f, arg = 0.0f;
+        if (KIND == 1) prev = (i0 >= 1) ? dm_atan2_approx2(s[1].y, s[1].x) : prev_s;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float2 v = s[2 + r], m1 = s[1 + r], m2 = s[r];
+            a0[r] = 0.0f; a1[r] = 0.0f;
+            if (KIND == 0) {
+                // Complex d(std::conj(m_m1Sample) * sample); atan2(d.imag(), d.real()) / M_PI * m_fmScaling     (phasediscri.h:48-53)
+                const float dr = __fadd_rn(__fmul_rn(m1.x, v.x), __fmul_rn(m1.y, v.y));
+                const float di = __fsub_rn(__fmul_rn(m1.x, v.y), __fmul_rn(m1.y, v.x));
+                o[r] = (float) __dmul_rn(__ddiv_rn((double) atan2f(di, dr), PI), (double) p.scaling);
+            } else if (KIND == 1) {
+                // phaseDiscriminatorDelta (phasediscri.h:59-77)
+                a0[r] = __fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y));
+                arg = dm_atan2_approx2(v.y, v.x);
+                float dev = (float) __ddiv_rn((double) __fsub_rn(arg, prev), PI);
+                if (dev < -1.0f) dev = __fadd_rn(dev, 2.0f);
+                else if (dev > 1.0f) dev = __fsub_rn(dev, 2.0f);
+                a1[r] = dev;
+                o[r] = __fmul_rn(dev, p.scaling);
+                if (i0 + r == n - 1) so[4] = arg;
+                prev = arg;
+            } else if (KIND == 2) {
+                // phaseDiscriminator2 (phasediscri.h:84-96)
+                const float ip = __fsub_rn(v.x, m2.x), qp = __fsub_rn(v.y, m2.y);
+                o[r] = __fmul_rn(__fsub_rn(__fmul_rn(m1.x, qp), __fmul_rn(m1.y, ip)), p.scaling);
+            } else {
+                // AMDemod::processOneSample (amdemod.cpp:154-156,241)
+                const float re = __fdiv_rn(v.x, 32768.0f), im = __fdiv_rn(v.y, 32768.0f);
+                a0[r] = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));
+                o[r] = __fsqrt_rn(a0[r]);
+            }
+            if (i0 + r == n - 1) {
+                // the object's members after the block: kinds 0 and 1 leave m_m2Sample alone, kind 1 also m_m1Sample
+                const bool upd1 = (KIND == 0 || KIND == 2);
+                so[0] = upd1 ? v.x : m1s.x; so[1] = upd1 ? v.y : m1s.y;
+                const float2 m2n = (KIND == 2) ? m1 : m2s;
+                so[2] = m2n.x; so[3] = m2n.y;
+                if (KIND != 1) so[4] = prev_s;
+                so[5] = 0.0f; so[6] = 0.0f; so[7] = 0.0f;
+            }
+        }
+        const long long ob = (long long) c * p.out_stride + i0;
+        if (vec && i0 + 4 <= n) {
+            *reinterpret_cast<float4*>(p.out + ob) = make_float4(o[0], o[1], o[2], o[3]);
+            if (p.aux0) *reinterpret_cast<float4*>(p.aux0 + ob) = make_float4(a0[0], a0[1], a0[2], a0[3]);
+            if (p.aux1) *reinterpret_cast<float4*>(p.aux1 + ob) = make_float4(a1[0], a1[1], a1[2], a1[3]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) if (i0 + r < n) {
+                p.out[ob + r] = o[r];
+                if (p.aux0) p.aux0[ob + r] = a0[r];
+                if (p.aux1) p.aux1[ob + r] = a1[r];
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) demod_kernel(const DemodParams p)
 {
     const int c = blockIdx.y;
@@ -62,57 +143,14 @@ __global__ void __launch_bounds__(256) demod_kernel(const DemodParams p)
     const float2* __restrict__ x = p.pool + (long long) c * p.stride;
     const float* si = p.st_in + c * DM_STATE;
     float* so = p.st_out + c * DM_STATE;
-    const double PI = 3.14159265358979323846;
     if (n <= 0) {
         if (blockIdx.x == 0 && threadIdx.x < DM_STATE) so[threadIdx.x] = si[threadIdx.x];
         return;
     }
-    const float2 m1s = make_float2(si[0], si[1]), m2s = make_float2(si[2], si[3]);
-    const float prev_s = si[4];
-    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) {
-        const float2 s = x[i];
-        const float2 m1 = (i >= 1) ? x[i - 1] : m1s;
-        float o = 0.0f, a0 = 0.0f, a1 = 0.0f;
-        float arg = 0.0f;
-        if (p.kind == 0) {
-            // Complex d(std::conj(m_m1Sample) * sample); atan2(d.imag(), d.real()) / M_PI * m_fmScaling     (phasediscri.h:48-53)
-            const float dr = __fadd_rn(__fmul_rn(m1.x, s.x), __fmul_rn(m1.y, s.y));
-            const float di = __fsub_rn(__fmul_rn(m1.x, s.y), __fmul_rn(m1.y, s.x));
-            o = (float) __dmul_rn(__ddiv_rn((double) atan2f(di, dr), PI), (double) p.scaling);
-        } else if (p.kind == 1) {
-            // phaseDiscriminatorDelta (phasediscri.h:59-77)
-            a0 = __fadd_rn(__fmul_rn(s.x, s.x), __fmul_rn(s.y, s.y));
-            arg = dm_atan2_approx2(s.y, s.x);
-            const float prev = (i >= 1) ? dm_atan2_approx2(m1.y, m1.x) : prev_s;
-            float dev = (float) __ddiv_rn((double) __fsub_rn(arg, prev), PI);
-            if (dev < -1.0f) dev = __fadd_rn(dev, 2.0f);
-            else if (dev > 1.0f) dev = __fsub_rn(dev, 2.0f);
-            a1 = dev;
-            o = __fmul_rn(dev, p.scaling);
-        } else if (p.kind == 2) {
-            // phaseDiscriminator2 (phasediscri.h:84-96)
-            const float2 m2 = (i >= 2) ? x[i - 2] : ((i == 1) ? m1s : m2s);
-            const float ip = __fsub_rn(s.x, m2.x), qp = __fsub_rn(s.y, m2.y);
-            o = __fmul_rn(__fsub_rn(__fmul_rn(m1.x, qp), __fmul_rn(m1.y, ip)), p.scaling);
-        } else {
-            // AMDemod::processOneSample (amdemod.cpp:154-156,241)
-            const float re = __fdiv_rn(s.x, 32768.0f), im = __fdiv_rn(s.y, 32768.0f);
-            a0 = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));
-            o = __fsqrt_rn(a0);
-        }
-        p.out[(long long) c * p.out_stride + i] = o;
-        if (p.aux0) p.aux0[(long long) c * p.out_stride + i] = a0;
-        if (p.aux1) p.aux1[(long long) c * p.out_stride + i] = a1;
-        if (i == n - 1) {
-            // the object's members after the block: kinds 0 and 1 leave m_m2Sample alone, kind 1 also m_m1Sample
-            const bool upd1 = (p.kind == 0 || p.kind == 2);
-            so[0] = upd1 ? s.x : m1s.x; so[1] = upd1 ? s.y : m1s.y;
-            const float2 m2n = (p.kind == 2) ? m1 : m2s;
-            so[2] = m2n.x; so[3] = m2n.y;
-            so[4] = (p.kind == 1) ? arg : prev_s;
-            so[5] = 0.0f; so[6] = 0.0f; so[7] = 0.0f;
-        }
-    }
+    if (p.kind == 0) demod_run4<0>(p, x, n, si, so, c);
+    else if (p.kind == 1) demod_run4<1>(p, x, n, si, so, c);
+    else if (p.kind == 2) demod_run4<2>(p, x, n, si, so, c);
+    else demod_run4<3>(p, x, n, si, so, c);
 }
 
 } // namespace
@@ -196,6 +234,8 @@ int b200dsp_demod_run_pool_dev(b200dsp_demod_t* h, const void* d_pool_c64, int64
     p.out = d_out; p.out_stride = out_stride; p.aux0 = d_aux0; p.aux1 = d_aux1;
     p.st_in = h->d_state[h->cur]; p.st_out = h->d_state[h->cur ^ 1];
     p.scaling = h->scaling; p.kind = h->kind;
+    p.vec = ((stride_samples & 1) == 0 && (out_stride & 3) == 0 && ((uintptr_t) d_pool_c64 & 15) == 0 && ((uintptr_t) d_out & 15) == 0 &&
+             ((uintptr_t) d_aux0 & 15) == 0 && ((uintptr_t) d_aux1 & 15) == 0) ? 1 : 0;
     long long gx = (stride_samples + 1023) / 1024;
     if (gx < 1) gx = 1;
     const long long want = (long long) b200_sm_count_of(h->device) * 8 / n_channels + 1;       // enough CTAs to fill the chip, no more

@@ -113,9 +113,11 @@ def test_demod_pooled_bank_layout_vs_oracle(gpu_lib, port):
     pool = torch.zeros((nc, stride, 2), dtype=torch.float32, device="cuda")
     counts = torch.zeros(nc, dtype=torch.int64, device="cuda")
     out = torch.zeros((3, nc, stride), dtype=torch.float32, device="cuda")
-    st = torch.cuda.current_stream().cuda_stream
+    stream = torch.cuda.Stream()              # an explicit stream: a NULL stream argument would mean "each handle's own stream"
+    st = stream.cuda_stream
     for part in (x[:250_001], x[250_001:]):
         dx = torch.from_numpy(part).cuda()
+        torch.cuda.synchronize()
         bank.feed_dev(dx.data_ptr(), part.shape[0], stream=st)
         bank.gather_dev(capi.STAGE_FRONTEND, pool.data_ptr(), stride, counts.data_ptr(), stream=st)
         dm.run_pool_dev(pool.data_ptr(), stride, counts.data_ptr(), out[0].data_ptr(), stride, out[1].data_ptr(), out[2].data_ptr(), stream=st)

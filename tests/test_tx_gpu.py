@@ -91,11 +91,14 @@ def test_device_forms_and_bad_arguments(gpu_lib, port):
     n = 30_000
     x = rs.randint(-32768, 32768, size=(n, 2)).astype(np.int16)
     dx = torch.from_numpy(x).cuda()
+    stream = torch.cuda.Stream()              # an explicit stream: a NULL stream argument would mean "the handle's own stream"
+    sp = stream.cuda_stream
     for bits, log2 in ((16, 3), (8, 6), (12, 5)):
         g = Interpolators(bits)
         dt = torch.int8 if bits == 8 else torch.int16
         dbuf = torch.full((n * (2 << log2),), 21, dtype=dt, device="cuda")
-        used = g.run_dev(log2, dx.data_ptr(), dbuf.data_ptr(), dbuf.numel(), stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()              # the fill above ran on torch's stream
+        used = g.run_dev(log2, dx.data_ptr(), dbuf.data_ptr(), dbuf.numel(), stream=sp)
         torch.cuda.synchronize()
         want, nw = port.PortInterpolators(bits).run(log2, x, None, fill=21)
         assert used == nw and np.array_equal(dbuf.cpu().numpy(), want), (bits, log2)
@@ -105,7 +108,8 @@ def test_device_forms_and_bad_arguments(gpu_lib, port):
     n_out = 100_001
     need = u.source_count(n_out)
     dout = torch.zeros((n_out, 2), dtype=torch.int16, device="cuda")
-    u.pull_dev(dx.data_ptr(), need, dout.data_ptr(), n_out, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    u.pull_dev(dx.data_ptr(), need, dout.data_ptr(), n_out, stream=sp)
     torch.cuda.synchronize()
     want, used = o.pull(x, n_out)
     assert used == need and np.array_equal(dout.cpu().numpy(), want)
