@@ -343,6 +343,23 @@ int b200dsp_demod_run(b200dsp_demod_t* h, const float* in_c64, int64_t n_samples
 int b200dsp_demod_run_pool_dev(b200dsp_demod_t* h, const void* d_pool_c64, int64_t stride_samples, const int64_t* d_counts, int n_channels,
                                float* d_out, int64_t out_stride, float* d_aux0, float* d_aux1, void* cuda_stream);
 
+/* K11 == fftfilt (sdrbase/dsp/fftfilt.cpp:49-360, Fldigi's overlap-add FFT filter over g_fft): the SSB / DSB demodulators' channel
+ *    filter, called per Interpolator::decimate output (plugins/channelrx/demodssb/ssbdemod.cpp:91-92,165-175; amdemod.cpp:199-207).
+ *    kind 0 == fftfilt(f1, f2, len) / create_filter (band-pass, frequencies relative to the sample rate), kind 1 == fftfilt(f2, len) /
+ *    create_dsb_filter.  len a power of two, 16..4096.  Block form of runFilt (op 0) / runSSB(usb, getDC) (op 1) / runDSB(getDC)
+ *    (op 2): every len/2 input samples (counted across calls, like inptr) yield len/2 outputs.  Agreement with the reference is
+ *    to float32 rounding (another FFT factorisation than g_fft). */
+typedef struct b200dsp_fftfilt b200dsp_fftfilt_t;
+int b200dsp_fftfilt_create(b200dsp_fftfilt_t** h, int kind, float f1, float f2, int len);
+int b200dsp_fftfilt_destroy(b200dsp_fftfilt_t* h);
+int b200dsp_fftfilt_set_filter(b200dsp_fftfilt_t* h, int kind, float f1, float f2);
+int b200dsp_fftfilt_filter(b200dsp_fftfilt_t* h, float* out_c64, int cap_samples);            /* the frequency response; returns len */
+int64_t b200dsp_fftfilt_out_count(b200dsp_fftfilt_t* h, int64_t n_samples);                      /* outputs the next run of n_samples yields */
+int b200dsp_fftfilt_run(b200dsp_fftfilt_t* h, int op, int usb, int get_dc, const float* in_c64, int64_t n_samples, float* out_c64,
+                        int64_t cap_samples, int64_t* n_out);
+int b200dsp_fftfilt_run_dev(b200dsp_fftfilt_t* h, int op, int usb, int get_dc, const void* d_in_c64, int64_t n_samples, void* d_out_c64,
+                            int64_t cap_samples, int64_t* n_out, void* cuda_stream);
+
 /* ---- .sdriq record files: FileRecord / the file-source plugin's on-disk format -----------------------
  * == FileRecord::writeHeader / readHeader / feed (sdrbase/dsp/filerecord.cpp:72-148): 24-byte header (qint32 sample rate,
  *    quint64 centre frequency, 8-byte time_t start, quint32 sample size), then raw Samples.  Pure host code, no device. */

@@ -17,6 +17,8 @@ from oracle import refbind  # noqa: E402
 SEED = 8844
 CUTS = [0, 1, 2, 3, 1000, 6000]
 SCALING = 0.37
+FF_CASES = [(0, 300 / 48000.0, 3000 / 48000.0, 1024), (1, 0.0, 6000 / 48000.0, 2048), (0, 0.2, 0.05, 64)]
+FF_OPS = [(1, True, False), (1, False, True), (0, True, True), (2, True, False), (2, True, True)]
 
 
 def demod_input(seed, n):
@@ -37,6 +39,17 @@ def main():
             outs = [d.run(x[a:b]) for a, b in zip(CUTS[:-1], CUTS[1:])]
             for j, name in enumerate(("out", "aux0", "aux1")):
                 arrays["demod/%s/%d/%s" % (tag, kind, name)] = np.concatenate([o[j] for o in outs])
+    # fftfilt (SSB / DSB channel filter): the SSB demodulator's filter (ssbFftLen 1024, 300..3000 Hz at 48 kS/s), the DSB one
+    # (2048), a short band-reject one; per-sample calls, two call splits, both sidebands, DC kept / rejected
+    meta["fftfilt"] = {"cases": FF_CASES, "ops": FF_OPS, "seed": SEED + 2, "n": 6000, "split": 777}
+    xf = demod_input(SEED + 2, 6000)
+    for strict in (False, True):
+        tag = "strict" if strict else "fast"
+        for ci, (kind, f1, f2, flen) in enumerate(FF_CASES):
+            arrays["fftfilt/%s/%d/filter" % (tag, ci)] = refbind.RefFftFilt(kind, f1, f2, flen, strict=strict).filter()
+            for oi, (op, usb, dc) in enumerate(FF_OPS):
+                f = refbind.RefFftFilt(kind, f1, f2, flen, strict=strict)
+                arrays["fftfilt/%s/%d/%d" % (tag, ci, oi)] = np.concatenate([f.run(op, xf[:777], usb, dc), f.run(op, xf[777:], usb, dc)])
     rs = np.random.RandomState(SEED + 1)
     iq = rs.randint(-32768, 32768, size=(1000, 2)).astype(np.int16)
     path = os.path.join(tempfile.mkdtemp(), "golden.sdriq")

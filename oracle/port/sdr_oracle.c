@@ -1232,3 +1232,104 @@ void orc_sdriq_header(int32_t rate, uint64_t center, int64_t ts, uint32_t sample
 {
     memcpy(out24, &rate, 4); memcpy(out24 + 4, &center, 8); memcpy(out24 + 12, &ts, 8); memcpy(out24 + 20, &sample_size, 4);
 }
+
+/* ---- fftfilt (sdrbase/dsp/fftfilt.cpp:49-360): Fldigi's overlap-add FFT filter.  The reference's g_fft<float> (gfft.h) is
+ * replaced by a plain radix-2 transform in double: agreement with the reference is to float32 rounding (~2e-7 of the block
+ * maximum), which is also what its own two builds differ by. ---- */
+typedef struct { int flen, flen2, inptr; double (*filter)[2]; double (*data)[2]; double (*ovl)[2]; } fftfilt_t;
+
+static void fft_d(double (*a)[2], int n, int inverse)
+{
+    for (int i = 1, j = 0; i < n; i++) {
+        int bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) { double t0 = a[i][0], t1 = a[i][1]; a[i][0] = a[j][0]; a[i][1] = a[j][1]; a[j][0] = t0; a[j][1] = t1; }
+    }
+    for (int len = 2; len <= n; len <<= 1) {
+        const double ang = (inverse ? 2.0 : -2.0) * 3.14159265358979323846 / len;
+        for (int i = 0; i < n; i += len)
+            for (int k = 0; k < len / 2; k++) {
+                const double wr = cos(ang * k), wi = sin(ang * k);
+                double* u = a[i + k]; double* v = a[i + k + len / 2];
+                const double vr = v[0] * wr - v[1] * wi, vi = v[0] * wi + v[1] * wr;
+                v[0] = u[0] - vr; v[1] = u[1] - vi; u[0] += vr; u[1] += vi;
+            }
+    }
+    if (inverse) for (int i = 0; i < n; i++) { a[i][0] /= n; a[i][1] /= n; }        /* InverseComplexFFT comes out scaled by 1/N */
+}
+
+static float ff_fsinc(float fc, int i, int len)      /* fftfilt.h:52-57 */
+{
+    int len2 = len / 2;
+    return (i == len2) ? (float) (2.0 * fc) : (float) (sin(2 * 3.14159265358979323846 * fc * (i - len2)) / (3.14159265358979323846 * (i - len2)));
+}
+static float ff_blackman(int i, int len)             /* fftfilt.h:59-64 */
+{
+    return (float) (0.42 - 0.50 * cos(2.0 * 3.14159265358979323846 * i / len) + 0.08 * cos(4.0 * 3.14159265358979323846 * i / len));
+}
+
+void orc_fftfilt_set(void* h, int kind, float f1, float f2)
+{
+    fftfilt_t* f = (fftfilt_t*) h;
+    memset(f->filter, 0, (size_t) f->flen * sizeof(*f->filter));
+    for (int i = 0; i < f->flen2; i++) {
+        float v = 0;
+        if (kind == 0) {                               /* create_filter, fftfilt.cpp:107-145 */
+            if (f2 != 0) v += ff_fsinc(f2, i, f->flen2);
+            if (f1 != 0) v -= ff_fsinc(f1, i, f->flen2);
+        } else v = ff_fsinc(f2, i, f->flen2);          /* create_dsb_filter, :148-166 */
+        f->filter[i][0] = v;
+    }
+    if (kind == 0 && f1 != 0 && f2 < f1) f->filter[f->flen2 / 2][0] = (float) (f->filter[f->flen2 / 2][0] + 1);
+    for (int i = 0; i < f->flen2; i++) f->filter[i][0] = (float) ((float) f->filter[i][0] * ff_blackman(i, f->flen2));
+    fft_d(f->filter, f->flen, 0);
+    float scale = 0;
+    for (int i = 0; i < f->flen2; i++) { float mag = (float) hypot(f->filter[i][0], f->filter[i][1]); if (mag > scale) scale = mag; }
+    if (scale != 0) for (int i = 0; i < f->flen; i++) { f->filter[i][0] /= scale; f->filter[i][1] /= scale; }
+}
+
+void* orc_fftfilt_create(int kind, float f1, float f2, int len)
+{
+    fftfilt_t* f = (fftfilt_t*) calloc(1, sizeof(fftfilt_t));
+    f->flen = len; f->flen2 = len >> 1;
+    f->filter = calloc((size_t) len, sizeof(*f->filter)); f->data = calloc((size_t) len, sizeof(*f->data)); f->ovl = calloc((size_t) len / 2, sizeof(*f->ovl));
+    orc_fftfilt_set(f, kind, f1, f2);
+    return f;
+}
+void orc_fftfilt_destroy(void* h) { fftfilt_t* f = (fftfilt_t*) h; if (f) { free(f->filter); free(f->data); free(f->ovl); free(f); } }
+void orc_fftfilt_filter(void* h, float* out_c64) { fftfilt_t* f = (fftfilt_t*) h; for (int i = 0; i < f->flen; i++) { out_c64[2 * i] = (float) f->filter[i][0]; out_c64[2 * i + 1] = (float) f->filter[i][1]; } }
+
+/* op 0 runFilt (:261-282), 1 runSSB(usb = flag & 1, getDC = flag & 2) (:285-325), 2 runDSB(getDC = flag & 2) (:328-357), per input sample */
+int orc_fftfilt_run(void* h, int op, int flag, const float* in, int n, float* out, int cap)
+{
+    fftfilt_t* f = (fftfilt_t*) h;
+    const int N = f->flen, N2 = f->flen2;
+    int m = 0;
+    for (int s = 0; s < n; s++) {
+        f->data[f->inptr][0] = in[2 * s]; f->data[f->inptr][1] = in[2 * s + 1];
+        if (++f->inptr < N2) continue;
+        f->inptr = 0;
+        fft_d(f->data, N, 0);
+        for (int i = 0; i < N; i++) {
+            double mr = f->filter[i][0], mi = f->filter[i][1];
+            if (op == 1) {
+                const int usb = flag & 1, dc = flag & 2;
+                if (i == 0) { if (!dc) { mr = 0; mi = 0; } }
+                else if (i == N2) { mr = 1; mi = 0; }                                  /* the loops run i = 1 .. flen2-1: bin flen2 is untouched */
+                else if ((i < N2) != (usb != 0)) { mr = 0; mi = 0; }
+            } else if (op == 2 && i == 0 && !(flag & 2)) { mr = 0; mi = 0; }
+            const double r = f->data[i][0] * mr - f->data[i][1] * mi, q = f->data[i][0] * mi + f->data[i][1] * mr;
+            f->data[i][0] = r; f->data[i][1] = q;
+        }
+        fft_d(f->data, N, 1);
+        if (m + N2 > cap) return -1;
+        for (int i = 0; i < N2; i++) {
+            out[2 * (m + i)] = (float) (f->ovl[i][0] + f->data[i][0]); out[2 * (m + i) + 1] = (float) (f->ovl[i][1] + f->data[i][1]);
+            f->ovl[i][0] = f->data[i + N2][0]; f->ovl[i][1] = f->data[i + N2][1];
+        }
+        m += N2;
+        memset(f->data, 0, (size_t) N * sizeof(*f->data));
+    }
+    return m;
+}

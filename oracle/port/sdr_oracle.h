@@ -93,6 +93,12 @@ void  orc_hb_interp_coeffs(int order, int32_t* out);
 void* orc_discri_create(float fm_scaling);
 void  orc_discri_destroy(void* h);
 void  orc_discri_run(void* h, int kind, const float* in_c64, int n, float* out, float* aux0, float* aux1);
+/* fftfilt: sdrbase/dsp/fftfilt.cpp:49-360 (kind 0 fftfilt(f1,f2,len), 1 fftfilt(f2,len); op 0 runFilt, 1 runSSB, 2 runDSB; flag bit 0 usb, bit 1 getDC) */
+void* orc_fftfilt_create(int kind, float f1, float f2, int len);
+void  orc_fftfilt_destroy(void* h);
+void  orc_fftfilt_set(void* h, int kind, float f1, float f2);
+void  orc_fftfilt_filter(void* h, float* out_c64);
+int   orc_fftfilt_run(void* h, int op, int flag, const float* in_c64, int n, float* out_c64, int cap);
 /* .sdriq header: FileRecord::writeHeader, sdrbase/dsp/filerecord.cpp:129-137 */
 void  orc_sdriq_header(int32_t rate, uint64_t center, int64_t ts, uint32_t sample_size, uint8_t* out24);
 

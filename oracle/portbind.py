@@ -63,6 +63,8 @@ def load():
         "orc_upchan_configure": (i32, [vp, i32, i32, i32, pi32, pi32, pi32, i32]),
         "orc_upchan_pull": (i32, [vp, pi16, i32, pi16, i32]), "orc_hb_interp_coeffs": (None, [i32, pi32]),
         "orc_discri_create": (vp, [f32]), "orc_discri_destroy": (None, [vp]), "orc_discri_run": (None, [vp, i32, pf32, i32, pf32, pf32, pf32]),
+        "orc_fftfilt_create": (vp, [i32, f32, f32, i32]), "orc_fftfilt_destroy": (None, [vp]), "orc_fftfilt_set": (None, [vp, i32, f32, f32]),
+        "orc_fftfilt_filter": (None, [vp, pf32]), "orc_fftfilt_run": (i32, [vp, i32, i32, pf32, i32, pf32, i32]),
         "orc_sdriq_header": (None, [C.c_int32, C.c_uint64, C.c_int64, C.c_uint32, vp]),
     }
     for name, (res, args) in sig.items():
@@ -316,3 +318,27 @@ def sdriq_header(rate, center, ts, sample_size=16):
     b = np.zeros(24, dtype=np.uint8)
     load().orc_sdriq_header(rate, center, ts, sample_size, b.ctypes.data)
     return b.tobytes()
+
+
+class PortFftFilt(_Handle):
+    """fftfilt restated (orc_fftfilt_*): kind 0 fftfilt(f1, f2, len), 1 fftfilt(f2, len); op 0 runFilt, 1 runSSB, 2 runDSB."""
+
+    def __init__(self, kind, f1, f2, length):
+        L = load()
+        super().__init__(L.orc_fftfilt_create(kind, f1, f2, length), L.orc_fftfilt_destroy)
+        self.flen = length
+
+    def set_filter(self, kind, f1, f2):
+        load().orc_fftfilt_set(self.h, kind, f1, f2)
+
+    def filter(self):
+        out = np.zeros(self.flen, dtype=np.complex64)
+        load().orc_fftfilt_filter(self.h, _p(out.view(np.float32), C.c_float))
+        return out
+
+    def run(self, op, x, usb=True, get_dc=True):
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        out = np.zeros(x.size + self.flen, dtype=np.complex64)
+        m = load().orc_fftfilt_run(self.h, op, (1 if usb else 0) | (2 if get_dc else 0), _p(x.view(np.float32), C.c_float), x.size, _p(out.view(np.float32), C.c_float), out.size)
+        assert m >= 0
+        return out[:m].copy()

@@ -242,3 +242,44 @@ int ref_filerecord_read_header(const char* path, int* sample_rate, unsigned long
 }
 
 } // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// SURVEY.md 8f-4, SSB back-end: fftfilt (sdrbase/dsp/fftfilt.cpp:49-360, Fldigi's overlap-add FFT filter over g_fft, gfft.h),
+// reference code compiled in place.  SSBDemod::feed calls runSSB / runDSB per Interpolator::decimate output
+// (plugins/channelrx/demodssb/ssbdemod.cpp:91-92,165-175).
+// ---------------------------------------------------------------------------------------------------------
+#define protected public
+#include "dsp/fftfilt.h"
+#undef protected
+
+extern "C" {
+
+// kind 0: fftfilt(f1, f2, len) (band-pass, SSB), 1: fftfilt(f2, len) (DSB low-pass)
+void* ref_fftfilt_create(int kind, float f1, float f2, int len)
+{
+    return kind == 0 ? new fftfilt(f1, f2, len) : new fftfilt(f2, len);
+}
+void ref_fftfilt_destroy(void* p) { delete (fftfilt*) p; }
+void ref_fftfilt_set(void* p, int kind, float f1, float f2)
+{
+    if (kind == 0) ((fftfilt*) p)->create_filter(f1, f2); else ((fftfilt*) p)->create_dsb_filter(f2);
+}
+void ref_fftfilt_filter(void* p, float* out_c64) { fftfilt* f = (fftfilt*) p; memcpy(out_c64, f->filter, (std::size_t) f->flen * sizeof(fftfilt::cmplx)); }
+
+// op 0: runFilt, 1: runSSB(usb = flag & 1, getDC = flag & 2), 2: runDSB(getDC = flag & 2); one call per input sample, outputs appended.
+int ref_fftfilt_run(void* p, int op, int flag, const float* in_c64, int n, float* out_c64, int cap)
+{
+    fftfilt* f = (fftfilt*) p;
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+        fftfilt::cmplx* o = 0;
+        const fftfilt::cmplx ci(in_c64[2 * i], in_c64[2 * i + 1]);
+        int k = op == 0 ? f->runFilt(ci, &o) : op == 1 ? f->runSSB(ci, &o, (flag & 1) != 0, (flag & 2) != 0) : f->runDSB(ci, &o, (flag & 2) != 0);
+        if (m + k > cap) return -1;
+        if (k > 0) memcpy(out_c64 + 2 * m, o, (std::size_t) k * sizeof(fftfilt::cmplx));
+        m += k;
+    }
+    return m;
+}
+
+} // extern "C"

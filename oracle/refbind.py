@@ -70,6 +70,8 @@ def load(strict=False):
         "ref_upchan_configure": (i32, [vp, i32, i32, i32, pi32, pi32, pi32, i32]),
         "ref_upchan_pull": (i32, [vp, pi16, i32, pi16, i32]),
         "ref_discri_create": (vp, [f32]), "ref_discri_destroy": (None, [vp]), "ref_discri_run": (None, [vp, i32, pf32, i32, pf32, pf32, pf32]),
+        "ref_fftfilt_create": (vp, [i32, f32, f32, i32]), "ref_fftfilt_destroy": (None, [vp]), "ref_fftfilt_set": (None, [vp, i32, f32, f32]),
+        "ref_fftfilt_filter": (None, [vp, pf32]), "ref_fftfilt_run": (i32, [vp, i32, i32, pf32, i32, pf32, i32]),
         "ref_filerecord_write": (i32, [C.c_char_p, i32, C.c_longlong, pi16, i32, i32]),
         "ref_filerecord_read_header": (i32, [C.c_char_p, pi32, C.POINTER(C.c_ulonglong), C.POINTER(C.c_longlong), C.POINTER(C.c_uint)]),
     }
@@ -355,3 +357,27 @@ def filerecord_read_header(path):
     r, c, t, s = C.c_int32(), C.c_ulonglong(), C.c_longlong(), C.c_uint()
     pos = load().ref_filerecord_read_header(path.encode(), C.byref(r), C.byref(c), C.byref(t), C.byref(s))
     return {"sample_rate": r.value, "center_frequency": c.value, "timestamp": t.value, "sample_size": s.value, "data_offset": pos}
+
+
+class RefFftFilt(_Handle):
+    """The reference's fftfilt (sdrbase/dsp/fftfilt.cpp over gfft.h), driven one sample per call like the demodulators do."""
+
+    def __init__(self, kind, f1, f2, length, strict=False):
+        L = load(strict)
+        super().__init__(L, L.ref_fftfilt_create(kind, f1, f2, length), L.ref_fftfilt_destroy)
+        self.flen = length
+
+    def set_filter(self, kind, f1, f2):
+        self.lib.ref_fftfilt_set(self.h, kind, f1, f2)
+
+    def filter(self):
+        out = np.zeros(self.flen, dtype=np.complex64)
+        self.lib.ref_fftfilt_filter(self.h, _p(out.view(np.float32), C.c_float))
+        return out
+
+    def run(self, op, x, usb=True, get_dc=True):
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        out = np.zeros(x.size + self.flen, dtype=np.complex64)
+        m = self.lib.ref_fftfilt_run(self.h, op, (1 if usb else 0) | (2 if get_dc else 0), _p(x.view(np.float32), C.c_float), x.size, _p(out.view(np.float32), C.c_float), out.size)
+        assert m >= 0
+        return out[:m].copy()

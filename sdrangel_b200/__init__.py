@@ -6,6 +6,6 @@ classes for the path (dsp.Decimators, ...).  There is no CPU fallback: importing
 library raises, and every compute call fails loudly without a CUDA device.
 """
 from . import capi  # noqa: F401
-from .dsp import Decimators, Decimators8, DecimatorsU, DecimatorsFI, DecimatorsFF, DecimatorsIF, DownChannelizerBank, ShardedBank, SpectrumVis, Interpolator, NCO, IQCorrections, Interpolators, UpChannelizer, Demod, SdriqFile  # noqa: F401
+from .dsp import Decimators, Decimators8, DecimatorsU, DecimatorsFI, DecimatorsFF, DecimatorsIF, DownChannelizerBank, ShardedBank, SpectrumVis, Interpolator, NCO, IQCorrections, Interpolators, UpChannelizer, Demod, SdriqFile, FftFilt  # noqa: F401
 
-__all__ = ["capi", "Decimators", "Decimators8", "DecimatorsU", "DecimatorsFI", "DecimatorsFF", "DecimatorsIF", "DownChannelizerBank", "ShardedBank", "SpectrumVis", "Interpolator", "NCO", "IQCorrections", "Interpolators", "UpChannelizer", "Demod", "SdriqFile"]
+__all__ = ["capi", "Decimators", "Decimators8", "DecimatorsU", "DecimatorsFI", "DecimatorsFF", "DecimatorsIF", "DownChannelizerBank", "ShardedBank", "SpectrumVis", "Interpolator", "NCO", "IQCorrections", "Interpolators", "UpChannelizer", "Demod", "SdriqFile", "FftFilt"]

@@ -126,6 +126,13 @@ SIGNATURES = {
     "b200dsp_demod_set_fm_scaling": (_i32, [_vp, _f32]),
     "b200dsp_demod_run": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "b200dsp_demod_run_pool_dev": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _i64, _vp, _vp, _vp]),
+    "b200dsp_fftfilt_create": (_i32, [_pvp, _i32, _f32, _f32, _i32]),
+    "b200dsp_fftfilt_destroy": (_i32, [_vp]),
+    "b200dsp_fftfilt_set_filter": (_i32, [_vp, _i32, _f32, _f32]),
+    "b200dsp_fftfilt_filter": (_i32, [_vp, _vp, _i32]),
+    "b200dsp_fftfilt_out_count": (_i64, [_vp, _i64]),
+    "b200dsp_fftfilt_run": (_i32, [_vp, _i32, _i32, _i32, _vp, _i64, _vp, _i64, _pi64]),
+    "b200dsp_fftfilt_run_dev": (_i32, [_vp, _i32, _i32, _i32, _vp, _i64, _vp, _i64, _pi64, _vp]),
     "b200dsp_sdriq_header_encode": (_i32, [_i32, C.c_uint64, _i64, C.c_uint32, _vp]),
     "b200dsp_sdriq_header_decode": (_i32, [_vp, _pi32, C.POINTER(C.c_uint64), _pi64, C.POINTER(C.c_uint32)]),
     "b200dsp_sdriq_open": (_i32, [_pvp, C.c_char_p, _pi32, C.POINTER(C.c_uint64), _pi64, C.POINTER(C.c_uint32), _pi64]),

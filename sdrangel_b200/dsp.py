@@ -739,3 +739,46 @@ class SdriqFile:
             self.close()
         except Exception:
             pass
+
+
+class FftFilt:
+    """fftfilt (sdrbase/dsp/fftfilt.cpp:49-360): kind 0 == fftfilt(f1, f2, len), 1 == fftfilt(f2, len); block forms of runFilt /
+    runSSB / runDSB (ops 0 / 1 / 2)."""
+
+    def __init__(self, kind, f1, f2, length, device=None):
+        if device is not None:
+            capi.init(device)
+        h = C.c_void_p()
+        capi.check(capi.lib().b200dsp_fftfilt_create(C.byref(h), kind, float(f1), float(f2), length))
+        self._h, self.flen = h, length
+
+    def close(self):
+        if getattr(self, "_h", None):
+            capi.lib().b200dsp_fftfilt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_filter(self, kind, f1, f2):
+        capi.check(capi.lib().b200dsp_fftfilt_set_filter(self._h, kind, float(f1), float(f2)))
+
+    def filter(self):
+        out = np.zeros(self.flen, dtype=np.complex64)
+        capi.lib().b200dsp_fftfilt_filter(self._h, out.ctypes.data, self.flen)
+        return out
+
+    def run(self, op, x, usb=True, get_dc=True):
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        out = np.zeros(x.size + self.flen, dtype=np.complex64)
+        n = C.c_int64(0)
+        capi.check(capi.lib().b200dsp_fftfilt_run(self._h, op, int(bool(usb)), int(bool(get_dc)), x.ctypes.data if x.size else None, x.size, out.ctypes.data, out.size, C.byref(n)))
+        return out[:n.value].copy()
+
+    def run_dev(self, op, d_in, n, d_out, cap, usb=True, get_dc=True, stream=None):
+        m = C.c_int64(0)
+        capi.check(capi.lib().b200dsp_fftfilt_run_dev(self._h, op, int(bool(usb)), int(bool(get_dc)), d_in, n, d_out, cap, C.byref(m), stream))
+        return m.value

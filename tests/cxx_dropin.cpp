@@ -20,6 +20,7 @@
 #include "sdrangel_b200/dsp/interpolators.h"
 #include "sdrangel_b200/dsp/phasediscri.h"
 #include "sdrangel_b200/dsp/filerecord.h"
+#include "sdrangel_b200/dsp/fftfilt.h"
 
 static uint64_t fnv(const void* p, size_t n_u16)
 {
@@ -279,6 +280,21 @@ int main()
             bool same = true;
             for (int k = 0; k < 64; k++) same = same && (o1[k] == o2[k]);
             printf("phasediscri %s\n", same ? "same" : "DIFFERENT");
+            // SSB channel filter: the reference's per-sample runSSB (ssbdemod.cpp:171) == the block form
+            {
+                fftfilt f1(300.0f / 48000.0f, 3000.0f / 48000.0f, 1024), f2(300.0f / 48000.0f, 3000.0f / 48000.0f, 1024);
+                std::vector<fftfilt::cmplx> xin(2000), oa, ob(2048);
+                for (int k = 0; k < 2000; k++) xin[k] = fftfilt::cmplx(1000.0f * std::cos(0.05f * k), 700.0f * std::sin(0.021f * k));
+                for (int k = 0; k < 2000; k++) {
+                    fftfilt::cmplx* sideband = 0;
+                    int n_out = f1.runSSB(xin[k], &sideband, true);
+                    for (int q = 0; q < n_out; q++) oa.push_back(sideband[q]);
+                }
+                int nb = f2.runSSB(&xin[0], 2000, &ob[0], 2048, true);
+                bool sameF = ((int) oa.size() == nb);
+                for (int k = 0; sameF && k < nb; k++) sameF = (oa[k] == ob[k]);
+                printf("fftfilt %s n=%d\n", sameF ? "same" : "DIFFERENT", nb);
+            }
             // FileRecord: record, read the header back the way the file-source plugin does
             const char* path = "/tmp/b200dsp_cxx_dropin.sdriq";
             FileRecord rec(path);

@@ -72,3 +72,4 @@ def test_sdrbench_decimateii_through_cxx_wrappers(gpu_lib, port, golden_meta, go
     assert lines["interpolators8_cen"] == "consumed=%d tail=77 out=%s" % (n, fnv1a64_u16(dev))
     assert lines["phasediscri"] == "same"
     assert lines["filerecord"] == "rate=2400000 fc=434000000 size=16 count=1000 bytes=4024"
+    assert lines["fftfilt"] == "same n=1536"

@@ -135,3 +135,64 @@ def test_demod_pooled_bank_layout_vs_oracle(gpu_lib, port):
             # end to end against the oracle chain: the front-end's 1e-5 budget, seen through atan2 (small signals excluded)
             we = port.PortDemod(1, 0.25).run(zc)[1]
             assert np.max(np.abs(o[1, c, :cn[c]] - we)) <= 1e-4 * max(1.0, float(np.max(we)))
+
+
+def _check_fftfilt(make, gdm, tol):
+    """Every golden fftfilt case through `make(kind, f1, f2, len)`: frequency response and outputs within tol of the block maximum
+    of both reference builds (their own difference is ~2e-7)."""
+    arrays, meta = gdm
+    m = meta["fftfilt"]
+    x = demod_input(m["seed"], m["n"])
+    for ci, (kind, f1, f2, flen) in enumerate(m["cases"]):
+        for tag in ("fast", "strict"):
+            want = arrays["fftfilt/%s/%d/filter" % (tag, ci)]
+            assert np.max(np.abs(make(kind, f1, f2, flen).filter() - want)) <= tol * np.max(np.abs(want)), (ci, tag)
+        for oi, (op, usb, dc) in enumerate(m["ops"]):
+            f = make(kind, f1, f2, flen)
+            got = np.concatenate([f.run(op, x[:m["split"]], usb, dc), f.run(op, x[m["split"]:], usb, dc)])
+            for tag in ("fast", "strict"):
+                want = arrays["fftfilt/%s/%d/%d" % (tag, ci, oi)]
+                assert got.shape == want.shape and want.size >= flen, (ci, oi)
+                assert np.max(np.abs(got - want)) <= tol * np.max(np.abs(want)), (ci, oi, tag)
+
+
+def test_port_fftfilt_equals_reference_goldens(port, gdm):
+    _check_fftfilt(port.PortFftFilt, gdm, 2e-6)
+
+
+@pytest.mark.gpu
+def test_fftfilt_equals_reference_goldens(gpu_lib, gdm):
+    from sdrangel_b200 import FftFilt
+    _check_fftfilt(FftFilt, gdm, 1e-5)
+
+
+@pytest.mark.gpu
+def test_fftfilt_long_run_many_ctas_and_filter_change(gpu_lib, port):
+    """Ranges of blocks on many CTAs (each range recomputes the block before it), ragged call splits (inptr carried),
+    create_filter on a live object, the device form; against the oracle."""
+    torch = pytest.importorskip("torch")
+    from sdrangel_b200 import FftFilt
+    rs = np.random.RandomState(21)
+    n = 300_000
+    x = ((rs.randn(n) + 1j * rs.randn(n)) * 3000).astype(np.complex64)
+    g, o = FftFilt(0, 300 / 48000.0, 3000 / 48000.0, 1024), port.PortFftFilt(0, 300 / 48000.0, 3000 / 48000.0, 1024)
+    pos = 0
+    for k, cnt in enumerate((1, 510, 1, 100_003, 0, 511, 199_000 - 26)):
+        if k == 4:
+            g.set_filter(0, 0.01, 0.1); o.set_filter(0, 0.01, 0.1)
+        a, b = g.run(1, x[pos:pos + cnt], usb=(k % 2 == 0), get_dc=False), o.run(1, x[pos:pos + cnt], usb=(k % 2 == 0), get_dc=False)
+        assert a.shape == b.shape, (k, cnt)
+        if b.size:
+            assert np.max(np.abs(a - b)) <= 1e-5 * np.max(np.abs(b)), (k, cnt)
+        pos += cnt
+    g2, o2 = FftFilt(1, 0.0, 0.125, 2048), port.PortFftFilt(1, 0.0, 0.125, 2048)
+    dx = torch.from_numpy(x.view(np.float32).reshape(-1, 2)).cuda()
+    dy = torch.zeros((n, 2), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    st = torch.cuda.Stream()
+    m = g2.run_dev(2, dx.data_ptr(), n, dy.data_ptr(), n, get_dc=True, stream=st.cuda_stream)
+    torch.cuda.synchronize()
+    want = o2.run(2, x, get_dc=True)
+    assert m == want.size
+    got = dy[:m].cpu().numpy().view(np.complex64).ravel()
+    assert np.max(np.abs(got - want)) <= 1e-5 * np.max(np.abs(want))
