@@ -73,14 +73,14 @@ struct InterpParams {
     int tiles, tiles_per_cta;
 };
 
-__device__ __forceinline__ int ip_hist(int l) { return l == 0 ? 32 : (l == 1 ? 16 : 8); }
+__host__ __device__ __forceinline__ constexpr int ip_hist(int l) { return l == 0 ? 32 : (l == 1 ? 16 : 8); }
 // level l: [2][len_l] ints, len_l = hist_l + (TN << l) + 4 (window overrun of the last group), a multiple of 4; levels are laid
 // out back to back, so the offsets are closed forms (no per-thread table in local memory)
-__device__ __forceinline__ int ip_len(int l, int TN) { return ip_hist(l) + (TN << l) + 4; }
-__device__ __forceinline__ int ip_off(int l, int TN)
+__host__ __device__ __forceinline__ constexpr int ip_len(int l, int TN) { return ip_hist(l) + (TN << l) + 4; }
+__host__ __device__ __forceinline__ constexpr int ip_off(int l, int TN)
 {
-    const int hs = l == 0 ? 0 : (l == 1 ? 32 : 32 + 8 * l);        // hist_0 + ... + hist_{l-1}
-    return 2 * (hs + 4 * l + TN * ((1 << l) - 1));
+    // hist_0 + ... + hist_{l-1} = 0, 32, 48, 56, ...
+    return 2 * ((l == 0 ? 0 : (l == 1 ? 32 : 32 + 8 * l)) + 4 * l + TN * ((1 << l) - 1));
 }
 
 template<int H, bool LAST>
@@ -160,11 +160,95 @@ __device__ __forceinline__ void ip_stage(const InterpParams& p, int* cur, int cu
     }
 }
 
-__global__ void __launch_bounds__(IP_THREADS) interps_cascade_kernel(const InterpParams p)
+// The last stage: a thread owns 4 consecutive inputs of BOTH components (two register windows), so the 8 output samples are
+// packed in registers (no exchange, no selects) and leave as one or two 128-bit stores.
+template<int H>
+__device__ __forceinline__ void ip_stage_last(const InterpParams& p, const int* cur, int cur_len, int n_new, long long out_sample0, bool store)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int groups = (n_new + 3) >> 2;
+    const int shm = p.post, shf = 11 + p.post;          // (acc >> 11) >> post == acc >> (11 + post): arithmetic shifts compose
+    for (int g = warp * 32 + lane; g < groups; g += IP_THREADS) {
+        const int n0 = 4 * g;
+        int wr[H + 4], wi[H + 4];
+        const int4* sr = reinterpret_cast<const int4*>(cur + n0);
+        const int4* si = reinterpret_cast<const int4*>(cur + cur_len + n0);
+#pragma unroll
+        for (int q = 0; q < (H + 4) / 4; ++q) {
+            const int4 a = sr[q], b = si[q];
+            wr[4 * q] = a.x; wr[4 * q + 1] = a.y; wr[4 * q + 2] = a.z; wr[4 * q + 3] = a.w;
+            wi[4 * q] = b.x; wi[4 * q + 1] = b.y; wi[4 * q + 2] = b.z; wi[4 * q + 3] = b.w;
+        }
+        int fr[4], fi[4];
+        hbint_group<H>(wr, fr);
+        hbint_group<H>(wi, fi);
+        if (!store) continue;
+        const long long s0 = out_sample0 + 2ll * n0;               // first of this thread's 8 output samples (index within the call)
+        int lim = 2 * n_new - 2 * n0;                               // output samples of this tile from s0 on
+        if (lim > 8) lim = 8;
+        if (p.quirk110) { const int q = 55 - (int) (s0 & 63); if (q < lim) lim = q; }      // samples 55..63 of every 64 are never written
+        if (p.out_i8) {
+            uint32_t h16[8];                                        // one output sample = (int8 re, int8 im)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                h16[2 * r] = __byte_perm((uint32_t) (wr[H / 2 + r] >> shm), (uint32_t) (wi[H / 2 + r] >> shm), 0x0040);
+                h16[2 * r + 1] = __byte_perm((uint32_t) (fr[r] >> shf), (uint32_t) (fi[r] >> shf), 0x0040);
+            }
+            uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) + s0;
+            if (lim == 8) {
+                *reinterpret_cast<uint4*>(dst) = make_uint4(__byte_perm(h16[0], h16[1], 0x5410), __byte_perm(h16[2], h16[3], 0x5410),
+                                                            __byte_perm(h16[4], h16[5], 0x5410), __byte_perm(h16[6], h16[7], 0x5410));
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) if (k < lim) dst[k] = (uint16_t) (h16[k] & 0xffffu);
+            }
+        } else {
+            uint32_t v[8];                                          // one output sample = (int16 re, int16 im)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                v[2 * r] = __byte_perm((uint32_t) (wr[H / 2 + r] >> shm), (uint32_t) (wi[H / 2 + r] >> shm), 0x5410);
+                v[2 * r + 1] = __byte_perm((uint32_t) (fr[r] >> shf), (uint32_t) (fi[r] >> shf), 0x5410);
+            }
+            uint32_t* dst = reinterpret_cast<uint32_t*>(p.out) + s0;
+            if (lim == 8) {
+                reinterpret_cast<uint4*>(dst)[0] = make_uint4(v[0], v[1], v[2], v[3]);
+                reinterpret_cast<uint4*>(dst)[1] = make_uint4(v[4], v[5], v[6], v[7]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) if (k < lim) dst[k] = v[k];
+            }
+        }
+    }
+}
+
+// the levels of one tile, unrolled at compile time: every offset and length is a constant of the instantiation
+template<int L, int l>
+struct IpLevels {
+    static __device__ __forceinline__ void run(const InterpParams& p, int* smem, int nv, long long os0, bool store)
+    {
+        constexpr int TN = 4096 >> L, H = ip_hist(l);
+        int* cur = smem + ip_off(l, TN);
+        const int n_new = nv << l;
+        if constexpr (l == L - 1) {
+            ip_stage_last<H>(p, cur, ip_len(l, TN), n_new, os0, store);
+            __syncthreads();
+        } else {
+            ip_stage<H, false>(p, cur, ip_len(l, TN), smem + ip_off(l + 1, TN), ip_len(l + 1, TN), ip_hist(l + 1), n_new, os0, store);
+            __syncthreads();
+            IpLevels<L, l + 1>::run(p, smem, nv, os0, store);
+        }
+    }
+};
+
+#ifndef IP_MINB
+#define IP_MINB 4
+#endif
+template<int L>
+__global__ void __launch_bounds__(IP_THREADS, IP_MINB) interps_cascade_kernel(const InterpParams p)
 {
     extern __shared__ __align__(16) int ip_smem[];
     const int tid = threadIdx.x;
-    const int L = p.L, TN = 4096 >> L;
+    constexpr int TN = 4096 >> L;
     const int t_begin = blockIdx.x * p.tiles_per_cta;
     int t_end = t_begin + p.tiles_per_cta;
     if (t_end > p.tiles) t_end = p.tiles;
@@ -187,19 +271,7 @@ __global__ void __launch_bounds__(IP_THREADS) interps_cascade_kernel(const Inter
             ip_smem[ip_len(0, TN) + 32 + i] = ((int) wd >> 16) << p.pre;
         }
         __syncthreads();
-        for (int l = 0; l < L; ++l) {
-            int* cur = ip_smem + ip_off(l, TN);
-            const int cl = ip_len(l, TN);
-            const int n_new = nv << l;
-            const bool last = (l == L - 1);
-            int* nxt = last ? nullptr : ip_smem + ip_off(l + 1, TN);
-            const int nl = last ? 0 : ip_len(l + 1, TN), nh = last ? 0 : ip_hist(l + 1);
-            const long long os0 = i0 << L;                          // first output sample of the tile
-            if (l == 0) { if (last) ip_stage<32, true>(p, cur, cl, nxt, nl, nh, n_new, os0, store); else ip_stage<32, false>(p, cur, cl, nxt, nl, nh, n_new, os0, store); }
-            else if (l == 1) { if (last) ip_stage<16, true>(p, cur, cl, nxt, nl, nh, n_new, os0, store); else ip_stage<16, false>(p, cur, cl, nxt, nl, nh, n_new, os0, store); }
-            else { if (last) ip_stage<8, true>(p, cur, cl, nxt, nl, nh, n_new, os0, store); else ip_stage<8, false>(p, cur, cl, nxt, nl, nh, n_new, os0, store); }
-            __syncthreads();
-        }
+        IpLevels<L, 0>::run(p, ip_smem, nv, i0 << L, store);
         // slide: the newest hist_l samples of every level become the next tile's history (read, barrier, write: they may overlap)
         int keep = 0, kdst = -1;
         if (tid < IP_LEVELS * 2 * 32) {
@@ -476,7 +548,14 @@ int b200dsp_interps_run_dev(b200dsp_interps_t* h, int log2_interp, const void* d
     ctas = (tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
     size_t smem = 0;
     for (int l = 0; l < log2_interp; ++l) smem += 2 * (size_t) ((l == 0 ? 32 : (l == 1 ? 16 : 8)) + (TN << l) + 4) * 4;
-    interps_cascade_kernel<<<(unsigned) ctas, IP_THREADS, smem, st>>>(p);
+    switch (log2_interp) {
+    case 1: interps_cascade_kernel<1><<<(unsigned) ctas, IP_THREADS, smem, st>>>(p); break;
+    case 2: interps_cascade_kernel<2><<<(unsigned) ctas, IP_THREADS, smem, st>>>(p); break;
+    case 3: interps_cascade_kernel<3><<<(unsigned) ctas, IP_THREADS, smem, st>>>(p); break;
+    case 4: interps_cascade_kernel<4><<<(unsigned) ctas, IP_THREADS, smem, st>>>(p); break;
+    case 5: interps_cascade_kernel<5><<<(unsigned) ctas, IP_THREADS, smem, st>>>(p); break;
+    default: interps_cascade_kernel<6><<<(unsigned) ctas, IP_THREADS, smem, st>>>(p); break;
+    }
     if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
     h->cur ^= 1;
     return 0;
