@@ -909,7 +909,7 @@ def _bank_e2e(c, args, fs, fcs, cutoff, n, x, sb):
     torch, capi, dist = c.torch, c.capi, c.dist
     K = 16
     nb_ = n // K
-    ksteps = 3
+    ksteps = 10 if sb is None else 5           # a step is ~5 ms of wall clock: enough of them to average out host scheduling noise
     if sb is None:
         bank = S.DownChannelizerBank(fs)
         bank.set_chunk(nb_)

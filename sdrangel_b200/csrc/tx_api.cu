@@ -34,16 +34,26 @@ template<> struct HbTaps<16> { static __host__ __device__ constexpr int h(int i)
 template<> struct HbTaps<32> { static __host__ __device__ constexpr int h(int i) { constexpr int t[16] = { -1, 2, -5, 8, -12, 17, -25, 35, -47, 64, -86, 117, -164, 244, -424, 1300 }; return t[i]; } };
 template<> struct HbTaps<48> { static __host__ __device__ constexpr int h(int i) { constexpr int t[24] = { -1, 3, -6, 11, -19, 31, -47, 70, -99, 139, -189, 254, -335, 436, -563, 722, -923, 1181, -1525, 2004, -2730, 3990, -6842, 20823 }; return t[i]; } };
 
+// Pipe placement: ptxas turns 2-input integer adds into IMAD.IADD and piles them onto the FMA-heavy pipe
+// next to the multiply-adds; a 3-input add with an opaque zero stays an IADD3 on the ALU pipe, so the pre-adds and the
+// multiply-adds of the FIR share the two 64-lane integer pipes evenly.
+__device__ __forceinline__ int tx_add3(int a, int b, int z)
+{
+    int r;
+    asm("{.reg .s32 t; add.s32 t, %1, %2; add.s32 %0, t, %3;}" : "=r"(r) : "r"(a), "r"(b), "r"(z));
+    return r;
+}
+
 // four consecutive FIR outputs from the register window w[q] = x[n0 - H + q], q in [0, H + 4):
 //   fir[r] = sum_i h[i] * ( w[H + r - i] + w[r + 1 + i] )          mid[r] = w[H / 2 + r]
 template<int H>
-__device__ __forceinline__ void hbint_group(const int (&w)[H + 4], int (&fir)[4])
+__device__ __forceinline__ void hbint_group(const int (&w)[H + 4], int (&fir)[4], int zero)
 {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         int acc = 0;
 #pragma unroll
-        for (int i = 0; i < H / 2; ++i) acc += HbTaps<H>::h(i) * (w[H + r - i] + w[r + 1 + i]);
+        for (int i = 0; i < H / 2; ++i) acc += HbTaps<H>::h(i) * tx_add3(w[H + r - i], w[r + 1 + i], zero);
         fir[r] = acc;
     }
 }
@@ -71,6 +81,7 @@ struct InterpParams {
     int out_i8;
     int quirk110;              // interpolate64_cen writes only scalars 0..109 of each block of 128 (interpolators.h, its last loop)
     int tiles, tiles_per_cta;
+    int opq_zero;              // 0, passed as data (tx_add3)
 };
 
 __host__ __device__ __forceinline__ constexpr int ip_hist(int l) { return l == 0 ? 32 : (l == 1 ? 16 : 8); }
@@ -100,7 +111,7 @@ __device__ __forceinline__ void ip_stage(const InterpParams& p, int* cur, int cu
 #pragma unroll
         for (int q = 0; q < (H + 4) / 4; ++q) { const int4 v = src[q]; w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w; }
         int fir[4];
-        hbint_group<H>(w, fir);
+        hbint_group<H>(w, fir, p.opq_zero);
         int y[8];
 #pragma unroll
         for (int r = 0; r < 4; ++r) { y[2 * r] = w[H / 2 + r]; y[2 * r + 1] = fir[r] >> 11; }
@@ -180,8 +191,8 @@ __device__ __forceinline__ void ip_stage_last(const InterpParams& p, const int* 
             wi[4 * q] = b.x; wi[4 * q + 1] = b.y; wi[4 * q + 2] = b.z; wi[4 * q + 3] = b.w;
         }
         int fr[4], fi[4];
-        hbint_group<H>(wr, fr);
-        hbint_group<H>(wi, fi);
+        hbint_group<H>(wr, fr, p.opq_zero);
+        hbint_group<H>(wi, fi, p.opq_zero);
         if (!store) continue;
         const long long s0 = out_sample0 + 2ll * n0;               // first of this thread's 8 output samples (index within the call)
         int lim = 2 * n_new - 2 * n0;                               // output samples of this tile from s0 on
@@ -334,6 +345,7 @@ struct UpParams {
     int ns;                    // calls in this block
     int n_new;                 // consumptions in this block = ((ks & 1) + ns) >> 1
     int mode;                  // 0 centre, 1 lower half, 2 upper half
+    int opq_zero;              // 0, passed as data (tx_add3)
 };
 
 __device__ __forceinline__ uint32_t up_u(const UpParams& p, int j)
@@ -372,7 +384,7 @@ __global__ void __launch_bounds__(UP_THREADS) upchan_stage_kernel(const UpParams
         for (int r = 0; r < 4; ++r) {
             int acc = 0;
 #pragma unroll
-            for (int i = 0; i < 24; ++i) acc += HbTaps<48>::h(i) * (w[47 + r - i] + w[r + i]);
+            for (int i = 0; i < 24; ++i) acc += HbTaps<48>::h(i) * (w[47 + r - i] + w[r + i]);      // (the 3-input-add form of K8 measured 5 % slower here)
             y[2 * r] = w[23 + r];
             y[2 * r + 1] = (int) (short) (acc >> 15);              // stored into a Sample: int16 wrap
         }
