@@ -147,6 +147,10 @@ int b200dsp_bank_feed_dev(b200dsp_bank_t* b, const void* d_iq, int64_t n_samples
 /* outputs produced by the last feed for one channel; stage selects int16 IQ (4 bytes/sample) or complex64 (8 bytes) */
 int b200dsp_bank_fetch(b200dsp_bank_t* b, int chan_id, int stage, void* out, int64_t cap_samples, int64_t* n_samples);
 int b200dsp_bank_fetch_dev(b200dsp_bank_t* b, int chan_id, int stage, const void** d_ptr, int64_t* n_samples);
+/* what Interpolator::decimate's float32 distance recurrence decided (interpolator.h:23-36, nfmdemod.cpp:155,315) in the
+ * channel's last internal pass: for every front-end output the index (within that pass) of the channel sample that emitted
+ * it and the polyphase phase.  For parity checks of the schedule itself; a feed no longer than the chunk is one pass. */
+int b200dsp_bank_fetch_schedule(b200dsp_bank_t* b, int chan_id, int32_t* idx, int32_t* phase, int64_t cap, int64_t* n);
 /* every channel's outputs of the last feed in one transfer (what DSPDeviceSourceEngine::work's loop over the channel sinks
  * hands out, dspdevicesourceengine.cpp:325-408): channel c's samples land at out + c * stride_samples (samples of 4 or 8
  * bytes by stage), counts[c] = its sample count (0 for a channel without that stage); waits for the stream (NULL: the

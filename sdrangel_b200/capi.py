@@ -55,6 +55,7 @@ SIGNATURES = {
     "b200dsp_bank_feed": (_i32, [_vp, _vp, _i64]),
     "b200dsp_bank_feed_dev": (_i32, [_vp, _vp, _i64, _vp]),
     "b200dsp_bank_fetch": (_i32, [_vp, _i32, _i32, _vp, _i64, _pi64]),
+    "b200dsp_bank_fetch_schedule": (_i32, [_vp, _i32, _vp, _vp, _i64, _pi64]),
     "b200dsp_bank_fetch_dev": (_i32, [_vp, _i32, _i32, _pvp, _pi64]),
     "b200dsp_bank_fetch_all": (_i32, [_vp, _i32, _vp, _i64, _vp, _vp]),
     "b200dsp_bank_gather_dev": (_i32, [_vp, _i32, _vp, _i64, _vp, _vp]),

@@ -1113,6 +1113,36 @@ int b200dsp_bank_fetch(b200dsp_bank_t* b, int chan_id, int stage, void* out, int
     return b200_fail(B200DSP_EINVAL, "bank_fetch: bad stage");
 }
 
+// The front-end schedule of the channel's LAST internal pass: for each output the index of the channel sample that emitted
+// it (within that pass) and the polyphase filter phase -- what Interpolator::decimate's distance recurrence decided.  Listed
+// outputs come from the schedule kernel's array, closed-form outputs (lattice ratios) are expanded here from the plan.
+int b200dsp_bank_fetch_schedule(b200dsp_bank_t* b, int chan_id, int32_t* idx, int32_t* phase, int64_t cap, int64_t* n)
+{
+    if (!b || chan_id < 0 || chan_id >= (int) b->chans.size()) return b200_fail(B200DSP_EINVAL, "bank_fetch_schedule: bad channel");
+    Channel& c = b->chans[chan_id];
+    if (!c.fe) return b200_fail(B200DSP_ESTATE, "bank_fetch_schedule: channel has no front-end");
+    int rc = B200_CUDA_CHECK(cudaSetDevice(b->device));
+    if (rc) return rc;
+    if ((rc = B200_CUDA_CHECK(cudaStreamSynchronize(b->stream)))) return rc;
+    if (n) *n = 0;
+    if (!b->built || !c.d_plan || !c.d_sched) return 0;
+    long long plan[4];
+    if ((rc = B200_CUDA_CHECK(cudaMemcpy(plan, c.d_plan, sizeof(plan), cudaMemcpyDeviceToHost)))) return rc;
+    const long long k0 = plan[0], i0 = plan[1], D0 = plan[2], ncf = plan[3], total = k0 + ncf;
+    if (n) *n = total;
+    if (total > cap) return b200_fail(B200DSP_EINVAL, "bank_fetch_schedule: buffer too small (%lld needed)", total);
+    if (total == 0 || !idx || !phase) return 0;
+    std::vector<int> raw((size_t) k0);
+    if (k0 > 0 && (rc = B200_CUDA_CHECK(cudaMemcpy(raw.data(), c.d_sched, (size_t) k0 * sizeof(int), cudaMemcpyDeviceToHost)))) return rc;
+    for (long long o = 0; o < k0; ++o) { idx[o] = (int32_t) ((unsigned) raw[(size_t) o] >> 8); phase[o] = raw[(size_t) o] & 0xff; }
+    for (long long o = k0; o < total; ++o) {
+        const long long E = D0 + (o - k0) * c.A;                  // units of 2^-23 inputs (frontend.cuh: closed-form region)
+        idx[o] = (int32_t) (i0 + (E >> 23) - 1);
+        phase[o] = (int32_t) ((E & 0x7fffffll) >> c.phshift);
+    }
+    return 0;
+}
+
 int b200dsp_bank_fetch_dev(b200dsp_bank_t* b, int chan_id, int stage, const void** d_ptr, int64_t* n)
 {
     if (!b || chan_id < 0 || chan_id >= (int) b->chans.size() || !d_ptr) return b200_fail(B200DSP_EINVAL, "bank_fetch_dev: bad argument");

@@ -264,6 +264,15 @@ class DownChannelizerBank:
         capi.check(capi.lib().b200dsp_bank_fetch(self._h, chan_id, stage, out.ctypes.data, out.shape[0], C.byref(n)))
         return out[:n.value]
 
+    def fetch_schedule(self, chan_id):
+        """(input index, phase) of every front-end output of the channel's last internal pass."""
+        n = C.c_int64(0)
+        capi.check(capi.lib().b200dsp_bank_fetch_schedule(self._h, chan_id, None, None, 1 << 62, C.byref(n)))
+        idx, ph = np.empty(n.value, dtype=np.int32), np.empty(n.value, dtype=np.int32)
+        if n.value:
+            capi.check(capi.lib().b200dsp_bank_fetch_schedule(self._h, chan_id, idx.ctypes.data, ph.ctypes.data, n.value, C.byref(n)))
+        return idx, ph
+
     def process(self, iq_ptr, n_samples, stage, out_ptr, stride):
         """== b200dsp_bank_process: host buffer in (pointer), every channel's outputs to out_ptr [channel][stride]; returns counts."""
         counts = np.zeros(max(self._n_channels, 1), dtype=np.int64)

@@ -676,3 +676,29 @@ def test_bank_shard_chain_cascade_vs_oracle(gpu_lib, port, golden_meta, lo, hi):
             assert np.array_equal(plain.fetch(i), want), (sz, i)
     fused.close()
     plain.close()
+
+
+@pytest.mark.gpu
+def test_frontend_schedule_indices_and_phases_equal_oracle(gpu_lib, port, golden_meta):
+    """SURVEY.md 8d's K4 gate checked directly: for every front-end output the index of the channel sample that emitted it and
+    the polyphase phase equal what the reference's float32 distance recurrence decides -- closed-form (1.25), exact parallel scan
+    (3.2552, 1.6276) and a ratio below 2^21 ulps -- over several feeds (the distance carries), incl. feeds without new samples."""
+    from sdrangel_b200 import DownChannelizerBank
+    cutoff = float(np.float32(np.float32(12500) / np.float32(2.2)))
+    rs = np.random.RandomState(31)
+    for fs, fc, outr in ((122_880_000, 61_381_250, 48000), (10_000_000, 1_234_567, 48000), (10_000_000, -3_000_000, 48000), (2_000_000, 100_000, 44100)):
+        b = DownChannelizerBank(fs)
+        cid, rate, ofs, path = b.add_channel(48000, fc)
+        b.set_frontend(cid, -ofs, cutoff, outr)
+        oc = port.PortDownChannelizer(); oc.configure(fs, 48000, fc)
+        fe = port.PortFrontEnd(-ofs, rate, outr, cutoff)
+        S = len(path)
+        # (every feed is one internal pass: an aligned feed of a whole number of 2^(S+1) blocks, then ragged ones below the chunk)
+        for n in (4 << S, 1, (2_000 << S) + 5, 0, 7, (5_001 << S)):
+            x = rs.randint(-8000, 8000, size=(n, 2)).astype(np.int16)
+            b.feed(x)
+            _, widx, wph = fe.feed(oc.feed(x), want_schedule=True)
+            gidx, gph = b.fetch_schedule(cid)
+            assert gidx.shape == widx.shape, (fs, fc, n)
+            assert np.array_equal(gidx, widx) and np.array_equal(gph, wph), (fs, fc, n)
+        b.close()
