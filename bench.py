@@ -891,12 +891,54 @@ def bench_bank(c, args, wl_name, wl, steps, warmup, want_e2e=True, want_parity=T
                       "broadcast_trials_ms_per_step": bcast_trials},
            "roofline": roofline, "dtype": "s32", "scaling": "strong"}
     if want_e2e:
-        res["e2e"] = _bank_e2e(c, args, fs, fcs, cutoff, n, x, sb)
+        with _NearGpu(c) as near:
+            res["e2e"] = _bank_e2e(c, args, fs, fcs, cutoff, n, x, sb)
+            res["e2e"]["host_cpus"] = ("GPU-local NUMA node: %d CPUs" % len(near.cpus)) if near.cpus else "no affinity change"
     if sb is not None:
         sb.close()
     else:
         bank.close()
     return res
+
+
+class _NearGpu:
+    """Host side of an end-to-end measurement on the CPUs of the GPU's own NUMA node (what a device plugin's thread would be
+    pinned to): pinned staging buffers are first touched there and the PCIe copies do not cross the socket interconnect.
+    B200_BENCH_NO_AFFINITY=1 disables it.  The CPU-baseline legs run outside, on every core."""
+
+    def __init__(self, c):
+        self.c, self.old, self.cpus = c, None, None
+
+    def __enter__(self):
+        if os.environ.get("B200_BENCH_NO_AFFINITY"):
+            return self
+        try:
+            pr = self.c.torch.cuda.get_device_properties(self.c.local)
+            bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            txt = open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read().strip()
+            cpus = set()
+            for part in txt.split(","):
+                if "-" in part:
+                    a, b = part.split("-")
+                    cpus.update(range(int(a), int(b) + 1))
+                elif part:
+                    cpus.add(int(part))
+            old = os.sched_getaffinity(0)
+            cpus &= old
+            if cpus and cpus != old:
+                os.sched_setaffinity(0, cpus)
+                self.old, self.cpus = old, cpus
+        except Exception:
+            pass
+        return self
+
+    def __exit__(self, *a):
+        if self.old is not None:
+            try:
+                os.sched_setaffinity(0, self.old)
+            except Exception:
+                pass
+        return False
 
 
 def _bank_e2e(c, args, fs, fcs, cutoff, n, x, sb):
