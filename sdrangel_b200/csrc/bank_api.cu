@@ -104,6 +104,7 @@ struct Channel {
     uint32_t* d_hist; float* d_taps; float2* d_fe_out; int* d_sched; int* d_tile; int* d_state; long long* d_plan; long long fe_cap;
     long long A; int lattice, phshift;
     int scan_kb; long long scan_A;       // non-lattice ratio: parameters of the parallel exact replay
+    int fe_lead;                         // the channel whose schedule this one shares (itself when it leads), see build()
 };
 
 const double PI_D = 3.14159265358979323846;
@@ -215,6 +216,7 @@ struct b200dsp_bank {
     int tcur;
     LeafChan* d_leaf; FrontendChan* d_fe; float* d_nco;
     std::vector<LeafChan> h_leaf; std::vector<FrontendChan> h_fe;
+    FrontendChan* d_fe_lead; std::vector<FrontendChan> h_fe_lead; std::vector<int> fe_leaders;    // the schedule kernel's table: one entry per distinct schedule
     int fe_parity;                               // current half of the front-ends' ping-pong carried state
     bool tables_dirty;                           // channel pointer tables must be re-uploaded (after a (re)allocation)
     std::vector<long long> out_count_depth;      // channel outputs per depth produced in the current feed
@@ -236,7 +238,8 @@ void free_device(b200dsp_bank* b)
     b->d_level.clear(); b->d_fam.clear(); b->stride.clear();
     if (b->d_leaf) cudaFree(b->d_leaf);
     if (b->d_fe) cudaFree(b->d_fe);
-    b->d_leaf = nullptr; b->d_fe = nullptr;
+    if (b->d_fe_lead) cudaFree(b->d_fe_lead);
+    b->d_leaf = nullptr; b->d_fe = nullptr; b->d_fe_lead = nullptr;
     if (b->d_pool) cudaFree(b->d_pool);
     if (b->d_gsrc) cudaFree(b->d_gsrc);
     if (b->d_gcnt) cudaFree(b->d_gcnt);
@@ -456,12 +459,14 @@ int build(b200dsp_bank* b)
     const size_t nc = b->chans.size();
     if (nc) {
         if ((rc = B200_CUDA_CHECK(cudaMalloc(&b->d_leaf, nc * sizeof(LeafChan)))) ||
-            (rc = B200_CUDA_CHECK(cudaMalloc(&b->d_fe, nc * sizeof(FrontendChan))))) return rc;
+            (rc = B200_CUDA_CHECK(cudaMalloc(&b->d_fe, nc * sizeof(FrontendChan)))) ||
+            (rc = B200_CUDA_CHECK(cudaMalloc(&b->d_fe_lead, nc * sizeof(FrontendChan))))) return rc;
     }
     b->h_leaf.resize(nc);
     b->tables_dirty = true;
     b->out_count_depth.assign(32, 0);
     b->fe_index.clear();
+    b->fe_leaders.clear();
     size_t max_taps = 0;
     for (size_t i = 0; i < nc; ++i) {
         Channel& c = b->chans[i];
@@ -481,7 +486,20 @@ int build(b200dsp_bank* b)
             Channel& c = b->chans[b->fe_index[k]];
             std::copy(c.taps.begin(), c.taps.end(), all.begin() + k * b->taps_pitch);
             c.d_taps = b->slab_taps + k * b->taps_pitch;
-            c.d_state = b->slab_state + 4 * k; c.d_plan = b->slab_plan + 4 * k; c.d_hist = b->slab_hist + 2 * FE_HIST_WORDS * k;
+            c.d_hist = b->slab_hist + 2 * FE_HIST_WORDS * k;
+            // The schedule (which samples emit an output, at which phase) depends only on the ratio, the channel's depth and the
+            // distance carried so far -- not on the data.  All channels of a bank see the same feeds from the same zero state, so
+            // channels with equal (depth, ratio, phase steps) have the same schedule for ever: one of them leads, the others share
+            // its schedule, tile table, plan and counters (64 NFM channels at 10 MS/s: 2 schedules; the 1024-channel plan: 1).
+            size_t lead = k;
+            for (size_t q = 0; q < k; ++q) {
+                const Channel& o = b->chans[b->fe_index[q]];
+                if (o.fe_lead == b->fe_index[q] && o.S == c.S && memcmp(&o.ratio, &c.ratio, sizeof(float)) == 0 && o.phase_steps == c.phase_steps &&
+                    o.lattice == c.lattice && o.A == c.A && o.phshift == c.phshift && o.scan_kb == c.scan_kb && o.scan_A == c.scan_A) { lead = q; break; }
+            }
+            c.fe_lead = b->fe_index[lead];
+            if (lead == k) b->fe_leaders.push_back(b->fe_index[k]);
+            c.d_state = b->slab_state + 4 * lead; c.d_plan = b->slab_plan + 4 * lead;
         }
         if ((rc = B200_CUDA_CHECK(cudaMemcpy(b->slab_taps, all.data(), all.size() * sizeof(float), cudaMemcpyHostToDevice)))) return rc;
     }
@@ -530,7 +548,8 @@ int reserve_outputs(b200dsp_bank* b, long long n)
         for (size_t i = 0; i < nc; ++i) {
             Channel& c = b->chans[i];
             if (!c.fe) continue;
-            c.d_fe_out = b->slab_fe + i * (size_t) need; c.d_sched = b->slab_sched + i * (size_t) need; c.d_tile = b->slab_tile + i * (size_t) tp;
+            c.d_fe_out = b->slab_fe + i * (size_t) need;
+            c.d_sched = b->slab_sched + (size_t) c.fe_lead * (size_t) need; c.d_tile = b->slab_tile + (size_t) c.fe_lead * (size_t) tp;
             c.fe_cap = need;
         }
         b->tables_dirty = true;
@@ -591,6 +610,9 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
         }
         if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(b->d_leaf, b->h_leaf.data(), nc * sizeof(LeafChan), cudaMemcpyHostToDevice, st)))) return rc;
         if (!b->h_fe.empty() && (rc = B200_CUDA_CHECK(cudaMemcpyAsync(b->d_fe, b->h_fe.data(), b->h_fe.size() * sizeof(FrontendChan), cudaMemcpyHostToDevice, st)))) return rc;
+        b->h_fe_lead.clear();
+        for (size_t k = 0; k < b->fe_index.size(); ++k) if (b->chans[b->fe_index[k]].fe_lead == b->fe_index[k]) b->h_fe_lead.push_back(b->h_fe[k]);
+        if (!b->h_fe_lead.empty() && (rc = B200_CUDA_CHECK(cudaMemcpyAsync(b->d_fe_lead, b->h_fe_lead.data(), b->h_fe_lead.size() * sizeof(FrontendChan), cudaMemcpyHostToDevice, st)))) return rc;
         b->tables_dirty = false;
     }
     // front-end schedules depend only on counts: replay them on the side stream while the tree runs
@@ -598,8 +620,8 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
     const bool run_sched = !b->fe_index.empty() && (max_new > 0 || first_pass);
     if (run_sched) {
         if ((rc = B200_CUDA_CHECK(cudaEventRecord(b->ev_begin, st))) || (rc = B200_CUDA_CHECK(cudaStreamWaitEvent(b->side, b->ev_begin, 0)))) return rc;
-        const int nfe = (int) b->h_fe.size();
-        frontend_schedule_kernel<<<nfe, 32 * FE_SW, 0, b->side>>>(b->d_fe, nfe, pi);      // one CTA per channel
+        const int nfe = (int) b->fe_leaders.size();
+        frontend_schedule_kernel<<<nfe, 32 * FE_SW, 0, b->side>>>(b->d_fe_lead, nfe, pi);      // one CTA per distinct schedule
         if ((rc = B200_CUDA_CHECK(cudaGetLastError())) || (rc = B200_CUDA_CHECK(cudaEventRecord(b->ev_sched, b->side)))) return rc;
     }
     const int tc = b->tcur, tn = tc ^ 1;
@@ -637,6 +659,14 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
         ++b->tree_launches;
     }
     if (fused) {
+        // A schedule kernel CTA on the scan path (256 threads x 128 registers, ~0.1 ms) takes half an SM's registers, i.e. one of
+        // that SM's two pyramid CTA slots -- both when two of them land on one SM; the pyramid's ranges are a static partition,
+        // so a CTA without a slot would run after the others.  The launch that overlaps the schedule kernel therefore gets two
+        // CTAs fewer per schedule CTA, all of them resident at once (measured on the 64-channel plan, 2 schedule CTAs: 296 / 294
+        // pyramid CTAs 0.56 ms per step, 292 and 288: 0.486).
+        int displaced = 0;
+        if (run_sched) for (int ci : b->fe_leaders) if (b->chans[ci].scan_kb > 0) displaced += 2;
+        if (displaced > b->sm_count / 4) displaced = b->sm_count / 4;
         for (const auto& fl : b->flaunch) {
             if (fl.n_groups == 0) continue;
             FusedParams q;
@@ -659,6 +689,8 @@ int feed_chunk(b200dsp_bank* b, const uint32_t* d_in, long long n, cudaStream_t 
             const long long tot = (long long) q.n_groups * q.tpr;
             // persistent CTAs over contiguous (group, tile) ranges; a range that starts inside a stream pays one warm-up tile
             long long ctas = (long long) b->sm_count * ((fl.smem <= FZ_SMEM_LIMIT) ? FZ_CTAS_PER_SM : 1);
+            if (ctas > displaced + b->sm_count) ctas -= displaced;
+            displaced = 0;                                        // later launches start after the schedule kernel has drained
             if (ctas > (tot + 3) / 4) ctas = (tot + 3) / 4;
             if (ctas < 1) ctas = 1;
             if ((rc = B200_CUDA_CHECK(cudaFuncSetAttribute((const void*) hb48_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fl.smem)))) return rc;
@@ -797,9 +829,9 @@ int empty_feed(b200dsp_bank* b, cudaStream_t st)
     PassInfo pi;
     memset(&pi, 0, sizeof(pi));
     pi.first_pass = 1;
-    const int nfe = (int) b->h_fe.size();
+    const int nfe = (int) b->fe_leaders.size();
     if (b->tables_dirty) return 0;            // never fed: the device tables do not exist yet and every count is still zero
-    frontend_schedule_kernel<<<nfe, 32 * FE_SW, 0, st>>>(b->d_fe, nfe, pi);
+    frontend_schedule_kernel<<<nfe, 32 * FE_SW, 0, st>>>(b->d_fe_lead, nfe, pi);
     return B200_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -854,7 +886,7 @@ int b200dsp_bank_create(b200dsp_bank_t** out, int input_rate_hz)
     b->slab_out = nullptr; b->slab_fe = nullptr; b->slab_sched = nullptr; b->slab_tile = nullptr;
     b->slab_taps = nullptr; b->slab_state = nullptr; b->slab_plan = nullptr; b->slab_hist = nullptr;
     b->out_pitch = b->fe_pitch = b->tile_pitch = b->taps_pitch = 0; b->d2h = nullptr; b->ev_pass = nullptr;
-    b->d_leaf = nullptr; b->d_fe = nullptr; b->d_nco = nullptr; b->tcur = 0;
+    b->d_leaf = nullptr; b->d_fe = nullptr; b->d_fe_lead = nullptr; b->d_nco = nullptr; b->tcur = 0;
     if ((rc = B200_CUDA_CHECK(cudaSetDevice(b->device))) || (rc = B200_CUDA_CHECK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking))) ||
         (rc = B200_CUDA_CHECK(cudaStreamCreateWithPriority(&b->side, cudaStreamNonBlocking, -5))) ||
         (rc = B200_CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_begin, cudaEventDisableTiming))) ||
@@ -1210,7 +1242,8 @@ int stage_counts(b200dsp_bank* b, int stage, int64_t* counts, cudaStream_t st)
     int rc;
     if ((rc = B200_CUDA_CHECK(cudaMemcpyAsync(stt.data(), b->slab_state, nfe * 4 * sizeof(int), cudaMemcpyDeviceToHost, st))) ||
         (rc = B200_CUDA_CHECK(cudaStreamSynchronize(st)))) return rc;
-    for (size_t k = 0; k < nfe; ++k) counts[b->fe_index[k]] = stt[4 * k + 3];
+    // (a channel's counters are its schedule leader's: c.d_state points into the leader's slot)
+    for (size_t k = 0; k < nfe; ++k) counts[b->fe_index[k]] = stt[(size_t) (b->chans[b->fe_index[k]].d_state - b->slab_state) + 3];
     return 0;
 }
 
