@@ -949,7 +949,7 @@ def _bank_e2e(c, args, fs, fcs, cutoff, n, x, sb):
     NCCL all-gather completes the block on every GPU -- then b200dsp_dist_feed and the pooled D2H of this rank's channels."""
     import sdrangel_b200 as S
     torch, capi, dist = c.torch, c.capi, c.dist
-    K = 16
+    K = int(os.environ.get("B200_BENCH_E2E_PASSES", "16"))
     nb_ = n // K
     ksteps = 10 if sb is None else 5           # a step is ~5 ms of wall clock: enough of them to average out host scheduling noise
     if sb is None:

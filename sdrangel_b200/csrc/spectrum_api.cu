@@ -35,6 +35,7 @@ struct SpecParams {
     const uint32_t* partial;   // carried partial frame (fill samples)
     const float*    window;    // [n]
     const float2*   tw;        // [SPEC_MAX_N] exp(-2 pi i t / SPEC_MAX_N)
+    const float2*   tw1;       // 4096-point kernel: [16][256] W_4096^(n2 k1) laid out so that a warp's loads are contiguous, then [16][16] W_256^(m2 j1)
     float*          out;       // [frames_out][n]
     float*          power;     // moving mode: [hist + frames][n] raw |X|^2 of every frame (hist = avg_nb - 1 carried frames first)
     const double*   fix_sum;   // fixed mode: carried partial sums [n] of the previous feed (read by CTA 0)
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(SPEC_THREADS, 2) spectrum_kernel_4096(const Sp
         if (f + 1 < f1) fetch(f + 1);                 // next frame's samples: in flight during the three passes
         fft16(v);
 #pragma unroll
-        for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], __ldg(&p.tw[tid * k1]));       // W_4096^{n2 k1}
+        for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], __ldg(&p.tw1[k1 * 256 + tid]));       // W_4096^{n2 k1}: the same table values, coalesced
 #pragma unroll
         for (int k1 = 0; k1 < 16; ++k1) sm[k1 * 256 + tid] = v[k1];
         __syncthreads();
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(SPEC_THREADS, 2) spectrum_kernel_4096(const Sp
             for (int m1 = 0; m1 < 16; ++m1) v[m1] = sm[k1 * 256 + 16 * m1 + m2];
             fft16(v);
 #pragma unroll
-            for (int j1 = 1; j1 < 16; ++j1) v[j1] = cmul(v[j1], __ldg(&p.tw[16 * m2 * j1]));   // W_256^{m2 j1}
+            for (int j1 = 1; j1 < 16; ++j1) v[j1] = cmul(v[j1], __ldg(&p.tw1[16 * 256 + j1 * 16 + m2]));   // W_256^{m2 j1}
             __syncthreads();                                                       // every thread has read its pass-1 values
 #pragma unroll
             for (int j1 = 0; j1 < 16; ++j1) sm[k1 * K1S + m2 * 17 + j1] = v[j1];
@@ -400,7 +401,7 @@ struct b200dsp_spectrum {
     float scalef;
     int n, log2n, avg_nb, mode, window, linear;
     bool configured;
-    float* d_window; float2* d_tw;
+    float* d_window; float2* d_tw; float2* d_tw1;
     uint32_t* d_partial[2]; int pcur; int fill;         // carried partial frame (ping-pong)
     double* d_fix_sum; int fix_idx; int fix_cur;     // d_fix_sum: two halves of SPEC_MAX_N doubles, fix_cur = the one last written
     float* d_power; long long power_cap;                // moving mode history + frames
@@ -430,7 +431,7 @@ int spectrum_feed_impl(b200dsp_spectrum* s, const uint32_t* d_in, long long n_sa
     const int n = s->n;
     SpecParams p;
     memset(&p, 0, sizeof(p));
-    p.in = d_in; p.partial = s->d_partial[s->pcur]; p.window = s->d_window; p.tw = s->d_tw; p.out = d_out;
+    p.in = d_in; p.partial = s->d_partial[s->pcur]; p.window = s->d_window; p.tw = s->d_tw; p.tw1 = s->d_tw1; p.out = d_out;
     p.fix_sum = s->d_fix_sum + (size_t) s->fix_cur * SPEC_MAX_N; p.fix_sum_out = s->d_fix_sum + (size_t) (s->fix_cur ^ 1) * SPEC_MAX_N; p.n = n; p.log2n = s->log2n; p.fill = s->fill; p.frames = (int) frames;
     p.mode = s->mode; p.avg_nb = s->avg_nb; p.linear = s->linear; p.positive_only = positive_only; p.fix_idx = s->fix_idx;
     p.frames_out = (int) frames_out; p.save_sums = -1;
@@ -517,7 +518,12 @@ int b200dsp_spectrum_create(b200dsp_spectrum_t** out, float scalef)
     std::vector<float2> tw(SPEC_MAX_N);
     const double PI = 3.14159265358979323846;
     for (int t = 0; t < SPEC_MAX_N; ++t) tw[t] = make_float2((float) cos(-2.0 * PI * t / SPEC_MAX_N), (float) sin(-2.0 * PI * t / SPEC_MAX_N));
-    if ((rc = B200_CUDA_CHECK(cudaMalloc(&s->d_tw, SPEC_MAX_N * sizeof(float2)))) ||
+    std::vector<float2> tw1(16 * 256 + 16 * 16);
+    for (int k1 = 0; k1 < 16; ++k1) for (int t = 0; t < 256; ++t) tw1[(size_t) (k1 * 256 + t)] = tw[(size_t) ((t * k1) & 4095)];
+    for (int j1 = 0; j1 < 16; ++j1) for (int m2 = 0; m2 < 16; ++m2) tw1[(size_t) (16 * 256 + j1 * 16 + m2)] = tw[(size_t) ((16 * m2 * j1) & 4095)];
+    if ((rc = B200_CUDA_CHECK(cudaMalloc(&s->d_tw1, tw1.size() * sizeof(float2)))) ||
+        (rc = B200_CUDA_CHECK(cudaMemcpy(s->d_tw1, tw1.data(), tw1.size() * sizeof(float2), cudaMemcpyHostToDevice))) ||
+        (rc = B200_CUDA_CHECK(cudaMalloc(&s->d_tw, SPEC_MAX_N * sizeof(float2)))) ||
         (rc = B200_CUDA_CHECK(cudaMemcpy(s->d_tw, tw.data(), SPEC_MAX_N * sizeof(float2), cudaMemcpyHostToDevice))) ||
         (rc = B200_CUDA_CHECK(cudaMalloc(&s->d_window, SPEC_MAX_N * sizeof(float)))) ||
         (rc = B200_CUDA_CHECK(cudaMalloc(&s->d_partial[0], SPEC_MAX_N * 4))) || (rc = B200_CUDA_CHECK(cudaMalloc(&s->d_partial[1], SPEC_MAX_N * 4))) ||
@@ -533,6 +539,7 @@ int b200dsp_spectrum_destroy(b200dsp_spectrum_t* s)
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->d_tw) cudaFree(s->d_tw);
+    if (s->d_tw1) cudaFree(s->d_tw1);
     if (s->d_window) cudaFree(s->d_window);
     if (s->d_partial[0]) cudaFree(s->d_partial[0]);
     if (s->d_partial[1]) cudaFree(s->d_partial[1]);
