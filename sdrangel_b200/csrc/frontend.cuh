@@ -442,10 +442,11 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel_t(const FrontendCh
     const int ntp = nts * c.phase_steps;
     float* taps = fe_smem;
     float2* z = reinterpret_cast<float2*>(fe_smem + ((ntp + 3) & ~3));
-    for (int i = tid; i < ntp; i += FE_THREADS) {
-        const int ph = i / nts, k = i - ph * nts - FE_PAD;
-        taps[i] = (k >= 0 && k < nt) ? c.taps[ph * nt + k] : 0.0f;
-    }
+    for (int ph = tid >> 5; ph < c.phase_steps; ph += FE_THREADS / 32)        // a warp per phase row: no division by the row length
+        for (int kk = tid & 31; kk < nts; kk += 32) {
+            const int k = kk - FE_PAD;
+            taps[ph * nts + kk] = (k >= 0 && k < nt) ? c.taps[ph * nt + k] : 0.0f;
+        }
     const unsigned phase0 = c.in_f32 ? 0u : hin[FE_MAX_TAPS];
     const int t1 = (t0 + FE_TILE < m) ? t0 + FE_TILE : m;
     // z[k] holds mixed sample (t0 - FE_MAX_TAPS + k), k in [0, FE_MAX_TAPS + t1 - t0)
