@@ -8,8 +8,11 @@
 // MovingAverageUtil (sdrbase/util/movingaverage.h): running total of the last 1024 pushed samples (fewer while filling
 // up, but the divisor is always N), operator T() = total / N with C++ truncation toward zero.  So
 //     y[i] = (int16) (x[i] - trunc(S_i / 1024)),   S_i = sum of the (raw) samples x[max(0, i-1023) .. i] of the stream.
-// The sequential running total becomes a windowed sum of raw inputs: a block-wide prefix scan over a tile plus a
-// 1024-sample halo; the carried state is the last 1024 raw samples (zeros at start == the fill-up phase).
+// The sequential running total becomes a windowed sum of raw inputs.  A block takes a tile of the stream plus a 1024-sample
+// halo; a thread owns 16 consecutive samples in registers; one warp-shuffle scan of the thread totals gives every thread
+// the window sum at its first sample, S(16t + k) = sum of the 64 thread totals before t + sum_{m<=k} (x_t[m] - x_{t-64}[m]),
+// and the samples of thread t-64 (the ones that leave the window) come through shared memory as packed words.  The
+// carried state is the last 1024 raw samples (zeros at start == the fill-up phase).
 #include "common.cuh"
 
 using namespace b200dsp;
@@ -20,6 +23,9 @@ constexpr int DC_N = 1024;            // MovingAverageUtil<..., 1024>
 constexpr int DC_TILE = 3072;         // samples per block (measured: 3072/256 threads 2.9 TB/s; 7168/512 threads 2.7 TB/s -- more, smaller CTAs per SM win)
 constexpr int DC_THREADS = 256;
 constexpr int DC_PER = (DC_TILE + DC_N) / DC_THREADS;     // 16 consecutive elements of (halo + tile) per thread
+constexpr int DC_HALO_THREADS = DC_N / DC_PER;            // 64: thread t's window loses the samples of thread t - 64
+constexpr int DC_SLOT = DC_PER + 4;                       // words per thread in the exchange array: 128-bit accesses without bank conflicts
+static_assert(DC_PER == 16 && DC_HALO_THREADS == 64 && DC_THREADS % 32 == 0, "the window arithmetic below assumes 16 samples per thread and a halo of two warps");
 
 struct DcParams {
     const uint32_t* in;        // packed int16 IQ
@@ -27,83 +33,74 @@ struct DcParams {
     const uint32_t* hist_in;   // last DC_N raw samples before this call (oldest first)
     uint32_t* hist_out;
     long long n;
+    int in_vec, out_vec;       // in / out is 16-byte aligned: 128-bit accesses
 };
 
-// shared arrays are padded by one word per 16 so that "thread t owns elements 16t .. 16t+15" is bank-conflict-free
-__device__ __forceinline__ int dc_pad(int e) { return e + (e >> 4); }
-constexpr int DC_WORDS = DC_TILE + DC_N + ((DC_TILE + DC_N) >> 4);
-
-template<bool VEC>
 __global__ void __launch_bounds__(DC_THREADS) dc_correct_kernel(const DcParams p)
 {
-    extern __shared__ int dc_smem[];                // sA: packed raw samples, then the I prefix; sB: the Q prefix
-    int* sA = dc_smem;
-    int* sB = dc_smem + DC_WORDS;
-    __shared__ int wre[DC_THREADS / 32], wim[DC_THREADS / 32];
+    __shared__ __align__(16) uint32_t sraw[DC_THREADS * DC_SLOT];      // every thread's 16 packed raw samples
+    __shared__ int sex_r[DC_THREADS], sex_i[DC_THREADS];               // sum of the totals of the lower lanes of its warp
+    __shared__ int wre[DC_THREADS / 32], wim[DC_THREADS / 32];         // warp totals
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const long long t0 = (long long) blockIdx.x * DC_TILE;
-    const long long w0 = t0 - DC_N;                 // stream index of window element 0 (a multiple of 1024)
-    // 1. coalesced load of the window (halo + tile): element e is stream sample w0 + e
-    if (VEC) {
+    const long long i0 = t0 - DC_N + DC_PER * tid;      // stream index of this thread's first sample (a multiple of 16; < 0: history)
+    // 1. the thread's 16 samples: four 128-bit loads; a copy goes to shared memory for thread tid + 64
+    uint32_t raw[DC_PER];
+    const bool hist = i0 < 0;                           // (i0 is a multiple of 16: all 16 samples are history, or none)
+    const long long left = p.n - i0;
+    const int rem = hist ? DC_PER : (left > DC_PER ? DC_PER : (left < 0 ? 0 : (int) left));    // samples of the call among the thread's 16
+    const uint32_t* src = hist ? p.hist_in + (DC_N + i0) : p.in + i0;
+    const bool vec = hist || p.in_vec;
 #pragma unroll
-        for (int k = 0; k < DC_PER / 4; ++k) {
-            const int e = 4 * (k * DC_THREADS + tid);
-            const long long i = w0 + e;
-            uint4 v;
-            if (i >= 0 && i + 4 <= p.n) v = *reinterpret_cast<const uint4*>(p.in + i);
-            else if (i < 0) v = *reinterpret_cast<const uint4*>(p.hist_in + (DC_N + i));      // the halo of block 0: all of it history
-            else {
-                v.x = (i < p.n) ? p.in[i] : 0u;         v.y = (i + 1 < p.n) ? p.in[i + 1] : 0u;
-                v.z = (i + 2 < p.n) ? p.in[i + 2] : 0u; v.w = (i + 3 < p.n) ? p.in[i + 3] : 0u;
-            }
-            const int q = dc_pad(e);                 // e is a multiple of 4: the four words stay inside one group of 16
-            sA[q] = (int) v.x; sA[q + 1] = (int) v.y; sA[q + 2] = (int) v.z; sA[q + 3] = (int) v.w;
+    for (int g = 0; g < DC_PER / 4; ++g) {
+        uint4 v;
+        if (vec && 4 * g + 4 <= rem) v = __ldg(reinterpret_cast<const uint4*>(src + 4 * g));
+        else {
+            v.x = (4 * g < rem) ? src[4 * g] : 0u;         v.y = (4 * g + 1 < rem) ? src[4 * g + 1] : 0u;
+            v.z = (4 * g + 2 < rem) ? src[4 * g + 2] : 0u; v.w = (4 * g + 3 < rem) ? src[4 * g + 3] : 0u;
         }
-    } else {
-        for (int e = tid; e < DC_TILE + DC_N; e += DC_THREADS) {
-            const long long i = w0 + e;
-            uint32_t w = 0;
-            if (i < 0) w = p.hist_in[DC_N + i];
-            else if (i < p.n) w = p.in[i];
-            sA[dc_pad(e)] = (int) w;
-        }
+        raw[4 * g] = v.x; raw[4 * g + 1] = v.y; raw[4 * g + 2] = v.z; raw[4 * g + 3] = v.w;
+        *reinterpret_cast<uint4*>(&sraw[tid * DC_SLOT + 4 * g]) = v;
     }
-    __syncthreads();
-    // 2. thread-local inclusive prefix over 16 consecutive elements, block-wide exclusive prefix of the thread sums
-    int vr[DC_PER], vi[DC_PER];
+    // 2. thread totals, inclusive warp scan
     int sr = 0, si = 0;
-    const int base = tid * DC_PER + tid;            // dc_pad(16 tid)
 #pragma unroll
-    for (int k = 0; k < DC_PER; ++k) {
-        const int w = sA[base + k];
-        sr += (int) (short) (w & 0xffff); si += w >> 16;
-        vr[k] = sr; vi[k] = si;
-    }
+    for (int k = 0; k < DC_PER; ++k) { sr += (int) (short) (raw[k] & 0xffffu); si += (int) raw[k] >> 16; }
     int xr = sr, xi = si;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const int a = __shfl_up_sync(0xffffffffu, xr, d), b = __shfl_up_sync(0xffffffffu, xi, d);
         if (lane >= d) { xr += a; xi += b; }
     }
+    sex_r[tid] = xr - sr; sex_i[tid] = xi - si;
     if (lane == 31) { wre[wid] = xr; wim[wid] = xi; }
-    __syncthreads();                                 // also: every thread has read its raw words
-    int br = 0, bi = 0;
-    for (int w2 = 0; w2 < wid; ++w2) { br += wre[w2]; bi += wim[w2]; }
-    const int offr = br + xr - sr, offi = bi + xi - si;
-#pragma unroll
-    for (int k = 0; k < DC_PER; ++k) { sA[base + k] = vr[k] + offr; sB[base + k] = vi[k] + offi; }
     __syncthreads();
-    // 3. outputs: window sum S = P[e] - P[e - 1024]; own raw sample = P[e] - P[e - 1]
-    for (int o = tid; o < DC_TILE; o += DC_THREADS) {
-        const long long i = t0 + o;
-        if (i >= p.n) break;
-        const int e = o + DC_N;
-        const int pe = dc_pad(e), pw = dc_pad(e - DC_N), p1 = dc_pad(e - 1);
-        const int Pr = sA[pe], Pi = sB[pe];
-        const int Sr = Pr - sA[pw], Si = Pi - sB[pw];
-        const int x = Pr - sA[p1], y = Pi - sB[p1];
-        const int re = x - Sr / DC_N, im = y - Si / DC_N;         // C++ integer division: toward zero, like total / N
-        p.out[i] = ((uint32_t) re & 0xffffu) | ((uint32_t) im << 16);
+    // 3. outputs (tile threads): S = sum of the 1024 samples that end at the current one, y = x - trunc(S / 1024)
+    if (tid >= DC_HALO_THREADS && rem > 0) {
+        const int pt = tid - DC_HALO_THREADS;           // same lane, two warps down
+        int Sr = wre[wid - 2] + wre[wid - 1] + (xr - sr) - sex_r[pt];
+        int Si = wim[wid - 2] + wim[wid - 1] + (xi - si) - sex_i[pt];
+#pragma unroll
+        for (int g = 0; g < DC_PER / 4; ++g) {
+            const uint4 pv = *reinterpret_cast<const uint4*>(&sraw[pt * DC_SLOT + 4 * g]);
+            const uint32_t pw[4] = { pv.x, pv.y, pv.z, pv.w };
+            uint32_t ow[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const uint32_t w = raw[4 * g + m], q = pw[m];
+                const int x = (int) (short) (w & 0xffffu), y = (int) w >> 16;
+                Sr += x - (int) (short) (q & 0xffffu);
+                Si += y - ((int) q >> 16);
+                const int re = x - Sr / DC_N, im = y - Si / DC_N;         // C++ integer division: toward zero, like total / N
+                ow[m] = ((uint32_t) re & 0xffffu) | ((uint32_t) im << 16);
+            }
+            uint32_t* dst = p.out + i0 + 4 * g;
+            if (p.out_vec && 4 * g + 4 <= rem) *reinterpret_cast<uint4*>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            else {
+#pragma unroll
+                for (int m = 0; m < 4; ++m) if (4 * g + m < rem) dst[m] = ow[m];
+            }
+        }
     }
     // carry: the last DC_N raw samples of the stream so far (block 0 also covers calls shorter than DC_N)
     if (blockIdx.x == 0) {
@@ -237,12 +234,8 @@ int launch_dc(b200dsp_iqcorr* h, const uint32_t* d_in, uint32_t* d_out, long lon
     DcParams p;
     p.in = d_in; p.out = d_out; p.hist_in = h->d_hist[h->cur]; p.hist_out = h->d_hist[h->cur ^ 1]; p.n = n;
     const long long blocks = (n + DC_TILE - 1) / DC_TILE;
-    const size_t smem = 2 * DC_WORDS * sizeof(int);
-    // per launch: the attribute belongs to the current device and the call is cheap
-    cudaFuncSetAttribute((const void*) dc_correct_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    cudaFuncSetAttribute((const void*) dc_correct_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    if (((uintptr_t) d_in & 15) == 0) dc_correct_kernel<true><<<(unsigned) blocks, DC_THREADS, smem, st>>>(p);
-    else                              dc_correct_kernel<false><<<(unsigned) blocks, DC_THREADS, smem, st>>>(p);
+    p.in_vec = (((uintptr_t) d_in & 15) == 0) ? 1 : 0; p.out_vec = (((uintptr_t) d_out & 15) == 0) ? 1 : 0;
+    dc_correct_kernel<<<(unsigned) blocks, DC_THREADS, 0, st>>>(p);
     int rc = B200_CUDA_CHECK(cudaGetLastError());
     if (rc == 0) h->cur ^= 1;
     return rc;

@@ -1,10 +1,12 @@
 #!/usr/bin/env python
-"""Developer aid: print the key metrics + region breakdown of an .ncu-rep (run where ncu is installed)."""
+"""Developer aid: print the key metrics + region breakdown of an .ncu-rep (run where ncu is installed).
+usage: ncu_summary.py report.ncu-rep [k]    k = index of the captured launch within the report (default 0)"""
 import csv, subprocess, sys, io
 rep = sys.argv[1]
+which = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, units, r = rows[0], rows[1], rows[2]
+hdr, units, r = rows[0], rows[1], rows[2 + which]
 keys = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg.per_second", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "sm__inst_executed.avg.per_cycle_elapsed", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed",
@@ -23,8 +25,12 @@ for i, h in enumerate(hdr):
         print("%-70s %s" % (h, r[i]))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-ks = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]      # several captured launches: the first
-rows = rows[ks[0]:ks[1]]
+ks = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]      # several captured launches: the k-th
+secs = []
+for a, b in zip(ks[:-1], ks[1:]):          # (ncu prints a launch's section twice when the report carries imported source)
+    if not secs or rows[secs[-1][0]:secs[-1][1]] != rows[a:b]:
+        secs.append((a, b))
+rows = rows[secs[which][0]:secs[which][1]]
 hdr, data = rows[1], [r for r in rows[2:] if len(r) > 10]
 iS, iI, iN = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
 tot = sum(int(x[iI]) for x in data)
