@@ -102,6 +102,161 @@ __global__ void __launch_bounds__(FF_THREADS) fftfilt_kernel(const FfParams p)
     if (b1 == p.nb) for (int k = tid; k < N2; k += FF_THREADS) p.ovl_out[k] = ovl[k];
 }
 
+// ---- flen 1024 / 2048 (the reference's SSB and DSB filter lengths: ssbdemod.h:36, ssbdemod.cpp:91-92, amdemod.cpp:72-73) ----
+// The same radix-2 butterflies as above, in the same order, but FOUR stages at a time on 16 values in registers: a thread
+// owns the 16 elements that differ in index bits [P, P+4) ("field P"), so a 1024-point transform is 3 passes through
+// shared memory instead of 10 and the CTA is flen/16 threads.  Forward fields: top, middle ..., 0; inverse: 0, middle ..., top.
+//   * the block's samples go from global memory straight into the top-field pass (its upper half is the zero padding);
+//   * the last forward pass, the multiplier and the first inverse pass all work on field 0: one visit;
+//   * the last inverse pass (top field) holds k and k + flen/2 in one thread: scaling, overlap-add and the store follow in
+//     registers, and the overlap itself never leaves the thread's registers between blocks.
+// Shared arrays are padded by one element per 16 (every pass then reads and writes without bank conflicts); the twiddles are
+// stored per stage (tws[2^s - 1 + r] = exp(-2 pi i r / 2^(s+1))), so a stage's loads are contiguous or a broadcast.
+__device__ __forceinline__ int ff_idx(int e) { return e + (e >> 4); }
+
+// stages S_HI .. S_LO (forward, decimation in frequency) or S_LO .. S_HI (inverse, decimation in time) of field P on v[16];
+// low = the element index bits below P
+template<bool INV, int P, int S_LO, int S_HI>
+__device__ __forceinline__ void ff_stages(float2 (&v)[16], const float2* __restrict__ tws, int low)
+{
+#pragma unroll
+    for (int bb = 0; bb < 4; ++bb) {
+        const int b = INV ? bb : 3 - bb;
+        const int s = P + b;
+        if (s < S_LO || s > S_HI) continue;
+        const float2* t = tws + ((1 << s) - 1);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            if (m & (1 << b)) continue;
+            const float2 w = t[low + ((m & ((1 << b) - 1)) << P)];
+            const float2 a = v[m], c = v[m | (1 << b)];
+            if (!INV) {
+                v[m] = make_float2(a.x + c.x, a.y + c.y);
+                v[m | (1 << b)] = cmul(make_float2(a.x - c.x, a.y - c.y), w);
+            } else {
+                const float2 u = cmul(c, make_float2(w.x, -w.y));
+                v[m] = make_float2(a.x + u.x, a.y + u.y);
+                v[m | (1 << b)] = make_float2(a.x - u.x, a.y - u.y);
+            }
+        }
+    }
+}
+
+template<int P>
+__device__ __forceinline__ void ff_field_load(const float2* x, int G, float2 (&v)[16])
+{
+    const int e0 = ((G >> P) << (P + 4)) | (G & ((1 << P) - 1));
+#pragma unroll
+    for (int m = 0; m < 16; ++m) v[m] = x[ff_idx(e0 + (m << P))];
+}
+template<int P>
+__device__ __forceinline__ void ff_field_store(float2* x, int G, const float2 (&v)[16])
+{
+    const int e0 = ((G >> P) << (P + 4)) | (G & ((1 << P) - 1));
+#pragma unroll
+    for (int m = 0; m < 16; ++m) x[ff_idx(e0 + (m << P))] = v[m];
+}
+
+// middle passes (fields strictly between 0 and the top one), forward from the top down / inverse from the bottom up
+template<int LOG2N, int P>
+__device__ __forceinline__ void ff_mid_forward(float2* x, const float2* tws, int G)
+{
+    if constexpr (P > 0) {
+        float2 v[16];
+        ff_field_load<P>(x, G, v);
+        ff_stages<false, P, P, P + 3>(v, tws, G & ((1 << P) - 1));
+        ff_field_store<P>(x, G, v);
+        __syncthreads();
+        ff_mid_forward<LOG2N, P - 4>(x, tws, G);
+    }
+}
+template<int LOG2N, int S>
+__device__ __forceinline__ void ff_mid_inverse(float2* x, const float2* tws, int G)
+{
+    if constexpr (LOG2N - S > 4) {
+        float2 v[16];
+        ff_field_load<S>(x, G, v);
+        ff_stages<true, S, S, S + 3>(v, tws, G & ((1 << S) - 1));
+        ff_field_store<S>(x, G, v);
+        __syncthreads();
+        ff_mid_inverse<LOG2N, S + 4>(x, tws, G);
+    }
+}
+template<int LOG2N> constexpr int ff_last_inverse_stage() { int s = 4; while (LOG2N - s > 4) s += 4; return s; }
+
+template<int LOG2N>
+__global__ void __launch_bounds__((1 << LOG2N) / 16) fftfilt_fast_kernel(const FfParams p)
+{
+    constexpr int N = 1 << LOG2N, N2 = N / 2, NT = N / 16, TOP = LOG2N - 4;
+    constexpr int F0_HI = (LOG2N % 4 == 0) ? 3 : (LOG2N % 4) - 1;      // field 0 ends the forward transform with stages F0_HI .. 0
+    constexpr int SL = ff_last_inverse_stage<LOG2N>();                 // the top field ends the inverse transform with stages SL .. LOG2N-1
+    static_assert(LOG2N >= 8 && LOG2N <= 12, "field layout");
+    extern __shared__ float2 ff_smem[];
+    float2* x = ff_smem;                      // [N + N / 16]
+    float2* tws = ff_smem + N + N / 16;       // [N]: per-stage twiddles
+    const int G = threadIdx.x;
+    const int b0 = blockIdx.x * p.blocks_per_cta;
+    int b1 = b0 + p.blocks_per_cta;
+    if (b1 > p.nb) b1 = p.nb;
+    if (b0 >= b1) return;
+    for (int s = 0; s < LOG2N; ++s)
+        for (int r = G; r < (1 << s); r += NT) tws[(1 << s) - 1 + r] = p.tw[r << (LOG2N - 1 - s)];
+    __syncthreads();
+    float2 ov[8];                             // overlap of output samples k = m NT + G, m < 8
+#pragma unroll
+    for (int m = 0; m < 8; ++m) ov[m] = (b0 == 0) ? p.ovl_in[m * NT + G] : make_float2(0.0f, 0.0f);
+    const float inv = 1.0f / (float) N;
+    for (int b = (b0 == 0 ? 0 : b0 - 1); b < b1; ++b) {
+        const bool emit = (b >= b0);
+        float2 v[16];
+        // block b = samples [b N2, (b + 1) N2) of (pending | new input); elements m >= 8 of the top field are the zero padding
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const long long g = (long long) b * N2 + m * NT + G;
+            v[m] = (g < p.inptr) ? p.pend[g] : p.in[g - p.inptr];
+        }
+        {
+            const float2* t = tws + ((1 << (LOG2N - 1)) - 1);          // stage LOG2N-1 on (a, 0): a stays, the partner is a w
+#pragma unroll
+            for (int m = 0; m < 8; ++m) v[m + 8] = cmul(v[m], t[G + (m << TOP)]);
+        }
+        ff_stages<false, TOP, TOP, LOG2N - 2>(v, tws, G);
+        __syncthreads();                      // (the previous block's last pass has read x)
+        ff_field_store<TOP>(x, G, v);
+        __syncthreads();
+        ff_mid_forward<LOG2N, TOP - 4>(x, tws, G);
+        // field 0: end of the forward transform, multiplier (bit-reversed table), start of the inverse transform
+        ff_field_load<0>(x, G, v);
+        ff_stages<false, 0, 0, F0_HI>(v, tws, 0);
+        {
+            const float4* mt = reinterpret_cast<const float4*>(p.mult + 16 * G);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 mm = __ldg(mt + q);
+                v[2 * q] = cmul(v[2 * q], make_float2(mm.x, mm.y));
+                v[2 * q + 1] = cmul(v[2 * q + 1], make_float2(mm.z, mm.w));
+            }
+        }
+        ff_stages<true, 0, 0, 3>(v, tws, 0);
+        ff_field_store<0>(x, G, v);
+        __syncthreads();
+        ff_mid_inverse<LOG2N, 4>(x, tws, G);
+        ff_field_load<TOP>(x, G, v);
+        ff_stages<true, TOP, SL, LOG2N - 1>(v, tws, G);
+        // overlap and add (fftfilt.cpp:274-277)
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const float2 lo = v[m], hi = v[m + 8], o = ov[m];
+            if (emit) p.out[(long long) b * N2 + m * NT + G] = make_float2(o.x + lo.x * inv, o.y + lo.y * inv);
+            ov[m] = make_float2(hi.x * inv, hi.y * inv);
+        }
+    }
+    if (b1 == p.nb) {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) p.ovl_out[m * NT + G] = ov[m];
+    }
+}
+
 // iterative radix-2 FFT in double (host): the filter's frequency response
 void host_fft(std::vector<std::complex<double>>& a)
 {
@@ -298,9 +453,15 @@ int b200dsp_fftfilt_run_dev(b200dsp_fftfilt_t* h, int op, int usb, int get_dc, c
         if (ctas < 1) ctas = 1;
         p.blocks_per_cta = (int) ((nb + ctas - 1) / ctas);
         ctas = (nb + p.blocks_per_cta - 1) / p.blocks_per_cta;
-        const size_t smem = (size_t) 2 * N * sizeof(float2);
-        if (smem > 48 * 1024 && (rc = B200_CUDA_CHECK(cudaFuncSetAttribute((const void*) fftfilt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)))) return rc;
-        fftfilt_kernel<<<(unsigned) ctas, FF_THREADS, smem, st>>>(p);
+        if (N == 1024 || N == 2048) {
+            const size_t smem = (size_t) (2 * N + N / 16) * sizeof(float2);          // 16.5 / 33 KB: under the 48 KB default
+            if (N == 1024) fftfilt_fast_kernel<10><<<(unsigned) ctas, N / 16, smem, st>>>(p);
+            else           fftfilt_fast_kernel<11><<<(unsigned) ctas, N / 16, smem, st>>>(p);
+        } else {
+            const size_t smem = (size_t) 2 * N * sizeof(float2);
+            if (smem > 48 * 1024 && (rc = B200_CUDA_CHECK(cudaFuncSetAttribute((const void*) fftfilt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)))) return rc;
+            fftfilt_kernel<<<(unsigned) ctas, FF_THREADS, smem, st>>>(p);
+        }
         if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
         h->cur ^= 1;
     }
