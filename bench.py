@@ -47,7 +47,7 @@ WORKLOADS = {
                        desc="sdrbench decimateii: Decimators<qint32,qint16,16,12>::decimate16_cen, synthetic int16 IQ"),
     "decimatefi": dict(type="decim", kind="fi", log2=6, mode=2, in_dtype="float32", in_bytes=8, out_bytes=4 / 64, n=1 << 27,
                        desc="sdrbench decimatefi: DecimatorsFI::decimate64_cen, synthetic float IQ"),
-    "bank64": dict(type="bank", plan=plan64, n=3 << 22,
+    "bank64": dict(type="bank", plan=plan64, n=1 << 26,        # 2^26 samples (6.7 s of baseband; 256 MiB > L2)
                    desc="64 NFM 12.5 kHz channels off a synthetic 10 MS/s int16 baseband: DownChannelizer tree + NCO + Interpolator to 48 kS/s"),
     "spectrum": dict(type="spectrum", n=1 << 26, fft=4096, avg_nb=10, avg_mode=2,
                      desc="SpectrumVis: 4096-pt Blackman-Harris windowed FFT, log power, fixed averaging over 10 frames, synthetic int16 IQ (61.44 MS/s LimeSDR-rate stream)"),
