@@ -114,6 +114,18 @@ __global__ void __launch_bounds__(FF_THREADS) fftfilt_kernel(const FfParams p)
 // stored per stage (tws[2^s - 1 + r] = exp(-2 pi i r / 2^(s+1))), so a stage's loads are contiguous or a broadcast.
 __device__ __forceinline__ int ff_idx(int e) { return e + (e >> 4); }
 
+// exp(-2 pi i q / 16), q = 0 .. 7 (the float values of the double cosines, like the table's)
+__device__ __forceinline__ constexpr float ff_w16_re(int q)
+{
+    return q == 0 ? 1.0f : q == 1 ? 0.92387953251128674f : q == 2 ? 0.70710678118654752f : q == 3 ? 0.38268343236508977f :
+           q == 4 ? 0.0f : q == 5 ? -0.38268343236508977f : q == 6 ? -0.70710678118654752f : -0.92387953251128674f;
+}
+__device__ __forceinline__ constexpr float ff_w16_im(int q)
+{
+    return q == 0 ? 0.0f : q == 1 ? -0.38268343236508977f : q == 2 ? -0.70710678118654752f : q == 3 ? -0.92387953251128674f :
+           q == 4 ? -1.0f : q == 5 ? -0.92387953251128674f : q == 6 ? -0.70710678118654752f : -0.38268343236508977f;
+}
+
 // stages S_HI .. S_LO (forward, decimation in frequency) or S_LO .. S_HI (inverse, decimation in time) of field P on v[16];
 // low = the element index bits below P
 template<bool INV, int P, int S_LO, int S_HI>
@@ -128,13 +140,18 @@ __device__ __forceinline__ void ff_stages(float2 (&v)[16], const float2* __restr
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
             if (m & (1 << b)) continue;
-            const float2 w = t[low + ((m & ((1 << b) - 1)) << P)];
             const float2 a = v[m], c = v[m | (1 << b)];
+            // field 0: the twiddle exp(-2 pi i q / 16), q = r << (3 - s), is known at compile time; q = 0 and q = 4 (1 and -j) cost nothing
+            const int q16 = (P == 0) ? ((m & ((1 << b) - 1)) << (3 - s)) : -1;
+            float2 w;
+            if (P == 0) w = make_float2(ff_w16_re(q16), ff_w16_im(q16));
+            else        w = t[low + ((m & ((1 << b) - 1)) << P)];
             if (!INV) {
+                const float2 d = make_float2(a.x - c.x, a.y - c.y);
                 v[m] = make_float2(a.x + c.x, a.y + c.y);
-                v[m | (1 << b)] = cmul(make_float2(a.x - c.x, a.y - c.y), w);
+                v[m | (1 << b)] = (q16 == 0) ? d : (q16 == 4) ? make_float2(d.y, -d.x) : cmul(d, w);
             } else {
-                const float2 u = cmul(c, make_float2(w.x, -w.y));
+                const float2 u = (q16 == 0) ? c : (q16 == 4) ? make_float2(-c.y, c.x) : cmul(c, make_float2(w.x, -w.y));
                 v[m] = make_float2(a.x + u.x, a.y + u.y);
                 v[m | (1 << b)] = make_float2(a.x - u.x, a.y - u.y);
             }
