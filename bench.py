@@ -61,7 +61,7 @@ WORKLOADS = {
                     desc="SSB back-end: fftfilt::runSSB (1024-point overlap-add FFT filter, 300-3000 Hz at 48 kS/s) on one complex64 stream"),
     "demod": dict(type="tx", kind="demod", channels=1024, n=1 << 26,
                   desc="NFM back-end: PhaseDiscriminators::phaseDiscriminatorDelta on the pooled front-end outputs of 1024 channels, n = channel samples"),
-    "bank1024": dict(type="bank", plan=plan1024, n=3 << 24,
+    "bank1024": dict(type="bank", plan=plan1024, n=3 << 25,       # 100.7 M samples (384 MiB) per step; SURVEY.md 8(d) runs 2^27
                      desc="1024 channels over a synthetic 122.88 MS/s int16 stream: DownChannelizer tree + NCO + Interpolator to 48 kS/s, channels sharded"),
 }
 
@@ -942,14 +942,15 @@ class _NearGpu:
 
 
 def _bank_e2e(c, args, fs, fcs, cutoff, n, x, sb):
-    """End to end through the plugin-facing calls, host buffers both sides, 16 sub-blocks per step.
+    """End to end through the plugin-facing calls, host buffers both sides, K sub-blocks per step (16, or 32 for steps of 100 M samples and more).
     N = 1: b200dsp_bank_process (one call per step: pinned host baseband in, every channel's 48 kS/s complex64 output to pinned
     host memory; H2D / kernels / D2H of finished columns overlapped inside the library).
     N > 1: b200dsp_dist_ingest_begin per sub-block -- every rank copies ITS 1/N time slice over its own PCIe link, an in-place
     NCCL all-gather completes the block on every GPU -- then b200dsp_dist_feed and the pooled D2H of this rank's channels."""
     import sdrangel_b200 as S
     torch, capi, dist = c.torch, c.capi, c.dist
-    K = int(os.environ.get("B200_BENCH_E2E_PASSES", "16"))
+    # passes of ~3.1 M samples (12.6 MB of H2D each: measured -- half that size is launch-bound, 9.95e3 against 1.13e4 MS/s)
+    K = int(os.environ.get("B200_BENCH_E2E_PASSES", "32" if n >= (3 << 25) else "16"))
     nb_ = n // K
     ksteps = 10 if sb is None else 5           # a step is ~5 ms of wall clock: enough of them to average out host scheduling noise
     if sb is None:

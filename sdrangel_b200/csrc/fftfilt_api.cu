@@ -201,8 +201,11 @@ __device__ __forceinline__ void ff_mid_inverse(float2* x, const float2* tws, int
 }
 template<int LOG2N> constexpr int ff_last_inverse_stage() { int s = 4; while (LOG2N - s > 4) s += 4; return s; }
 
+#ifndef FF_FAST_WARPS_PER_SM
+#define FF_FAST_WARPS_PER_SM 16       // resident warps the register budget is sized for (16: 128 registers, no spills)
+#endif
 template<int LOG2N>
-__global__ void __launch_bounds__((1 << LOG2N) / 16) fftfilt_fast_kernel(const FfParams p)
+__global__ void __launch_bounds__((1 << LOG2N) / 16, 32 * FF_FAST_WARPS_PER_SM / ((1 << LOG2N) / 16)) fftfilt_fast_kernel(const FfParams p)
 {
     constexpr int N = 1 << LOG2N, N2 = N / 2, NT = N / 16, TOP = LOG2N - 4;
     constexpr int F0_HI = (LOG2N % 4 == 0) ? 3 : (LOG2N % 4) - 1;      // field 0 ends the forward transform with stages F0_HI .. 0
@@ -465,15 +468,22 @@ int b200dsp_fftfilt_run_dev(b200dsp_fftfilt_t* h, int op, int usb, int get_dc, c
         memset(&p, 0, sizeof(p));
         p.in = in; p.pend = h->d_pend[h->pcur]; p.ovl_in = h->d_ovl[h->cur]; p.ovl_out = h->d_ovl[h->cur ^ 1];
         p.mult = h->d_mult; p.tw = h->d_tw; p.out = (float2*) d_out_c64; p.inptr = h->inptr; p.nb = (int) nb; p.flen = N; p.log2n = h->log2n;
-        long long ctas = (long long) h->sm_count * 4;
+        const bool fast = (N == 1024 || N == 2048);
+        // the fast kernel's CTAs are len/16 threads: as many ranges as CTAs fit the GPU at once
+        int per_sm = 4;
+        const size_t fast_smem = (size_t) (2 * N + N / 16) * sizeof(float2);          // 16.5 / 33 KB: under the 48 KB default
+        if (fast) {
+            const void* fn = (N == 1024) ? (const void*) fftfilt_fast_kernel<10> : (const void*) fftfilt_fast_kernel<11>;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, N / 16, fast_smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 4; }
+        }
+        long long ctas = (long long) h->sm_count * per_sm;
         if (ctas > (nb + 7) / 8) ctas = (nb + 7) / 8;             // a range pays one recomputed block: at least 8 blocks per CTA
         if (ctas < 1) ctas = 1;
         p.blocks_per_cta = (int) ((nb + ctas - 1) / ctas);
         ctas = (nb + p.blocks_per_cta - 1) / p.blocks_per_cta;
-        if (N == 1024 || N == 2048) {
-            const size_t smem = (size_t) (2 * N + N / 16) * sizeof(float2);          // 16.5 / 33 KB: under the 48 KB default
-            if (N == 1024) fftfilt_fast_kernel<10><<<(unsigned) ctas, N / 16, smem, st>>>(p);
-            else           fftfilt_fast_kernel<11><<<(unsigned) ctas, N / 16, smem, st>>>(p);
+        if (fast) {
+            if (N == 1024) fftfilt_fast_kernel<10><<<(unsigned) ctas, N / 16, fast_smem, st>>>(p);
+            else           fftfilt_fast_kernel<11><<<(unsigned) ctas, N / 16, fast_smem, st>>>(p);
         } else {
             const size_t smem = (size_t) 2 * N * sizeof(float2);
             if (smem > 48 * 1024 && (rc = B200_CUDA_CHECK(cudaFuncSetAttribute((const void*) fftfilt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)))) return rc;

@@ -36,19 +36,13 @@ struct DcParams {
     int in_vec, out_vec;       // in / out is 16-byte aligned: 128-bit accesses
 };
 
-__global__ void __launch_bounds__(DC_THREADS) dc_correct_kernel(const DcParams p)
+// the thread's 16 samples of one tile: four 128-bit loads.  rem = how many of them belong to the call (history counts)
+__device__ __forceinline__ void dc_load(const DcParams& p, long long tile, int tid, uint32_t (&raw)[DC_PER], int& rem)
 {
-    __shared__ __align__(16) uint32_t sraw[DC_THREADS * DC_SLOT];      // every thread's 16 packed raw samples
-    __shared__ int sex_r[DC_THREADS], sex_i[DC_THREADS];               // sum of the totals of the lower lanes of its warp
-    __shared__ int wre[DC_THREADS / 32], wim[DC_THREADS / 32];         // warp totals
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const long long t0 = (long long) blockIdx.x * DC_TILE;
-    const long long i0 = t0 - DC_N + DC_PER * tid;      // stream index of this thread's first sample (a multiple of 16; < 0: history)
-    // 1. the thread's 16 samples: four 128-bit loads; a copy goes to shared memory for thread tid + 64
-    uint32_t raw[DC_PER];
-    const bool hist = i0 < 0;                           // (i0 is a multiple of 16: all 16 samples are history, or none)
+    const long long i0 = tile * DC_TILE - DC_N + DC_PER * tid;      // stream index of the first sample (a multiple of 16; < 0: history)
+    const bool hist = i0 < 0;                                       // (all 16 samples are history, or none)
     const long long left = p.n - i0;
-    const int rem = hist ? DC_PER : (left > DC_PER ? DC_PER : (left < 0 ? 0 : (int) left));    // samples of the call among the thread's 16
+    rem = hist ? DC_PER : (left > DC_PER ? DC_PER : (left < 0 ? 0 : (int) left));
     const uint32_t* src = hist ? p.hist_in + (DC_N + i0) : p.in + i0;
     const bool vec = hist || p.in_vec;
 #pragma unroll
@@ -60,54 +54,84 @@ __global__ void __launch_bounds__(DC_THREADS) dc_correct_kernel(const DcParams p
             v.z = (4 * g + 2 < rem) ? src[4 * g + 2] : 0u; v.w = (4 * g + 3 < rem) ? src[4 * g + 3] : 0u;
         }
         raw[4 * g] = v.x; raw[4 * g + 1] = v.y; raw[4 * g + 2] = v.z; raw[4 * g + 3] = v.w;
-        *reinterpret_cast<uint4*>(&sraw[tid * DC_SLOT + 4 * g]) = v;
     }
-    // 2. thread totals, inclusive warp scan
-    int sr = 0, si = 0;
-#pragma unroll
-    for (int k = 0; k < DC_PER; ++k) { sr += (int) (short) (raw[k] & 0xffffu); si += (int) raw[k] >> 16; }
-    int xr = sr, xi = si;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int a = __shfl_up_sync(0xffffffffu, xr, d), b = __shfl_up_sync(0xffffffffu, xi, d);
-        if (lane >= d) { xr += a; xi += b; }
-    }
-    sex_r[tid] = xr - sr; sex_i[tid] = xi - si;
-    if (lane == 31) { wre[wid] = xr; wim[wid] = xi; }
-    __syncthreads();
-    // 3. outputs (tile threads): S = sum of the 1024 samples that end at the current one, y = x - trunc(S / 1024)
-    if (tid >= DC_HALO_THREADS && rem > 0) {
-        const int pt = tid - DC_HALO_THREADS;           // same lane, two warps down
-        int Sr = wre[wid - 2] + wre[wid - 1] + (xr - sr) - sex_r[pt];
-        int Si = wim[wid - 2] + wim[wid - 1] + (xi - si) - sex_i[pt];
-#pragma unroll
-        for (int g = 0; g < DC_PER / 4; ++g) {
-            const uint4 pv = *reinterpret_cast<const uint4*>(&sraw[pt * DC_SLOT + 4 * g]);
-            const uint32_t pw[4] = { pv.x, pv.y, pv.z, pv.w };
-            uint32_t ow[4];
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                const uint32_t w = raw[4 * g + m], q = pw[m];
-                const int x = (int) (short) (w & 0xffffu), y = (int) w >> 16;
-                Sr += x - (int) (short) (q & 0xffffu);
-                Si += y - ((int) q >> 16);
-                const int re = x - Sr / DC_N, im = y - Si / DC_N;         // C++ integer division: toward zero, like total / N
-                ow[m] = ((uint32_t) re & 0xffffu) | ((uint32_t) im << 16);
-            }
-            uint32_t* dst = p.out + i0 + 4 * g;
-            if (p.out_vec && 4 * g + 4 <= rem) *reinterpret_cast<uint4*>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-            else {
-#pragma unroll
-                for (int m = 0; m < 4; ++m) if (4 * g + m < rem) dst[m] = ow[m];
-            }
-        }
-    }
-    // carry: the last DC_N raw samples of the stream so far (block 0 also covers calls shorter than DC_N)
+}
+
+// persistent: block b takes tiles b, b + gridDim.x, ...; the next tile's loads are issued before this tile's arithmetic
+__global__ void __launch_bounds__(DC_THREADS, 4) dc_correct_kernel(const DcParams p)
+{
+    __shared__ __align__(16) uint32_t sraw[DC_THREADS * DC_SLOT];      // every thread's 16 packed raw samples
+    __shared__ int sex_r[DC_THREADS], sex_i[DC_THREADS];               // sum of the totals of the lower lanes of its warp
+    __shared__ int wre[DC_THREADS / 32], wim[DC_THREADS / 32];         // warp totals
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long tiles = (p.n + DC_TILE - 1) / DC_TILE;
+    // carry: the last DC_N raw samples of the stream so far (also covers calls shorter than DC_N)
     if (blockIdx.x == 0) {
         for (int t = tid; t < DC_N; t += DC_THREADS) {
             const long long i = p.n - DC_N + t;
             p.hist_out[t] = (i < 0) ? p.hist_in[DC_N + i] : p.in[i];
         }
+    }
+    long long tile = blockIdx.x;
+    if (tile >= tiles) return;
+    uint32_t raw[DC_PER];
+    int rem;
+    dc_load(p, tile, tid, raw, rem);
+    for (;;) {
+        const long long nxt = tile + gridDim.x;
+        // 1. a copy of the samples goes to shared memory for thread tid + 64
+#pragma unroll
+        for (int g = 0; g < DC_PER / 4; ++g)
+            *reinterpret_cast<uint4*>(&sraw[tid * DC_SLOT + 4 * g]) = make_uint4(raw[4 * g], raw[4 * g + 1], raw[4 * g + 2], raw[4 * g + 3]);
+        uint32_t nraw[DC_PER];
+        int nrem = 0;
+        if (nxt < tiles) dc_load(p, nxt, tid, nraw, nrem);
+        // 2. thread totals, inclusive warp scan
+        int sr = 0, si = 0;
+#pragma unroll
+        for (int k = 0; k < DC_PER; ++k) { sr += (int) (short) (raw[k] & 0xffffu); si += (int) raw[k] >> 16; }
+        int xr = sr, xi = si;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int a = __shfl_up_sync(0xffffffffu, xr, d), b = __shfl_up_sync(0xffffffffu, xi, d);
+            if (lane >= d) { xr += a; xi += b; }
+        }
+        sex_r[tid] = xr - sr; sex_i[tid] = xi - si;
+        if (lane == 31) { wre[wid] = xr; wim[wid] = xi; }
+        __syncthreads();
+        // 3. outputs (tile threads): S = sum of the 1024 samples that end at the current one, y = x - trunc(S / 1024)
+        if (tid >= DC_HALO_THREADS && rem > 0) {
+            const int pt = tid - DC_HALO_THREADS;           // same lane, two warps down
+            int Sr = wre[wid - 2] + wre[wid - 1] + (xr - sr) - sex_r[pt];
+            int Si = wim[wid - 2] + wim[wid - 1] + (xi - si) - sex_i[pt];
+            uint32_t* out0 = p.out + (tile * DC_TILE - DC_N + DC_PER * tid);
+#pragma unroll
+            for (int g = 0; g < DC_PER / 4; ++g) {
+                const uint4 pv = *reinterpret_cast<const uint4*>(&sraw[pt * DC_SLOT + 4 * g]);
+                const uint32_t pw[4] = { pv.x, pv.y, pv.z, pv.w };
+                uint32_t ow[4];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    const uint32_t w = raw[4 * g + m], q = pw[m];
+                    const int x = (int) (short) (w & 0xffffu), y = (int) w >> 16;
+                    Sr += x - (int) (short) (q & 0xffffu);
+                    Si += y - ((int) q >> 16);
+                    const int re = x - Sr / DC_N, im = y - Si / DC_N;         // C++ integer division: toward zero, like total / N
+                    ow[m] = ((uint32_t) re & 0xffffu) | ((uint32_t) im << 16);
+                }
+                uint32_t* dst = out0 + 4 * g;
+                if (p.out_vec && 4 * g + 4 <= rem) *reinterpret_cast<uint4*>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                else {
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) if (4 * g + m < rem) dst[m] = ow[m];
+                }
+            }
+        }
+        if (nxt >= tiles) break;
+        __syncthreads();                                    // every thread has read this tile's shared arrays
+#pragma unroll
+        for (int k = 0; k < DC_PER; ++k) raw[k] = nraw[k];
+        rem = nrem; tile = nxt;
     }
 }
 
@@ -235,7 +259,11 @@ int launch_dc(b200dsp_iqcorr* h, const uint32_t* d_in, uint32_t* d_out, long lon
     p.in = d_in; p.out = d_out; p.hist_in = h->d_hist[h->cur]; p.hist_out = h->d_hist[h->cur ^ 1]; p.n = n;
     const long long blocks = (n + DC_TILE - 1) / DC_TILE;
     p.in_vec = (((uintptr_t) d_in & 15) == 0) ? 1 : 0; p.out_vec = (((uintptr_t) d_out & 15) == 0) ? 1 : 0;
-    dc_correct_kernel<<<(unsigned) blocks, DC_THREADS, 0, st>>>(p);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*) dc_correct_kernel, DC_THREADS, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+    long long grid = (long long) b200_sm_count_of(h->device) * per_sm;      // persistent: one resident wave, tiles dealt round-robin
+    if (grid > blocks) grid = blocks;
+    dc_correct_kernel<<<(unsigned) grid, DC_THREADS, 0, st>>>(p);
     int rc = B200_CUDA_CHECK(cudaGetLastError());
     if (rc == 0) h->cur ^= 1;
     return rc;
