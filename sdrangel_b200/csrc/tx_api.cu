@@ -553,13 +553,18 @@ int b200dsp_interps_run_dev(b200dsp_interps_t* h, int log2_interp, const void* d
     const int TN = 4096 >> log2_interp;
     const long long tiles = (n + TN - 1) / TN;
     if (tiles >= (1ll << 31)) return b200_fail(B200DSP_EINVAL, "interps_run: call too long");
-    long long ctas = (long long) h->sm_count * 4;
+    size_t smem = 0;
+    for (int l = 0; l < log2_interp; ++l) smem += 2 * (size_t) ((l == 0 ? 32 : (l == 1 ? 16 : 8)) + (TN << l) + 4) * 4;
+    typedef void (*ip_fn)(const InterpParams);
+    const ip_fn fns[7] = { nullptr, interps_cascade_kernel<1>, interps_cascade_kernel<2>, interps_cascade_kernel<3>,
+                           interps_cascade_kernel<4>, interps_cascade_kernel<5>, interps_cascade_kernel<6> };
+    int per_sm = 0;         // ranges = the CTAs the GPU holds at once (4 by the launch bound, 5 where registers and shared memory allow)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*) fns[log2_interp], IP_THREADS, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 4; }
+    long long ctas = (long long) h->sm_count * per_sm;
     if (ctas > (tiles + 7) / 8) ctas = (tiles + 7) / 8;          // a range pays one warm-up tile: at least 8 tiles per CTA
     if (ctas < 1) ctas = 1;
     p.tiles = (int) tiles; p.tiles_per_cta = (int) ((tiles + ctas - 1) / ctas);
     ctas = (tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
-    size_t smem = 0;
-    for (int l = 0; l < log2_interp; ++l) smem += 2 * (size_t) ((l == 0 ? 32 : (l == 1 ? 16 : 8)) + (TN << l) + 4) * 4;
     switch (log2_interp) {
     case 1: interps_cascade_kernel<1><<<(unsigned) ctas, IP_THREADS, smem, st>>>(p); break;
     case 2: interps_cascade_kernel<2><<<(unsigned) ctas, IP_THREADS, smem, st>>>(p); break;
