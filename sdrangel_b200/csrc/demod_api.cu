@@ -236,10 +236,22 @@ int b200dsp_demod_run_pool_dev(b200dsp_demod_t* h, const void* d_pool_c64, int64
     p.scaling = h->scaling; p.kind = h->kind;
     p.vec = ((stride_samples & 1) == 0 && (out_stride & 3) == 0 && ((uintptr_t) d_pool_c64 & 15) == 0 && ((uintptr_t) d_out & 15) == 0 &&
              ((uintptr_t) d_aux0 & 15) == 0 && ((uintptr_t) d_aux1 & 15) == 0) ? 1 : 0;
-    long long gx = (stride_samples + 1023) / 1024;
-    if (gx < 1) gx = 1;
-    const long long want = (long long) b200_sm_count_of(h->device) * 8 / n_channels + 1;       // enough CTAs to fill the chip, no more
-    if (gx > want) gx = want;
+    // CTAs per channel: enough to fill the chip, and a total that is close to a whole number of resident waves (2 x 1024
+    // CTAs on 1184 slots ran 1.73 waves: the second one three quarters full)
+    long long gmax = (stride_samples + 1023) / 1024;
+    if (gmax < 1) gmax = 1;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*) demod_kernel, 256, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 8; }
+    const long long slots = (long long) b200_sm_count_of(h->device) * per_sm;
+    const long long want = slots / n_channels + 1;
+    long long gx = want < gmax ? want : gmax;
+    double best = 0.0;
+    for (long long g = want; g <= 8 * want && g <= gmax; ++g) {
+        const double waves = (double) (g * n_channels) / (double) slots;
+        const double eff = waves / (double) (long long) (waves + 0.999999);
+        if (eff > best + 0.01) { best = eff; gx = g; }
+        if (eff >= 0.97) break;
+    }
     demod_kernel<<<dim3((unsigned) gx, (unsigned) n_channels), 256, 0, st>>>(p);
     if ((rc = B200_CUDA_CHECK(cudaGetLastError()))) return rc;
     h->cur ^= 1;
