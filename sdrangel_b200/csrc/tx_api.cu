@@ -332,7 +332,11 @@ __global__ void interps_copy_kernel(const uint32_t* __restrict__ in, void* __res
 // the real parts, lanes 16-31 the imaginary parts of 16 groups, exchanged by shuffle for the rotation and the packed stores.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int UP_THREADS = 256;
-constexpr int UP_DMT = 512;                  // consumption indices per CTA
+#ifndef UP_DMT_DEF
+#define UP_DMT_DEF 512
+#endif
+constexpr int UP_DMT = UP_DMT_DEF;           // consumption indices per CTA (a multiple of 512: 16 groups of 4 per warp and trip)
+static_assert(UP_DMT % 512 == 0, "a trip of the 8 warps covers 512 consumption indices");
 constexpr int UP_LEN = 48 + UP_DMT + 8;      // shared array per component (560 + pad)
 constexpr int UP_STATE_WORDS = 49;
 
