@@ -61,3 +61,45 @@ def test_committed_bench_lines_keep_the_contract(name):
 def test_strong_scaling_series_is_monotonic():
     v = [load(n)["value"] for n in ("r01_bench_default_n1.json", "r01_bench_bank1024_n2.json", "r01_bench_bank1024_n4.json", "r01_bench_bank1024_n8.json")]
     assert v[0] < v[1] < v[2] < v[3]
+
+
+# ---- round 2: the bank line's roofline is the binding (issue) roof with the HBM view beside it ----
+LINES_R02 = {
+    "r02_bench_default_n1_final.json": dict(n_gpus=1, impl=None),
+    "r02_bench_bank1024_n2_final.json": dict(n_gpus=2, impl=None),
+    "r02_bench_bank1024_n4.json": dict(n_gpus=4, impl=None),
+    "r02_bench_reference_arm.json": dict(n_gpus=1, impl="reference"),
+}
+
+
+@pytest.mark.parametrize("name", sorted(LINES_R02))
+def test_committed_round2_lines_keep_the_contract(name):
+    d, exp = load(name), LINES_R02[name]
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in d, (name, k)
+    assert d["metric"].startswith("input MS/s") and d["unit"] == "input MS/s" and d["higher_is_better"] is True
+    assert d["n_gpus"] == exp["n_gpus"] and d["value"] > 0 and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert d["config"]["workload"] == "bank1024" and d["scaling"] == "strong"
+    e = d["e2e"]
+    assert e["value"] > 0 and e["unit"] == "input MS/s"
+    if exp["impl"] == "reference":
+        assert d["impl"] == "reference" and d["gpu_launches"] == 0 and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+        assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] == d["value"]
+        return
+    assert d["warmup"] >= 3 and d["gpu_launches"] > 0 and d["parity_checked_vs_oracle"] is True
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"] and "bank_process" in e["api"] or exp["n_gpus"] > 1
+    r = d["roofline"]
+    assert r["bound"] == "issue" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9       # the binding roof of SURVEY.md 8(d)
+    h = r["hbm"]
+    assert h["unit"] == "GB/s" and abs(h["frac"] - h["achieved"] / h["peak"]) < 1e-9 and h["algorithmic_bytes_per_sample"] > 0
+    assert abs(r["issue"]["frac"] - r["frac"]) < 1e-9 and r["issue"]["instr_per_sample"] > 0
+    cl = d["clocks"]
+    assert cl["sm_mhz"] and not set(cl["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    if exp["n_gpus"] == 1:
+        assert r["traffic"] is not None and h["traffic_over_algorithmic"] > 1.0
+        assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] > 0
+        for w in ("decimateii", "decimatefi", "bank64", "spectrum", "iqcorr", "interps", "upchan", "ssbfilt", "demod"):
+            assert d["also"][w]["parity_checked_vs_oracle"] is True, w
+    else:
+        assert d["cpu_baseline"] is None and d["config"]["broadcast_trials_ms_per_step"]
